@@ -1,0 +1,191 @@
+// awb_common.cuh -- shared device/host structures of the B200 threading-HMM path.
+//
+// Data layout in HBM (one AwbChain per independent problem, all arrays flat):
+//
+//   per block b (local tree), B = ntrees:
+//     nstates[b]                true state count S_b (0 allowed in internal mode)
+//     row_off[b]                offset of the block's per-state rows; a row has
+//                               max(S_b,1) entries ("zero-state blocks are size 1",
+//                               reference sample_thread.cpp:349-351)
+//     fw_off[b]                 offset (doubles) of the block's slab of the
+//                               forward table: fw[fw_off[b] + (i-start_b)*S1 + j]
+//                               with j in the reference's state order
+//   per state (node-major = reference order, index row_off[b]+j):
+//     st_node, st_time, inv_emit, band_j1/band_len/band_boff, sw_start/sw_cnt
+//   per state in time-major order (index row_off[b]+q): perm (-> j), pslot
+//
+// The forward kernel runs one CTA per chain with one thread per state in
+// TIME-MAJOR order, so that the per-time group sums of the SMC transition are
+// contiguous lane segments (warp-shuffle segmented reduction).
+#ifndef AWB_COMMON_CUH
+#define AWB_COMMON_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define AWB_HD __host__ __device__
+#else
+#define AWB_HD
+#endif
+
+#define AWB_MAXT 64      // == AWB_MAX_NTIMES
+#define AWB_MAXV 1024    // == AWB_MAX_NNODES
+#define AWB_MAXS 1024    // == AWB_MAX_NSTATES
+
+enum { AWB_TM_D = 0, AWB_TM_E, AWB_TM_LNB, AWB_TM_LNE2, AWB_TM_LNNEGG1,
+       AWB_TM_G2, AWB_TM_G3, AWB_TM_LNG4, AWB_TM_NORECOMBS, AWB_TM_NVEC };
+
+enum { AWB_SITE_INVARIANT = 0, AWB_SITE_VARIANT = 1, AWB_SITE_MASKED = 2 };
+
+// ArgModel time grid (reference model.h:41-354)
+struct AwbModel {
+    int ntimes;
+    int removed_root_time;             // ntimes + 1 (model.h:207)
+    double rho, mu, mintime;           // mintime = 0.1 * times[1] (model.h:211)
+    double times[AWB_MAXT];
+    double time_steps[AWB_MAXT];       // last = inf (model.h:322-333)
+    double popsizes[AWB_MAXT];
+    double coal_time_steps[2 * AWB_MAXT]; // model.cpp:9-23
+};
+
+struct AwbChain {
+    AwbModel model;
+    int internal, minage;
+    int nleaves, nrows, nseqs, seqlen;
+    int ntrees, nnodes, nsites, start_coord;
+    int maxS;                 // max over blocks of max(S_b, 1)
+    int maxband;              // max over blocks of the band size (doubles)
+    int keep_debug;
+
+    // ---- inputs
+    const int *ptrees;        // [B][V]
+    const int *ages;          // [B][V]
+    const int *sprs;          // [B][4]
+    const int *blocklens;     // [B]
+    const int *subtree_roots; // [B] (internal) or NULL
+    const int *rowidx;        // [nrows] rows of seqs compared for invariance:
+                              //   leaves' seqids, then new_chrom (external)
+    const unsigned char *seqs; // [nseqs][seqlen]
+
+    // ---- layout (host computed)
+    const int *block_start;   // [B+1] site offset of each block (0-based in chain)
+    const int *nstates;       // [B]
+    const long long *row_off; // [B+1]
+    const long long *fw_off;  // [B+1]
+    const long long *band_off;// [B+1]
+    const long long *ent_off; // [B+1]
+    const long long *sw1_off; // [B+1] (debug arrays of the switch matrix)
+
+    // ---- block setup outputs (K1)
+    short *st_node;           // [rows]
+    signed char *st_time;     // [rows]
+    unsigned short *perm;     // [rows] time-major q -> node-major j
+    unsigned short *pslot;    // [rows] partial-sum slot of time-major q
+    unsigned short *band_j1;  // [rows] first state of this state's branch
+    unsigned char *band_len;  // [rows] number of states on the branch
+    int *band_boff;           // [rows] offset of this state's coefficients in the block band
+    double *inv_emit;         // [rows] invariant-site emission
+    double *band;             // [band_off[B]] same-branch coefficients (tmatrix2)
+    double *tmatrix;          // [B][T*T]  tmatrix[a*T+b]
+    double *tmvec;            // [B][9][T]
+    unsigned short *rowstart; // [B][T+1] time-major start of each time row
+    unsigned short *pstart;   // [B][T+1] first partial slot of each time row
+    short *node_first;        // [B][V] first state index of node (or -1)
+    short *node_cnt;          // [B][V]
+    short *child0, *child1;   // [B][V]
+    short *order;             // [B][V] post-order (local_tree.h:274-304)
+    short *root;              // [B]
+    int *lineages;            // [B][3][T] nbranches, nrecombs, ncoals
+    double *treelen;          // [B] get_treelen / get_treelen_internal
+    int *tm_minage;           // [B]
+
+    // ---- switch setup outputs (K2), CSR over targets of block b
+    unsigned short *sw_start; // [rows]
+    unsigned short *sw_cnt;   // [rows]
+    unsigned short *sw_src;   // [ent_off[B]] source state (previous block order)
+    double *sw_prob;          // [ent_off[B]]
+    // debug copies in the reference's representation (keep_debug)
+    int *sw_determ;           // [sw1_off[B]]
+    double *sw_determprob;    // [sw1_off[B]]
+    double *sw_recombrow;     // [rows]
+    double *sw_recoalrow;     // [rows]
+    int *sw_recombsrc;        // [B]
+    int *sw_recoalsrc;        // [B]
+
+    // ---- sites, tables, results
+    unsigned char *kind;      // [nsites]
+    double *fw;               // [fw_off[B]]
+    int *path;                // [nsites]
+    const int *rand_ints;     // [nsites]
+    double *logz;             // [1]
+    int *status;              // [1] first bad site or -1
+    int last_state;           // traceback: -1 = sample last column
+};
+
+// ------------------------------------------------------------------ math
+
+// common.h:157-163
+AWB_HD inline double awb_logadd(double lna, double lnb)
+{
+    if (lna == -INFINITY) return lnb;
+    if (lnb == -INFINITY) return lna;
+    return fmax(lna, lnb) + log1p(exp(-fabs(lna - lnb)));
+}
+
+// trans.h:89-128 TransMatrix::get_time.  v points at 9 vectors of stride T.
+AWB_HD inline double awb_get_time(const double *v, int T, int a, int b, int c,
+                                  int minage, bool same_node)
+{
+    if (a < minage || b < minage)
+        return 0.0;
+    const double *D = v + AWB_TM_D * T, *E = v + AWB_TM_E * T,
+        *lnB = v + AWB_TM_LNB * T, *lnE2 = v + AWB_TM_LNE2 * T,
+        *lnNegG1 = v + AWB_TM_LNNEGG1 * T, *G2 = v + AWB_TM_G2 * T,
+        *G3 = v + AWB_TM_G3 * T, *lnG4 = v + AWB_TM_LNG4 * T,
+        *norecombs = v + AWB_TM_NORECOMBS * T;
+    const double term1 = D[a] * E[b];
+    double minage_term = 0.0;
+    if (minage > 0)
+        minage_term = exp(lnG4[b] + lnB[minage - 1]);
+
+    if (!same_node) {
+        if (a < b)
+            return term1 * (exp(lnE2[b] + lnB[a]) - exp(lnE2[b] + lnNegG1[a])
+                            - minage_term);
+        else if (a == b)
+            return term1 * ((b > 0 ? exp(lnE2[b] + lnB[b - 1]) : 0.0) + G3[b]
+                            - minage_term);
+        else
+            return term1 * ((b > 0 ? exp(lnE2[b] + lnB[b - 1]) : 0.0) + G2[b]
+                            - minage_term);
+    } else {
+        const double c_term = (c > 0 ? exp(lnG4[b] + lnB[c - 1]) : 0.0);
+        if (a < b)
+            return term1 * (2 * (exp(lnE2[b] + lnB[a]) -
+                                 exp(lnE2[b] + lnNegG1[a]))
+                            - c_term - minage_term);
+        else if (a == b)
+            return term1 * ((2 * ((b > 0 ? exp(lnE2[b] + lnB[b - 1]) : 0.0) +
+                                  G3[b])) - c_term - minage_term)
+                + norecombs[a];
+        else
+            return term1 * ((2 * ((b > 0 ? exp(lnE2[b] + lnB[b - 1]) : 0.0) +
+                                  G2[b])) - c_term - minage_term);
+    }
+}
+
+// emit.cpp:86-93 (Jukes-Cantor)
+AWB_HD inline double awb_prob_branch(double t, double mu, bool mut)
+{
+    const double f = 4. / 3.;
+    if (!mut)
+        return .25 * (1.0 + 3. * exp(-f * mu * t));
+    else
+        return .25 * (1.0 - exp(-f * mu * t));
+}
+
+AWB_HD inline int awb_imax(int a, int b) { return a > b ? a : b; }
+AWB_HD inline int awb_imin(int a, int b) { return a < b ? a : b; }
+
+#endif // AWB_COMMON_CUH

@@ -1,0 +1,237 @@
+// awb_emit.cuh -- emissions of the threading HMM (reference emit.cpp:650-845,
+// phased, no infinite-sites penalty).
+//
+// Invariant sites (~97 % of compressed sites) share one per-state constant per
+// block (inv_emit, computed by awb_block_setup); masked sites emit 1.  Only
+// VARIANT sites need Felsenstein pruning: awb_emit_site computes the inner
+// (post-order) and outer (pre-order) partial likelihoods of one site and the
+// per-state emission with the new branch attached, and stores the row into
+// the forward table's own slab for that site (fw[i][*]); the forward kernel
+// reads it there before overwriting the row with the forward column, so the
+// emissions never occupy separate HBM.
+//
+// awb_emit_site is lane-cooperative: `nlanes` workers (a warp on the GPU, 1 on
+// the host emulation) call it with the same arguments and their own `lane`.
+#ifndef AWB_EMIT_CUH
+#define AWB_EMIT_CUH
+
+#include "awb_common.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define AWB_LANESYNC() __syncwarp()
+#else
+#define AWB_LANESYNC() ((void) 0)
+#endif
+
+// emit.cpp:30-58 (find_invariant_sites, find_masked_sites) for one site
+AWB_HD inline void awb_site_kind(const AwbChain &ch, int i)
+{
+    const size_t col = (size_t) ch.start_coord + i;
+    const unsigned char c = ch.seqs[(size_t) ch.rowidx[0] * ch.seqlen + col];
+    bool mut = false;
+    for (int r = 1; r < ch.nrows; r++) {
+        if (ch.seqs[(size_t) ch.rowidx[r] * ch.seqlen + col] != c) {
+            mut = true;
+            break;
+        }
+    }
+    ch.kind[i] = mut ? AWB_SITE_VARIANT :
+        (c == 'N' ? AWB_SITE_MASKED : AWB_SITE_INVARIANT);
+}
+
+AWB_HD inline void awb_leaf_row(unsigned char c, double *row)
+{
+    int x = -1;                       // seq.cpp:15-43 (dna2int)
+    switch (c) {
+    case 'A': case 'a': x = 0; break;
+    case 'C': case 'c': x = 1; break;
+    case 'G': case 'g': x = 2; break;
+    case 'T': case 't': x = 3; break;
+    }
+    if (x < 0) {                      // 'N' (emit.cpp:162-166); other symbols as N
+        row[0] = row[1] = row[2] = row[3] = 1.0;
+    } else {
+        row[0] = row[1] = row[2] = row[3] = 0.0;
+        row[x] = 1.0;
+    }
+}
+
+// Binary search: block containing site i (block_start is [B+1], ascending)
+AWB_HD inline int awb_find_block(const AwbChain &ch, int i)
+{
+    int lo = 0, hi = ch.ntrees - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ch.block_start[mid] <= i) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+// scratch per worker group: inner[4V], outer[4V], mut[V], nomut[V] doubles and
+// inmain[V] bytes
+AWB_HD inline size_t awb_emit_scratch_bytes(int V)
+{
+    return (size_t) V * (10 * sizeof(double)) + (((size_t) V + 7) & ~(size_t) 7);
+}
+
+AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int lane, int nlanes,
+                                 unsigned char *scratch)
+{
+    const AwbModel &m = ch.model;
+    const int V = ch.nnodes;
+    const int T = m.ntimes;
+    const int b = awb_find_block(ch, i);
+    const int S = ch.nstates[b];
+    if (S == 0)
+        return;                         // emit.cpp:665-669
+    const bool internal = ch.internal != 0;
+    const int *parent = ch.ptrees + (size_t) b * V;
+    const int *age = ch.ages + (size_t) b * V;
+    const short *c0 = ch.child0 + (size_t) b * V;
+    const short *c1 = ch.child1 + (size_t) b * V;
+    const short *order = ch.order + (size_t) b * V;
+    const int root = ch.root[b];
+    const int maintree_root = internal ? c1[root] : root;
+    const int subtree_root = internal ? c0[root] : root;
+    const size_t col = (size_t) ch.start_coord + i;
+
+    double *inner = (double *) scratch;
+    double *outer = inner + 4 * (size_t) V;
+    double *mut = outer + 4 * (size_t) V;
+    double *nomut = mut + V;
+    unsigned char *inmain = (unsigned char *) (nomut + V);
+
+    // branch mutation probabilities (emit.cpp:97-116) and leaf rows (:159-173)
+    for (int j = lane; j < V; j += nlanes) {
+        double mu_j = 0.0, nomu_j = 0.0;
+        if (j != root) {
+            const int pa = age[parent[j]];
+            if (pa != m.removed_root_time) {
+                const double t = fmax(m.times[pa] - m.times[age[j]], m.mintime);
+                mu_j = awb_prob_branch(t, m.mu, true);
+                nomu_j = awb_prob_branch(t, m.mu, false);
+            }
+        }
+        mut[j] = mu_j;
+        nomut[j] = nomu_j;
+        inmain[j] = 0;
+        if (c0[j] == -1)
+            awb_leaf_row(ch.seqs[(size_t) ch.rowidx[j] * ch.seqlen + col],
+                         inner + 4 * j);
+    }
+    AWB_LANESYNC();
+
+    // inner partials, post-order (emit.cpp:175-194)
+    for (int q = 0; q < V; q++) {
+        const int j = order[q];
+        if (c0[j] != -1) {
+            const int k1 = c0[j], k2 = c1[j];
+            for (int a = lane; a < 4; a += nlanes) {
+                double p1 = 0.0, p2 = 0.0;
+                for (int x = 0; x < 4; x++) {
+                    if (a == x) {
+                        p1 += inner[4 * k1 + x] * nomut[k1];
+                        p2 += inner[4 * k2 + x] * nomut[k2];
+                    } else {
+                        p1 += inner[4 * k1 + x] * mut[k1];
+                        p2 += inner[4 * k2 + x] * mut[k2];
+                    }
+                }
+                inner[4 * j + a] = p1 * p2;
+            }
+            AWB_LANESYNC();
+        }
+    }
+
+    // outer partials, parents before children = reverse post-order
+    // (emit.cpp:200-296); only nodes of the main tree
+    for (int q = V - 1; q >= 0; q--) {
+        const int j = order[q];
+        bool in;
+        if (j == maintree_root) {
+            in = true;
+            for (int a = lane; a < 4; a += nlanes)
+                outer[4 * j + a] = 1.0;
+        } else {
+            const int p = parent[j];
+            in = (p != -1) && inmain[p];
+            if (in) {
+                const int sib = (c0[p] == j) ? c1[p] : c0[p];
+                for (int a = lane; a < 4; a += nlanes) {
+                    double p1 = 0.0, p2 = 0.0;
+                    for (int x = 0; x < 4; x++) {
+                        if (a == x) {
+                            p1 += inner[4 * sib + x] * nomut[sib];
+                            p2 += outer[4 * p + x] * nomut[p];
+                        } else {
+                            p1 += inner[4 * sib + x] * mut[sib];
+                            p2 += outer[4 * p + x] * mut[p];
+                        }
+                    }
+                    outer[4 * j + a] = (p != maintree_root) ? p1 * p2 : p1;
+                }
+            }
+        }
+        AWB_LANESYNC();
+        if (lane == 0)
+            inmain[j] = in ? 1 : 0;
+        AWB_LANESYNC();
+    }
+
+    // the branch being threaded: new leaf (external) or the subtree root
+    double in2[4];
+    if (internal) {
+        for (int x = 0; x < 4; x++)
+            in2[x] = inner[4 * subtree_root + x];
+    } else {
+        awb_leaf_row(ch.seqs[(size_t) ch.rowidx[ch.nrows - 1] * ch.seqlen + col],
+                     in2);
+    }
+    const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
+
+    // per-state emission (emit.cpp:778-805, calc_emit :620-645)
+    const long long row0 = ch.row_off[b];
+    double *out = ch.fw + ch.fw_off[b] + (long long) (i - ch.block_start[b]) * S;
+    for (int k = lane; k < S; k += nlanes) {
+        const int node2 = ch.st_node[row0 + k];
+        const int p = parent[node2];
+        const double time2 = m.times[age[node2]];
+        const double parent_time = (p != -1) ?
+            m.times[awb_imin(age[p], T - 1)] : 0.0;
+        const double coal_time = m.times[ch.st_time[row0 + k]];
+        const double d0 = fmax(coal_time - time1, m.mintime);
+        const double d1 = fmax(coal_time - time2, m.mintime);
+        const double d2 = fmax(parent_time - coal_time, m.mintime);
+        const double mu0 = awb_prob_branch(d0, m.mu, true);
+        const double mu1 = awb_prob_branch(d1, m.mu, true);
+        const double mu2 = awb_prob_branch(d2, m.mu, true);
+        const double no0 = awb_prob_branch(d0, m.mu, false);
+        const double no1 = awb_prob_branch(d1, m.mu, false);
+        const double no2 = awb_prob_branch(d2, m.mu, false);
+        const double *in_n = inner + 4 * node2;
+        const double *out_n = outer + 4 * node2;
+        double emit = 0.0;
+        for (int a = 0; a < 4; a++) {
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            for (int x = 0; x < 4; x++) {
+                if (a == x) {
+                    p1 += in2[x] * no0;
+                    p2 += in_n[x] * no1;
+                    p3 += out_n[x] * no2;
+                } else {
+                    p1 += in2[x] * mu0;
+                    p2 += in_n[x] * mu1;
+                    p3 += out_n[x] * mu2;
+                }
+            }
+            if (node2 != maintree_root)
+                emit += p1 * p2 * p3 * .25;
+            else
+                emit += p1 * p2 * .25;
+        }
+        out[k] = emit;
+    }
+}
+
+#endif // AWB_EMIT_CUH

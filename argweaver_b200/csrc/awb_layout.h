@@ -1,0 +1,497 @@
+// awb_layout.h -- host-side (pure C++) layout of one problem's arrays.
+//
+// Integer-only host logic: counts the HMM states of every local tree
+// (reference states.cpp:53-74,109-166), derives the offsets of the per-state
+// rows, the forward-table slabs, the same-branch bands and the switch CSR
+// lists, validates the inputs, and assigns every device array a position in
+// one arena.  Used by awb_api.cu (arena in HBM) and by the CPU emulation
+// harness tests/host_emul.cpp (arena in host memory).
+#ifndef AWB_LAYOUT_H
+#define AWB_LAYOUT_H
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "argweaver_b200.h"
+#include "awb_common.cuh"
+
+struct AwbCopy {            // one host -> arena copy of an input array
+    size_t dst_off;
+    const void *src;
+    size_t bytes;
+};
+
+struct AwbLayout {
+    int B, V, T, n, nrows;
+    int maxS, maxband;
+    int keep_debug;
+    double states_sites;                 // sum blocklen * nstates
+    std::vector<int> nstates, block_start, rowidx;
+    std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off;
+    AwbModel model;
+
+    // arena
+    size_t total_bytes;
+    size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
+        o_seqs, o_block_start, o_nstates, o_row_off, o_fw_off, o_band_off,
+        o_ent_off, o_sw1_off, o_st_node, o_st_time, o_perm, o_pslot, o_band_j1,
+        o_band_len, o_band_boff, o_inv_emit, o_band, o_tmatrix, o_tmvec,
+        o_rowstart, o_pstart, o_node_first, o_node_cnt, o_child0, o_child1,
+        o_order, o_root, o_lineages, o_treelen, o_tm_minage, o_sw_start,
+        o_sw_cnt, o_sw_src, o_sw_prob, o_sw_determ, o_sw_determprob,
+        o_sw_recombrow, o_sw_recoalrow, o_sw_recombsrc, o_sw_recoalsrc, o_kind,
+        o_fw, o_path, o_rand, o_logz, o_status;
+    bool has_subtree_roots;
+    std::vector<AwbCopy> copies;         // inputs taken straight from the caller
+};
+
+// model.h:322-333, model.cpp:9-23
+inline void awb_model_fill(AwbModel &m, const awb_problem &p)
+{
+    memset(&m, 0, sizeof(m));
+    const int T = p.ntimes;
+    m.ntimes = T;
+    m.removed_root_time = T + 1;
+    m.rho = p.rho;
+    m.mu = p.mu;
+    for (int i = 0; i < T; i++) {
+        m.times[i] = p.times[i];
+        m.popsizes[i] = p.popsizes[i];
+    }
+    m.mintime = p.times[1] * .1;
+    for (int i = 0; i < T - 1; i++)
+        m.time_steps[i] = p.times[i + 1] - p.times[i];
+    m.time_steps[T - 1] = INFINITY;
+    std::vector<double> t2(2 * T + 1, p.times[T - 1]);
+    for (int i = 0; i < T - 1; i++) {
+        t2[2 * i] = p.times[i];
+        t2[2 * i + 1] = sqrt((p.times[i + 1] + 1.0) * (p.times[i] + 1.0));
+    }
+    for (int i = 0; i < 2 * T - 2; i++)
+        m.coal_time_steps[i] = t2[i + 1] - t2[i];
+    m.coal_time_steps[2 * T - 2] = INFINITY;
+    m.coal_time_steps[2 * T - 1] = INFINITY;
+}
+
+// Number of states of one tree and the sum of squared branch state counts.
+// Returns false on a malformed tree.
+inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
+                             std::vector<int> &c1, std::vector<int> &stack,
+                             std::vector<char> &ignore, int &S, int &band,
+                             std::string &err)
+{
+    const int V = p.nnodes, T = p.ntimes;
+    const int *parent = p.ptrees + (size_t) b * V;
+    const int *age = p.ages + (size_t) b * V;
+    int root = -1, nroots = 0;
+    for (int i = 0; i < V; i++) {
+        c0[i] = c1[i] = -1;
+        ignore[i] = 0;
+    }
+    for (int i = 0; i < V; i++) {
+        const int pa = parent[i];
+        if (pa == -1) {
+            root = i;
+            nroots++;
+            continue;
+        }
+        if (pa < 0 || pa >= V || pa == i) {
+            err = "tree " + std::to_string(b) + ": bad parent index";
+            return false;
+        }
+        if (c0[pa] == -1) c0[pa] = i;
+        else if (c1[pa] == -1) c1[pa] = i;
+        else {
+            err = "tree " + std::to_string(b) + ": node with three children";
+            return false;
+        }
+    }
+    if (nroots != 1) {
+        err = "tree " + std::to_string(b) + ": expected exactly one root";
+        return false;
+    }
+    const bool internal = p.internal != 0;
+    for (int i = 0; i < V; i++) {
+        const int a = age[i];
+        const bool vroot = internal && i == root && a == T + 1;
+        if (!vroot && (a < 0 || a > T - 2)) {
+            err = "tree " + std::to_string(b) + ": node age out of range";
+            return false;
+        }
+        if (parent[i] != -1 && age[parent[i]] < a) {
+            err = "tree " + std::to_string(b) + ": parent younger than child";
+            return false;
+        }
+    }
+    S = 0;
+    band = 0;
+    int minage = p.minage;
+    if (internal) {
+        if (V < 3 || c0[root] == -1) {
+            err = "internal mode needs a root with two children";
+            return false;
+        }
+        if (age[root] < T)
+            return true;                    // fully specified tree: no states
+        int sub = c0[root];
+        if (p.subtree_roots && p.subtree_roots[b] >= 0) {
+            sub = p.subtree_roots[b];
+            if (sub != c0[root] && sub != c1[root]) {
+                err = "tree " + std::to_string(b) +
+                    ": subtree_root is not a child of the root";
+                return false;
+            }
+        }
+        if (age[sub] > minage) minage = age[sub];
+        ignore[root] = 1;
+        int top = 0;
+        stack[top++] = sub;
+        while (top > 0) {
+            const int node = stack[--top];
+            ignore[node] = 1;
+            if (c0[node] != -1) {
+                stack[top++] = c0[node];
+                stack[top++] = c1[node];
+            }
+        }
+    }
+    for (int i = 0; i < V; i++) {
+        if (ignore[i]) continue;
+        const int pa = parent[i];
+        const int lo = age[i] > minage ? age[i] : minage;
+        const int hi = (pa == -1 || (internal && pa == root)) ? T - 2 : age[pa];
+        const int cnt = hi - lo + 1;
+        if (cnt > 0) {
+            S += cnt;
+            band += cnt * cnt;
+        }
+    }
+    return true;
+}
+
+inline size_t awb_align(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+// Build the layout.  Returns false and sets err on invalid input.
+inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
+                             std::string &err)
+{
+    const int B = p.ntrees, V = p.nnodes, T = p.ntimes;
+    if (T < 3 || T > AWB_MAXT) { err = "ntimes must be in [3, 64]"; return false; }
+    if (V < 1 || V > AWB_MAXV) { err = "nnodes must be in [1, 1024]"; return false; }
+    if (B < 1) { err = "ntrees must be >= 1"; return false; }
+    if (!p.times || !p.popsizes || !p.seqs || !p.seqids || !p.ptrees ||
+        !p.ages || !p.sprs || !p.blocklens) {
+        err = "null input array";
+        return false;
+    }
+    if (p.nleaves != (V + 1) / 2) { err = "nleaves != (nnodes+1)/2"; return false; }
+    for (int i = 0; i + 1 < T; i++)
+        if (!(p.times[i + 1] > p.times[i])) { err = "times must increase"; return false; }
+    L.B = B; L.V = V; L.T = T;
+    L.keep_debug = keep_debug;
+    awb_model_fill(L.model, p);
+
+    // rows compared for invariance (matrices.cpp:30-34 / :108-112)
+    L.rowidx.clear();
+    for (int i = 0; i < p.nleaves; i++) {
+        if (p.seqids[i] < 0 || p.seqids[i] >= p.nseqs) { err = "bad seqid"; return false; }
+        L.rowidx.push_back(p.seqids[i]);
+    }
+    if (!p.internal) {
+        if (p.new_chrom < 0 || p.new_chrom >= p.nseqs) { err = "bad new_chrom"; return false; }
+        L.rowidx.push_back(p.new_chrom);
+    }
+    L.nrows = (int) L.rowidx.size();
+
+    L.nstates.assign(B, 0);
+    L.block_start.assign(B + 1, 0);
+    L.row_off.assign(B + 1, 0);
+    L.fw_off.assign(B + 1, 0);
+    L.band_off.assign(B + 1, 0);
+    L.ent_off.assign(B + 1, 0);
+    L.sw1_off.assign(B + 1, 0);
+    L.maxS = 1;
+    L.maxband = 0;
+    L.states_sites = 0;
+    std::vector<int> c0(V), c1(V), stack(V + 2);
+    std::vector<char> ignore(V);
+    for (int b = 0; b < B; b++) {
+        int S = 0, band = 0;
+        if (!awb_count_states(p, b, c0, c1, stack, ignore, S, band, err))
+            return false;
+        if (S > AWB_MAXS) {
+            err = "block with more than 1024 states is not supported by this build";
+            return false;
+        }
+        if (p.blocklens[b] < 1) { err = "blocklen must be >= 1"; return false; }
+        if (!p.internal && S == 0) { err = "external block without states"; return false; }
+        const int S1 = S > 0 ? S : 1;
+        L.nstates[b] = S;
+        L.block_start[b + 1] = L.block_start[b] + p.blocklens[b];
+        L.row_off[b + 1] = L.row_off[b] + S1;
+        L.fw_off[b + 1] = L.fw_off[b] + (long long) S1 * p.blocklens[b];
+        L.band_off[b + 1] = L.band_off[b] + band;
+        const int prevS1 = b > 0 ? (L.nstates[b - 1] > 0 ? L.nstates[b - 1] : 1) : 0;
+        L.ent_off[b + 1] = L.ent_off[b] + (b > 0 ? prevS1 + T + 4 : 0);
+        L.sw1_off[b + 1] = L.sw1_off[b] + (b > 0 ? prevS1 : 0);
+        if (S1 > L.maxS) L.maxS = S1;
+        if (band > L.maxband) L.maxband = band;
+        L.states_sites += (double) S * p.blocklens[b];
+
+        if (b > 0) {
+            const int *spr = p.sprs + 4 * (size_t) b;
+            const int *lp = p.ptrees + (size_t) (b - 1) * V;
+            if (spr[0] < 0 || spr[0] >= V || spr[2] < 0 || spr[2] >= V ||
+                spr[1] < 0 || spr[3] < spr[1] || lp[spr[0]] < 0) {
+                err = "tree " + std::to_string(b) + ": invalid SPR";
+                return false;
+            }
+            if (p.mappings) {
+                const int broken = lp[spr[0]];
+                const int *mp = p.mappings + (size_t) b * V;
+                for (int x = 0; x < V; x++) {
+                    if (mp[x] != (x == broken ? -1 : x)) {
+                        err = "tree " + std::to_string(b) +
+                            ": node mapping is not identity-except-broken-node";
+                        return false;
+                    }
+                }
+            }
+        }
+    }
+    L.n = L.block_start[B];
+    if (p.start_coord < 0 || p.start_coord + L.n > p.seqlen) {
+        err = "blocks exceed the sequence length";
+        return false;
+    }
+    L.has_subtree_roots = p.internal && p.subtree_roots;
+
+    // ---- arena
+    size_t off = 0;
+    const size_t rows = (size_t) L.row_off[B];
+    const size_t BV = (size_t) B * V;
+#define AWB_PLACE(name, bytes) do { L.name = off; off = awb_align(off + (bytes)); } while (0)
+    AWB_PLACE(o_ptrees, BV * sizeof(int));
+    AWB_PLACE(o_ages, BV * sizeof(int));
+    AWB_PLACE(o_sprs, (size_t) B * 4 * sizeof(int));
+    AWB_PLACE(o_blocklens, (size_t) B * sizeof(int));
+    AWB_PLACE(o_subtree_roots, (size_t) B * sizeof(int));
+    AWB_PLACE(o_rowidx, (size_t) L.nrows * sizeof(int));
+    AWB_PLACE(o_seqs, (size_t) p.nseqs * p.seqlen);
+    AWB_PLACE(o_block_start, (size_t) (B + 1) * sizeof(int));
+    AWB_PLACE(o_nstates, (size_t) B * sizeof(int));
+    AWB_PLACE(o_row_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_fw_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_band_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_ent_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_sw1_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_st_node, rows * sizeof(short));
+    AWB_PLACE(o_st_time, rows);
+    AWB_PLACE(o_perm, rows * sizeof(short));
+    AWB_PLACE(o_pslot, rows * sizeof(short));
+    AWB_PLACE(o_band_j1, rows * sizeof(short));
+    AWB_PLACE(o_band_len, rows);
+    AWB_PLACE(o_band_boff, rows * sizeof(int));
+    AWB_PLACE(o_inv_emit, rows * sizeof(double));
+    AWB_PLACE(o_band, (size_t) L.band_off[B] * sizeof(double) + 8);
+    AWB_PLACE(o_tmatrix, (size_t) B * T * T * sizeof(double));
+    AWB_PLACE(o_tmvec, (size_t) B * AWB_TM_NVEC * T * sizeof(double));
+    AWB_PLACE(o_rowstart, (size_t) B * (T + 1) * sizeof(short));
+    AWB_PLACE(o_pstart, (size_t) B * (T + 1) * sizeof(short));
+    AWB_PLACE(o_node_first, BV * sizeof(short));
+    AWB_PLACE(o_node_cnt, BV * sizeof(short));
+    AWB_PLACE(o_child0, BV * sizeof(short));
+    AWB_PLACE(o_child1, BV * sizeof(short));
+    AWB_PLACE(o_order, BV * sizeof(short));
+    AWB_PLACE(o_root, (size_t) B * sizeof(short));
+    AWB_PLACE(o_lineages, (size_t) B * 3 * T * sizeof(int));
+    AWB_PLACE(o_treelen, (size_t) B * sizeof(double));
+    AWB_PLACE(o_tm_minage, (size_t) B * sizeof(int));
+    AWB_PLACE(o_sw_start, rows * sizeof(short));
+    AWB_PLACE(o_sw_cnt, rows * sizeof(short));
+    AWB_PLACE(o_sw_src, (size_t) L.ent_off[B] * sizeof(short) + 8);
+    AWB_PLACE(o_sw_prob, (size_t) L.ent_off[B] * sizeof(double) + 8);
+    if (keep_debug) {
+        AWB_PLACE(o_sw_determ, (size_t) L.sw1_off[B] * sizeof(int) + 8);
+        AWB_PLACE(o_sw_determprob, (size_t) L.sw1_off[B] * sizeof(double) + 8);
+        AWB_PLACE(o_sw_recombrow, rows * sizeof(double));
+        AWB_PLACE(o_sw_recoalrow, rows * sizeof(double));
+        AWB_PLACE(o_sw_recombsrc, (size_t) B * sizeof(int));
+        AWB_PLACE(o_sw_recoalsrc, (size_t) B * sizeof(int));
+    } else {
+        L.o_sw_determ = L.o_sw_determprob = L.o_sw_recombrow = 0;
+        L.o_sw_recoalrow = L.o_sw_recombsrc = L.o_sw_recoalsrc = 0;
+    }
+    AWB_PLACE(o_kind, (size_t) L.n);
+    AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
+    AWB_PLACE(o_path, (size_t) L.n * sizeof(int));
+    AWB_PLACE(o_rand, (size_t) L.n * sizeof(int));
+    AWB_PLACE(o_logz, sizeof(double));
+    AWB_PLACE(o_status, sizeof(int));
+#undef AWB_PLACE
+    L.total_bytes = off;
+
+    // ---- input copies
+    L.copies.clear();
+    L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int) });
+    L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int) });
+    L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int) });
+    L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int) });
+    if (L.has_subtree_roots)
+        L.copies.push_back({ L.o_subtree_roots, p.subtree_roots, (size_t) B * sizeof(int) });
+    L.copies.push_back({ L.o_rowidx, L.rowidx.data(), (size_t) L.nrows * sizeof(int) });
+    L.copies.push_back({ L.o_seqs, p.seqs, (size_t) p.nseqs * p.seqlen });
+    L.copies.push_back({ L.o_block_start, L.block_start.data(), (size_t) (B + 1) * sizeof(int) });
+    L.copies.push_back({ L.o_nstates, L.nstates.data(), (size_t) B * sizeof(int) });
+    L.copies.push_back({ L.o_row_off, L.row_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    L.copies.push_back({ L.o_fw_off, L.fw_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    L.copies.push_back({ L.o_band_off, L.band_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    L.copies.push_back({ L.o_ent_off, L.ent_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    L.copies.push_back({ L.o_sw1_off, L.sw1_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    return true;
+}
+
+// Point an AwbChain at an arena (device or host base pointer).
+inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base,
+                            AwbChain &ch)
+{
+    memset(&ch, 0, sizeof(ch));
+    ch.model = L.model;
+    ch.internal = p.internal;
+    ch.minage = p.minage;
+    ch.nleaves = p.nleaves;
+    ch.nrows = L.nrows;
+    ch.nseqs = p.nseqs;
+    ch.seqlen = p.seqlen;
+    ch.ntrees = L.B;
+    ch.nnodes = L.V;
+    ch.nsites = L.n;
+    ch.start_coord = p.start_coord;
+    ch.maxS = L.maxS;
+    ch.maxband = L.maxband;
+    ch.keep_debug = L.keep_debug;
+    ch.last_state = -1;
+#define AWB_P(type, field, off) ch.field = (type) (base + L.off)
+    AWB_P(const int *, ptrees, o_ptrees);
+    AWB_P(const int *, ages, o_ages);
+    AWB_P(const int *, sprs, o_sprs);
+    AWB_P(const int *, blocklens, o_blocklens);
+    ch.subtree_roots = L.has_subtree_roots ?
+        (const int *) (base + L.o_subtree_roots) : 0;
+    AWB_P(const int *, rowidx, o_rowidx);
+    AWB_P(const unsigned char *, seqs, o_seqs);
+    AWB_P(const int *, block_start, o_block_start);
+    AWB_P(const int *, nstates, o_nstates);
+    AWB_P(const long long *, row_off, o_row_off);
+    AWB_P(const long long *, fw_off, o_fw_off);
+    AWB_P(const long long *, band_off, o_band_off);
+    AWB_P(const long long *, ent_off, o_ent_off);
+    AWB_P(const long long *, sw1_off, o_sw1_off);
+    AWB_P(short *, st_node, o_st_node);
+    AWB_P(signed char *, st_time, o_st_time);
+    AWB_P(unsigned short *, perm, o_perm);
+    AWB_P(unsigned short *, pslot, o_pslot);
+    AWB_P(unsigned short *, band_j1, o_band_j1);
+    AWB_P(unsigned char *, band_len, o_band_len);
+    AWB_P(int *, band_boff, o_band_boff);
+    AWB_P(double *, inv_emit, o_inv_emit);
+    AWB_P(double *, band, o_band);
+    AWB_P(double *, tmatrix, o_tmatrix);
+    AWB_P(double *, tmvec, o_tmvec);
+    AWB_P(unsigned short *, rowstart, o_rowstart);
+    AWB_P(unsigned short *, pstart, o_pstart);
+    AWB_P(short *, node_first, o_node_first);
+    AWB_P(short *, node_cnt, o_node_cnt);
+    AWB_P(short *, child0, o_child0);
+    AWB_P(short *, child1, o_child1);
+    AWB_P(short *, order, o_order);
+    AWB_P(short *, root, o_root);
+    AWB_P(int *, lineages, o_lineages);
+    AWB_P(double *, treelen, o_treelen);
+    AWB_P(int *, tm_minage, o_tm_minage);
+    AWB_P(unsigned short *, sw_start, o_sw_start);
+    AWB_P(unsigned short *, sw_cnt, o_sw_cnt);
+    AWB_P(unsigned short *, sw_src, o_sw_src);
+    AWB_P(double *, sw_prob, o_sw_prob);
+    if (L.keep_debug) {
+        AWB_P(int *, sw_determ, o_sw_determ);
+        AWB_P(double *, sw_determprob, o_sw_determprob);
+        AWB_P(double *, sw_recombrow, o_sw_recombrow);
+        AWB_P(double *, sw_recoalrow, o_sw_recoalrow);
+        AWB_P(int *, sw_recombsrc, o_sw_recombsrc);
+        AWB_P(int *, sw_recoalsrc, o_sw_recoalsrc);
+    }
+    AWB_P(unsigned char *, kind, o_kind);
+    AWB_P(double *, fw, o_fw);
+    AWB_P(int *, path, o_path);
+    AWB_P(const int *, rand_ints, o_rand);
+    AWB_P(double *, logz, o_logz);
+    AWB_P(int *, status, o_status);
+#undef AWB_P
+}
+
+// Named access to arena arrays (tests / AWB_KEEP_DEBUG).  Returns false if the
+// name is unknown or the array is not kept.
+inline bool awb_layout_find(const AwbLayout &L, const char *name, size_t &off,
+                            size_t &bytes)
+{
+    const size_t rows = (size_t) L.row_off[L.B];
+    const size_t BV = (size_t) L.B * L.V;
+    const size_t B = L.B, T = L.T;
+    struct Ent { const char *name; size_t off; size_t bytes; bool dbg; };
+    const Ent table[] = {
+        { "st_node", L.o_st_node, rows * 2, false },
+        { "st_time", L.o_st_time, rows, false },
+        { "perm", L.o_perm, rows * 2, false },
+        { "pslot", L.o_pslot, rows * 2, false },
+        { "band_j1", L.o_band_j1, rows * 2, false },
+        { "band_len", L.o_band_len, rows, false },
+        { "band_boff", L.o_band_boff, rows * 4, false },
+        { "inv_emit", L.o_inv_emit, rows * 8, false },
+        { "band", L.o_band, (size_t) L.band_off[L.B] * 8, false },
+        { "tmatrix", L.o_tmatrix, B * T * T * 8, false },
+        { "tmvec", L.o_tmvec, B * AWB_TM_NVEC * T * 8, false },
+        { "rowstart", L.o_rowstart, B * (T + 1) * 2, false },
+        { "pstart", L.o_pstart, B * (T + 1) * 2, false },
+        { "node_first", L.o_node_first, BV * 2, false },
+        { "node_cnt", L.o_node_cnt, BV * 2, false },
+        { "child0", L.o_child0, BV * 2, false },
+        { "child1", L.o_child1, BV * 2, false },
+        { "order", L.o_order, BV * 2, false },
+        { "root", L.o_root, B * 2, false },
+        { "lineages", L.o_lineages, B * 3 * T * 4, false },
+        { "treelen", L.o_treelen, B * 8, false },
+        { "tm_minage", L.o_tm_minage, B * 4, false },
+        { "sw_start", L.o_sw_start, rows * 2, false },
+        { "sw_cnt", L.o_sw_cnt, rows * 2, false },
+        { "sw_src", L.o_sw_src, (size_t) L.ent_off[L.B] * 2, false },
+        { "sw_prob", L.o_sw_prob, (size_t) L.ent_off[L.B] * 8, false },
+        { "sw_determ", L.o_sw_determ, (size_t) L.sw1_off[L.B] * 4, true },
+        { "sw_determprob", L.o_sw_determprob, (size_t) L.sw1_off[L.B] * 8, true },
+        { "sw_recombrow", L.o_sw_recombrow, rows * 8, true },
+        { "sw_recoalrow", L.o_sw_recoalrow, rows * 8, true },
+        { "sw_recombsrc", L.o_sw_recombsrc, B * 4, true },
+        { "sw_recoalsrc", L.o_sw_recoalsrc, B * 4, true },
+        { "kind", L.o_kind, (size_t) L.n, false },
+        { "fw", L.o_fw, (size_t) L.fw_off[L.B] * 8, false },
+        { "path", L.o_path, (size_t) L.n * 4, false },
+        { "ent_off", L.o_ent_off, (B + 1) * 8, false },
+        { "band_off", L.o_band_off, (B + 1) * 8, false },
+    };
+    for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
+        if (strcmp(table[i].name, name) == 0) {
+            if (table[i].dbg && !L.keep_debug)
+                return false;
+            off = table[i].off;
+            bytes = table[i].bytes;
+            return true;
+        }
+    }
+    return false;
+}
+
+#endif // AWB_LAYOUT_H

@@ -1,0 +1,901 @@
+// awb_setup.cuh -- per-block setup of the threading HMM.
+//
+//   awb_block_setup   (K1)  states, lineage counts, tree lengths, the 9 SMC
+//                           transition vectors, the (T x T) time matrix, the
+//                           same-branch band, invariant-site emissions, priors
+//   awb_switch_setup  (K2)  switch matrix at a local-tree breakpoint, as a CSR
+//                           gather list over the target states
+//
+// Both are written as __host__ __device__ workers over one block so the same
+// code is unit-tested on the CPU (tests/host_emul.cpp) and launched one CUDA
+// thread per block by the kernels in awb_api.cu: per-block setup is ~0.5 % of
+// the work, embarrassingly parallel over 10^4-10^5 blocks, and off the
+// critical path of the forward recursion.
+//
+// Reference behaviour restated here (file:line in mdrasmus/argweaver):
+//   states.cpp:53-74,109-166          local_tree.cpp:34-219
+//   trans.cpp:13-115 (+ trans.h:89-128) trans.cpp:156-739, 785-831
+//   emit.cpp:744-819                  sample_thread.cpp:209-247
+#ifndef AWB_SETUP_CUH
+#define AWB_SETUP_CUH
+
+#include "awb_common.cuh"
+
+// ---------------------------------------------------------------------------
+// K1
+
+AWB_HD inline double awb_state_prior(int b, const int *nbranches,
+                                     const int *ncoals, int minage,
+                                     const AwbModel &m)
+{
+    // trans.cpp:785-812
+    if (b < minage)
+        return 0.0;
+    double sum = 0.0;
+    for (int k = 2 * minage; k < 2 * b - 1; k++)
+        sum += m.coal_time_steps[k] * nbranches[k / 2] /
+            (2.0 * m.popsizes[k / 2]);
+    double p = exp(-sum) / ncoals[b];
+    if (b < m.ntimes - 2) {
+        double Z = 0.0;
+        if (b > minage)
+            Z = m.coal_time_steps[2 * b - 1] * nbranches[b - 1] /
+                (2.0 * m.popsizes[b - 1]);
+        p *= 1.0 - exp(-m.coal_time_steps[2 * b] * nbranches[b] /
+                       (2.0 * m.popsizes[b]) - Z);
+    }
+    return p;
+}
+
+// Returns 0 on success, a positive code on a layout mismatch.
+AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
+{
+    const AwbModel &m = ch.model;
+    const int T = m.ntimes;
+    const int V = ch.nnodes;
+    const bool internal = ch.internal != 0;
+    const int *parent = ch.ptrees + (size_t) b * V;
+    const int *age = ch.ages + (size_t) b * V;
+    short *c0 = ch.child0 + (size_t) b * V;
+    short *c1 = ch.child1 + (size_t) b * V;
+    short *nfirst = ch.node_first + (size_t) b * V;
+    short *ncnt = ch.node_cnt + (size_t) b * V;
+    const long long row0 = ch.row_off[b];
+    const int S = ch.nstates[b];
+
+    // ---- children in node-index order (local_tree.h:188-229)
+    int root = -1;
+    for (int i = 0; i < V; i++) {
+        c0[i] = -1;
+        c1[i] = -1;
+    }
+    for (int i = 0; i < V; i++) {
+        const int p = parent[i];
+        if (p != -1) {
+            if (c0[p] == -1) c0[p] = (short) i;
+            else c1[p] = (short) i;
+        } else {
+            root = i;
+        }
+    }
+    if (internal && ch.subtree_roots) {
+        const int want = ch.subtree_roots[b];
+        if (want >= 0 && c1[root] == want) {
+            const short tmp = c0[root];
+            c0[root] = c1[root];
+            c1[root] = tmp;
+        }
+    }
+    ch.root[b] = (short) root;
+
+    // ---- post-order (local_tree.h:274-304); ncnt doubles as the visit counter
+    {
+        short *order = ch.order + (size_t) b * V;
+        int i;
+        for (i = 0; i < V; i++)
+            ncnt[i] = 0;
+        for (i = 0; i < V; i++) {
+            if (c0[i] != -1)
+                break;
+            order[i] = (short) i;
+        }
+        int end = i;
+        for (i = 0; i < V && i < end; i++) {
+            const int p = parent[order[i]];
+            if (p != -1) {
+                ncnt[p]++;
+                if (ncnt[p] == 2)
+                    order[end++] = (short) p;
+            }
+        }
+        if (end != V)
+            return 5;   // not a binary tree with leaves listed first
+    }
+
+    const int subtree_root = internal ? c0[root] : root;
+    const int maintree_root = internal ? c1[root] : root;
+    const bool full_tree = internal && age[root] < T;  // no states (states.cpp:116)
+    int minage = ch.minage;
+    if (internal)
+        minage = awb_imax(minage, age[subtree_root]);  // states.cpp:122, trans.cpp:69
+    ch.tm_minage[b] = minage;
+
+    // ---- tree lengths for the invariant-site emission (emit.cpp:744-774):
+    //      explicit-stack preorder, child[0] pushed first, so child[1]'s
+    //      subtree is summed first -- kept for bit-level agreement.
+    //      (nfirst is used as the stack; it is filled in later.)
+    double maintreelen = 0.0, subtreelen = 0.0;
+    {
+        int top = 0;
+        nfirst[top++] = (short) maintree_root;
+        while (top > 0) {
+            const int node = nfirst[--top];
+            if (node != maintree_root) {
+                const int p = parent[node];
+                const double d = (p != -1) ?
+                    m.times[age[p]] - m.times[age[node]] : 0.0;
+                maintreelen += fmax(d, m.mintime);
+            }
+            if (c0[node] != -1) {
+                nfirst[top++] = c0[node];
+                nfirst[top++] = c1[node];
+            }
+        }
+        if (internal) {
+            nfirst[top++] = (short) subtree_root;
+            while (top > 0) {
+                const int node = nfirst[--top];
+                if (node != subtree_root) {
+                    const int p = parent[node];
+                    const double d = (p != -1) ?
+                        m.times[age[p]] - m.times[age[node]] : 0.0;
+                    subtreelen += fmax(d, m.mintime);
+                }
+                if (c0[node] != -1) {
+                    nfirst[top++] = c0[node];
+                    nfirst[top++] = c1[node];
+                }
+            }
+        }
+    }
+
+    // ---- which nodes carry states (states.cpp:124-143): ncnt = -1 marks ignored
+    for (int i = 0; i < V; i++)
+        ncnt[i] = 0;
+    if (internal) {
+        ncnt[root] = -1;
+        int top = 0;
+        nfirst[top++] = (short) subtree_root;
+        while (top > 0) {
+            const int node = nfirst[--top];
+            ncnt[node] = -1;
+            if (c0[node] != -1) {
+                nfirst[top++] = c0[node];
+                nfirst[top++] = c1[node];
+            }
+        }
+    }
+
+    // ---- states, node-major (states.cpp:53-74 / :146-165)
+    int ns = 0;
+    for (int i = 0; i < V; i++) {
+        if (full_tree || ncnt[i] < 0) {
+            nfirst[i] = -1;
+            ncnt[i] = 0;
+            continue;
+        }
+        const int p = parent[i];
+        const int lo = awb_imax(age[i], minage);
+        const int hi = (p == -1 || (internal && p == root)) ? T - 2 : age[p];
+        const int cnt = hi - lo + 1;
+        if (cnt <= 0) {
+            nfirst[i] = -1;
+            ncnt[i] = 0;
+            continue;
+        }
+        nfirst[i] = (short) ns;
+        ncnt[i] = (short) cnt;
+        if (ns + cnt <= S) {
+            for (int t = lo; t <= hi; t++) {
+                ch.st_node[row0 + ns + (t - lo)] = (short) i;
+                ch.st_time[row0 + ns + (t - lo)] = (signed char) t;
+            }
+        }
+        ns += cnt;
+    }
+    if (ns != S)
+        return 1;   // host layout and device enumeration disagree
+    if (S == 0) {
+        ch.st_node[row0] = -1;
+        ch.st_time[row0] = -1;
+    }
+
+    // ---- lineage counts (local_tree.cpp:34-69 / :82-131)
+    int *nbranches = ch.lineages + (size_t) b * 3 * T;
+    int *nrecombs = nbranches + T;
+    int *ncoals = nrecombs + T;
+    for (int i = 0; i < T; i++)
+        nbranches[i] = nrecombs[i] = ncoals[i] = 0;
+    for (int i = 0; i < V; i++) {
+        if (internal && (i == subtree_root || i == root))
+            continue;
+        const int p = parent[i];
+        const bool top = internal ? (p == root) : (p == -1);
+        const int pa = top ? T - 2 : age[p];
+        for (int j = age[i]; j < pa; j++) {
+            nbranches[j]++;
+            nrecombs[j]++;
+            ncoals[j]++;
+        }
+        nrecombs[pa]++;
+        ncoals[pa]++;
+        if (top)
+            nbranches[pa]++;
+    }
+    if (internal) {
+        const int sa = age[subtree_root];
+        for (int i = 0; i < sa; i++) {
+            nbranches[i]--;
+            ncoals[i]--;
+            nrecombs[i]--;
+        }
+    }
+    nbranches[T - 1] = 1;
+
+    // ---- tree length (local_tree.cpp:136-176), summed in node order
+    double treelen = 0.0;
+    for (int i = 0; i < V; i++) {
+        const int p = parent[i];
+        if (p == -1 || (internal && p == root))
+            continue;
+        treelen += m.times[age[p]] - m.times[age[i]];
+    }
+    ch.treelen[b] = treelen;
+
+    // ---- transition vectors (trans.cpp:26-115)
+    double *tv = ch.tmvec + (size_t) b * AWB_TM_NVEC * T;
+    {
+        int root_age_index;
+        double root_age, tl;
+        if (internal) {
+            root_age_index = age[maintree_root];
+            root_age = m.times[root_age_index];
+            tl = treelen - m.times[age[subtree_root]];
+        } else {
+            root_age_index = age[root];
+            root_age = m.times[root_age_index];
+            tl = treelen;
+        }
+        // running cumulative coalescent rates C[2b-2], C[2b-1] (trans.cpp:44-54)
+        double Cm2 = 0.0, Cm1 = 0.0;       // C[2b-2], C[2b-1] for b = 0
+        double cr_m1 = 0.0;                // coal_rates[2b-1]
+        for (int bb = 0; bb < T - 1; bb++) {
+            const double cr0 = m.coal_time_steps[2 * bb] * nbranches[bb] /
+                (2.0 * m.popsizes[bb]);                       // coal_rates[2b]
+            const double cr1 = m.coal_time_steps[2 * bb + 1] * nbranches[bb] /
+                (2.0 * m.popsizes[bb]);                       // coal_rates[2b+1]
+            double treelen2 = tl + m.times[bb];
+            double treelen2_b;
+            if (bb > root_age_index) {
+                treelen2 += m.times[bb] - root_age;
+                treelen2_b = treelen2 + m.time_steps[bb];
+            } else {
+                treelen2_b = treelen2 + m.time_steps[root_age_index];
+            }
+            const double nb = nbranches[bb], nr = nrecombs[bb];
+            const double term = Cm1 + log(m.time_steps[bb] * (nb + 1.0) / (nr + 1.0));
+            tv[AWB_TM_LNB * T + bb] = (bb == 0) ? term :
+                awb_logadd(tv[AWB_TM_LNB * T + bb - 1], term);
+            const double le2 = -Cm2 +
+                (bb < T - 2 ? log(1 - exp(-cr0 - cr_m1)) : 0.0);
+            tv[AWB_TM_LNE2 * T + bb] = le2;
+            const int below = (bb < root_age_index) ? 1 : 0;
+            tv[AWB_TM_LNNEGG1 * T + bb] = Cm1 + log(-m.time_steps[bb] * (
+                (nb / (nr + 1.0 + below)) - (nb + 1.0) / (nr + 1.0)));
+            const double g = (bb < T - 2 ? 1.0 - exp(-cr0) : 1.0);
+            tv[AWB_TM_G2 * T + bb] = g * m.time_steps[bb] * (nb + 1.0) / (nr + 1.0);
+            tv[AWB_TM_G3 * T + bb] = g * m.time_steps[bb] *
+                (nb / (nr + 1.0 + below));
+            tv[AWB_TM_LNG4 * T + bb] = -Cm2 +
+                (bb < T - 2 ? log(1.0 - exp(-cr0 - cr_m1)) : 0.0);
+            tv[AWB_TM_D * T + bb] = (1.0 - exp(-m.rho * treelen2)) / treelen2_b;
+            tv[AWB_TM_E * T + bb] = 1.0 / ncoals[bb];
+            tv[AWB_TM_NORECOMBS * T + bb] = exp(-fmax(m.rho * treelen2, m.rho));
+            // advance: C[2b] = C[2b-1] + cr0 ; C[2b+1] = C[2b] + cr1
+            const double C2b = Cm1 + cr0;
+            Cm2 = C2b;
+            Cm1 = C2b + cr1;
+            cr_m1 = cr1;
+        }
+        for (int k = 0; k < AWB_TM_NVEC; k++)
+            tv[k * T + T - 1] = 0.0;
+    }
+
+    // ---- time-major permutation, row starts, partial slots
+    unsigned short *rowstart = ch.rowstart + (size_t) b * (T + 1);
+    unsigned short *pstart = ch.pstart + (size_t) b * (T + 1);
+    {
+        int q = 0;
+        for (int t = 0; t < T; t++) {
+            rowstart[t] = (unsigned short) q;
+            if (S > 0 && t < T - 1) {
+                for (int i = 0; i < V; i++) {
+                    const int cnt = ncnt[i];
+                    if (cnt <= 0) continue;
+                    const int lo = awb_imax(age[i], minage);
+                    if (t >= lo && t < lo + cnt)
+                        ch.perm[row0 + q++] = (unsigned short) (nfirst[i] + (t - lo));
+                }
+            }
+        }
+        rowstart[T] = (unsigned short) q;
+        if (S == 0)
+            ch.perm[row0] = 0;
+        // partial slots: a new slot starts at each warp boundary and each new row
+        int slot = -1;
+        int t = 0;
+        for (int qq = 0; qq < S; qq++) {
+            bool newrow = false;
+            while (t < T && rowstart[t + 1] <= qq) t++;   // row of qq
+            if (qq == rowstart[t]) newrow = true;
+            if (newrow || (qq & 31) == 0) slot++;
+            ch.pslot[row0 + qq] = (unsigned short) slot;
+        }
+        if (S == 0)
+            ch.pslot[row0] = 0;
+        // first slot of each row (rows without states get the next row's slot)
+        int cur = 0;
+        for (int tt = 0; tt <= T; tt++) {
+            if (tt < T && rowstart[tt] < S)
+                cur = ch.pslot[row0 + rowstart[tt]];
+            else
+                cur = slot + 1;
+            pstart[tt] = (unsigned short) cur;
+        }
+    }
+
+    if (S == 0) {
+        ch.inv_emit[row0] = 1.0;
+        ch.band_j1[row0] = 0;
+        ch.band_len[row0] = 0;
+        ch.band_boff[row0] = 0;
+        if (b == 0)
+            ch.fw[ch.fw_off[0]] = 1.0;        // trans.cpp:822-825
+        return 0;
+    }
+
+    // ---- (T x T) time matrix (sample_thread.cpp:212-216)
+    double *tm = ch.tmatrix + (size_t) b * T * T;
+    for (int a = 0; a < T - 1; a++)
+        for (int bb = 0; bb < T - 1; bb++)
+            tm[a * T + bb] = awb_get_time(tv, T, a, bb, 0, minage, false);
+
+    // ---- same-branch band (tmatrix2, sample_thread.cpp:218-225, :282-286),
+    //      invariant-site emission (emit.cpp:786-819)
+    double *band = ch.band + ch.band_off[b];
+    int boff = 0;
+    const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
+    for (int k = 0; k < S; k++) {
+        const int node = ch.st_node[row0 + k];
+        const int bt = ch.st_time[row0 + k];
+        const int c = age[node];
+        const int lo = awb_imax(c, minage);
+        const int len = ncnt[node];
+        ch.band_j1[row0 + k] = (unsigned short) nfirst[node];
+        ch.band_len[row0 + k] = (unsigned char) len;
+        ch.band_boff[row0 + k] = boff;
+        for (int i = 0; i < len; i++) {
+            const int a = lo + i;
+            band[boff + i] = awb_get_time(tv, T, a, bt, c, minage, true) -
+                awb_get_time(tv, T, a, bt, 0, minage, false);
+        }
+        boff += len;
+
+        const double coal_time = m.times[bt];
+        double tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime);
+        if (node == maintree_root)
+            tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime)
+                + fmax(coal_time - m.times[age[maintree_root]], m.mintime);
+        ch.inv_emit[row0 + k] = .25 * exp(-m.mu * fmax(tl2, m.mintime));
+    }
+    if ((long long) boff != ch.band_off[b + 1] - ch.band_off[b])
+        return 2;
+
+    // ---- prior column of the first block (sample_thread.cpp:425-429)
+    if (b == 0) {
+        double *col = ch.fw + ch.fw_off[0];
+        for (int k = 0; k < S; k++)
+            col[k] = awb_state_prior(ch.st_time[row0 + k], nbranches, ncoals,
+                                     ch.minage, m);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K2
+
+struct AwbTreeView {
+    const int *parent;
+    const int *age;
+    const short *c0, *c1;
+    const short *nfirst, *ncnt;
+    int root;
+    int minage;
+};
+
+// NodeStateLookup::lookup (states.h:109-123): index of state (node,time) or -1
+AWB_HD inline int awb_lookup(const AwbTreeView &t, int node, int time)
+{
+    const int cnt = t.ncnt[node];
+    if (cnt <= 0)
+        return -1;
+    const int lo = awb_imax(t.age[node], t.minage);
+    const int idx = time - lo;
+    if (idx < 0 || idx >= cnt)
+        return -1;
+    return t.nfirst[node] + idx;
+}
+
+struct AwbSpr { int recomb_node, recomb_time, coal_node, coal_time; };
+
+struct AwbLineages { const int *nbranches, *nrecombs, *ncoals; };
+
+// trans.cpp:317-413
+AWB_HD inline double awb_calc_recomb(const AwbTreeView &lt, const AwbModel &m,
+                                     const AwbLineages &L, const AwbSpr &spr,
+                                     int s_node, int s_time,
+                                     double last_treelen, bool internal)
+{
+    const int a = s_time;
+    const int k = spr.recomb_time;
+    double last_treelen_b;
+    int root_age;
+
+    if (internal) {
+        const int subtree_root = lt.c0[lt.root];
+        const int maintree_root = lt.c1[lt.root];
+        root_age = lt.age[maintree_root];
+
+        if (spr.coal_node == subtree_root) {
+            if (a < spr.coal_time)
+                return 0.0;
+            if (spr.recomb_node == maintree_root && s_node != maintree_root)
+                return 0.0;
+        }
+        int ptr = spr.coal_node;
+        int ptr2 = -1, ptr3 = -1;
+        while (ptr != lt.root) {
+            ptr2 = ptr;
+            ptr = lt.parent[ptr];
+        }
+        ptr = spr.recomb_node;
+        while (ptr != lt.root) {
+            ptr3 = ptr;
+            ptr = lt.parent[ptr];
+        }
+        if (ptr2 == subtree_root && ptr3 == maintree_root &&
+            s_time == spr.recomb_time) {
+            ptr = lt.parent[s_node];
+            while (ptr != lt.root) {
+                if (ptr == spr.recomb_node)
+                    return 0.0;
+                ptr = lt.parent[ptr];
+            }
+        }
+        last_treelen += m.times[a] - m.times[lt.age[subtree_root]];
+        if (a > root_age) {
+            last_treelen += m.times[a] - m.times[root_age];
+            last_treelen_b = last_treelen + m.time_steps[a];
+        } else {
+            last_treelen_b = last_treelen + m.time_steps[root_age];
+        }
+    } else {
+        root_age = lt.age[lt.root];
+        // get_treelen_branch / get_basal_branch (local_tree.cpp:179-219)
+        const double blen = m.times[a];
+        double treelen2 = last_treelen + blen;
+        double root_time;
+        if (s_node == lt.root) {
+            treelen2 += blen - m.times[lt.age[lt.root]];
+            root_time = m.times[a + 1] - m.times[a];
+        } else {
+            const int rooti = lt.age[lt.root];
+            root_time = m.times[rooti + 1] - m.times[rooti];
+        }
+        last_treelen = treelen2;
+        last_treelen_b = treelen2 + root_time;
+    }
+
+    const int nbranches_k = L.nbranches[k] + (k < a ? 1 : 0);
+    const int nrecombs_k = L.nrecombs[k] + (k <= a ? 1 : 0) + (k == a ? 1 : 0) -
+        (k >= awb_imax(root_age, a) ? 1 : 0);
+    return nbranches_k * m.time_steps[k] / (nrecombs_k * last_treelen_b) *
+        (1.0 - exp(-fmax(m.rho * last_treelen, m.rho)));
+}
+
+// trans.cpp:443-502
+AWB_HD inline double awb_calc_recoal(const AwbTreeView &lt, const AwbModel &m,
+                                     const AwbLineages &L, const AwbSpr &spr,
+                                     int a, int recomb_parent_age, bool internal)
+{
+    const int k = spr.recomb_time;
+    const int j = spr.coal_time;
+    int nbranches_j = L.nbranches[j] - (j < recomb_parent_age ? 1 : 0) +
+        (j < a ? 1 : 0);
+    int ncoals_j = L.ncoals[j] - (j <= recomb_parent_age ? 1 : 0) -
+        (j == recomb_parent_age ? 1 : 0) + (j <= a ? 1 : 0) + (j == a ? 1 : 0);
+    bool over = false;
+    if (internal) {
+        const int subtree_root = lt.c0[lt.root];
+        const int maintree_root = lt.c1[lt.root];
+        if (spr.recomb_node == maintree_root &&
+            spr.coal_time >= lt.age[subtree_root]) {
+            over = true;
+            nbranches_j = 1;
+            ncoals_j++;
+        }
+    }
+    double p = 1.0 / ncoals_j;
+    if (j < m.ntimes - 2) {
+        double Z = 0.0;
+        if (j > k) {
+            int b1 = L.nbranches[j - 1] - (j - 1 < recomb_parent_age ? 1 : 0) +
+                (j - 1 < a ? 1 : 0);
+            if (over)
+                b1 = 1;
+            Z = m.coal_time_steps[2 * j - 1] * b1 / (2.0 * m.popsizes[j - 1]);
+        }
+        p *= 1.0 - exp(-m.coal_time_steps[2 * j] * nbranches_j /
+                       (2.0 * m.popsizes[j]) - Z);
+    }
+    return p;
+}
+
+// trans.cpp:505-534
+AWB_HD inline double awb_calc_recomb_recoal(
+    const AwbTreeView &lt, const AwbModel &m, const AwbLineages &L,
+    const AwbSpr &spr, int s_node, int s_time, int recomb_parent_age,
+    double last_treelen, bool internal)
+{
+    const int a = s_time;
+    const int k = spr.recomb_time;
+    const int j = spr.coal_time;
+    double p = awb_calc_recomb(lt, m, L, spr, s_node, s_time, last_treelen,
+                               internal);
+    double sum = 0.0;
+    for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
+        const int nbranches_m = L.nbranches[mm / 2] -
+            (mm / 2 < recomb_parent_age ? 1 : 0) + (mm / 2 < a ? 1 : 0);
+        sum += m.coal_time_steps[mm] * nbranches_m / (2.0 * m.popsizes[mm / 2]);
+    }
+    p *= exp(-sum);
+    p *= awb_calc_recoal(lt, m, L, spr, s_time, recomb_parent_age, internal);
+    return p;
+}
+
+// trans.cpp:156-275, one source state
+AWB_HD inline int awb_determ_one(const AwbTreeView &lt, const AwbTreeView &t,
+                                 const AwbSpr &spr, int broken, int node1,
+                                 int time1, bool internal)
+{
+#define AWB_MAP(x) ((x) == broken ? -1 : (x))
+    if ((node1 == spr.coal_node && time1 == spr.coal_time) ||
+        (node1 == spr.recomb_node && time1 == spr.recomb_time))
+        return -1;
+
+    if (node1 != spr.recomb_node) {
+        int node2;
+        bool disrupt = false;
+        if (lt.c0[node1] == -1) {
+            node2 = node1;
+        } else {
+            const int child1 = lt.c0[node1], child2 = lt.c1[node1];
+            if (spr.recomb_node == child1) {
+                node2 = AWB_MAP(child2);
+                disrupt = true;
+            } else if (spr.recomb_node == child2) {
+                node2 = AWB_MAP(child1);
+                disrupt = true;
+            } else {
+                node2 = AWB_MAP(node1);
+            }
+        }
+        if ((spr.coal_node == node1 && spr.coal_time < time1) ||
+            (AWB_MAP(spr.coal_node) == node2 && spr.coal_time < time1) ||
+            (disrupt && AWB_MAP(spr.coal_node) == node2 &&
+             spr.coal_time <= time1))
+            node2 = t.parent[node2];
+
+        if (internal && t.age[node2] > time1)
+            return -1;
+        const int p = t.parent[node2];
+        if (p != -1 && internal && time1 > t.age[p])
+            return -1;
+        return awb_lookup(t, node2, time1);
+    }
+
+    if (spr.recomb_time > time1)
+        return awb_lookup(t, AWB_MAP(spr.recomb_node), time1);
+
+    const int parent = lt.parent[spr.recomb_node];
+    const int time2 = lt.age[parent];
+    const int other = (lt.c1[parent] == spr.recomb_node ? lt.c0[parent] :
+                       lt.c1[parent]);
+    const int node2 = (other == spr.coal_node ? t.parent[AWB_MAP(other)] :
+                       AWB_MAP(other));
+    return awb_lookup(t, node2, time2);
+}
+
+AWB_HD inline void awb_tree_view(const AwbChain &ch, int b, AwbTreeView &t)
+{
+    const int V = ch.nnodes;
+    t.parent = ch.ptrees + (size_t) b * V;
+    t.age = ch.ages + (size_t) b * V;
+    t.c0 = ch.child0 + (size_t) b * V;
+    t.c1 = ch.child1 + (size_t) b * V;
+    t.nfirst = ch.node_first + (size_t) b * V;
+    t.ncnt = ch.node_cnt + (size_t) b * V;
+    t.root = ch.root[b];
+    t.minage = ch.tm_minage[b];
+}
+
+// Build the switch matrix of block b (b >= 1) as a CSR gather list:
+// target k (state order of block b) <- sources (state order of block b-1).
+// Entry order per target = the reference's accumulation order
+// (sample_thread.cpp:357-373): deterministic sources ascending, then the
+// recombination source, then the re-coalescence source.
+AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
+{
+    const AwbModel &m = ch.model;
+    const int T = m.ntimes;
+    const bool internal = ch.internal != 0;
+    const int S1 = ch.nstates[b - 1], S2 = ch.nstates[b];
+    const int n1 = awb_imax(S1, 1), n2 = awb_imax(S2, 1);
+    const long long r1 = ch.row_off[b - 1], r2 = ch.row_off[b];
+    const long long e0 = ch.ent_off[b];
+    const int ecap = (int) (ch.ent_off[b + 1] - e0);
+
+    AwbTreeView lt, t;
+    awb_tree_view(ch, b - 1, lt);
+    awb_tree_view(ch, b, t);
+    AwbSpr spr = { ch.sprs[4 * b], ch.sprs[4 * b + 1], ch.sprs[4 * b + 2],
+                   ch.sprs[4 * b + 3] };
+    AwbLineages L;
+    L.nbranches = ch.lineages + (size_t) (b - 1) * 3 * T;
+    L.nrecombs = L.nbranches + T;
+    L.ncoals = L.nrecombs + T;
+    const double last_treelen = ch.treelen[b - 1];
+
+    unsigned short *cnt = ch.sw_cnt + r2;
+    unsigned short *start = ch.sw_start + r2;
+    unsigned short *esrc = ch.sw_src + e0;
+    double *eprob = ch.sw_prob + e0;
+    for (int k = 0; k < n2; k++)
+        cnt[k] = 0;
+
+    int *dbg_determ = ch.keep_debug ? ch.sw_determ + ch.sw1_off[b] : 0;
+    double *dbg_dprob = ch.keep_debug ? ch.sw_determprob + ch.sw1_off[b] : 0;
+    double *dbg_rrow = ch.keep_debug ? ch.sw_recombrow + r2 : 0;
+    double *dbg_crow = ch.keep_debug ? ch.sw_recoalrow + r2 : 0;
+    if (ch.keep_debug) {
+        for (int j = 0; j < n1; j++) { dbg_determ[j] = -1; dbg_dprob[j] = 0.0; }
+        for (int k = 0; k < n2; k++) { dbg_rrow[k] = 0.0; dbg_crow[k] = 0.0; }
+        ch.sw_recombsrc[b] = -1;
+        ch.sw_recoalsrc[b] = -1;
+    }
+
+    // ---- internal-mode corner cases (trans.cpp:554-603)
+    if (internal && S1 == 0) {
+        int target = 0;
+        if (S2 > 0) {
+            const int maintree_root = t.c1[t.root];
+            target = awb_lookup(t, maintree_root, spr.coal_time);
+            if (target < 0)
+                return 3;
+        }
+        for (int k = 0; k < n2; k++) {
+            start[k] = (unsigned short) (k > target ? 1 : 0);
+            cnt[k] = (unsigned short) (k == target ? 1 : 0);
+        }
+        esrc[0] = 0;
+        eprob[0] = 1.0;
+        if (ch.keep_debug) { dbg_determ[0] = target; dbg_dprob[0] = 1.0; }
+        return 0;
+    }
+    if (internal && S2 == 0) {
+        if (S1 > ecap)
+            return 4;
+        for (int i = 0; i < S1; i++) {
+            const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+            int rpa;
+            if (node1 == spr.recomb_node && time1 > spr.recomb_time)
+                rpa = time1;
+            else
+                rpa = lt.age[lt.parent[spr.recomb_node]];
+            const double p = awb_calc_recomb_recoal(lt, m, L, spr, node1, time1,
+                                                    rpa, last_treelen, internal);
+            esrc[i] = (unsigned short) i;
+            eprob[i] = p;
+            if (ch.keep_debug) { dbg_determ[i] = 0; dbg_dprob[i] = p; }
+        }
+        start[0] = 0;
+        cnt[0] = (unsigned short) S1;
+        return 0;
+    }
+
+    const int broken = lt.parent[spr.recomb_node];
+    const int recomb_parent_age0 = lt.age[broken];
+
+    // ---- per-time tables (trans.cpp:616-621, 417-440)
+    double sums = 0.0;
+    double sums2[2 * AWB_MAXT + 1];
+    double recoals[AWB_MAXT];
+    {
+        const int k = spr.recomb_time, j = spr.coal_time;
+        double sum = 0.0;
+        for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
+            const int nbm = L.nbranches[mm / 2] -
+                (mm / 2 < recomb_parent_age0 ? 1 : 0);
+            sum += m.coal_time_steps[mm] * nbm / (2.0 * m.popsizes[mm / 2]);
+        }
+        sums = sum;
+        sum = 0.0;
+        for (int mm = 0; mm < 2 * T + 1; mm++) sums2[mm] = 0.0;
+        sums2[2 * k] = sum;
+        for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
+            sum += m.coal_time_steps[mm] / (2.0 * m.popsizes[mm / 2]);
+            sums2[mm + 1] = sum;
+        }
+        for (int a = 0; a < T; a++)
+            recoals[a] = awb_calc_recoal(lt, m, L, spr, a, recomb_parent_age0,
+                                         false /* sic, trans.cpp:620 */);
+    }
+
+    // ---- pass 1: classify sources, count entries per target
+    int recombsrc = -1, recoalsrc = -1;
+    for (int i = 0; i < S1; i++) {
+        const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+        if (node1 == spr.recomb_node && time1 == spr.recomb_time)
+            recombsrc = i;
+        else if (node1 == spr.coal_node && time1 == spr.coal_time)
+            recoalsrc = i;
+        const int d = awb_determ_one(lt, t, spr, broken, node1, time1, internal);
+        if (d >= 0)
+            cnt[d]++;
+    }
+
+    // recombination row (trans.cpp:665-693): "stay" and "escape"
+    int rk[2] = { -1, -1 };
+    double rv[2] = { 0.0, 0.0 };
+    if (recombsrc != -1) {
+        const int parent = lt.parent[spr.recomb_node];
+        const int time2 = lt.age[parent];
+        const int other = (lt.c0[parent] == spr.recomb_node ? lt.c1[parent] :
+                           lt.c0[parent]);
+        const int node2 = (other == spr.coal_node ? t.parent[AWB_MAP(other)] :
+                           AWB_MAP(other));
+        rk[0] = awb_lookup(t, AWB_MAP(spr.recomb_node), spr.recomb_time);
+        rk[1] = awb_lookup(t, node2, time2);
+        const int sn = ch.st_node[r1 + recombsrc], stime = ch.st_time[r1 + recombsrc];
+        if (rk[0] != -1)
+            rv[0] = awb_calc_recomb_recoal(lt, m, L, spr, sn, stime,
+                                           recomb_parent_age0, last_treelen,
+                                           internal);
+        if (rk[1] != -1)
+            rv[1] = awb_calc_recomb_recoal(lt, m, L, spr, sn, stime, stime,
+                                           last_treelen, internal);
+        if (rk[0] != -1 && rk[0] == rk[1]) {
+            // the second assignment overwrites the first (trans.cpp:678,688)
+            rv[0] = rv[1];
+            rk[1] = -1;
+        }
+        for (int q = 0; q < 2; q++)
+            if (rk[q] != -1 && rv[q] > 0.0)
+                cnt[rk[q]]++;
+    }
+
+    // re-coalescence row (trans.cpp:697-738)
+    int node3 = -1, cparent = -1, ctime1 = -1, cnode1 = -1;
+    if (recoalsrc != -1) {
+        cnode1 = ch.st_node[r1 + recoalsrc];
+        ctime1 = ch.st_time[r1 + recoalsrc];
+        if (broken == cnode1)
+            node3 = AWB_MAP(lt.c1[broken] == spr.recomb_node ? lt.c0[broken] :
+                            lt.c1[broken]);
+        else
+            node3 = AWB_MAP(cnode1);
+        cparent = t.parent[AWB_MAP(spr.recomb_node)];
+    }
+
+    // prefix over targets
+    // (recoal entries are appended after this prefix by a second count below)
+    // first count recoal entries
+    if (recoalsrc != -1) {
+        for (int k = 0; k < S2; k++) {
+            const int node2 = ch.st_node[r2 + k], time2 = ch.st_time[r2 + k];
+            if (!((node2 == AWB_MAP(spr.recomb_node) && time2 >= spr.recomb_time) ||
+                  (node2 == node3 && time2 == ctime1) ||
+                  (node2 == cparent && time2 == ctime1)))
+                continue;
+            AwbSpr spr2 = spr;
+            spr2.coal_time = time2;
+            const double p = awb_calc_recomb_recoal(
+                lt, m, L, spr2, cnode1, ctime1, recomb_parent_age0,
+                last_treelen, internal);
+            if (ch.keep_debug) dbg_crow[k] = p;
+            if (p > 0.0)
+                cnt[k]++;
+        }
+    }
+    int total = 0;
+    for (int k = 0; k < n2; k++) {
+        start[k] = (unsigned short) total;
+        total += cnt[k];
+        cnt[k] = 0;
+    }
+    if (total > ecap)
+        return 4;
+
+    // ---- pass 2: deterministic entries in ascending source order
+    for (int i = 0; i < S1; i++) {
+        const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+        const int d = awb_determ_one(lt, t, spr, broken, node1, time1, internal);
+        if (ch.keep_debug) dbg_determ[i] = d;
+        if (d < 0)
+            continue;
+        double p;
+        if (node1 == spr.recomb_node && time1 > spr.recomb_time) {
+            p = awb_calc_recomb_recoal(lt, m, L, spr, node1, time1, time1,
+                                       last_treelen, internal);
+        } else {
+            const int idx = awb_imax(awb_imin(2 * spr.coal_time - 1, 2 * time1),
+                                     2 * spr.recomb_time);
+            p = awb_calc_recomb(lt, m, L, spr, node1, time1, last_treelen,
+                                internal) *
+                exp(-sums - sums2[idx]) * recoals[time1];
+        }
+        if (ch.keep_debug) dbg_dprob[i] = p;
+        const int pos = start[d] + cnt[d]++;
+        esrc[pos] = (unsigned short) i;
+        eprob[pos] = p;
+    }
+    // recombination source
+    for (int q = 0; q < 2; q++) {
+        if (rk[q] != -1) {
+            if (ch.keep_debug) dbg_rrow[rk[q]] = rv[q];
+            if (rv[q] > 0.0) {
+                const int pos = start[rk[q]] + cnt[rk[q]]++;
+                esrc[pos] = (unsigned short) recombsrc;
+                eprob[pos] = rv[q];
+            }
+        }
+    }
+    // re-coalescence source
+    if (recoalsrc != -1) {
+        for (int k = 0; k < S2; k++) {
+            const int node2 = ch.st_node[r2 + k], time2 = ch.st_time[r2 + k];
+            if (!((node2 == AWB_MAP(spr.recomb_node) && time2 >= spr.recomb_time) ||
+                  (node2 == node3 && time2 == ctime1) ||
+                  (node2 == cparent && time2 == ctime1)))
+                continue;
+            AwbSpr spr2 = spr;
+            spr2.coal_time = time2;
+            const double p = awb_calc_recomb_recoal(
+                lt, m, L, spr2, cnode1, ctime1, recomb_parent_age0,
+                last_treelen, internal);
+            if (p > 0.0) {
+                const int pos = start[k] + cnt[k]++;
+                esrc[pos] = (unsigned short) recoalsrc;
+                eprob[pos] = p;
+            }
+        }
+    }
+    if (ch.keep_debug) {
+        ch.sw_recombsrc[b] = recombsrc;
+        ch.sw_recoalsrc[b] = recoalsrc;
+    }
+#undef AWB_MAP
+    return 0;
+}
+
+#endif // AWB_SETUP_CUH

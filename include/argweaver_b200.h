@@ -1,0 +1,221 @@
+/* argweaver_b200.h -- C ABI of the B200-native threading-HMM path.
+ *
+ * This library replaces ONE path of ARGweaver (mdrasmus/argweaver): the
+ * threading HMM that arg-sample runs for every MCMC step --
+ *   emissions            src/argweaver/emit.cpp:650-869      (calc_emissions)
+ *   transition setup     src/argweaver/trans.cpp:26-115      (calc_transition_probs)
+ *                        src/argweaver/trans.cpp:538-739     (calc_transition_probs_switch)
+ *   forward recursion    src/argweaver/sample_thread.cpp:186-296,345-460
+ *   stochastic traceback src/argweaver/sample_thread.cpp:470-569
+ * All compute runs in hand-written CUDA kernels for sm_100a; there is no CPU
+ * fallback: every entry point fails (non-zero return + awb_last_error()) when
+ * no CUDA device is usable.
+ *
+ * Two layers are exported:
+ *
+ *  (1) the flat ABI (awb_*): plain pointers and sizes, no C++ types.  It is what
+ *      the reference's L2 wrappers (sample_arg_thread, sample_arg_thread_internal,
+ *      cond_sample_arg_thread*, sample_thread.cpp:578-865) would call after
+ *      flattening LocalTrees / ArgModel / Sequences; INTEGRATION.md shows that
+ *      adapter.
+ *
+ *  (2) the reference's own extern "C" symbols for this path, with identical
+ *      signatures (argweaver/argweaverc.py:19-349 binds them through ctypes);
+ *      declared at the end of this header.
+ */
+#ifndef ARGWEAVER_B200_H
+#define ARGWEAVER_B200_H
+
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AWB_MAX_NTIMES 64     /* model time points supported by this build */
+#define AWB_MAX_NNODES 1024   /* nodes per local tree (k <= 512 sequences)  */
+#define AWB_MAX_NSTATES 1024  /* HMM states per block (one CUDA thread each) */
+
+/* One thread-sampling problem ("chain"): the flattened arguments of
+ * arghmm_forward_alg(trees, model, sequences, matrix_iter, ...) and
+ * stochastic_traceback(...) (sample_thread.h:130-138).                     */
+typedef struct awb_problem {
+    /* ArgModel (model.h:41-354): time grid, population sizes, rates already
+     * multiplied by the site-compression factor (arg-sample.cpp:428-436)     */
+    int ntimes;
+    const double *times;        /* [ntimes] */
+    const double *popsizes;     /* [ntimes] */
+    double rho, mu;
+
+    /* Sequences (sequences.h:31): dense char rows, borrowed, not NUL-terminated */
+    int nseqs, seqlen;
+    const unsigned char *seqs;  /* [nseqs][seqlen] */
+    int nleaves;
+    const int *seqids;          /* [nleaves] LocalTrees::seqids              */
+    int new_chrom;              /* external mode: row being threaded          */
+
+    /* StatesModel (states.h:156): mode */
+    int internal;               /* 0: thread a new leaf; 1: re-thread a subtree */
+    int minage;                 /* always 0 at live call sites                */
+
+    /* LocalTrees (local_tree.h:504): one entry per local block               */
+    int ntrees, nnodes;
+    int start_coord;            /* first site (index into seqs rows)          */
+    const int *ptrees;          /* [ntrees][nnodes] parent, -1 = root         */
+    const int *ages;            /* [ntrees][nnodes] time index                */
+    const int *sprs;            /* [ntrees][4] recomb_node, recomb_time, coal_node, coal_time */
+    const int *mappings;        /* [ntrees][nnodes] or NULL (= identity except broken node) */
+    const int *blocklens;       /* [ntrees] */
+    const int *subtree_roots;   /* [ntrees] child[0] of the root (internal) or NULL */
+} awb_problem;
+
+typedef struct awb_ctx awb_ctx;       /* one CUDA device + stream             */
+typedef struct awb_batch awb_batch;   /* a set of independent problems        */
+
+/* flags for awb_batch_create */
+#define AWB_KEEP_DEBUG 1   /* keep per-block setup arrays readable (tests)   */
+
+const char *awb_last_error(void);
+int awb_device_count(void);
+
+int awb_ctx_create(int device, awb_ctx **out);
+void awb_ctx_destroy(awb_ctx *ctx);
+
+/* Validate the problems, compute the table layout, allocate device memory.
+ * The problem structs and the arrays they point to must stay valid until
+ * awb_batch_upload() returns. */
+int awb_batch_create(awb_ctx *ctx, int nproblems, const awb_problem *problems,
+                     int flags, awb_batch **out);
+void awb_batch_destroy(awb_batch *b);
+
+/* host -> device copy of every problem's inputs (trees, SPRs, sequences) */
+int awb_batch_upload(awb_batch *b);
+int64_t awb_batch_h2d_bytes(const awb_batch *b);
+
+/* Per-block setup (states, lineage counts, transition vectors, switch
+ * matrices, site classification, variant-site emissions), then the forward
+ * recursion for every problem of the batch.  Asynchronous on the ctx stream.
+ * priors: NULL, or per problem a host pointer (or NULL) to a caller-supplied
+ * first column (prior_given, sample_thread.cpp:416-429). */
+int awb_batch_setup(awb_batch *b);
+int awb_batch_forward(awb_batch *b, const double *const *priors);
+
+/* Stochastic traceback.  rand_ints[i] points to the libc rand() draws for
+ * problem i in consumption order (last site first; common.h:272-290), one per
+ * site; rand_max is RAND_MAX.  last_states: NULL or per problem the given last
+ * state (-1 = sample it). */
+int awb_batch_traceback(awb_batch *b, const int *const *rand_ints, int rand_max,
+                        const int *last_states);
+
+int awb_batch_sync(awb_batch *b);
+
+/* milliseconds spent in the most recent setup / forward / traceback launches,
+ * measured with CUDA events on the launching stream */
+int awb_batch_timings(awb_batch *b, float *setup_ms, float *forward_ms,
+                      float *traceback_ms);
+/* sum over blocks of blocklen * nstates for problem i */
+double awb_batch_states_sites(const awb_batch *b, int i);
+int64_t awb_batch_fw_doubles(const awb_batch *b, int i);
+int awb_batch_nsites(const awb_batch *b, int i);
+int awb_batch_kernel_launches(const awb_batch *b);
+
+/* results (device -> host) */
+int awb_batch_get_path(awb_batch *b, int i, int *path /*[nsites]*/);
+int awb_batch_get_logz(awb_batch *b, int i, double *logz);
+int awb_batch_get_status(awb_batch *b, int i, int *first_bad_site);
+int awb_batch_get_fw(awb_batch *b, int i, double *fw /*[fw_doubles]*/);
+int awb_batch_get_nstates(awb_batch *b, int i, int *nstates /*[ntrees]*/);
+int awb_batch_get_layout(awb_batch *b, int i, int64_t *row_off, int64_t *fw_off,
+                         int64_t *sw1_off /* each [ntrees+1] */);
+/* AWB_KEEP_DEBUG only: named per-block arrays, see awb_api.cu (debug_fetch) */
+int awb_batch_get_debug(awb_batch *b, int i, const char *name, void *dst,
+                        int64_t dst_bytes);
+
+/* One-shot convenience over host buffers: create + upload + setup + forward +
+ * traceback + download, for a single problem. */
+int awb_thread_sample(const awb_problem *p, const int *rand_ints, int rand_max,
+                      int *path, double *logz);
+int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
+                      double *logz);
+
+/* ------------------------------------------------------------------------
+ * Reference-compatible symbols (same names / signatures as libargweaver.so).
+ * `LocalTrees` is an opaque handle owned by this library.
+ * ---------------------------------------------------------------------- */
+typedef struct LocalTrees LocalTrees;
+typedef int intstate[2];
+
+/* local_tree.cpp:1817-1825, :1895 */
+LocalTrees *arghmm_new_trees(int **ptrees, int **ages, int **sprs,
+                             int *blocklens, int ntrees, int nnodes,
+                             int start_coord);
+void delete_local_trees(LocalTrees *trees);
+int get_local_trees_ntrees(LocalTrees *trees);
+int get_local_trees_nnodes(LocalTrees *trees);
+
+/* states.cpp:209-261 */
+void arghmm_get_nstates(LocalTrees *trees, int ntimes, bool internal,
+                        int *nstates);
+intstate **get_state_spaces(LocalTrees *trees, int ntimes, bool internal);
+void delete_state_spaces(intstate **all_states, int ntrees);
+
+/* sample_thread.cpp:887-1042 */
+double **arghmm_forward_alg(LocalTrees *trees, double *times, int ntimes,
+                            double *popsizes, double rho, double mu,
+                            char **seqs, int nseqs, int seqlen,
+                            bool prior_given, double *prior, bool internal,
+                            bool slow);
+intstate *arghmm_sample_posterior(int **ptrees, int **ages, int **sprs,
+                                  int *blocklens, int ntrees, int nnodes,
+                                  double *times, int ntimes, double *popsizes,
+                                  double rho, double mu, char **seqs, int nseqs,
+                                  int seqlen, intstate *path);
+void arghmm_sample_arg_thread_internal(LocalTrees *trees, double *times,
+                                       int ntimes, double *popsizes, double rho,
+                                       double mu, char **seqs, int nseqs,
+                                       int seqlen, int *thread_path);
+void delete_path(int *path);
+void delete_double_matrix(double **mat, int nrows);
+void delete_forward_matrix(double **mat, int nrows);
+
+/* emit.cpp:1288-1310 */
+double **new_emissions(intstate *istates, int nstates, int *ptree, int nnodes,
+                       int *ages_index, char **seqs, int nseqs, int seqlen,
+                       double *times, int ntimes, double mu);
+void delete_emissions(double **emit, int seqlen);
+
+/* trans.cpp:1190-1251 (both return LOG probabilities, dense) */
+double **new_transition_probs(int nnodes, int *ptree, int *ages, double treelen,
+                              intstate *istates, int nstates, int ntimes,
+                              double *times, double *time_steps, int *nbranches,
+                              int *nrecombs, int *ncoals, double *popsizes,
+                              double rho);
+double **new_transition_probs_switch(
+    int *ptree, int *last_ptree, int nnodes, int recomb_node, int recomb_time,
+    int coal_node, int coal_time, int *ages_index, int *last_ages_index,
+    double treelen, double last_treelen, intstate *istates1, int nstates1,
+    intstate *istates2, int nstates2, int ntimes, double *times,
+    double *time_steps, int *nbranches, int *nrecombs, int *ncoals,
+    double *popsizes, double rho);
+void delete_transition_probs(double **transmat, int nstates);
+
+/* hmm.cpp:13-98 generic dense log-space HMM */
+void forward_step(double *col1, double *col2, int nstates1, int nstates2,
+                  double **trans, double *emit);
+void forward_alg(int n, int nstates, double **trans, double **emit,
+                 double **fw);
+void backward_alg(int n, int nstates, double **trans, double **emit,
+                  double **bw);
+void sample_hmm_posterior(int n, int nstates, double **trans, double **fw,
+                          int *path);
+int sample_hmm_posterior_step(int nstates1, double **trans, double *col1,
+                              int state2);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ARGWEAVER_B200_H */

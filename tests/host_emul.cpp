@@ -1,0 +1,186 @@
+// host_emul.cpp -- TEST HARNESS (CPU, no CUDA).  Compiles the product's
+// __host__ __device__ setup/emission workers (argweaver_b200/csrc/awb_setup.cuh,
+// awb_emit.cuh) and the host layout code (awb_layout.h) with g++ and runs them
+// sequentially over one problem, so their outputs can be compared with the
+// oracle on the CPU box before any GPU time is spent.
+//
+// It also contains a plain sequential walk over the device data structures
+// (time matrix + same-branch band + switch CSR + site kinds) that reproduces
+// the forward table -- this validates the *tables* the CUDA forward kernel
+// consumes.  It is NOT a product path and is never shipped or benchmarked.
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "argweaver_b200.h"
+#include "awb_common.cuh"
+#include "awb_emit.cuh"
+#include "awb_layout.h"
+#include "awb_setup.cuh"
+
+struct Emul {
+    AwbLayout L;
+    AwbChain ch;
+    std::vector<char> arena;
+    std::vector<unsigned char> scratch;
+    std::string err;
+    int code;
+};
+
+extern "C" {
+
+void *emul_create(const awb_problem *p)
+{
+    Emul *e = new Emul;
+    e->code = 0;
+    if (!awb_layout_build(*p, 1, e->L, e->err)) {
+        e->code = -1;
+        return e;
+    }
+    e->arena.assign(e->L.total_bytes, 0);
+    for (size_t i = 0; i < e->L.copies.size(); i++)
+        memcpy(&e->arena[e->L.copies[i].dst_off], e->L.copies[i].src,
+               e->L.copies[i].bytes);
+    awb_layout_bind(e->L, *p, e->arena.data(), e->ch);
+    e->scratch.assign(awb_emit_scratch_bytes(p->nnodes) + 64, 0);
+    return e;
+}
+
+const char *emul_error(void *h) { return ((Emul *) h)->err.c_str(); }
+int emul_code(void *h) { return ((Emul *) h)->code; }
+
+int emul_setup(void *h)
+{
+    Emul *e = (Emul *) h;
+    const AwbChain &ch = e->ch;
+    for (int i = 0; i < ch.nsites; i++)
+        awb_site_kind(ch, i);
+    for (int b = 0; b < ch.ntrees; b++) {
+        int rc = awb_block_setup(ch, b);
+        if (rc) { e->code = 100 + rc; return e->code; }
+    }
+    for (int b = 1; b < ch.ntrees; b++) {
+        int rc = awb_switch_setup(ch, b);
+        if (rc) { e->code = 200 + rc; return e->code; }
+    }
+    for (int i = 0; i < ch.nsites; i++)
+        if (ch.kind[i] == AWB_SITE_VARIANT)
+            awb_emit_site(ch, i, 0, 1, e->scratch.data());
+    return 0;
+}
+
+// sequential walk over the device tables; overwrites ch.fw with the forward
+// table (same semantics as the CUDA forward kernel)
+int emul_forward(void *h, double *logz_out)
+{
+    Emul *e = (Emul *) h;
+    const AwbChain &ch = e->ch;
+    const int T = ch.model.ntimes;
+    std::vector<double> col(ch.maxS), col2(ch.maxS), F(T), R(T);
+    double logz = 0.0;
+    int Sprev1 = 0;
+    for (int b = 0; b < ch.ntrees; b++) {
+        const int S = ch.nstates[b];
+        const int S1 = S > 0 ? S : 1;
+        const long long r0 = ch.row_off[b];
+        double *fw = ch.fw + ch.fw_off[b];
+        const int blen = ch.blocklens[b];
+        const int s0 = ch.block_start[b];
+        const double *tm = ch.tmatrix + (size_t) b * T * T;
+        const double *band = ch.band + ch.band_off[b];
+        for (int i = 0; i < blen; i++) {
+            const int site = s0 + i;
+            if (site == 0) {
+                for (int k = 0; k < S1; k++) col[k] = fw[k];
+                continue;     // prior column stays unnormalised
+            }
+            // emission of this site
+            const int kd = ch.kind[site];
+            if (i == 0) {
+                // switch (sample_thread.cpp:345-389)
+                for (int k = 0; k < S1; k++) {
+                    double sum = 0.0;
+                    const int st = ch.sw_start[r0 + k], cn = ch.sw_cnt[r0 + k];
+                    for (int q = 0; q < cn; q++)
+                        sum += col[ch.sw_src[ch.ent_off[b] + st + q]] *
+                            ch.sw_prob[ch.ent_off[b] + st + q];
+                    col2[k] = sum;
+                }
+            } else if (S == 0) {
+                col2[0] = col[0];
+            } else {
+                for (int a = 0; a < T; a++) F[a] = 0.0;
+                for (int k = 0; k < S; k++) F[ch.st_time[r0 + k]] += col[k];
+                for (int bb = 0; bb < T - 1; bb++) {
+                    double sum = 0.0;
+                    for (int a = 0; a < T - 1; a++) sum += tm[a * T + bb] * F[a];
+                    R[bb] = sum;
+                }
+                for (int k = 0; k < S; k++) {
+                    double sum = R[ch.st_time[r0 + k]];
+                    const int j1 = ch.band_j1[r0 + k], len = ch.band_len[r0 + k];
+                    const double *cf = band + ch.band_boff[r0 + k];
+                    for (int q = 0; q < len; q++) sum += cf[q] * col[j1 + q];
+                    col2[k] = sum;
+                }
+            }
+            double norm = 0.0;
+            for (int k = 0; k < S1; k++) {
+                double em = 1.0;
+                if (S > 0) {
+                    if (kd == AWB_SITE_VARIANT) em = fw[(size_t) i * S1 + k];
+                    else if (kd == AWB_SITE_INVARIANT) em = ch.inv_emit[r0 + k];
+                }
+                col2[k] *= em;
+                norm += col2[k];
+            }
+            for (int k = 0; k < S1; k++) {
+                col[k] = col2[k] / norm;
+                fw[(size_t) i * S1 + k] = col[k];
+            }
+            logz += log(norm);
+        }
+        Sprev1 = S1;
+    }
+    (void) Sprev1;
+    if (logz_out) *logz_out = logz;
+    return 0;
+}
+
+long long emul_array_bytes(void *h, const char *name)
+{
+    Emul *e = (Emul *) h;
+    size_t off, bytes;
+    if (!awb_layout_find(e->L, name, off, bytes)) return -1;
+    return (long long) bytes;
+}
+
+int emul_get(void *h, const char *name, void *dst, long long dst_bytes)
+{
+    Emul *e = (Emul *) h;
+    size_t off, bytes;
+    if (!awb_layout_find(e->L, name, off, bytes)) return -1;
+    if ((long long) bytes > dst_bytes) return -2;
+    memcpy(dst, &e->arena[off], bytes);
+    return 0;
+}
+
+void emul_layout(void *h, int *nstates, long long *row_off, long long *fw_off,
+                 long long *sw1_off, int *maxS, int *maxband)
+{
+    Emul *e = (Emul *) h;
+    const int B = e->L.B;
+    memcpy(nstates, e->L.nstates.data(), B * sizeof(int));
+    memcpy(row_off, e->L.row_off.data(), (B + 1) * sizeof(long long));
+    memcpy(fw_off, e->L.fw_off.data(), (B + 1) * sizeof(long long));
+    memcpy(sw1_off, e->L.sw1_off.data(), (B + 1) * sizeof(long long));
+    *maxS = e->L.maxS;
+    *maxband = e->L.maxband;
+}
+
+void emul_destroy(void *h) { delete (Emul *) h; }
+
+} // extern "C"
