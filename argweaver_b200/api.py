@@ -1,0 +1,283 @@
+"""Python binding of the C ABI (include/argweaver_b200.h) via ctypes.
+
+The host-side names mirror the reference's Python/ctypes layer
+(argweaver/argweaverc.py): ``forward_algorithm`` ~ ``argweaver_forward_algorithm``
+(:529), ``sample_thread`` ~ the path of ``arghmm_sample_posterior`` (:930 in
+sample_thread.cpp).  All compute happens in libargweaver_b200.so on the GPU; the
+library has no CPU fallback and raises :class:`AwbError` when CUDA is missing.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+from .problem import AwbProblem, make_problem
+
+KEEP_DEBUG = 1
+RAND_MAX = 2147483647
+
+_lib = None
+
+
+class AwbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building if needed) libargweaver_b200.so."""
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_build.build_cuda())
+        L.awb_last_error.restype = C.c_char_p
+        L.awb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.awb_ctx_destroy.argtypes = [C.c_void_p]
+        L.awb_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.POINTER(C.c_void_p)]
+        L.awb_batch_destroy.argtypes = [C.c_void_p]
+        L.awb_batch_upload.argtypes = [C.c_void_p]
+        L.awb_batch_h2d_bytes.restype = C.c_int64
+        L.awb_batch_h2d_bytes.argtypes = [C.c_void_p]
+        L.awb_batch_setup.argtypes = [C.c_void_p]
+        L.awb_batch_forward.argtypes = [C.c_void_p, C.c_void_p]
+        L.awb_batch_traceback.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p]
+        L.awb_batch_sync.argtypes = [C.c_void_p]
+        L.awb_batch_timings.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 3
+        L.awb_batch_states_sites.restype = C.c_double
+        L.awb_batch_states_sites.argtypes = [C.c_void_p, C.c_int]
+        L.awb_batch_fw_doubles.restype = C.c_int64
+        L.awb_batch_fw_doubles.argtypes = [C.c_void_p, C.c_int]
+        L.awb_batch_nsites.argtypes = [C.c_void_p, C.c_int]
+        L.awb_batch_kernel_launches.argtypes = [C.c_void_p]
+        L.awb_batch_get_path.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.awb_batch_get_logz.argtypes = [C.c_void_p, C.c_int,
+                                         C.POINTER(C.c_double)]
+        L.awb_batch_get_status.argtypes = [C.c_void_p, C.c_int,
+                                           C.POINTER(C.c_int)]
+        L.awb_batch_get_fw.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.awb_batch_get_nstates.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.awb_batch_get_layout.argtypes = [C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.awb_batch_get_debug.argtypes = [C.c_void_p, C.c_int, C.c_char_p,
+                                          C.c_void_p, C.c_int64]
+        L.awb_batch_debug_bytes.restype = C.c_int64
+        L.awb_batch_debug_bytes.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AwbError(lib().awb_last_error().decode())
+
+
+def device_count():
+    return lib().awb_device_count()
+
+
+class Context(object):
+    """One CUDA device + stream (``awb_ctx``)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().awb_ctx_create(int(device), C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().awb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+DEBUG_DTYPES = {
+    "st_node": np.int16, "st_time": np.int8, "perm": np.uint16,
+    "pslot": np.uint16, "band_j1": np.uint16, "band_len": np.uint8,
+    "band_boff": np.int32, "inv_emit": np.float64, "band": np.float64,
+    "tmatrix": np.float64, "tmvec": np.float64, "rowstart": np.uint16,
+    "pstart": np.uint16, "node_first": np.int16, "node_cnt": np.int16,
+    "child0": np.int16, "child1": np.int16, "order": np.int16,
+    "root": np.int16, "lineages": np.int32, "treelen": np.float64,
+    "tm_minage": np.int32, "sw_start": np.uint16, "sw_cnt": np.uint16,
+    "sw_src": np.uint16, "sw_prob": np.float64, "sw_determ": np.int32,
+    "sw_determprob": np.float64, "sw_recombrow": np.float64,
+    "sw_recoalrow": np.float64, "sw_recombsrc": np.int32,
+    "sw_recoalsrc": np.int32, "kind": np.uint8, "fw": np.float64,
+    "path": np.int32,
+}
+
+
+class Batch(object):
+    """A set of independent thread-sampling problems on one device
+    (``awb_batch``).  ``problems`` is a list of problem dicts (see sim.py)."""
+
+    def __init__(self, problems, ctx=None, keep_debug=False):
+        self.ctx = ctx or default_context()
+        self.n = len(problems)
+        arr = (AwbProblem * self.n)()
+        self._keep = []
+        for i, d in enumerate(problems):
+            p, keep = make_problem(d)
+            arr[i] = p
+            self._keep.append(keep)
+        self._arr = arr
+        self.h = C.c_void_p()
+        _check(lib().awb_batch_create(self.ctx.h, self.n, arr,
+                                      KEEP_DEBUG if keep_debug else 0,
+                                      C.byref(self.h)))
+        self.ntrees = [arr[i].ntrees for i in range(self.n)]
+
+    def close(self):
+        if self.h:
+            lib().awb_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pipeline
+    def upload(self):
+        _check(lib().awb_batch_upload(self.h))
+        return self
+
+    def setup(self):
+        _check(lib().awb_batch_setup(self.h))
+        return self
+
+    def forward(self, priors=None):
+        ptr = None
+        if priors is not None:
+            self._priors = [None if p is None else
+                            np.ascontiguousarray(p, np.float64) for p in priors]
+            pa = (C.c_void_p * self.n)()
+            for i, p in enumerate(self._priors):
+                pa[i] = None if p is None else p.ctypes.data
+            ptr = pa
+        _check(lib().awb_batch_forward(self.h, ptr))
+        return self
+
+    def traceback(self, rand_ints, rand_max=RAND_MAX, last_states=None):
+        self._rand = [np.ascontiguousarray(r, np.int32) for r in rand_ints]
+        ra = (C.c_void_p * self.n)()
+        for i, r in enumerate(self._rand):
+            if len(r) < self.nsites(i):
+                raise ValueError("need one rand() draw per site")
+            ra[i] = r.ctypes.data
+        ls = None
+        if last_states is not None:
+            self._ls = np.ascontiguousarray(last_states, np.int32)
+            ls = self._ls.ctypes.data
+        _check(lib().awb_batch_traceback(self.h, ra, int(rand_max), ls))
+        return self
+
+    def sync(self):
+        _check(lib().awb_batch_sync(self.h))
+        return self
+
+    # ---- info
+    def nsites(self, i=0):
+        return lib().awb_batch_nsites(self.h, i)
+
+    def states_sites(self, i=0):
+        return lib().awb_batch_states_sites(self.h, i)
+
+    def total_states_sites(self):
+        return sum(self.states_sites(i) for i in range(self.n))
+
+    def h2d_bytes(self):
+        return lib().awb_batch_h2d_bytes(self.h)
+
+    def kernel_launches(self):
+        return lib().awb_batch_kernel_launches(self.h)
+
+    def timings(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().awb_batch_timings(self.h, C.byref(a), C.byref(b),
+                                       C.byref(c)))
+        return dict(setup_ms=a.value, forward_ms=b.value, traceback_ms=c.value)
+
+    # ---- results
+    def path(self, i=0):
+        out = np.empty(self.nsites(i), np.int32)
+        _check(lib().awb_batch_get_path(self.h, i, out.ctypes.data))
+        return out
+
+    def logz(self, i=0):
+        z = C.c_double()
+        _check(lib().awb_batch_get_logz(self.h, i, C.byref(z)))
+        return z.value
+
+    def status(self, i=0):
+        s = C.c_int()
+        _check(lib().awb_batch_get_status(self.h, i, C.byref(s)))
+        return s.value
+
+    def fw(self, i=0):
+        out = np.empty(lib().awb_batch_fw_doubles(self.h, i), np.float64)
+        _check(lib().awb_batch_get_fw(self.h, i, out.ctypes.data))
+        return out
+
+    def nstates(self, i=0):
+        out = np.empty(self.ntrees[i], np.int32)
+        _check(lib().awb_batch_get_nstates(self.h, i, out.ctypes.data))
+        return out
+
+    def layout(self, i=0):
+        B = self.ntrees[i]
+        ro = np.empty(B + 1, np.int64)
+        fo = np.empty(B + 1, np.int64)
+        so = np.empty(B + 1, np.int64)
+        _check(lib().awb_batch_get_layout(self.h, i, ro.ctypes.data,
+                                          fo.ctypes.data, so.ctypes.data))
+        return dict(row_off=ro, fw_off=fo, sw1_off=so)
+
+    def debug(self, name, i=0):
+        """A named per-block array (needs keep_debug for the sw_* copies)."""
+        dt = np.dtype(DEBUG_DTYPES[name])
+        nb = lib().awb_batch_debug_bytes(self.h, i, name.encode())
+        if nb < 0:
+            raise AwbError("unknown or unavailable array: " + name)
+        out = np.empty(nb // dt.itemsize, dt)
+        _check(lib().awb_batch_get_debug(self.h, i, name.encode(),
+                                         out.ctypes.data, out.nbytes))
+        return out
+
+
+def forward_algorithm(problem, prior=None, ctx=None):
+    """Forward table of one problem; returns (fw_flat, layout, logZ).
+
+    Counterpart of argweaver_forward_algorithm (argweaverc.py:529-567)."""
+    b = Batch([problem], ctx)
+    try:
+        b.upload().setup().forward(None if prior is None else [prior]).sync()
+        return b.fw(0), b.layout(0), b.logz(0)
+    finally:
+        b.close()
+
+
+def sample_thread(problem, rand_ints, rand_max=RAND_MAX, ctx=None):
+    """Forward + stochastic traceback; returns (path, logZ)."""
+    b = Batch([problem], ctx)
+    try:
+        b.upload().setup().forward().traceback([rand_ints], rand_max).sync()
+        return b.path(0), b.logz(0)
+    finally:
+        b.close()

@@ -27,8 +27,8 @@ NVCC_FLAGS = [
 ]
 
 CUDA_SOURCES = ["awb_api.cu"]
-CUDA_DEPS = ["awb_kernels.cuh", "awb_setup.cuh", "awb_forward.cuh",
-             "awb_traceback.cuh", "awb_emit.cuh", "awb_common.cuh"]
+CUDA_DEPS = ["awb_setup.cuh", "awb_forward.cuh", "awb_traceback.cuh",
+             "awb_emit.cuh", "awb_common.cuh", "awb_layout.h"]
 
 
 def _stale(target, sources):

@@ -1,0 +1,544 @@
+// awb_api.cu -- the flat C ABI (include/argweaver_b200.h) over the CUDA kernels.
+//
+// Kernels launched per batch (one launch each, all chains of the batch):
+//   awb_kind_kernel          thread per site     site classification
+//   awb_block_setup_kernel   thread per block    K1 (awb_setup.cuh)
+//   awb_switch_setup_kernel  thread per block    K2 (awb_setup.cuh)
+//   awb_emit_kernel          warp per site       K3 (awb_emit.cuh), variant sites
+//   awb_forward_kernel       CTA per chain       K4 (awb_forward.cuh)
+//   awb_traceback_kernel     CTA per chain       K5 (awb_traceback.cuh)
+//
+// There is no CPU fallback: without a usable CUDA device every entry point
+// returns an error.
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "argweaver_b200.h"
+#include "awb_common.cuh"
+#include "awb_emit.cuh"
+#include "awb_forward.cuh"
+#include "awb_layout.h"
+#include "awb_setup.cuh"
+#include "awb_traceback.cuh"
+
+// ---------------------------------------------------------------- errors
+
+static thread_local std::string g_err;
+
+static int fail(const std::string &msg)
+{
+    g_err = msg;
+    return 1;
+}
+
+#define CUDA_OK(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess)                                               \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char *awb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int awb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+// ---------------------------------------------------------------- kernels
+
+__global__ void awb_kind_kernel(const AwbChain *chains)
+{
+    const AwbChain &ch = chains[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ch.nsites;
+         i += gridDim.x * blockDim.x)
+        awb_site_kind(ch, i);
+}
+
+__global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
+{
+    const AwbChain &ch = chains[blockIdx.y];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= ch.ntrees)
+        return;
+    const int rc = awb_block_setup(ch, b);
+    if (rc)
+        atomicMax(err, 100 + rc);
+}
+
+__global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err)
+{
+    const AwbChain &ch = chains[blockIdx.y];
+    const int b = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= ch.ntrees)
+        return;
+    const int rc = awb_switch_setup(ch, b);
+    if (rc)
+        atomicMax(err, 200 + rc);
+}
+
+// one warp per site; invariant / masked sites exit at once
+__global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
+{
+    extern __shared__ unsigned char emit_smem[];
+    const AwbChain &ch = chains[blockIdx.y];
+    const int wpc = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    unsigned char *scratch = emit_smem + (size_t) warp * scratch_bytes;
+    for (int i = blockIdx.x * wpc + warp; i < ch.nsites; i += gridDim.x * wpc) {
+        if (ch.kind[i] != AWB_SITE_VARIANT)
+            continue;
+        if (i == 0)
+            continue;       // the first column is the prior; no emission applied
+        awb_emit_site(ch, i, lane, 32, scratch);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- host side
+
+struct awb_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev[6];
+    int sm_count;
+};
+
+struct awb_batch {
+    awb_ctx *ctx;
+    int C;
+    std::vector<AwbLayout> L;
+    std::vector<awb_problem> P;
+    std::vector<size_t> arena_off;
+    std::vector<AwbChain> h_chains;
+    char *arena;
+    size_t arena_bytes;
+    AwbChain *d_chains;
+    int *d_err;
+    int maxB, maxn, maxS, maxV, maxT, maxband;
+    float ms[3];
+    int launches;
+    int64_t h2d_bytes;
+    bool uploaded, setup_done, forward_done;
+};
+
+extern "C" int awb_ctx_create(int device, awb_ctx **out)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        return fail("bad device ordinal");
+    CUDA_OK(cudaSetDevice(device));
+    awb_ctx *ctx = new awb_ctx;
+    ctx->device = device;
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++)
+        CUDA_OK(cudaEventCreate(&ctx->ev[i]));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_emit_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void awb_ctx_destroy(awb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < 6; i++)
+        cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void awb_batch_destroy(awb_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->arena) cudaFree(b->arena);
+    if (b->d_chains) cudaFree(b->d_chains);
+    if (b->d_err) cudaFree(b->d_err);
+    delete b;
+}
+
+extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
+                                const awb_problem *problems, int flags,
+                                awb_batch **out)
+{
+    if (!ctx) return fail("null context");
+    if (nproblems < 1) return fail("need at least one problem");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    awb_batch *b = new awb_batch;
+    b->ctx = ctx;
+    b->C = nproblems;
+    b->arena = NULL;
+    b->d_chains = NULL;
+    b->d_err = NULL;
+    b->L.resize(nproblems);
+    b->P.assign(problems, problems + nproblems);
+    b->arena_off.resize(nproblems);
+    b->h_chains.resize(nproblems);
+    b->maxB = b->maxn = b->maxS = b->maxV = b->maxT = b->maxband = 0;
+    b->ms[0] = b->ms[1] = b->ms[2] = 0;
+    b->launches = 0;
+    b->h2d_bytes = 0;
+    b->uploaded = b->setup_done = b->forward_done = false;
+
+    size_t total = 0;
+    for (int c = 0; c < nproblems; c++) {
+        std::string err;
+        if (!awb_layout_build(problems[c], (flags & AWB_KEEP_DEBUG) ? 1 : 0,
+                              b->L[c], err)) {
+            delete b;
+            return fail("problem " + std::to_string(c) + ": " + err);
+        }
+        const AwbLayout &L = b->L[c];
+        b->arena_off[c] = total;
+        total += awb_align(L.total_bytes);
+        if (L.B > b->maxB) b->maxB = L.B;
+        if (L.n > b->maxn) b->maxn = L.n;
+        if (L.maxS > b->maxS) b->maxS = L.maxS;
+        if (L.V > b->maxV) b->maxV = L.V;
+        if (L.T > b->maxT) b->maxT = L.T;
+        if (L.maxband > b->maxband) b->maxband = L.maxband;
+        for (size_t i = 0; i < L.copies.size(); i++)
+            b->h2d_bytes += (int64_t) L.copies[i].bytes;
+    }
+    b->arena_bytes = total;
+    cudaError_t e = cudaMalloc((void **) &b->arena, total);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("cudaMalloc of ") + std::to_string(total) +
+            " bytes failed: " + cudaGetErrorString(e);
+        delete b;
+        return fail(msg);
+    }
+    CUDA_OK(cudaMalloc((void **) &b->d_chains, sizeof(AwbChain) * nproblems));
+    CUDA_OK(cudaMalloc((void **) &b->d_err, sizeof(int)));
+    for (int c = 0; c < nproblems; c++)
+        awb_layout_bind(b->L[c], b->P[c], b->arena + b->arena_off[c],
+                        b->h_chains[c]);
+    *out = b;
+    return 0;
+}
+
+extern "C" int64_t awb_batch_h2d_bytes(const awb_batch *b)
+{
+    return b->h2d_bytes + (int64_t) sizeof(AwbChain) * b->C;
+}
+
+extern "C" int awb_batch_upload(awb_batch *b)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    for (int c = 0; c < b->C; c++) {
+        const AwbLayout &L = b->L[c];
+        char *base = b->arena + b->arena_off[c];
+        for (size_t i = 0; i < L.copies.size(); i++)
+            CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
+                                    L.copies[i].bytes, cudaMemcpyHostToDevice,
+                                    st));
+    }
+    CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
+                            sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+    b->uploaded = true;
+    b->setup_done = b->forward_done = false;
+    return 0;
+}
+
+extern "C" int awb_batch_setup(awb_batch *b)
+{
+    if (!b->uploaded) return fail("awb_batch_setup: inputs not uploaded");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    CUDA_OK(cudaEventRecord(b->ctx->ev[0], st));
+
+    {
+        dim3 grid((b->maxn + 255) / 256, b->C);
+        if (grid.x > 4096) grid.x = 4096;
+        awb_kind_kernel<<<grid, 256, 0, st>>>(b->d_chains);
+    }
+    {
+        dim3 grid((b->maxB + 63) / 64, b->C);
+        awb_block_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
+    }
+    if (b->maxB > 1) {
+        dim3 grid((b->maxB - 1 + 63) / 64, b->C);
+        awb_switch_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
+        b->launches++;
+    }
+    {
+        const int scratch = (int) ((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15);
+        int wpc = 8;
+        while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
+            wpc >>= 1;
+        if ((size_t) wpc * scratch > 200 * 1024)
+            return fail("tree too large for the emission kernel's shared memory");
+        int gx = (b->maxn + wpc - 1) / wpc;
+        const int cap = b->ctx->sm_count * 16;
+        if (gx > cap) gx = cap;
+        dim3 grid(gx, b->C);
+        awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
+            b->d_chains, scratch);
+    }
+    b->launches += 3;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(b->ctx->ev[1], st));
+    b->setup_done = true;
+    return 0;
+}
+
+extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
+{
+    if (!b->setup_done) return fail("awb_batch_forward: setup has not run");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (priors) {
+        for (int c = 0; c < b->C; c++) {
+            if (!priors[c]) continue;
+            const AwbLayout &L = b->L[c];
+            const int S1 = L.nstates[0] > 0 ? L.nstates[0] : 1;
+            CUDA_OK(cudaMemcpyAsync(b->h_chains[c].fw, priors[c],
+                                    sizeof(double) * S1, cudaMemcpyHostToDevice,
+                                    st));
+        }
+    }
+    const int NS = ((b->maxS + 31) / 32) * 32;
+    const size_t smem = awb_fwd_smem_bytes(NS, b->maxT, b->maxband);
+    if (smem > 200 * 1024)
+        return fail("forward kernel needs " + std::to_string(smem) +
+                    " bytes of shared memory (limit 200 KiB)");
+    CUDA_OK(cudaEventRecord(b->ctx->ev[2], st));
+    awb_forward_kernel<<<b->C, NS, smem, st>>>(b->d_chains, b->maxband);
+    b->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(b->ctx->ev[3], st));
+    b->forward_done = true;
+    return 0;
+}
+
+extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
+                                   int rand_max, const int *last_states)
+{
+    if (!b->forward_done) return fail("awb_batch_traceback: forward has not run");
+    if (!rand_ints) return fail("awb_batch_traceback: rand_ints is required");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    bool chains_dirty = false;
+    for (int c = 0; c < b->C; c++) {
+        CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints, rand_ints[c],
+                                sizeof(int) * b->L[c].n, cudaMemcpyHostToDevice,
+                                st));
+        const int ls = last_states ? last_states[c] : -1;
+        if (ls != b->h_chains[c].last_state) {
+            b->h_chains[c].last_state = ls;
+            chains_dirty = true;
+        }
+    }
+    if (chains_dirty)
+        CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
+                                sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice,
+                                st));
+    const int NS = ((b->maxS + 31) / 32) * 32;
+    CUDA_OK(cudaEventRecord(b->ctx->ev[4], st));
+    awb_traceback_kernel<<<b->C, NS, 0, st>>>(b->d_chains, rand_max);
+    b->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(b->ctx->ev[5], st));
+    return 0;
+}
+
+extern "C" int awb_batch_sync(awb_batch *b)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    int err = 0;
+    CUDA_OK(cudaMemcpy(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err)
+        return fail("device-side setup error code " + std::to_string(err));
+    return 0;
+}
+
+extern "C" int awb_batch_timings(awb_batch *b, float *setup_ms, float *forward_ms,
+                                 float *traceback_ms)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    float v = 0;
+    if (setup_ms) {
+        *setup_ms = 0;
+        if (cudaEventElapsedTime(&v, b->ctx->ev[0], b->ctx->ev[1]) == cudaSuccess)
+            *setup_ms = v;
+    }
+    if (forward_ms) {
+        *forward_ms = 0;
+        if (cudaEventElapsedTime(&v, b->ctx->ev[2], b->ctx->ev[3]) == cudaSuccess)
+            *forward_ms = v;
+    }
+    if (traceback_ms) {
+        *traceback_ms = 0;
+        if (cudaEventElapsedTime(&v, b->ctx->ev[4], b->ctx->ev[5]) == cudaSuccess)
+            *traceback_ms = v;
+    }
+    cudaGetLastError();
+    return 0;
+}
+
+extern "C" double awb_batch_states_sites(const awb_batch *b, int i)
+{
+    return b->L[i].states_sites;
+}
+
+extern "C" int64_t awb_batch_fw_doubles(const awb_batch *b, int i)
+{
+    return b->L[i].fw_off[b->L[i].B];
+}
+
+extern "C" int awb_batch_nsites(const awb_batch *b, int i) { return b->L[i].n; }
+
+extern "C" int awb_batch_kernel_launches(const awb_batch *b) { return b->launches; }
+
+extern "C" int awb_batch_get_path(awb_batch *b, int i, int *path)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaMemcpyAsync(path, b->h_chains[i].path, sizeof(int) * b->L[i].n,
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+extern "C" int awb_batch_get_logz(awb_batch *b, int i, double *logz)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaMemcpyAsync(logz, b->h_chains[i].logz, sizeof(double),
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+extern "C" int awb_batch_get_status(awb_batch *b, int i, int *first_bad_site)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaMemcpyAsync(first_bad_site, b->h_chains[i].status, sizeof(int),
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+extern "C" int awb_batch_get_fw(awb_batch *b, int i, double *fw)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaMemcpyAsync(fw, b->h_chains[i].fw,
+                            sizeof(double) * b->L[i].fw_off[b->L[i].B],
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+extern "C" int awb_batch_get_nstates(awb_batch *b, int i, int *nstates)
+{
+    memcpy(nstates, b->L[i].nstates.data(), sizeof(int) * b->L[i].B);
+    return 0;
+}
+
+extern "C" int awb_batch_get_layout(awb_batch *b, int i, int64_t *row_off,
+                                    int64_t *fw_off, int64_t *sw1_off)
+{
+    const AwbLayout &L = b->L[i];
+    for (int k = 0; k <= L.B; k++) {
+        if (row_off) row_off[k] = L.row_off[k];
+        if (fw_off) fw_off[k] = L.fw_off[k];
+        if (sw1_off) sw1_off[k] = L.sw1_off[k];
+    }
+    return 0;
+}
+
+extern "C" int awb_batch_get_debug(awb_batch *b, int i, const char *name,
+                                   void *dst, int64_t dst_bytes)
+{
+    size_t off, bytes;
+    if (!awb_layout_find(b->L[i], name, off, bytes))
+        return fail(std::string("unknown or unavailable array: ") + name);
+    if ((int64_t) bytes > dst_bytes)
+        return fail("destination too small");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    CUDA_OK(cudaMemcpy(dst, b->arena + b->arena_off[i] + off, bytes,
+                       cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int64_t awb_batch_debug_bytes(awb_batch *b, int i, const char *name)
+{
+    size_t off, bytes;
+    if (!awb_layout_find(b->L[i], name, off, bytes))
+        return -1;
+    return (int64_t) bytes;
+}
+
+// ---------------------------------------------------------------- one-shot
+
+static awb_ctx *g_default_ctx = NULL;
+
+static int default_ctx(awb_ctx **ctx)
+{
+    if (!g_default_ctx) {
+        int dev = 0;
+        const char *env = getenv("AWB_DEVICE");
+        if (env) dev = atoi(env);
+        if (awb_ctx_create(dev, &g_default_ctx))
+            return 1;
+    }
+    *ctx = g_default_ctx;
+    return 0;
+}
+
+extern "C" int awb_thread_sample(const awb_problem *p, const int *rand_ints,
+                                 int rand_max, int *path, double *logz)
+{
+    awb_ctx *ctx;
+    if (default_ctx(&ctx)) return 1;
+    awb_batch *b = NULL;
+    if (awb_batch_create(ctx, 1, p, 0, &b)) return 1;
+    int rc = awb_batch_upload(b) || awb_batch_setup(b) ||
+        awb_batch_forward(b, NULL) ||
+        awb_batch_traceback(b, &rand_ints, rand_max, NULL) || awb_batch_sync(b);
+    if (!rc && path) rc = awb_batch_get_path(b, 0, path);
+    if (!rc && logz) rc = awb_batch_get_logz(b, 0, logz);
+    awb_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int awb_forward_table(const awb_problem *p, const double *prior,
+                                 double *fw, double *logz)
+{
+    awb_ctx *ctx;
+    if (default_ctx(&ctx)) return 1;
+    awb_batch *b = NULL;
+    if (awb_batch_create(ctx, 1, p, 0, &b)) return 1;
+    const double *priors[1] = { prior };
+    int rc = awb_batch_upload(b) || awb_batch_setup(b) ||
+        awb_batch_forward(b, prior ? priors : NULL) || awb_batch_sync(b);
+    if (!rc && fw) rc = awb_batch_get_fw(b, 0, fw);
+    if (!rc && logz) rc = awb_batch_get_logz(b, 0, logz);
+    awb_batch_destroy(b);
+    return rc;
+}

@@ -62,6 +62,7 @@ struct AwbChain {
     const int *ptrees;        // [B][V]
     const int *ages;          // [B][V]
     const int *sprs;          // [B][4]
+    const int *mappings;      // [B][V] previous-tree node -> this tree, -1 = broken
     const int *blocklens;     // [B]
     const int *subtree_roots; // [B] (internal) or NULL
     const int *rowidx;        // [nrows] rows of seqs compared for invariance:

@@ -30,12 +30,13 @@ struct AwbLayout {
     int maxS, maxband;
     int keep_debug;
     double states_sites;                 // sum blocklen * nstates
-    std::vector<int> nstates, block_start, rowidx;
+    std::vector<int> nstates, block_start, rowidx, mappings;
     std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off;
     AwbModel model;
 
     // arena
     size_t total_bytes;
+    size_t o_mappings;
     size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
         o_seqs, o_block_start, o_nstates, o_row_off, o_fw_off, o_band_off,
         o_ent_off, o_sw1_off, o_st_node, o_st_time, o_perm, o_pslot, o_band_j1,
@@ -254,9 +255,9 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
                 const int broken = lp[spr[0]];
                 const int *mp = p.mappings + (size_t) b * V;
                 for (int x = 0; x < V; x++) {
-                    if (mp[x] != (x == broken ? -1 : x)) {
+                    if (mp[x] < -1 || mp[x] >= V || (mp[x] == -1) != (x == broken)) {
                         err = "tree " + std::to_string(b) +
-                            ": node mapping is not identity-except-broken-node";
+                            ": invalid node mapping (only the broken node maps to -1)";
                         return false;
                     }
                 }
@@ -270,6 +271,19 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     }
     L.has_subtree_roots = p.internal && p.subtree_roots;
 
+    // node mappings: the caller's, or identity except the broken node
+    // (make_node_mapping, local_tree.h:767-776)
+    L.mappings.clear();
+    if (!p.mappings) {
+        L.mappings.resize((size_t) B * V);
+        for (int b = 0; b < B; b++) {
+            int *mp = L.mappings.data() + (size_t) b * V;
+            for (int x = 0; x < V; x++) mp[x] = x;
+            if (b > 0)
+                mp[p.ptrees[(size_t) (b - 1) * V + p.sprs[4 * (size_t) b]]] = -1;
+        }
+    }
+
     // ---- arena
     size_t off = 0;
     const size_t rows = (size_t) L.row_off[B];
@@ -278,6 +292,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_ptrees, BV * sizeof(int));
     AWB_PLACE(o_ages, BV * sizeof(int));
     AWB_PLACE(o_sprs, (size_t) B * 4 * sizeof(int));
+    AWB_PLACE(o_mappings, BV * sizeof(int));
     AWB_PLACE(o_blocklens, (size_t) B * sizeof(int));
     AWB_PLACE(o_subtree_roots, (size_t) B * sizeof(int));
     AWB_PLACE(o_rowidx, (size_t) L.nrows * sizeof(int));
@@ -340,6 +355,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int) });
     L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int) });
     L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int) });
+    L.copies.push_back({ L.o_mappings, p.mappings ? (const void *) p.mappings :
+                         (const void *) L.mappings.data(), BV * sizeof(int) });
     L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int) });
     if (L.has_subtree_roots)
         L.copies.push_back({ L.o_subtree_roots, p.subtree_roots, (size_t) B * sizeof(int) });
@@ -379,6 +396,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(const int *, ptrees, o_ptrees);
     AWB_P(const int *, ages, o_ages);
     AWB_P(const int *, sprs, o_sprs);
+    AWB_P(const int *, mappings, o_mappings);
     AWB_P(const int *, blocklens, o_blocklens);
     ch.subtree_roots = L.has_subtree_roots ?
         (const int *) (base + L.o_subtree_roots) : 0;

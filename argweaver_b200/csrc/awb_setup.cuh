@@ -575,10 +575,10 @@ AWB_HD inline double awb_calc_recomb_recoal(
 
 // trans.cpp:156-275, one source state
 AWB_HD inline int awb_determ_one(const AwbTreeView &lt, const AwbTreeView &t,
-                                 const AwbSpr &spr, int broken, int node1,
-                                 int time1, bool internal)
+                                 const AwbSpr &spr, const int *mapping,
+                                 int node1, int time1, bool internal)
 {
-#define AWB_MAP(x) ((x) == broken ? -1 : (x))
+#define AWB_MAP(x) (mapping[(x)])
     if ((node1 == spr.coal_node && time1 == spr.coal_time) ||
         (node1 == spr.recomb_node && time1 == spr.recomb_time))
         return -1;
@@ -723,6 +723,7 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
         return 0;
     }
 
+    const int *mapping = ch.mappings + (size_t) b * ch.nnodes;
     const int broken = lt.parent[spr.recomb_node];
     const int recomb_parent_age0 = lt.age[broken];
 
@@ -759,7 +760,7 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
             recombsrc = i;
         else if (node1 == spr.coal_node && time1 == spr.coal_time)
             recoalsrc = i;
-        const int d = awb_determ_one(lt, t, spr, broken, node1, time1, internal);
+        const int d = awb_determ_one(lt, t, spr, mapping, node1, time1, internal);
         if (d >= 0)
             cnt[d]++;
     }
@@ -839,7 +840,7 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
     // ---- pass 2: deterministic entries in ascending source order
     for (int i = 0; i < S1; i++) {
         const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
-        const int d = awb_determ_one(lt, t, spr, broken, node1, time1, internal);
+        const int d = awb_determ_one(lt, t, spr, mapping, node1, time1, internal);
         if (ch.keep_debug) dbg_determ[i] = d;
         if (d < 0)
             continue;

@@ -133,6 +133,7 @@ int awb_batch_get_layout(awb_batch *b, int i, int64_t *row_off, int64_t *fw_off,
 /* AWB_KEEP_DEBUG only: named per-block arrays, see awb_api.cu (debug_fetch) */
 int awb_batch_get_debug(awb_batch *b, int i, const char *name, void *dst,
                         int64_t dst_bytes);
+int64_t awb_batch_debug_bytes(awb_batch *b, int i, const char *name);
 
 /* One-shot convenience over host buffers: create + upload + setup + forward +
  * traceback + download, for a single problem. */

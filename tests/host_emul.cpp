@@ -67,7 +67,7 @@ int emul_setup(void *h)
         if (rc) { e->code = 200 + rc; return e->code; }
     }
     for (int i = 0; i < ch.nsites; i++)
-        if (ch.kind[i] == AWB_SITE_VARIANT)
+        if (i > 0 && ch.kind[i] == AWB_SITE_VARIANT)
             awb_emit_site(ch, i, 0, 1, e->scratch.data());
     return 0;
 }

@@ -1,0 +1,160 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the
+reference's golden vectors.  Gates: integer structures bit-exact; forward
+tables, emissions, transition/switch tables and logZ within 1e-9 relative;
+sampled paths identical for identical rand() draws."""
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from argweaver_b200 import api, sim
+from conftest import golden_files, load_golden
+from helpers import assert_close, first_divergence
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def run_gpu(d, rand_ints, keep_debug=True):
+    b = api.Batch([d], keep_debug=keep_debug)
+    b.upload().setup().forward().traceback([rand_ints]).sync()
+    return b
+
+
+def compare_with_oracle(d, rand_ints, o=None):
+    if o is None:
+        o = ol.run_oracle(d, rand_ints)
+    b = run_gpu(d, rand_ints)
+    B = len(o["nstates"])
+    T = int(np.ravel(d["ntimes"])[0])
+    assert np.array_equal(b.nstates(), o["nstates"])
+    lay = b.layout()
+    for k in ["row_off", "fw_off", "sw1_off"]:
+        assert np.array_equal(lay[k], o[k]), k
+    rows = o["row_off"]
+    stn, stt = b.debug("st_node"), b.debug("st_time")
+    for blk in range(B):
+        S = o["nstates"][blk]
+        s = o["states"][o["state_off"][blk]:o["state_off"][blk] + S]
+        assert np.array_equal(stn[rows[blk]:rows[blk] + S], s[:, 0])
+        assert np.array_equal(stt[rows[blk]:rows[blk] + S], s[:, 1])
+    lin = b.debug("lineages").reshape(B, 3, T)
+    assert np.array_equal(lin[:, 0], o["nbranches"])
+    assert np.array_equal(lin[:, 1], o["nrecombs"])
+    assert np.array_equal(lin[:, 2], o["ncoals"])
+    tv = b.debug("tmvec").reshape(B, 9, T)
+    for k, nm in enumerate(ol.TM_NAMES):
+        assert_close(tv[:, k], o[nm], nm, RTOL)
+    assert np.array_equal(b.debug("sw_determ"), o["sw_determ"])
+    assert_close(b.debug("sw_determprob"), o["sw_determprob"], "determprob", RTOL)
+    assert_close(b.debug("sw_recombrow"), o["sw_recombrow"], "recombrow", RTOL)
+    assert_close(b.debug("sw_recoalrow"), o["sw_recoalrow"], "recoalrow", RTOL)
+    assert np.array_equal(b.debug("sw_recombsrc")[1:], o["sw_recombsrc"][1:])
+    assert np.array_equal(b.debug("sw_recoalsrc")[1:], o["sw_recoalsrc"][1:])
+
+    assert b.status() == -1
+    assert_close(b.fw(), o["fw"], "fw", RTOL)
+    assert abs(b.logz() - o["logZ"]) <= RTOL * abs(o["logZ"])
+    path = b.path()
+    div = first_divergence(path, o["path"])
+    assert div is None, "path diverges from the oracle at site %d" % div
+    b.close()
+    return o
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1])
+def test_golden_vectors(path):
+    g = load_golden(path)
+    o = compare_with_oracle(g, g["rand_ints"])
+    # and directly against what the reference itself produced
+    b = run_gpu(g, g["rand_ints"], keep_debug=False)
+    assert_close(b.fw(), g["fw"], "fw vs reference", RTOL)
+    assert np.array_equal(b.path(), g["path"])
+    b.close()
+    assert np.array_equal(o["path"], g["path"])
+
+
+CASES = [(8, 2000, 20, False, 1), (8, 2000, 20, True, 2), (20, 5000, 20, False, 3),
+         (20, 5000, 20, True, 4), (12, 3000, 30, False, 5), (6, 1500, 10, True, 6),
+         (2, 500, 20, False, 7), (3, 500, 20, True, 8), (40, 3000, 40, False, 9),
+         (50, 4000, 20, True, 10)]
+
+
+@pytest.mark.parametrize("k,n,T,internal,seed", CASES)
+def test_generated_problems(k, n, T, internal, seed, libc_rand):
+    d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
+    compare_with_oracle(d, libc_rand(100 + seed, n))
+
+
+def test_masked_and_missing_data(libc_rand):
+    d = sim.simulate_problem(6, 600, seed=21)
+    d["seqs"] = d["seqs"].copy()
+    d["seqs"][:, 40:60] = ord("N")
+    d["seqs"][2, 100:120] = ord("N")
+    compare_with_oracle(d, libc_rand(5, 600))
+
+
+def test_prior_given_and_last_state_given(libc_rand):
+    """cond_sample_arg_thread semantics (sample_thread.cpp:700-865): one-hot
+    first column supplied by the caller, last state fixed"""
+    d = sim.simulate_problem(10, 800, seed=31)
+    r = libc_rand(9, 800)
+    run = ol.OracleRun(d).setup()
+    S0 = run.outputs()["nstates"][0]
+    prior = np.zeros(S0)
+    prior[S0 // 2] = 1.0
+    run.forward(prior)
+    last = int(run.outputs()["nstates"][-1] // 3)
+    run.traceback(r, last_state=last)
+    o = run.outputs()
+    b = api.Batch([d])
+    b.upload().setup().forward([prior]).traceback([r], last_states=[last]).sync()
+    assert_close(b.fw(), o["fw"], "fw", RTOL)
+    assert np.array_equal(b.path(), o["path"])
+    assert b.path()[-1] == last
+    b.close()
+
+
+def test_batch_of_independent_chains(libc_rand):
+    """several problems of different shapes in one batch = independent windows"""
+    specs = [(8, 700, 20, False, 41), (12, 900, 20, True, 42), (5, 300, 20, False, 43),
+             (16, 1100, 20, True, 44)]
+    ds = [sim.simulate_problem(k, n, ntimes=T, seed=s, internal=i)
+          for (k, n, T, i, s) in specs]
+    rs = [libc_rand(s, n) for (k, n, T, i, s) in specs]
+    b = api.Batch(ds)
+    b.upload().setup().forward().traceback(rs).sync()
+    for c, (d, r) in enumerate(zip(ds, rs)):
+        o = ol.run_oracle(d, r)
+        assert_close(b.fw(c), o["fw"], "fw chain %d" % c, RTOL)
+        assert np.array_equal(b.path(c), o["path"])
+        assert abs(b.logz(c) - o["logZ"]) <= RTOL * abs(o["logZ"])
+    b.close()
+
+
+def test_full_size_properties(libc_rand):
+    """BASELINE config 2 size (k=20, 1 Mb at c=10 -> 1e5 sites): properties that
+    do not need the oracle -- columns sum to 1, idempotence, logZ finite -- plus
+    the oracle on a prefix window of the same data."""
+    n = 100000
+    d = sim.simulate_problem(20, n, seed=51)
+    r = libc_rand(77, n)
+    b = api.Batch([d])
+    b.upload().setup().forward().traceback([r]).sync()
+    fw = b.fw()
+    lay = b.layout()
+    ns = np.maximum(b.nstates(), 1)
+    # every column after the first is normalised
+    sums = np.add.reduceat(fw, np.concatenate(
+        [lay["fw_off"][blk] + np.arange(bl) * ns[blk]
+         for blk, bl in enumerate(d["blocklens"])]))
+    assert np.all(np.abs(sums[1:] - 1.0) < 1e-12)
+    assert np.isfinite(b.logz())
+    p1 = b.path()
+    assert np.all((p1 >= 0) & (p1 < np.repeat(ns, d["blocklens"])))
+    # idempotence: same inputs, same draws -> same table and path
+    b.upload().setup().forward().traceback([r]).sync()
+    assert np.array_equal(b.fw(), fw)
+    assert np.array_equal(b.path(), p1)
+    b.close()
