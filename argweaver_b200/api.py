@@ -32,6 +32,11 @@ def lib():
         L.awb_last_error.restype = C.c_char_p
         L.awb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.awb_ctx_destroy.argtypes = [C.c_void_p]
+        L.awb_ctx_record.argtypes = [C.c_void_p, C.c_int]
+        L.awb_ctx_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                         C.POINTER(C.c_float)]
+        L.awb_ctx_sync.argtypes = [C.c_void_p]
+        L.awb_batch_upload_rand.argtypes = [C.c_void_p, C.c_void_p]
         L.awb_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                        C.POINTER(C.c_void_p)]
         L.awb_batch_destroy.argtypes = [C.c_void_p]
@@ -83,6 +88,17 @@ class Context(object):
         self.h = C.c_void_p()
         _check(lib().awb_ctx_create(int(device), C.byref(self.h)))
         self.device = device
+
+    def record(self, slot):
+        _check(lib().awb_ctx_record(self.h, slot))
+
+    def elapsed_ms(self, slot0, slot1):
+        ms = C.c_float()
+        _check(lib().awb_ctx_elapsed_ms(self.h, slot0, slot1, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        _check(lib().awb_ctx_sync(self.h))
 
     def close(self):
         if self.h:
@@ -174,13 +190,21 @@ class Batch(object):
         _check(lib().awb_batch_forward(self.h, ptr))
         return self
 
-    def traceback(self, rand_ints, rand_max=RAND_MAX, last_states=None):
+    def _rand_ptrs(self, rand_ints):
         self._rand = [np.ascontiguousarray(r, np.int32) for r in rand_ints]
         ra = (C.c_void_p * self.n)()
         for i, r in enumerate(self._rand):
             if len(r) < self.nsites(i):
                 raise ValueError("need one rand() draw per site")
             ra[i] = r.ctypes.data
+        return ra
+
+    def upload_rand(self, rand_ints):
+        _check(lib().awb_batch_upload_rand(self.h, self._rand_ptrs(rand_ints)))
+        return self
+
+    def traceback(self, rand_ints=None, rand_max=RAND_MAX, last_states=None):
+        ra = None if rand_ints is None else self._rand_ptrs(rand_ints)
         ls = None
         if last_states is not None:
             self._ls = np.ascontiguousarray(last_states, np.int32)

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "argweaver_b200.h"
@@ -111,6 +112,7 @@ struct awb_ctx {
     int device;
     cudaStream_t stream;
     cudaEvent_t ev[6];
+    cudaEvent_t user_ev[8];
     int sm_count;
 };
 
@@ -129,7 +131,7 @@ struct awb_batch {
     float ms[3];
     int launches;
     int64_t h2d_bytes;
-    bool uploaded, setup_done, forward_done;
+    bool uploaded, setup_done, forward_done, rand_uploaded;
 };
 
 extern "C" int awb_ctx_create(int device, awb_ctx **out)
@@ -146,6 +148,8 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 6; i++)
         CUDA_OK(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < 8; i++)
+        CUDA_OK(cudaEventCreate(&ctx->user_ev[i]));
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -165,8 +169,35 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (int i = 0; i < 6; i++)
         cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; i++)
+        cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int awb_ctx_record(awb_ctx *ctx, int slot)
+{
+    if (slot < 0 || slot >= 8) return fail("bad event slot");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+    return 0;
+}
+
+extern "C" int awb_ctx_elapsed_ms(awb_ctx *ctx, int slot0, int slot1, float *ms)
+{
+    if (slot0 < 0 || slot0 >= 8 || slot1 < 0 || slot1 >= 8)
+        return fail("bad event slot");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaEventSynchronize(ctx->user_ev[slot1]));
+    CUDA_OK(cudaEventElapsedTime(ms, ctx->user_ev[slot0], ctx->user_ev[slot1]));
+    return 0;
+}
+
+extern "C" int awb_ctx_sync(awb_ctx *ctx)
+{
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" void awb_batch_destroy(awb_batch *b)
@@ -201,15 +232,36 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->launches = 0;
     b->h2d_bytes = 0;
     b->uploaded = b->setup_done = b->forward_done = false;
+    b->rand_uploaded = false;
 
+    // host layout of every problem (integer work), one host thread per problem
+    {
+        std::vector<std::string> errs(nproblems);
+        std::vector<char> ok(nproblems, 0);
+        const int keep = (flags & AWB_KEEP_DEBUG) ? 1 : 0;
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int) std::min<unsigned>(hw ? hw : 1, (unsigned) nproblems);
+        auto work = [&](int t) {
+            for (int c = t; c < nproblems; c += nthreads)
+                ok[c] = awb_layout_build(problems[c], keep, b->L[c], errs[c]) ? 1 : 0;
+        };
+        if (nthreads <= 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; t++) pool.emplace_back(work, t);
+            for (auto &th : pool) th.join();
+        }
+        for (int c = 0; c < nproblems; c++) {
+            if (!ok[c]) {
+                std::string msg = "problem " + std::to_string(c) + ": " + errs[c];
+                delete b;
+                return fail(msg);
+            }
+        }
+    }
     size_t total = 0;
     for (int c = 0; c < nproblems; c++) {
-        std::string err;
-        if (!awb_layout_build(problems[c], (flags & AWB_KEEP_DEBUG) ? 1 : 0,
-                              b->L[c], err)) {
-            delete b;
-            return fail("problem " + std::to_string(c) + ": " + err);
-        }
         const AwbLayout &L = b->L[c];
         b->arena_off[c] = total;
         total += awb_align(L.total_bytes);
@@ -339,14 +391,16 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
                                    int rand_max, const int *last_states)
 {
     if (!b->forward_done) return fail("awb_batch_traceback: forward has not run");
-    if (!rand_ints) return fail("awb_batch_traceback: rand_ints is required");
+    if (!rand_ints && !b->rand_uploaded)
+        return fail("awb_batch_traceback: rand_ints is required");
     CUDA_OK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     bool chains_dirty = false;
     for (int c = 0; c < b->C; c++) {
-        CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints, rand_ints[c],
-                                sizeof(int) * b->L[c].n, cudaMemcpyHostToDevice,
-                                st));
+        if (rand_ints)
+            CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints,
+                                    rand_ints[c], sizeof(int) * b->L[c].n,
+                                    cudaMemcpyHostToDevice, st));
         const int ls = last_states ? last_states[c] : -1;
         if (ls != b->h_chains[c].last_state) {
             b->h_chains[c].last_state = ls;
@@ -363,6 +417,17 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
     b->launches++;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[5], st));
+    return 0;
+}
+
+extern "C" int awb_batch_upload_rand(awb_batch *b, const int *const *rand_ints)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    for (int c = 0; c < b->C; c++)
+        CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints, rand_ints[c],
+                                sizeof(int) * b->L[c].n, cudaMemcpyHostToDevice,
+                                b->ctx->stream));
+    b->rand_uploaded = true;
     return 0;
 }
 

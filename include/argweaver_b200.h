@@ -83,6 +83,10 @@ int awb_device_count(void);
 
 int awb_ctx_create(int device, awb_ctx **out);
 void awb_ctx_destroy(awb_ctx *ctx);
+/* CUDA events on the context's stream (8 slots) for timing by the caller */
+int awb_ctx_record(awb_ctx *ctx, int slot);
+int awb_ctx_elapsed_ms(awb_ctx *ctx, int slot0, int slot1, float *ms);
+int awb_ctx_sync(awb_ctx *ctx);
 
 /* Validate the problems, compute the table layout, allocate device memory.
  * The problem structs and the arrays they point to must stay valid until
@@ -109,6 +113,10 @@ int awb_batch_forward(awb_batch *b, const double *const *priors);
  * state (-1 = sample it). */
 int awb_batch_traceback(awb_batch *b, const int *const *rand_ints, int rand_max,
                         const int *last_states);
+
+/* Upload the rand() draws ahead of time; awb_batch_traceback may then be
+ * called with rand_ints == NULL. */
+int awb_batch_upload_rand(awb_batch *b, const int *const *rand_ints);
 
 int awb_batch_sync(awb_batch *b);
 
