@@ -24,6 +24,7 @@
 #include "awb_common.cuh"
 #include "awb_emit.cuh"
 #include "awb_forward.cuh"
+#include "awb_forward_fast.cuh"
 #include "awb_layout.h"
 #include "awb_setup.cuh"
 #include "awb_traceback.cuh"
@@ -127,7 +128,7 @@ struct awb_batch {
     size_t arena_bytes;
     AwbChain *d_chains;
     int *d_err;
-    int maxB, maxn, maxS, maxV, maxT, maxband;
+    int maxB, maxn, maxS, maxV, maxT, maxband, maxNS, maxcnt;
     float ms[3];
     int launches;
     int64_t h2d_bytes;
@@ -157,6 +158,21 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
     CUDA_OK(cudaFuncSetAttribute(awb_emit_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<20, 512>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<20, 1024>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<40, 512>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<40, 1024>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<64, 384>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
     *out = ctx;
@@ -228,6 +244,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->arena_off.resize(nproblems);
     b->h_chains.resize(nproblems);
     b->maxB = b->maxn = b->maxS = b->maxV = b->maxT = b->maxband = 0;
+    b->maxNS = 32;
+    b->maxcnt = 1;
     b->ms[0] = b->ms[1] = b->ms[2] = 0;
     b->launches = 0;
     b->h2d_bytes = 0;
@@ -271,6 +289,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.V > b->maxV) b->maxV = L.V;
         if (L.T > b->maxT) b->maxT = L.T;
         if (L.maxband > b->maxband) b->maxband = L.maxband;
+        if (L.maxNS > b->maxNS) b->maxNS = L.maxNS;
+        if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
     }
@@ -374,12 +394,42 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
         }
     }
     const int NS = ((b->maxS + 31) / 32) * 32;
-    const size_t smem = awb_fwd_smem_bytes(NS, b->maxT, b->maxband);
-    if (smem > 200 * 1024)
-        return fail("forward kernel needs " + std::to_string(smem) +
-                    " bytes of shared memory (limit 200 KiB)");
+    // fast path (awb_forward_fast.cuh): node-major threads + 2 scribe warps,
+    // time-matrix column in registers (T-1 <= 20 / 40 / 63); else generic
+    const int Tm1 = b->maxT - 1;
+    const int FNS = b->maxNS;
+    const int threads = FNS + AWB_FWD_SCRIBES;
+    int maxd = 1;
+    while (maxd < b->maxcnt) maxd <<= 1;
+    int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
+    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax);
+    // (a branch longer than a warp would need a cross-warp carry in the scans)
+    bool fast = !getenv("AWB_FORCE_GENERIC") && threads <= 1024 &&
+        b->maxcnt <= 32 && !(tmax == 64 && threads > 384);
     CUDA_OK(cudaEventRecord(b->ctx->ev[2], st));
-    awb_forward_kernel<<<b->C, NS, smem, st>>>(b->d_chains, b->maxband);
+    if (fast) {
+        if (tmax == 20 && threads <= 512)
+            awb_forward_fast_kernel<20, 512><<<b->C, threads, fsmem, st>>>(
+                b->d_chains, maxd);
+        else if (tmax == 20)
+            awb_forward_fast_kernel<20, 1024><<<b->C, threads, fsmem, st>>>(
+                b->d_chains, maxd);
+        else if (tmax == 40 && threads <= 512)
+            awb_forward_fast_kernel<40, 512><<<b->C, threads, fsmem, st>>>(
+                b->d_chains, maxd);
+        else if (tmax == 40)
+            awb_forward_fast_kernel<40, 1024><<<b->C, threads, fsmem, st>>>(
+                b->d_chains, maxd);
+        else
+            awb_forward_fast_kernel<64, 384><<<b->C, threads, fsmem, st>>>(
+                b->d_chains, maxd);
+    } else {
+        const size_t smem = awb_fwd_smem_bytes(NS, b->maxT, b->maxband);
+        if (smem > 200 * 1024)
+            return fail("forward kernel needs " + std::to_string(smem) +
+                        " bytes of shared memory (limit 200 KiB)");
+        awb_forward_kernel<<<b->C, NS, smem, st>>>(b->d_chains, b->maxband);
+    }
     b->launches++;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[3], st));

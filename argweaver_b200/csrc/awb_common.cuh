@@ -56,6 +56,8 @@ struct AwbChain {
     int ntrees, nnodes, nsites, start_coord;
     int maxS;                 // max over blocks of max(S_b, 1)
     int maxband;              // max over blocks of the band size (doubles)
+    int maxNS;                // max over blocks of the padded thread count
+    int maxcnt;               // longest branch (states)
     int keep_debug;
 
     // ---- inputs
@@ -77,6 +79,7 @@ struct AwbChain {
     const long long *band_off;// [B+1]
     const long long *ent_off; // [B+1]
     const long long *sw1_off; // [B+1] (debug arrays of the switch matrix)
+    const long long *trow_off;// [B+1] offsets of the forward kernel's thread map
 
     // ---- block setup outputs (K1)
     short *st_node;           // [rows]
@@ -92,6 +95,17 @@ struct AwbChain {
     double *tmvec;            // [B][9][T]
     unsigned short *rowstart; // [B][T+1] time-major start of each time row
     unsigned short *pstart;   // [B][T+1] first partial slot of each time row
+    unsigned char *slotrow;   // [B][slotcap] time row of each partial slot
+    unsigned short *tmap;     // [trow_off] forward thread -> state (0xFFFF idle);
+                              //   node-major, a branch never straddles a warp
+    unsigned short *iperm;    // [rows] state -> time-major slot (inverse of perm)
+    signed char *st_age;      // [rows] age of the state's node
+    double *lin;              // [B][7][T] linear-domain transition vectors:
+                              //   D, h=B-NegG1, B, E*E2, E*(pre+G3), E*(pre+G2), norecombs
+    unsigned short *sc_start; // [B][64] scribe lane -> first time-major slot
+    unsigned short *sc_cnt;   // [B][64] scribe lane -> number of slots
+    unsigned char *sc_row;    // [B][64] scribe lane -> time row (255 idle)
+    int slotcap;              // ntimes + 32
     short *node_first;        // [B][V] first state index of node (or -1)
     short *node_cnt;          // [B][V]
     short *child0, *child1;   // [B][V]

@@ -28,15 +28,18 @@ struct AwbCopy {            // one host -> arena copy of an input array
 struct AwbLayout {
     int B, V, T, n, nrows;
     int maxS, maxband;
+    int maxNS;                           // forward kernel: padded threads per block
+    int maxcnt;                          // longest branch (states)
     int keep_debug;
     double states_sites;                 // sum blocklen * nstates
     std::vector<int> nstates, block_start, rowidx, mappings;
-    std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off;
+    std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off, trow_off;
     AwbModel model;
 
     // arena
     size_t total_bytes;
-    size_t o_mappings;
+    size_t o_mappings, o_slotrow, o_trow_off, o_tmap, o_iperm, o_st_age, o_lin,
+        o_sc_start, o_sc_cnt, o_sc_row;
     size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
         o_seqs, o_block_start, o_nstates, o_row_off, o_fw_off, o_band_off,
         o_ent_off, o_sw1_off, o_st_node, o_st_time, o_perm, o_pslot, o_band_j1,
@@ -83,7 +86,7 @@ inline void awb_model_fill(AwbModel &m, const awb_problem &p)
 inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
                              std::vector<int> &c1, std::vector<int> &stack,
                              std::vector<char> &ignore, int &S, int &band,
-                             std::string &err)
+                             int &tpos, int &maxcnt, std::string &err)
 {
     const int V = p.nnodes, T = p.ntimes;
     const int *parent = p.ptrees + (size_t) b * V;
@@ -130,6 +133,7 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     }
     S = 0;
     band = 0;
+    tpos = 1;
     int minage = p.minage;
     if (internal) {
         if (V < 3 || c0[root] == -1) {
@@ -161,6 +165,7 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
         }
     }
     for (int i = 0; i < V; i++) {
+        if (i == 0) tpos = 0;
         if (ignore[i]) continue;
         const int pa = parent[i];
         const int lo = age[i] > minage ? age[i] : minage;
@@ -169,8 +174,16 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
         if (cnt > 0) {
             S += cnt;
             band += cnt * cnt;
+            // node-major thread packing of the forward kernel: the states of
+            // one branch never straddle a warp
+            if ((tpos & 31) + cnt > 32)
+                tpos = (tpos + 31) & ~31;
+            tpos += cnt;
+            if (cnt > maxcnt) maxcnt = cnt;
         }
     }
+    if (S == 0)
+        tpos = 1;
     return true;
 }
 
@@ -215,15 +228,22 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.band_off.assign(B + 1, 0);
     L.ent_off.assign(B + 1, 0);
     L.sw1_off.assign(B + 1, 0);
+    L.trow_off.assign(B + 1, 0);
     L.maxS = 1;
+    L.maxNS = 32;
+    L.maxcnt = 1;
     L.maxband = 0;
     L.states_sites = 0;
     std::vector<int> c0(V), c1(V), stack(V + 2);
     std::vector<char> ignore(V);
     for (int b = 0; b < B; b++) {
-        int S = 0, band = 0;
-        if (!awb_count_states(p, b, c0, c1, stack, ignore, S, band, err))
+        int S = 0, band = 0, tpos = 1;
+        if (!awb_count_states(p, b, c0, c1, stack, ignore, S, band, tpos,
+                              L.maxcnt, err))
             return false;
+        const int NSb = (tpos + 31) & ~31;
+        L.trow_off[b + 1] = L.trow_off[b] + NSb;
+        if (NSb > L.maxNS) L.maxNS = NSb;
         if (S > AWB_MAXS) {
             err = "block with more than 1024 states is not supported by this build";
             return false;
@@ -304,6 +324,14 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_band_off, (size_t) (B + 1) * sizeof(long long));
     AWB_PLACE(o_ent_off, (size_t) (B + 1) * sizeof(long long));
     AWB_PLACE(o_sw1_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_trow_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_tmap, (size_t) L.trow_off[B] * sizeof(short));
+    AWB_PLACE(o_iperm, rows * sizeof(short));
+    AWB_PLACE(o_st_age, rows);
+    AWB_PLACE(o_lin, (size_t) B * 7 * T * sizeof(double));
+    AWB_PLACE(o_sc_start, (size_t) B * 64 * sizeof(short));
+    AWB_PLACE(o_sc_cnt, (size_t) B * 64 * sizeof(short));
+    AWB_PLACE(o_sc_row, (size_t) B * 64);
     AWB_PLACE(o_st_node, rows * sizeof(short));
     AWB_PLACE(o_st_time, rows);
     AWB_PLACE(o_perm, rows * sizeof(short));
@@ -317,6 +345,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_tmvec, (size_t) B * AWB_TM_NVEC * T * sizeof(double));
     AWB_PLACE(o_rowstart, (size_t) B * (T + 1) * sizeof(short));
     AWB_PLACE(o_pstart, (size_t) B * (T + 1) * sizeof(short));
+    AWB_PLACE(o_slotrow, (size_t) B * (T + 32));
     AWB_PLACE(o_node_first, BV * sizeof(short));
     AWB_PLACE(o_node_cnt, BV * sizeof(short));
     AWB_PLACE(o_child0, BV * sizeof(short));
@@ -369,6 +398,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.copies.push_back({ L.o_band_off, L.band_off.data(), (size_t) (B + 1) * sizeof(long long) });
     L.copies.push_back({ L.o_ent_off, L.ent_off.data(), (size_t) (B + 1) * sizeof(long long) });
     L.copies.push_back({ L.o_sw1_off, L.sw1_off.data(), (size_t) (B + 1) * sizeof(long long) });
+    L.copies.push_back({ L.o_trow_off, L.trow_off.data(), (size_t) (B + 1) * sizeof(long long) });
     return true;
 }
 
@@ -390,6 +420,8 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.start_coord = p.start_coord;
     ch.maxS = L.maxS;
     ch.maxband = L.maxband;
+    ch.maxNS = L.maxNS;
+    ch.maxcnt = L.maxcnt;
     ch.keep_debug = L.keep_debug;
     ch.last_state = -1;
 #define AWB_P(type, field, off) ch.field = (type) (base + L.off)
@@ -409,6 +441,14 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(const long long *, band_off, o_band_off);
     AWB_P(const long long *, ent_off, o_ent_off);
     AWB_P(const long long *, sw1_off, o_sw1_off);
+    AWB_P(const long long *, trow_off, o_trow_off);
+    AWB_P(unsigned short *, tmap, o_tmap);
+    AWB_P(unsigned short *, iperm, o_iperm);
+    AWB_P(signed char *, st_age, o_st_age);
+    AWB_P(double *, lin, o_lin);
+    AWB_P(unsigned short *, sc_start, o_sc_start);
+    AWB_P(unsigned short *, sc_cnt, o_sc_cnt);
+    AWB_P(unsigned char *, sc_row, o_sc_row);
     AWB_P(short *, st_node, o_st_node);
     AWB_P(signed char *, st_time, o_st_time);
     AWB_P(unsigned short *, perm, o_perm);
@@ -422,6 +462,8 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(double *, tmvec, o_tmvec);
     AWB_P(unsigned short *, rowstart, o_rowstart);
     AWB_P(unsigned short *, pstart, o_pstart);
+    AWB_P(unsigned char *, slotrow, o_slotrow);
+    ch.slotcap = L.T + 32;
     AWB_P(short *, node_first, o_node_first);
     AWB_P(short *, node_cnt, o_node_cnt);
     AWB_P(short *, child0, o_child0);
@@ -475,6 +517,10 @@ inline bool awb_layout_find(const AwbLayout &L, const char *name, size_t &off,
         { "tmvec", L.o_tmvec, B * AWB_TM_NVEC * T * 8, false },
         { "rowstart", L.o_rowstart, B * (T + 1) * 2, false },
         { "pstart", L.o_pstart, B * (T + 1) * 2, false },
+        { "tmap", L.o_tmap, (size_t) L.trow_off[L.B] * 2, false },
+        { "iperm", L.o_iperm, rows * 2, false },
+        { "lin", L.o_lin, B * 7 * T * 8, false },
+        { "slotrow", L.o_slotrow, B * (T + 32), false },
         { "node_first", L.o_node_first, BV * 2, false },
         { "node_cnt", L.o_node_cnt, BV * 2, false },
         { "child0", L.o_child0, BV * 2, false },

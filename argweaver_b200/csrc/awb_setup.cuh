@@ -338,7 +338,11 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             bool newrow = false;
             while (t < T && rowstart[t + 1] <= qq) t++;   // row of qq
             if (qq == rowstart[t]) newrow = true;
-            if (newrow || (qq & 31) == 0) slot++;
+            if (newrow || (qq & 31) == 0) {
+                slot++;
+                if (slot < ch.slotcap)
+                    ch.slotrow[(size_t) b * ch.slotcap + slot] = (unsigned char) t;
+            }
             ch.pslot[row0 + qq] = (unsigned short) slot;
         }
         if (S == 0)
@@ -351,6 +355,101 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             else
                 cur = slot + 1;
             pstart[tt] = (unsigned short) cur;
+        }
+    }
+
+    // ---- tables of the fast forward kernel (awb_forward_fast.cuh)
+    {
+        // node-major thread map; a branch never straddles a warp
+        const long long tr0 = ch.trow_off[b];
+        const int NSb = (int) (ch.trow_off[b + 1] - tr0);
+        for (int t = 0; t < NSb; t++)
+            ch.tmap[tr0 + t] = 0xFFFF;
+        if (S == 0) {
+            ch.tmap[tr0] = 0;
+            ch.iperm[row0] = 0;
+            ch.st_age[row0] = 0;
+        } else {
+            int tpos = 0;
+            for (int i = 0; i < V; i++) {
+                const int cnt = ncnt[i];
+                if (cnt <= 0) continue;
+                if ((tpos & 31) + cnt > 32)
+                    tpos = (tpos + 31) & ~31;
+                for (int t = 0; t < cnt; t++) {
+                    if (tpos + t < NSb)
+                        ch.tmap[tr0 + tpos + t] = (unsigned short) (nfirst[i] + t);
+                    ch.st_age[row0 + nfirst[i] + t] = (signed char) age[i];
+                }
+                tpos += cnt;
+            }
+            if (tpos > NSb)
+                return 6;
+            for (int q = 0; q < S; q++)
+                ch.iperm[row0 + ch.perm[row0 + q]] = (unsigned short) q;
+        }
+
+        // scribe lanes: each of 64 lanes sums a chunk of one time row
+        unsigned short *scs = ch.sc_start + (size_t) b * 64;
+        unsigned short *scc = ch.sc_cnt + (size_t) b * 64;
+        unsigned char *scr = ch.sc_row + (size_t) b * 64;
+        for (int l = 0; l < 64; l++) {
+            scs[l] = 0;
+            scc[l] = 0;
+            scr[l] = 255;
+        }
+        if (S == 0) {
+            scs[0] = 0;
+            scc[0] = 1;
+            scr[0] = 0;
+        } else {
+            int CH = 1;
+            for (;; CH++) {
+                int l = 0;
+                bool fits = true;
+                for (int t = 0; t < T - 1 && fits; t++) {
+                    const int w = rowstart[t + 1] - rowstart[t];
+                    if (w == 0) continue;
+                    const int nl = (w + CH - 1) / CH;
+                    if (nl > 32) { fits = false; break; }
+                    if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+                    l += nl;
+                    if (l > 64) fits = false;
+                }
+                if (fits) break;
+            }
+            int l = 0;
+            for (int t = 0; t < T - 1; t++) {
+                const int w = rowstart[t + 1] - rowstart[t];
+                if (w == 0) continue;
+                const int nl = (w + CH - 1) / CH;
+                if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+                for (int i = 0; i < nl; i++) {
+                    scs[l] = (unsigned short) (rowstart[t] + i * CH);
+                    scc[l] = (unsigned short) awb_imin(CH, w - i * CH);
+                    scr[l] = (unsigned char) t;
+                    l++;
+                }
+            }
+        }
+
+        // linear-domain transition vectors
+        double *lin = ch.lin + (size_t) b * 7 * T;
+        for (int t = 0; t < T; t++) {
+            const bool ok = t < T - 1;
+            const double Bx = ok ? exp(tv[AWB_TM_LNB * T + t]) : 0.0;
+            const double NG1 = ok ? exp(tv[AWB_TM_LNNEGG1 * T + t]) : 0.0;
+            const double e2 = ok ? exp(tv[AWB_TM_LNE2 * T + t]) : 0.0;
+            const double E = ok ? tv[AWB_TM_E * T + t] : 0.0;
+            const double pre = (ok && t > 0) ?
+                exp(tv[AWB_TM_LNE2 * T + t] + tv[AWB_TM_LNB * T + t - 1]) : 0.0;
+            lin[0 * T + t] = ok ? tv[AWB_TM_D * T + t] : 0.0;
+            lin[1 * T + t] = Bx - NG1;
+            lin[2 * T + t] = Bx;
+            lin[3 * T + t] = E * e2;
+            lin[4 * T + t] = ok ? E * (pre + tv[AWB_TM_G3 * T + t]) : 0.0;
+            lin[5 * T + t] = ok ? E * (pre + tv[AWB_TM_G2 * T + t]) : 0.0;
+            lin[6 * T + t] = ok ? tv[AWB_TM_NORECOMBS * T + t] : 0.0;
         }
     }
 
