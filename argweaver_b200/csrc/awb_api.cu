@@ -160,21 +160,6 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     CUDA_OK(cudaFuncSetAttribute(awb_emit_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<20, 512>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<20, 1024>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<40, 512>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<40, 1024>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<64, 384>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
     *out = ctx;
     return 0;
 }
@@ -398,7 +383,7 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
     // time-matrix column in registers (T-1 <= 20 / 40 / 63); else generic
     const int Tm1 = b->maxT - 1;
     const int FNS = b->maxNS;
-    const int threads = FNS + AWB_FWD_SCRIBES;
+    const int threads = FNS + AWB_FWD_HELPERS;
     int maxd = 1;
     while (maxd < b->maxcnt) maxd <<= 1;
     int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
@@ -408,21 +393,22 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
         b->maxcnt <= 32 && !(tmax == 64 && threads > 384);
     CUDA_OK(cudaEventRecord(b->ctx->ev[2], st));
     if (fast) {
-        if (tmax == 20 && threads <= 512)
-            awb_forward_fast_kernel<20, 512><<<b->C, threads, fsmem, st>>>(
-                b->d_chains, maxd);
-        else if (tmax == 20)
-            awb_forward_fast_kernel<20, 1024><<<b->C, threads, fsmem, st>>>(
-                b->d_chains, maxd);
-        else if (tmax == 40 && threads <= 512)
-            awb_forward_fast_kernel<40, 512><<<b->C, threads, fsmem, st>>>(
-                b->d_chains, maxd);
-        else if (tmax == 40)
-            awb_forward_fast_kernel<40, 1024><<<b->C, threads, fsmem, st>>>(
-                b->d_chains, maxd);
-        else
-            awb_forward_fast_kernel<64, 384><<<b->C, threads, fsmem, st>>>(
-                b->d_chains, maxd);
+#define AWB_LAUNCH_FAST(TM, NL, MT)                                              \
+    awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(b->d_chains)
+        const bool lev4 = maxd <= 16;
+        if (tmax == 20) {
+            if (threads <= 384) { if (lev4) AWB_LAUNCH_FAST(20, 4, 384); else AWB_LAUNCH_FAST(20, 5, 384); }
+            else if (threads <= 512) { if (lev4) AWB_LAUNCH_FAST(20, 4, 512); else AWB_LAUNCH_FAST(20, 5, 512); }
+            else if (threads <= 640) { if (lev4) AWB_LAUNCH_FAST(20, 4, 640); else AWB_LAUNCH_FAST(20, 5, 640); }
+            else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768);
+            else AWB_LAUNCH_FAST(20, 5, 1024);
+        } else if (tmax == 40) {
+            if (threads <= 512) AWB_LAUNCH_FAST(40, 5, 512);
+            else AWB_LAUNCH_FAST(40, 5, 1024);
+        } else {
+            AWB_LAUNCH_FAST(64, 5, 384);
+        }
+#undef AWB_LAUNCH_FAST
     } else {
         const size_t smem = awb_fwd_smem_bytes(NS, b->maxT, b->maxband);
         if (smem > 200 * 1024)

@@ -402,6 +402,11 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             scs[0] = 0;
             scc[0] = 1;
             scr[0] = 0;
+            for (int t = 1; t < T - 1; t++) {
+                scs[t] = 0;
+                scc[t] = 0;
+                scr[t] = (unsigned char) t;
+            }
         } else {
             int CH = 1;
             for (;; CH++) {
@@ -409,8 +414,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 bool fits = true;
                 for (int t = 0; t < T - 1 && fits; t++) {
                     const int w = rowstart[t + 1] - rowstart[t];
-                    if (w == 0) continue;
-                    const int nl = (w + CH - 1) / CH;
+                    const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
                     if (nl > 32) { fits = false; break; }
                     if ((l & 31) + nl > 32) l = (l + 31) & ~31;
                     l += nl;
@@ -420,13 +424,13 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             }
             int l = 0;
             for (int t = 0; t < T - 1; t++) {
+                // every row gets at least one lane: an empty row is written as 0
                 const int w = rowstart[t + 1] - rowstart[t];
-                if (w == 0) continue;
-                const int nl = (w + CH - 1) / CH;
+                const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
                 if ((l & 31) + nl > 32) l = (l + 31) & ~31;
                 for (int i = 0; i < nl; i++) {
-                    scs[l] = (unsigned short) (rowstart[t] + i * CH);
-                    scc[l] = (unsigned short) awb_imin(CH, w - i * CH);
+                    scs[l] = (unsigned short) (w == 0 ? 0 : rowstart[t] + i * CH);
+                    scc[l] = (unsigned short) (w == 0 ? 0 : awb_imin(CH, w - i * CH));
                     scr[l] = (unsigned char) t;
                     l++;
                 }
