@@ -447,7 +447,8 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
                                 sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice,
                                 st));
-    const int NS = ((b->maxS + 31) / 32) * 32;
+    int NS = ((b->maxS + 31) / 32) * 32;
+    if (NS < 512) NS = 512;            // >= 16 warps: 32-site speculative waves
     CUDA_OK(cudaEventRecord(b->ctx->ev[4], st));
     awb_traceback_kernel<<<b->C, NS, 0, st>>>(b->d_chains, rand_max);
     b->launches++;
