@@ -88,7 +88,8 @@ __global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err)
         atomicMax(err, 200 + rc);
 }
 
-// one warp per site; invariant / masked sites exit at once
+// one warp per site; invariant / masked sites exit at once.  The warp stages
+// the block's tree arrays in shared memory before the pruning passes.
 __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
 {
     extern __shared__ unsigned char emit_smem[];
@@ -96,13 +97,34 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
     const int wpc = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int V = ch.nnodes;
     unsigned char *scratch = emit_smem + (size_t) warp * scratch_bytes;
+    // staging area after the pruning scratch
+    int *sparent = (int *) (scratch + ((awb_emit_scratch_bytes(V) + 15) & ~(size_t) 15));
+    int *sage = sparent + V;
+    short *sc0 = (short *) (sage + V);
+    short *sc1 = sc0 + V;
+    short *sorder = sc1 + V;
+    int staged = -1;
     for (int i = blockIdx.x * wpc + warp; i < ch.nsites; i += gridDim.x * wpc) {
         if (ch.kind[i] != AWB_SITE_VARIANT)
             continue;
         if (i == 0)
             continue;       // the first column is the prior; no emission applied
-        awb_emit_site(ch, i, lane, 32, scratch);
+        const int b = awb_find_block(ch, i);
+        if (b != staged) {
+            const size_t o = (size_t) b * V;
+            for (int x = lane; x < V; x += 32) {
+                sparent[x] = ch.ptrees[o + x];
+                sage[x] = ch.ages[o + x];
+                sc0[x] = ch.child0[o + x];
+                sc1[x] = ch.child1[o + x];
+                sorder[x] = ch.order[o + x];
+            }
+            staged = b;
+            __syncwarp();
+        }
+        awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder);
         __syncwarp();
     }
 }
@@ -211,6 +233,17 @@ extern "C" void awb_batch_destroy(awb_batch *b)
     delete b;
 }
 
+// shapes the register-resident forward kernel covers (awb_forward_fast.cuh)
+static bool batch_fast_path(const awb_batch *b)
+{
+    const int Tm1 = b->maxT - 1;
+    const int threads = b->maxNS + AWB_FWD_HELPERS;
+    const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
+    // (a branch longer than a warp would need a cross-warp carry in the scans)
+    return !getenv("AWB_FORCE_GENERIC") && threads <= 1024 && b->maxcnt <= 32 &&
+        !(tmax == 64 && threads > 384);
+}
+
 extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
                                 const awb_problem *problems, int flags,
                                 awb_batch **out)
@@ -289,9 +322,12 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     }
     CUDA_OK(cudaMalloc((void **) &b->d_chains, sizeof(AwbChain) * nproblems));
     CUDA_OK(cudaMalloc((void **) &b->d_err, sizeof(int)));
-    for (int c = 0; c < nproblems; c++)
+    for (int c = 0; c < nproblems; c++) {
         awb_layout_bind(b->L[c], b->P[c], b->arena + b->arena_off[c],
                         b->h_chains[c]);
+        // the tmatrix2 band is only read by the generic forward kernel
+        b->h_chains[c].need_band = batch_fast_path(b) ? 0 : 1;
+    }
     *out = b;
     return 0;
 }
@@ -343,7 +379,8 @@ extern "C" int awb_batch_setup(awb_batch *b)
         b->launches++;
     }
     {
-        const int scratch = (int) ((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15);
+        const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
+                                   (((size_t) b->maxV * 14 + 15) & ~(size_t) 15));
         int wpc = 8;
         while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
             wpc >>= 1;
@@ -388,9 +425,7 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
     while (maxd < b->maxcnt) maxd <<= 1;
     int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
     const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax);
-    // (a branch longer than a warp would need a cross-warp carry in the scans)
-    bool fast = !getenv("AWB_FORCE_GENERIC") && threads <= 1024 &&
-        b->maxcnt <= 32 && !(tmax == 64 && threads > 384);
+    const bool fast = batch_fast_path(b);
     CUDA_OK(cudaEventRecord(b->ctx->ev[2], st));
     if (fast) {
 #define AWB_LAUNCH_FAST(TM, NL, MT)                                              \

@@ -59,6 +59,7 @@ struct AwbChain {
     int maxNS;                // max over blocks of the padded thread count
     int maxcnt;               // longest branch (states)
     int keep_debug;
+    int need_band;            // compute the tmatrix2 band (generic forward kernel only)
 
     // ---- inputs
     const int *ptrees;        // [B][V]

@@ -75,22 +75,22 @@ AWB_HD inline size_t awb_emit_scratch_bytes(int V)
     return (size_t) V * (10 * sizeof(double)) + (((size_t) V + 7) & ~(size_t) 7);
 }
 
-AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int lane, int nlanes,
-                                 unsigned char *scratch)
+// tree arrays of block b: parent/age (int), child0/child1/order (short).  The
+// CUDA kernel stages them in shared memory (the pruning loops walk them with
+// dependent accesses); the host emulation passes the global arrays.
+AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
+                                 int nlanes, unsigned char *scratch,
+                                 const int *parent, const int *age,
+                                 const short *c0, const short *c1,
+                                 const short *order)
 {
     const AwbModel &m = ch.model;
     const int V = ch.nnodes;
     const int T = m.ntimes;
-    const int b = awb_find_block(ch, i);
     const int S = ch.nstates[b];
     if (S == 0)
         return;                         // emit.cpp:665-669
     const bool internal = ch.internal != 0;
-    const int *parent = ch.ptrees + (size_t) b * V;
-    const int *age = ch.ages + (size_t) b * V;
-    const short *c0 = ch.child0 + (size_t) b * V;
-    const short *c1 = ch.child1 + (size_t) b * V;
-    const short *order = ch.order + (size_t) b * V;
     const int root = ch.root[b];
     const int maintree_root = internal ? c1[root] : root;
     const int subtree_root = internal ? c0[root] : root;

@@ -359,15 +359,15 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_sw_cnt, rows * sizeof(short));
     AWB_PLACE(o_sw_src, (size_t) L.ent_off[B] * sizeof(short) + 8);
     AWB_PLACE(o_sw_prob, (size_t) L.ent_off[B] * sizeof(double) + 8);
+    AWB_PLACE(o_sw_determ, (size_t) L.sw1_off[B] * sizeof(int) + 8);
     if (keep_debug) {
-        AWB_PLACE(o_sw_determ, (size_t) L.sw1_off[B] * sizeof(int) + 8);
         AWB_PLACE(o_sw_determprob, (size_t) L.sw1_off[B] * sizeof(double) + 8);
         AWB_PLACE(o_sw_recombrow, rows * sizeof(double));
         AWB_PLACE(o_sw_recoalrow, rows * sizeof(double));
         AWB_PLACE(o_sw_recombsrc, (size_t) B * sizeof(int));
         AWB_PLACE(o_sw_recoalsrc, (size_t) B * sizeof(int));
     } else {
-        L.o_sw_determ = L.o_sw_determprob = L.o_sw_recombrow = 0;
+        L.o_sw_determprob = L.o_sw_recombrow = 0;
         L.o_sw_recoalrow = L.o_sw_recombsrc = L.o_sw_recoalsrc = 0;
     }
     AWB_PLACE(o_kind, (size_t) L.n);
@@ -423,6 +423,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.maxNS = L.maxNS;
     ch.maxcnt = L.maxcnt;
     ch.keep_debug = L.keep_debug;
+    ch.need_band = 1;
     ch.last_state = -1;
 #define AWB_P(type, field, off) ch.field = (type) (base + L.off)
     AWB_P(const int *, ptrees, o_ptrees);
@@ -477,8 +478,8 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(unsigned short *, sw_cnt, o_sw_cnt);
     AWB_P(unsigned short *, sw_src, o_sw_src);
     AWB_P(double *, sw_prob, o_sw_prob);
+    AWB_P(int *, sw_determ, o_sw_determ);
     if (L.keep_debug) {
-        AWB_P(int *, sw_determ, o_sw_determ);
         AWB_P(double *, sw_determprob, o_sw_determprob);
         AWB_P(double *, sw_recombrow, o_sw_recombrow);
         AWB_P(double *, sw_recoalrow, o_sw_recoalrow);
@@ -534,7 +535,7 @@ inline bool awb_layout_find(const AwbLayout &L, const char *name, size_t &off,
         { "sw_cnt", L.o_sw_cnt, rows * 2, false },
         { "sw_src", L.o_sw_src, (size_t) L.ent_off[L.B] * 2, false },
         { "sw_prob", L.o_sw_prob, (size_t) L.ent_off[L.B] * 8, false },
-        { "sw_determ", L.o_sw_determ, (size_t) L.sw1_off[L.B] * 4, true },
+        { "sw_determ", L.o_sw_determ, (size_t) L.sw1_off[L.B] * 4, false },
         { "sw_determprob", L.o_sw_determprob, (size_t) L.sw1_off[L.B] * 8, true },
         { "sw_recombrow", L.o_sw_recombrow, rows * 8, true },
         { "sw_recoalrow", L.o_sw_recoalrow, rows * 8, true },

@@ -487,7 +487,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         ch.band_j1[row0 + k] = (unsigned short) nfirst[node];
         ch.band_len[row0 + k] = (unsigned char) len;
         ch.band_boff[row0 + k] = boff;
-        for (int i = 0; i < len; i++) {
+        for (int i = 0; i < len && ch.need_band; i++) {
             const int a = lo + i;
             band[boff + i] = awb_get_time(tv, T, a, bt, c, minage, true) -
                 awb_get_time(tv, T, a, bt, 0, minage, false);
@@ -776,12 +776,14 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
     for (int k = 0; k < n2; k++)
         cnt[k] = 0;
 
-    int *dbg_determ = ch.keep_debug ? ch.sw_determ + ch.sw1_off[b] : 0;
+    int *dbg_determ = ch.sw_determ + ch.sw1_off[b];   // also the pass-1 scratch
     double *dbg_dprob = ch.keep_debug ? ch.sw_determprob + ch.sw1_off[b] : 0;
     double *dbg_rrow = ch.keep_debug ? ch.sw_recombrow + r2 : 0;
     double *dbg_crow = ch.keep_debug ? ch.sw_recoalrow + r2 : 0;
+    for (int j = 0; j < n1; j++)
+        dbg_determ[j] = -1;
     if (ch.keep_debug) {
-        for (int j = 0; j < n1; j++) { dbg_determ[j] = -1; dbg_dprob[j] = 0.0; }
+        for (int j = 0; j < n1; j++) dbg_dprob[j] = 0.0;
         for (int k = 0; k < n2; k++) { dbg_rrow[k] = 0.0; dbg_crow[k] = 0.0; }
         ch.sw_recombsrc[b] = -1;
         ch.sw_recoalsrc[b] = -1;
@@ -802,7 +804,8 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
         }
         esrc[0] = 0;
         eprob[0] = 1.0;
-        if (ch.keep_debug) { dbg_determ[0] = target; dbg_dprob[0] = 1.0; }
+        dbg_determ[0] = target;
+        if (ch.keep_debug) dbg_dprob[0] = 1.0;
         return 0;
     }
     if (internal && S2 == 0) {
@@ -819,7 +822,8 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
                                                     rpa, last_treelen, internal);
             esrc[i] = (unsigned short) i;
             eprob[i] = p;
-            if (ch.keep_debug) { dbg_determ[i] = 0; dbg_dprob[i] = p; }
+            dbg_determ[i] = 0;
+            if (ch.keep_debug) dbg_dprob[i] = p;
         }
         start[0] = 0;
         cnt[0] = (unsigned short) S1;
@@ -864,6 +868,7 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
         else if (node1 == spr.coal_node && time1 == spr.coal_time)
             recoalsrc = i;
         const int d = awb_determ_one(lt, t, spr, mapping, node1, time1, internal);
+        dbg_determ[i] = d;
         if (d >= 0)
             cnt[d]++;
     }
@@ -911,9 +916,10 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
         cparent = t.parent[AWB_MAP(spr.recomb_node)];
     }
 
-    // prefix over targets
-    // (recoal entries are appended after this prefix by a second count below)
-    // first count recoal entries
+    // re-coalescence row entries, computed once (at most T+3 of them)
+    int nck = 0;
+    int ckk[AWB_MAXT + 4];
+    double ckv[AWB_MAXT + 4];
     if (recoalsrc != -1) {
         for (int k = 0; k < S2; k++) {
             const int node2 = ch.st_node[r2 + k], time2 = ch.st_time[r2 + k];
@@ -927,8 +933,12 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
                 lt, m, L, spr2, cnode1, ctime1, recomb_parent_age0,
                 last_treelen, internal);
             if (ch.keep_debug) dbg_crow[k] = p;
-            if (p > 0.0)
+            if (p > 0.0 && nck < AWB_MAXT + 4) {
+                ckk[nck] = k;
+                ckv[nck] = p;
+                nck++;
                 cnt[k]++;
+            }
         }
     }
     int total = 0;
@@ -943,8 +953,7 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
     // ---- pass 2: deterministic entries in ascending source order
     for (int i = 0; i < S1; i++) {
         const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
-        const int d = awb_determ_one(lt, t, spr, mapping, node1, time1, internal);
-        if (ch.keep_debug) dbg_determ[i] = d;
+        const int d = dbg_determ[i];
         if (d < 0)
             continue;
         double p;
@@ -975,24 +984,10 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
         }
     }
     // re-coalescence source
-    if (recoalsrc != -1) {
-        for (int k = 0; k < S2; k++) {
-            const int node2 = ch.st_node[r2 + k], time2 = ch.st_time[r2 + k];
-            if (!((node2 == AWB_MAP(spr.recomb_node) && time2 >= spr.recomb_time) ||
-                  (node2 == node3 && time2 == ctime1) ||
-                  (node2 == cparent && time2 == ctime1)))
-                continue;
-            AwbSpr spr2 = spr;
-            spr2.coal_time = time2;
-            const double p = awb_calc_recomb_recoal(
-                lt, m, L, spr2, cnode1, ctime1, recomb_parent_age0,
-                last_treelen, internal);
-            if (p > 0.0) {
-                const int pos = start[k] + cnt[k]++;
-                esrc[pos] = (unsigned short) recoalsrc;
-                eprob[pos] = p;
-            }
-        }
+    for (int q = 0; q < nck; q++) {
+        const int pos = start[ckk[q]] + cnt[ckk[q]]++;
+        esrc[pos] = (unsigned short) recoalsrc;
+        eprob[pos] = ckv[q];
     }
     if (ch.keep_debug) {
         ch.sw_recombsrc[b] = recombsrc;

@@ -67,8 +67,12 @@ int emul_setup(void *h)
         if (rc) { e->code = 200 + rc; return e->code; }
     }
     for (int i = 0; i < ch.nsites; i++)
-        if (i > 0 && ch.kind[i] == AWB_SITE_VARIANT)
-            awb_emit_site(ch, i, 0, 1, e->scratch.data());
+        if (i > 0 && ch.kind[i] == AWB_SITE_VARIANT) {
+            const int b = awb_find_block(ch, i);
+            const size_t o = (size_t) b * ch.nnodes;
+            awb_emit_site(ch, i, b, 0, 1, e->scratch.data(), ch.ptrees + o,
+                          ch.ages + o, ch.child0 + o, ch.child1 + o, ch.order + o);
+        }
     return 0;
 }
 
