@@ -26,8 +26,8 @@ NVCC_FLAGS = [
     "--fmad=true",
 ]
 
-CUDA_SOURCES = ["awb_api.cu"]
-CUDA_DEPS = ["awb_setup.cuh", "awb_forward.cuh", "awb_traceback.cuh",
+CUDA_SOURCES = ["awb_api.cu", "awb_compat.cu"]
+CUDA_DEPS = ["awb_setup.cuh", "awb_forward.cuh", "awb_forward_fast.cuh", "awb_traceback.cuh",
              "awb_emit.cuh", "awb_common.cuh", "awb_layout.h"]
 
 

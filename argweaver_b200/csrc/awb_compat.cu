@@ -148,7 +148,7 @@ static void fill_problem(CompatProblem &cp, const LocalTrees *trees,
 struct CompatRun {
     awb_batch *b;
     std::vector<int> nstates;
-    std::vector<int64_t> row_off, fw_off;
+    std::vector<int64_t> row_off, fw_off, sw1_off;
     explicit CompatRun(const CompatProblem &cp, int flags) : b(NULL)
     {
         COMPAT_OK(awb_batch_create(compat_ctx(), 1, &cp.p, flags, &b),
@@ -158,8 +158,9 @@ struct CompatRun {
         nstates.resize(cp.p.ntrees);
         row_off.resize(cp.p.ntrees + 1);
         fw_off.resize(cp.p.ntrees + 1);
+        sw1_off.resize(cp.p.ntrees + 1);
         awb_batch_get_nstates(b, 0, nstates.data());
-        awb_batch_get_layout(b, 0, row_off.data(), fw_off.data(), NULL);
+        awb_batch_get_layout(b, 0, row_off.data(), fw_off.data(), sw1_off.data());
     }
     ~CompatRun() { awb_batch_destroy(b); }
     template <typename T>
@@ -277,7 +278,11 @@ static void draw_rands(std::vector<int> &r, int n)
         r[i] = rand();
 }
 
-// sample_thread.cpp:930-977
+// sample_thread.cpp:930-977.  Deviation, on purpose: the reference's conversion
+// loop re-declares `end` inside the loop body (:958-961), so with more than one
+// local tree it rewrites path[0 .. blocklen) for every block and leaves the
+// rest of the path unset; here every site is converted with its own block's
+// states (identical to the reference for a single tree).
 extern "C" intstate *arghmm_sample_posterior(int **ptrees, int **ages, int **sprs,
                                              int *blocklens, int ntrees, int nnodes,
                                              double *times, int ntimes,
@@ -560,7 +565,7 @@ extern "C" double **new_transition_probs_switch(
                 double pr;
                 if (a == csrc[1]) pr = crow[run.row_off[1] + c];
                 else if (a == rsrc[1]) pr = rrow[run.row_off[1] + c];
-                else pr = (determ[a] == c) ? dprob[a] : 0.0;
+                else pr = (determ[run.sw1_off[1] + a] == c) ? dprob[run.sw1_off[1] + a] : 0.0;
                 v = log(pr);
             }
             mat[i][j] = v;
@@ -610,12 +615,7 @@ __global__ void awb_hmm_step_kernel(const double *col1, double *col2, int n1, in
 {
     __shared__ double red[33];
     const int k = blockIdx.x;
-    double acc = -INFINITY;
-    // strided partial logsum is not associative with the threshold rule, so
-    // every term goes through one block-wide logsum per chunk of blockDim terms
-    double best = -INFINITY, sum = 0.0;
-    (void) acc; (void) best; (void) sum;
-    // gather all terms' max first
+    // the threshold rule needs the global max first (common.h:182-202)
     double m = -INFINITY;
     for (int j = threadIdx.x; j < n1; j += blockDim.x) {
         const double t = transpose ? trans[(size_t) k * n1 + j] : trans[(size_t) j * n2 + k];
