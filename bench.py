@@ -248,7 +248,7 @@ def pinned_like(arr):
 def bench_b200(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from argweaver_b200 import api, sim
+    from argweaver_b200 import api, shard, sim
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -258,7 +258,7 @@ def bench_b200(a, rank, world, local_rank):
     W = a.windows
     problems, rands, keep = [], [], []
     for w in range(W):
-        seed = 1000 + rank * W + w
+        seed = 1000 + shard.my_windows(W * world, rank, world)[w]
         d = sim.simulate_problem(a.k, a.sites, ntimes=a.ntimes, seed=seed,
                                  internal=(w % 2 == 1))
         for key in ("seqs", "ptrees", "ages", "mappings", "sprs", "blocklens"):
@@ -333,33 +333,14 @@ def bench_b200(a, rank, world, local_rank):
         torch.cuda.synchronize()
         e2e_ms_local = (time.perf_counter() - t0) * 1e3 / max(1, min(a.steps, 3))
 
-    # ---- reduce over ranks: max time, sum work
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    ms = allmax(ms_local)
-    ss = allsum(ss_local)
-    fwd_ms = allmax(stage["forward_ms"])
-    e2e_ms = allmax(e2e_ms_local) if e2e_ms_local is not None else None
+    # ---- reduce over ranks: max time, sum work (argweaver_b200/shard.py)
+    d_ = dist if world > 1 else None
+    ms = shard.all_max(ms_local, d_)
+    ss = shard.all_sum(ss_local, d_)
+    fwd_ms = shard.all_max(stage["forward_ms"], d_)
+    e2e_ms = shard.all_max(e2e_ms_local, d_) if e2e_ms_local is not None else None
     # the only exchange of the workload: per-window log-likelihoods to rank 0
-    if world > 1:
-        lz = torch.tensor(logz_local, dtype=torch.float64, device="cuda")
-        allz = [torch.empty_like(lz) for _ in range(world)]
-        dist.all_gather(allz, lz)
-        logz_all = torch.cat(allz).cpu().numpy()
-    else:
-        logz_all = np.array(logz_local)
+    logz_all = shard.gather_window_values(logz_local, W * world, d_)
 
     if rank == 0:
         peaks = {}
@@ -370,7 +351,19 @@ def bench_b200(a, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else \
             "fallback 6650 GB/s (B200_PROFILING.md)"
-        achieved = fw_bytes / (stage["forward_ms"] * 1e-3) / 1e9
+        achieved = fw_bytes / (fwd_ms * 1e-3) / 1e9
+        # DRAM traffic of the same kernel from the committed ncu capture
+        # (profiles/), valid only for the configuration it was taken on
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles",
+                                             "r1_forward_traffic.json")))
+            c = tj["config"]
+            if (c["k"], c["ntimes"], c["sites_per_window"], c["windows_per_gpu"]) \
+                    == (a.k, a.ntimes, a.sites, W):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": ss / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -393,9 +386,9 @@ def bench_b200(a, rank, world, local_rank):
             "gpu_launches": int(launches),
             "stage_ms": stage,
             "roofline": {
-                "kernel": "awb_forward_kernel", "bound": "hbm",
+                "kernel": "awb_forward_fast_kernel", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fw_bytes,
                 "note": "8 B per site*state (FP64 forward-table store)"},
             "logz_mean": float(np.mean(logz_all)),
