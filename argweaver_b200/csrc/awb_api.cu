@@ -3,7 +3,7 @@
 // Kernels launched per batch (one launch each, all chains of the batch):
 //   awb_kind_kernel          thread per site     site classification
 //   awb_block_setup_kernel   thread per block    K1 (awb_setup.cuh)
-//   awb_switch_setup_kernel  thread per block    K2 (awb_setup.cuh)
+//   awb_switch_setup_kernel  warp per breakpoint K2 (awb_setup.cuh)
 //   awb_emit_kernel          warp per site       K3 (awb_emit.cuh), variant sites
 //   awb_forward_kernel       CTA per chain       K4 (awb_forward.cuh)
 //   awb_traceback_kernel     CTA per chain       K5 (awb_traceback.cuh)
@@ -77,14 +77,21 @@ __global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
         atomicMax(err, 100 + rc);
 }
 
-__global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err)
+// one warp per breakpoint
+__global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err,
+                                        int scratch_bytes)
 {
+    extern __shared__ unsigned char sw_smem[];
     const AwbChain &ch = chains[blockIdx.y];
-    const int b = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int wpc = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = 1 + blockIdx.x * wpc + warp;
     if (b >= ch.ntrees)
         return;
-    const int rc = awb_switch_setup(ch, b);
-    if (rc)
+    const int rc = awb_switch_setup_warp(ch, b, lane,
+                                         sw_smem + (size_t) warp * scratch_bytes);
+    if (rc && lane == 0)
         atomicMax(err, 200 + rc);
 }
 
@@ -374,8 +381,11 @@ extern "C" int awb_batch_setup(awb_batch *b)
         awb_block_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
     }
     if (b->maxB > 1) {
-        dim3 grid((b->maxB - 1 + 63) / 64, b->C);
-        awb_switch_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
+        const int wpc = 8;
+        const int scratch = (int) awb_sw_warp_scratch_bytes(b->maxS, b->maxT);
+        dim3 grid((b->maxB - 1 + wpc - 1) / wpc, b->C);
+        awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
+            b->d_chains, b->d_err, scratch);
         b->launches++;
     }
     {

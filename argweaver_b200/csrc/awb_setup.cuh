@@ -543,11 +543,35 @@ struct AwbSpr { int recomb_node, recomb_time, coal_node, coal_time; };
 
 struct AwbLineages { const int *nbranches, *nrecombs, *ncoals; };
 
+// The two ancestor walks of calc_recomb (trans.cpp:345-356) depend only on the
+// SPR, not on the state: child-of-root ancestors of coal_node and recomb_node.
+struct AwbRecombCtx { int ptr2, ptr3; };
+
+AWB_HD inline AwbRecombCtx awb_recomb_ctx(const AwbTreeView &lt, const AwbSpr &spr,
+                                          bool internal)
+{
+    AwbRecombCtx c = { -1, -1 };
+    if (!internal)
+        return c;
+    int ptr = spr.coal_node;
+    while (ptr != lt.root) {
+        c.ptr2 = ptr;
+        ptr = lt.parent[ptr];
+    }
+    ptr = spr.recomb_node;
+    while (ptr != lt.root) {
+        c.ptr3 = ptr;
+        ptr = lt.parent[ptr];
+    }
+    return c;
+}
+
 // trans.cpp:317-413
 AWB_HD inline double awb_calc_recomb(const AwbTreeView &lt, const AwbModel &m,
                                      const AwbLineages &L, const AwbSpr &spr,
                                      int s_node, int s_time,
-                                     double last_treelen, bool internal)
+                                     double last_treelen, bool internal,
+                                     const AwbRecombCtx *rcx = 0)
 {
     const int a = s_time;
     const int k = spr.recomb_time;
@@ -565,17 +589,9 @@ AWB_HD inline double awb_calc_recomb(const AwbTreeView &lt, const AwbModel &m,
             if (spr.recomb_node == maintree_root && s_node != maintree_root)
                 return 0.0;
         }
-        int ptr = spr.coal_node;
-        int ptr2 = -1, ptr3 = -1;
-        while (ptr != lt.root) {
-            ptr2 = ptr;
-            ptr = lt.parent[ptr];
-        }
-        ptr = spr.recomb_node;
-        while (ptr != lt.root) {
-            ptr3 = ptr;
-            ptr = lt.parent[ptr];
-        }
+        const AwbRecombCtx cx = rcx ? *rcx : awb_recomb_ctx(lt, spr, internal);
+        const int ptr2 = cx.ptr2, ptr3 = cx.ptr3;
+        int ptr;
         if (ptr2 == subtree_root && ptr3 == maintree_root &&
             s_time == spr.recomb_time) {
             ptr = lt.parent[s_node];
@@ -658,13 +674,13 @@ AWB_HD inline double awb_calc_recoal(const AwbTreeView &lt, const AwbModel &m,
 AWB_HD inline double awb_calc_recomb_recoal(
     const AwbTreeView &lt, const AwbModel &m, const AwbLineages &L,
     const AwbSpr &spr, int s_node, int s_time, int recomb_parent_age,
-    double last_treelen, bool internal)
+    double last_treelen, bool internal, const AwbRecombCtx *rcx = 0)
 {
     const int a = s_time;
     const int k = spr.recomb_time;
     const int j = spr.coal_time;
     double p = awb_calc_recomb(lt, m, L, spr, s_node, s_time, last_treelen,
-                               internal);
+                               internal, rcx);
     double sum = 0.0;
     for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
         const int nbranches_m = L.nbranches[mm / 2] -
@@ -996,5 +1012,347 @@ AWB_HD inline int awb_switch_setup(const AwbChain &ch, int b)
 #undef AWB_MAP
     return 0;
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// K2, warp-cooperative: one warp builds the switch CSR of one breakpoint.
+// Same result as awb_switch_setup above (entry order per target: deterministic
+// sources ascending, recombination source, re-coalescence source); sources are
+// classified 32 at a time, targets counted with __match_any groups (a stable
+// counting sort, so the order does not depend on scheduling).
+//
+// scratch per warp (shared memory): cnt[maxS] start[maxS] (u16) |
+// sums2[2T+1] recoals[T] ckv[T+4] (f64) | ckk[T+4] (i32)
+__host__ __device__ inline size_t awb_sw_warp_scratch_bytes(int maxS, int T)
+{
+    size_t n = (((size_t) (maxS > 0 ? maxS : 1) * 4) + 15) & ~(size_t) 15;
+    n += (size_t) (2 * T + 1 + T + T + 4) * sizeof(double);
+    n += (((size_t) (T + 4) * sizeof(int)) + 15) & ~(size_t) 15;
+    return (n + 15) & ~(size_t) 15;
+}
+
+__device__ inline int awb_switch_setup_warp(const AwbChain &ch, int b, int lane,
+                                            unsigned char *scr)
+{
+    const unsigned FULL = 0xffffffffu;
+    const AwbModel &m = ch.model;
+    const int T = m.ntimes;
+    const bool internal = ch.internal != 0;
+    const int S1 = ch.nstates[b - 1], S2 = ch.nstates[b];
+    const int n1 = awb_imax(S1, 1), n2 = awb_imax(S2, 1);
+    const long long r1 = ch.row_off[b - 1], r2 = ch.row_off[b];
+    const long long e0 = ch.ent_off[b];
+    const int ecap = (int) (ch.ent_off[b + 1] - e0);
+    const int capS = ch.maxS > 0 ? ch.maxS : 1;
+
+    unsigned short *cntS = (unsigned short *) scr;
+    unsigned short *startS = cntS + capS;
+    double *sums2 = (double *) (scr + ((((size_t) capS * 4) + 15) & ~(size_t) 15));
+    double *recoals = sums2 + (2 * T + 1);
+    double *ckv = recoals + T;
+    int *ckk = (int *) (ckv + (T + 4));
+
+    AwbTreeView lt, t;
+    awb_tree_view(ch, b - 1, lt);
+    awb_tree_view(ch, b, t);
+    AwbSpr spr = { ch.sprs[4 * b], ch.sprs[4 * b + 1], ch.sprs[4 * b + 2],
+                   ch.sprs[4 * b + 3] };
+    AwbLineages L;
+    L.nbranches = ch.lineages + (size_t) (b - 1) * 3 * T;
+    L.nrecombs = L.nbranches + T;
+    L.ncoals = L.nrecombs + T;
+    const double last_treelen = ch.treelen[b - 1];
+
+    unsigned short *cnt = ch.sw_cnt + r2;
+    unsigned short *start = ch.sw_start + r2;
+    unsigned short *esrc = ch.sw_src + e0;
+    double *eprob = ch.sw_prob + e0;
+    int *determ = ch.sw_determ + ch.sw1_off[b];
+    double *dbg_dprob = ch.keep_debug ? ch.sw_determprob + ch.sw1_off[b] : 0;
+    double *dbg_rrow = ch.keep_debug ? ch.sw_recombrow + r2 : 0;
+    double *dbg_crow = ch.keep_debug ? ch.sw_recoalrow + r2 : 0;
+
+    for (int k = lane; k < n2; k += 32)
+        cntS[k] = 0;
+    if (ch.keep_debug) {
+        for (int j = lane; j < n1; j += 32) dbg_dprob[j] = 0.0;
+        for (int k = lane; k < n2; k += 32) { dbg_rrow[k] = 0.0; dbg_crow[k] = 0.0; }
+        if (lane == 0) {
+            ch.sw_recombsrc[b] = -1;
+            ch.sw_recoalsrc[b] = -1;
+        }
+    }
+
+    // ---- internal-mode corner cases (trans.cpp:554-603)
+    if (internal && S1 == 0) {
+        int target = 0;
+        if (S2 > 0) {
+            const int maintree_root = t.c1[t.root];
+            target = awb_lookup(t, maintree_root, spr.coal_time);
+            if (target < 0)
+                return 3;
+        }
+        for (int k = lane; k < n2; k += 32) {
+            start[k] = (unsigned short) (k > target ? 1 : 0);
+            cnt[k] = (unsigned short) (k == target ? 1 : 0);
+        }
+        if (lane == 0) {
+            esrc[0] = 0;
+            eprob[0] = 1.0;
+            determ[0] = target;
+            if (ch.keep_debug) dbg_dprob[0] = 1.0;
+        }
+        return 0;
+    }
+    const AwbRecombCtx rcx = awb_recomb_ctx(lt, spr, internal);
+    if (internal && S2 == 0) {
+        if (S1 > ecap)
+            return 4;
+        for (int i = lane; i < S1; i += 32) {
+            const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+            int rpa;
+            if (node1 == spr.recomb_node && time1 > spr.recomb_time)
+                rpa = time1;
+            else
+                rpa = lt.age[lt.parent[spr.recomb_node]];
+            const double p = awb_calc_recomb_recoal(lt, m, L, spr, node1, time1,
+                                                    rpa, last_treelen, internal, &rcx);
+            esrc[i] = (unsigned short) i;
+            eprob[i] = p;
+            determ[i] = 0;
+            if (ch.keep_debug) dbg_dprob[i] = p;
+        }
+        if (lane == 0) {
+            start[0] = 0;
+            cnt[0] = (unsigned short) S1;
+        }
+        return 0;
+    }
+
+#define AWB_MAP(x) (mapping[(x)])
+    const int *mapping = ch.mappings + (size_t) b * ch.nnodes;
+    const int broken = lt.parent[spr.recomb_node];
+    const int recomb_parent_age0 = lt.age[broken];
+
+    // ---- per-time tables (trans.cpp:616-621, 417-440)
+    double sums = 0.0;
+    {
+        const int k = spr.recomb_time, j = spr.coal_time;
+        for (int mm = lane; mm < 2 * T + 1; mm += 32)
+            sums2[mm] = 0.0;
+        __syncwarp();
+        double sum = 0.0;
+        for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
+            const int nbm = L.nbranches[mm / 2] -
+                (mm / 2 < recomb_parent_age0 ? 1 : 0);
+            sum += m.coal_time_steps[mm] * nbm / (2.0 * m.popsizes[mm / 2]);
+        }
+        sums = sum;
+        if (lane == 0) {
+            sum = 0.0;
+            sums2[2 * k] = sum;
+            for (int mm = 2 * k; mm < 2 * j - 1; mm++) {
+                sum += m.coal_time_steps[mm] / (2.0 * m.popsizes[mm / 2]);
+                sums2[mm + 1] = sum;
+            }
+        }
+        for (int a = lane; a < T; a += 32)
+            recoals[a] = awb_calc_recoal(lt, m, L, spr, a, recomb_parent_age0,
+                                         false /* sic, trans.cpp:620 */);
+        __syncwarp();
+    }
+
+    // ---- pass 1: classify sources, count deterministic entries per target
+    int recombsrc = -1, recoalsrc = -1;
+    for (int base = 0; base < S1; base += 32) {
+        const int i = base + lane;
+        int d = -1;
+        if (i < S1) {
+            const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+            if (node1 == spr.recomb_node && time1 == spr.recomb_time)
+                recombsrc = i;
+            else if (node1 == spr.coal_node && time1 == spr.coal_time)
+                recoalsrc = i;
+            d = awb_determ_one(lt, t, spr, mapping, node1, time1, internal);
+            determ[i] = d;
+        }
+        const unsigned act = __ballot_sync(FULL, d >= 0);
+        if (d >= 0) {
+            const unsigned g = __match_any_sync(act, d);
+            if (lane == __ffs(g) - 1)
+                cntS[d] = (unsigned short) (cntS[d] + __popc(g));
+        }
+        __syncwarp();
+    }
+    recombsrc = __reduce_max_sync(FULL, recombsrc);
+    recoalsrc = __reduce_max_sync(FULL, recoalsrc);
+
+    // recombination row (trans.cpp:665-693): "stay" and "escape" (uniform)
+    int rk[2] = { -1, -1 };
+    double rv[2] = { 0.0, 0.0 };
+    if (recombsrc != -1) {
+        const int parent = lt.parent[spr.recomb_node];
+        const int time2 = lt.age[parent];
+        const int other = (lt.c0[parent] == spr.recomb_node ? lt.c1[parent] :
+                           lt.c0[parent]);
+        const int node2 = (other == spr.coal_node ? t.parent[AWB_MAP(other)] :
+                           AWB_MAP(other));
+        rk[0] = awb_lookup(t, AWB_MAP(spr.recomb_node), spr.recomb_time);
+        rk[1] = awb_lookup(t, node2, time2);
+        const int sn = ch.st_node[r1 + recombsrc], stime = ch.st_time[r1 + recombsrc];
+        if (rk[0] != -1)
+            rv[0] = awb_calc_recomb_recoal(lt, m, L, spr, sn, stime,
+                                           recomb_parent_age0, last_treelen,
+                                           internal, &rcx);
+        if (rk[1] != -1)
+            rv[1] = awb_calc_recomb_recoal(lt, m, L, spr, sn, stime, stime,
+                                           last_treelen, internal, &rcx);
+        if (rk[0] != -1 && rk[0] == rk[1]) {
+            rv[0] = rv[1];              // trans.cpp:678,688: second assignment wins
+            rk[1] = -1;
+        }
+        if (lane == 0)
+            for (int q = 0; q < 2; q++)
+                if (rk[q] != -1 && rv[q] > 0.0)
+                    cntS[rk[q]]++;
+    }
+    __syncwarp();
+
+    // re-coalescence row (trans.cpp:697-738): candidate targets tested 32 at a time
+    int nck = 0;
+    if (recoalsrc != -1) {
+        const int cnode1 = ch.st_node[r1 + recoalsrc];
+        const int ctime1 = ch.st_time[r1 + recoalsrc];
+        int node3;
+        if (broken == cnode1)
+            node3 = AWB_MAP(lt.c1[broken] == spr.recomb_node ? lt.c0[broken] :
+                            lt.c1[broken]);
+        else
+            node3 = AWB_MAP(cnode1);
+        const int cparent = t.parent[AWB_MAP(spr.recomb_node)];
+        const int rmap = AWB_MAP(spr.recomb_node);
+        for (int base = 0; base < S2; base += 32) {
+            const int k = base + lane;
+            bool hit = false;
+            double p = 0.0;
+            if (k < S2) {
+                const int node2 = ch.st_node[r2 + k], time2 = ch.st_time[r2 + k];
+                hit = (node2 == rmap && time2 >= spr.recomb_time) ||
+                    (node2 == node3 && time2 == ctime1) ||
+                    (node2 == cparent && time2 == ctime1);
+                if (hit) {
+                    AwbSpr spr2 = spr;
+                    spr2.coal_time = time2;
+                    p = awb_calc_recomb_recoal(lt, m, L, spr2, cnode1, ctime1,
+                                               recomb_parent_age0, last_treelen,
+                                               internal, &rcx);
+                    if (ch.keep_debug) dbg_crow[k] = p;
+                }
+            }
+            const bool keep = hit && p > 0.0;
+            const unsigned mk = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int pos = nck + __popc(mk & ((1u << lane) - 1u));
+                if (pos < T + 4) {
+                    ckk[pos] = k;
+                    ckv[pos] = p;
+                    cntS[k]++;          // one candidate per target: no conflict
+                }
+            }
+            nck += __popc(mk);
+        }
+        nck = awb_imin(nck, T + 4);
+    }
+    __syncwarp();
+
+    // ---- exclusive scan of the counts -> start[]
+    int total = 0;
+    for (int base = 0; base < n2; base += 32) {
+        const int k = base + lane;
+        const int c = (k < n2) ? cntS[k] : 0;
+        int x = c;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, dd);
+            if (lane >= dd)
+                x += y;
+        }
+        if (k < n2) {
+            const unsigned short st = (unsigned short) (total + x - c);
+            startS[k] = st;
+            start[k] = st;
+            cntS[k] = 0;
+        }
+        total += __shfl_sync(FULL, x, 31);
+    }
+    if (total > ecap)
+        return 4;
+    __syncwarp();
+
+    // ---- pass 2: deterministic entries, ascending source order per target
+    for (int base = 0; base < S1; base += 32) {
+        const int i = base + lane;
+        int d = -1;
+        double p = 0.0;
+        if (i < S1) {
+            d = determ[i];
+            if (d >= 0) {
+                const int node1 = ch.st_node[r1 + i], time1 = ch.st_time[r1 + i];
+                if (node1 == spr.recomb_node && time1 > spr.recomb_time) {
+                    p = awb_calc_recomb_recoal(lt, m, L, spr, node1, time1, time1,
+                                               last_treelen, internal, &rcx);
+                } else {
+                    const int idx = awb_imax(awb_imin(2 * spr.coal_time - 1, 2 * time1),
+                                             2 * spr.recomb_time);
+                    p = awb_calc_recomb(lt, m, L, spr, node1, time1, last_treelen,
+                                        internal, &rcx) *
+                        exp(-sums - sums2[idx]) * recoals[time1];
+                }
+                if (ch.keep_debug) dbg_dprob[i] = p;
+            }
+        }
+        const unsigned act = __ballot_sync(FULL, d >= 0);
+        if (d >= 0) {
+            const unsigned g = __match_any_sync(act, d);
+            const int pos = startS[d] + cntS[d] + __popc(g & ((1u << lane) - 1u));
+            esrc[pos] = (unsigned short) i;
+            eprob[pos] = p;
+            __syncwarp(act);
+            if (lane == __ffs(g) - 1)
+                cntS[d] = (unsigned short) (cntS[d] + __popc(g));
+        }
+        __syncwarp();
+    }
+
+    // recombination source, then re-coalescence source
+    if (lane == 0) {
+        for (int q = 0; q < 2; q++) {
+            if (rk[q] != -1) {
+                if (ch.keep_debug) dbg_rrow[rk[q]] = rv[q];
+                if (rv[q] > 0.0) {
+                    const int pos = startS[rk[q]] + cntS[rk[q]]++;
+                    esrc[pos] = (unsigned short) recombsrc;
+                    eprob[pos] = rv[q];
+                }
+            }
+        }
+        for (int q = 0; q < nck; q++) {
+            const int pos = startS[ckk[q]] + cntS[ckk[q]]++;
+            esrc[pos] = (unsigned short) recoalsrc;
+            eprob[pos] = ckv[q];
+        }
+        if (ch.keep_debug) {
+            ch.sw_recombsrc[b] = recombsrc;
+            ch.sw_recoalsrc[b] = recoalsrc;
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < n2; k += 32)
+        cnt[k] = cntS[k];
+#undef AWB_MAP
+    return 0;
+}
+#endif // __CUDACC__
+
 
 #endif // AWB_SETUP_CUH
