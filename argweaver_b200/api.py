@@ -8,6 +8,7 @@ library has no CPU fallback and raises :class:`AwbError` when CUDA is missing.
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -28,7 +29,8 @@ def lib():
     """Load (building if needed) libargweaver_b200.so."""
     global _lib
     if _lib is None:
-        L = C.CDLL(_build.build_cuda())
+        # AWB_LIB: load a specific build (kernel experiments); default = in-tree
+        L = C.CDLL(os.environ.get("AWB_LIB") or _build.build_cuda())
         L.awb_last_error.restype = C.c_char_p
         L.awb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.awb_ctx_destroy.argtypes = [C.c_void_p]

@@ -58,14 +58,18 @@
 
 #include "awb_common.cuh"
 
+#ifndef AWB_ABLATE
+#define AWB_ABLATE 0
+#endif
 #define AWB_FWD_RS 4          // rescale period (sites); power of two, >= 4
 #define AWB_FWD_FSCRIBES 64   // F-scribe lanes (2 warps)
 #define AWB_FWD_HELPERS 96    // F-scribes + norm warp
 
-// shared memory (doubles): zT[NS] | colS[2][NS] | Fs[2][TMAX+2] | scaleS[2] | invS[4]
+// shared memory (doubles): zT[NS] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
+// scaleS[2] | invS[4]
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX)
 {
-    return (3 * (size_t) NS + 2 * (size_t) (TMAX + 2) + 6) * sizeof(double);
+    return (3 * (size_t) NS + 4 * (size_t) (TMAX + 2) + 6) * sizeof(double);
 }
 
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
@@ -94,11 +98,12 @@ awb_forward_fast_kernel(const AwbChain *chains)
     double *colS = zT + NS;                    // [2][NS] last column of a block in
                                                //   state order, by block parity
     double *FsS = colS + 2 * NS;               // [2][TMAX+2] per-time sums
-    double *scaleS = FsS + 2 * (TMAX + 2);     // [2] rescale factors
+    double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
+    double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
 
-    for (int x = tid; x < 3 * NS + 2 * (TMAX + 2) + 6; x += blockDim.x)
-        smem_f[x] = (x < 3 * NS + 2 * (TMAX + 2)) ? 0.0 : 1.0;
+    for (int x = tid; x < 3 * NS + 4 * (TMAX + 2) + 6; x += blockDim.x)
+        smem_f[x] = (x < 3 * NS + 4 * (TMAX + 2)) ? 0.0 : 1.0;
     __syncthreads();
 
     if (tid >= NB1) {
@@ -150,6 +155,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
         // F-scribes: per-time sums between barrier 1 and barrier 2
         // =================================================================
         const int sl = tid - NS;                         // scribe lane 0..63
+        const double *__restrict__ tmatrixg = chg.tmatrix;
         const unsigned short *__restrict__ sc_startg = chg.sc_start;
         const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
         const unsigned char *__restrict__ sc_rowg = chg.sc_row;
@@ -170,6 +176,16 @@ awb_forward_fast_kernel(const AwbChain *chains)
             for (int l = 0; l < 5; l++)
                 um[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
             const double *z = zT + sc_start;
+            // column `sl` of the block's time-by-time matrix: this lane turns
+            // the per-time sums F into R[sl] for the compute warps
+            double tmc[TMAX];
+            {
+                const bool rl = (sl < T - 1) && nstatesg[b] > 0;
+                const double *tmg = tmatrixg + (size_t) b * T * T + (rl ? sl : 0);
+#pragma unroll
+                for (int a = 0; a < TMAX; a++)
+                    tmc[a] = (rl && a < T - 1) ? tmg[a * T] : 0.0;
+            }
 
             for (int i = 0; i < blen; i++, site++) {
                 double *Fs = FsS + (site & 1) * (TMAX + 2);
@@ -178,13 +194,16 @@ awb_forward_fast_kernel(const AwbChain *chains)
                 // combine with a segmented scan
                 double v0 = 0.0, v1 = 0.0;
                 int q = 0;
+#if AWB_ABLATE != 2 && AWB_ABLATE != 6
                 for (; q + 2 <= sc_cnt; q += 2) {
                     v0 += z[q];
                     v1 += z[q + 1];
                 }
                 if (q < sc_cnt)
                     v0 += z[q];
+#endif
                 double v = v0 + v1;
+#if AWB_ABLATE != 2 && AWB_ABLATE != 6 && AWB_ABLATE != 7
 #pragma unroll
                 for (int l = 0; l < 5; l++) {
                     if ((1 << l) <= span) {
@@ -192,8 +211,29 @@ awb_forward_fast_kernel(const AwbChain *chains)
                         v = fma(t, um[l], v);
                     }
                 }
+#endif
                 if (sc_last)
                     Fs[sc_row] = v;
+                awb_bar_sync(3, AWB_FWD_FSCRIBES);
+                if (i + 1 < blen && sl < T - 1) {
+                    const double2 *F2 = reinterpret_cast<const double2 *>(Fs);
+                    double2 f[(TMAX + 1) / 2];
+#pragma unroll
+                    for (int a = 0; a < (TMAX + 1) / 2; a++)
+                        f[a] = F2[a];
+                    double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
+#pragma unroll
+                    for (int a = 0; a + 3 < TMAX; a += 4) {
+                        ra = fma(tmc[a], f[a / 2].x, ra);
+                        rb = fma(tmc[a + 1], f[a / 2].y, rb);
+                        rc = fma(tmc[a + 2], f[a / 2 + 1].x, rc);
+                        rd = fma(tmc[a + 3], f[a / 2 + 1].y, rd);
+                    }
+#pragma unroll
+                    for (int a = TMAX - (TMAX % 4); a < TMAX; a++)
+                        ra = fma(tmc[a], (a & 1) ? f[a / 2].y : f[a / 2].x, ra);
+                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);
+                }
                 awb_bar_sync(2, NB2);
             }
         }
@@ -217,7 +257,6 @@ awb_forward_fast_kernel(const AwbChain *chains)
     const signed char *__restrict__ st_ageg = chg.st_age;
     const double *__restrict__ inv_emitg = chg.inv_emit;
     const double *__restrict__ ling = chg.lin;
-    const double *__restrict__ tmatrixg = chg.tmatrix;
     const unsigned short *__restrict__ sw_startg = chg.sw_start;
     const unsigned short *__restrict__ sw_cntg = chg.sw_cnt;
     const unsigned short *__restrict__ sw_srcg = chg.sw_src;
@@ -229,7 +268,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
     bool active = false, live = false;     // live: active and S > 0
     double inv_e = 1.0, Da = 0.0, ha = 0.0, Bc = 0.0, A1 = 0.0, A2 = 0.0,
         A3 = 0.0, nrb = 1.0;
-    double tmc[TMAX];
+    int atime = 0;
     double upm[NLEV], dnm[NLEV];
 
     auto load_compute = [&](int bb) {
@@ -244,7 +283,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
         active = (tj != 0xFFFF);
         live = active && S > 0;
         jj = active ? (int) tj : 0;
-        int atime = 0, cage = 0, node = -1;
+        int cage = 0, node = -1;
+        atime = 0;
         tpos = 0;
         inv_e = 1.0;
         if (live) {
@@ -277,10 +317,6 @@ awb_forward_fast_kernel(const AwbChain *chains)
             Da = 0.0; ha = 0.0; Bc = 0.0; A1 = 0.0; A2 = 0.0; A3 = 0.0;
             nrb = 1.0;
         }
-        const double *tmg = tmatrixg + (size_t) bb * T * T + atime;
-#pragma unroll
-        for (int a = 0; a < TMAX; a++)
-            tmc[a] = (live && a < T - 1) ? tmg[a * T] : 0.0;
     };
 
     load_compute(0);
@@ -297,7 +333,6 @@ awb_forward_fast_kernel(const AwbChain *chains)
 
         // ---------------- sites that are followed by a site of the same block
         for (int i = 0; i + 1 < blen; i++, site++) {
-            const double *Fs = FsS + (site & 1) * (TMAX + 2);
             if (active)
                 zT[tpos] = c;
             awb_bar_sync(1, NB1);
@@ -306,6 +341,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
             const double x0 = Da * c;
             const double x1 = x0 * ha;
             double p0 = x0, p1 = x1, q = x0;
+#if AWB_ABLATE != 4 && AWB_ABLATE != 6
 #pragma unroll
             for (int l = 0; l < NLEV; l++) {
                 const double t0 = __shfl_up_sync(0xffffffffu, p0, 1 << l);
@@ -315,43 +351,32 @@ awb_forward_fast_kernel(const AwbChain *chains)
                 p1 = fma(t1, upm[l], p1);
                 q = fma(tq, dnm[l], q);
             }
+#endif
             const double P0 = p0 - x0, P1 = p1 - x1, Q = q - x0;
             const double W = fma(A1, fma(-Bc, P0, P1),
                                  fma(x0, A2, fma(A3, Q, nrb * c)));
             // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
+#if AWB_ABLATE != 1 && AWB_ABLATE != 6
             if (fw2)
                 *fw2 = c2 * invS[(site - 2) & 3];
+#endif
             const unsigned char kd = kind_next;
             if (site + 2 < n)
                 kind_next = kindg[site + 2];
             double e = 1.0;
             if (live) {
                 e = inv_e;
+#if AWB_ABLATE != 5 && AWB_ABLATE != 6
                 if (kd == AWB_SITE_VARIANT)
                     e = fw0 ? fw0[S1] : fwg[fw_offg[b] + (long long) (i + 1) * S1 + jj];
                 else if (kd == AWB_SITE_MASKED)
                     e = 1.0;
+#endif
             }
             awb_bar_sync(2, NB2);
 
-            // R_k = sum_a tmc[a] * F[a]
-            const double2 *F2 = reinterpret_cast<const double2 *>(Fs);
-            double2 f[(TMAX + 1) / 2];
-#pragma unroll
-            for (int a = 0; a < (TMAX + 1) / 2; a++)
-                f[a] = F2[a];
-            double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
-#pragma unroll
-            for (int a = 0; a + 3 < TMAX; a += 4) {
-                ra = fma(tmc[a], f[a / 2].x, ra);
-                rb = fma(tmc[a + 1], f[a / 2].y, rb);
-                rc = fma(tmc[a + 2], f[a / 2 + 1].x, rc);
-                rd = fma(tmc[a + 3], f[a / 2 + 1].y, rd);
-            }
-#pragma unroll
-            for (int a = TMAX - (TMAX % 4); a < TMAX; a++)
-                ra = fma(tmc[a], (a & 1) ? f[a / 2].y : f[a / 2].x, ra);
-            double cn = ((ra + rb) + (rc + rd) + W) * e;
+            // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
+            double cn = (RsS[(site & 1) * (TMAX + 2) + atime] + W) * e;
             if ((site & (AWB_FWD_RS - 1)) == 2)
                 cn *= scaleS[((site - 2) / AWB_FWD_RS) & 1];
             c2 = c1;
