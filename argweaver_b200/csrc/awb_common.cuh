@@ -204,4 +204,52 @@ AWB_HD inline double awb_prob_branch(double t, double mu, bool mut)
 AWB_HD inline int awb_imax(int a, int b) { return a > b ? a : b; }
 AWB_HD inline int awb_imin(int a, int b) { return a < b ? a : b; }
 
+// Thread packing of the fast forward kernel: every branch (cnt[i] consecutive
+// states of node i) gets consecutive lanes of ONE warp.  First-fit in
+// decreasing branch length, so the number of warps is close to S/32.  Used by
+// the host layout (to size the thread map) and by K1 (to fill it): both must
+// run the same code.  tmap/nfirst may be NULL (count only).  Returns the number
+// of thread slots (a multiple of 32).  Branches longer than 32 states take
+// whole warps (such a block runs on the generic kernel anyway).
+AWB_HD inline int awb_pack_branches(const short *cnt, int V,
+                                    unsigned short *tmap, const short *nfirst,
+                                    int cap)
+{
+    unsigned char fill[AWB_MAXS / 32 + 2];
+    int nw = 0;
+    unsigned long long present = 0;
+    for (int i = 0; i < V; i++) {
+        const int c = cnt[i];
+        if (c > 0)
+            present |= 1ull << (c > 63 ? 63 : c - 1);
+    }
+    for (int len = 63; len >= 0; len--) {
+        if (!((present >> len) & 1ull))
+            continue;
+        for (int i = 0; i < V; i++) {
+            const int c = cnt[i];
+            if (c <= 0 || (c > 63 ? 63 : c - 1) != len)
+                continue;
+            int slot;
+            if (c > 32) {
+                slot = 32 * nw;
+                for (int x = 0; x < (c + 31) / 32; x++)
+                    fill[nw++] = 32;
+            } else {
+                int w = 0;
+                while (w < nw && fill[w] + c > 32)
+                    w++;
+                if (w == nw)
+                    fill[nw++] = 0;
+                slot = 32 * w + fill[w];
+                fill[w] = (unsigned char) (fill[w] + c);
+            }
+            if (tmap && slot + c <= cap)
+                for (int t = 0; t < c; t++)
+                    tmap[slot + t] = (unsigned short) (nfirst[i] + t);
+        }
+    }
+    return 32 * (nw > 0 ? nw : 1);
+}
+
 #endif // AWB_COMMON_CUH

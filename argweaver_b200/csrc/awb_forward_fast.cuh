@@ -14,8 +14,8 @@
 // and tmatrix2 (reference sample_thread.cpp:218-225) separates in (a, b), so
 // with x_a = D[a]*col[(n,a)] along the branch n of state k = (n, b):
 //
-//   W_k = E e2[b] * ( P1 - Bc*P0 ) + x_b * A2 + A3 * Q + norecombs[b]*col[k]
-//   P0 = sum_{a<b} x_a   P1 = sum_{a<b} x_a h[a]   Q = sum_{a>b} x_a
+//   W_k = E e2[b] * PY + x_b * A2 + A3 * Q + norecombs[b]*col[k]
+//   PY = sum_{a<b} x_a (h[a] - Bc)   Q = sum_{a>b} x_a
 //
 // (Bc, A2, A3 per-state constants, see load_compute).  P0, P1, Q are exclusive
 // prefix / suffix sums along one branch; the two forms agree to ~4e-15
@@ -266,7 +266,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
     int jj = 0, tpos = 0, S = 0, S1 = 1;
     long long r0 = 0;
     bool active = false, live = false;     // live: active and S > 0
-    double inv_e = 1.0, Da = 0.0, ha = 0.0, Bc = 0.0, A1 = 0.0, A2 = 0.0,
+    int span = 0;
+    double inv_e = 1.0, Da = 0.0, hb = 0.0, A1 = 0.0, A2 = 0.0,
         A3 = 0.0, nrb = 1.0;
     int atime = 0;
     double upm[NLEV], dnm[NLEV];
@@ -303,18 +304,19 @@ awb_forward_fast_kernel(const AwbChain *chains)
             upm[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
             dnm[l] = (lane + (1 << l) <= segend) ? 1.0 : 0.0;
         }
+        span = __reduce_max_sync(0xffffffffu, segend - seglane);
         if (live) {
             const double *lin = ling + (size_t) bb * 7 * T;
             Da = lin[0 * T + atime];
-            ha = lin[1 * T + atime];
-            Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
+            const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
+            hb = lin[1 * T + atime] - Bc;
             A1 = lin[3 * T + atime];
             A2 = lin[4 * T + atime] - A1 * Bc;
             A3 = lin[5 * T + atime] - A1 * Bc;
             nrb = lin[6 * T + atime];
         } else {
             // idle lane, or the size-1 state space (identity transition)
-            Da = 0.0; ha = 0.0; Bc = 0.0; A1 = 0.0; A2 = 0.0; A3 = 0.0;
+            Da = 0.0; hb = 0.0; A1 = 0.0; A2 = 0.0; A3 = 0.0;
             nrb = 1.0;
         }
     };
@@ -339,22 +341,22 @@ awb_forward_fast_kernel(const AwbChain *chains)
 
             // branch scans in registers while the F-scribes sum the rows
             const double x0 = Da * c;
-            const double x1 = x0 * ha;
-            double p0 = x0, p1 = x1, q = x0;
+            const double y0 = x0 * hb;
+            double py = y0, q = x0;
 #if AWB_ABLATE != 4 && AWB_ABLATE != 6
 #pragma unroll
             for (int l = 0; l < NLEV; l++) {
-                const double t0 = __shfl_up_sync(0xffffffffu, p0, 1 << l);
-                const double t1 = __shfl_up_sync(0xffffffffu, p1, 1 << l);
-                const double tq = __shfl_down_sync(0xffffffffu, q, 1 << l);
-                p0 = fma(t0, upm[l], p0);
-                p1 = fma(t1, upm[l], p1);
-                q = fma(tq, dnm[l], q);
+                if ((1 << l) <= span) {             // warp-uniform
+                    const double ty = __shfl_up_sync(0xffffffffu, py, 1 << l);
+                    const double tq = __shfl_down_sync(0xffffffffu, q, 1 << l);
+                    py = fma(ty, upm[l], py);
+                    q = fma(tq, dnm[l], q);
+                }
             }
 #endif
-            const double P0 = p0 - x0, P1 = p1 - x1, Q = q - x0;
-            const double W = fma(A1, fma(-Bc, P0, P1),
-                                 fma(x0, A2, fma(A3, Q, nrb * c)));
+            // exclusive sums: PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a
+            const double PY = py - y0, Q = q - x0;
+            const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
             // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
 #if AWB_ABLATE != 1 && AWB_ABLATE != 6
             if (fw2)

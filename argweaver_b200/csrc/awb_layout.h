@@ -81,6 +81,12 @@ inline void awb_model_fill(AwbModel &m, const awb_problem &p)
     m.coal_time_steps[2 * T - 1] = INFINITY;
 }
 
+inline std::vector<short> &awb_pack_scratch()
+{
+    static thread_local std::vector<short> v;
+    return v;
+}
+
 // Number of states of one tree and the sum of squared branch state counts.
 // Returns false on a malformed tree.
 inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
@@ -164,8 +170,9 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
             }
         }
     }
+    std::vector<short> &bcnt = awb_pack_scratch();
+    bcnt.assign(V, 0);
     for (int i = 0; i < V; i++) {
-        if (i == 0) tpos = 0;
         if (ignore[i]) continue;
         const int pa = parent[i];
         const int lo = age[i] > minage ? age[i] : minage;
@@ -174,16 +181,13 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
         if (cnt > 0) {
             S += cnt;
             band += cnt * cnt;
-            // node-major thread packing of the forward kernel: the states of
-            // one branch never straddle a warp
-            if ((tpos & 31) + cnt > 32)
-                tpos = (tpos + 31) & ~31;
-            tpos += cnt;
+            bcnt[i] = (short) cnt;
             if (cnt > maxcnt) maxcnt = cnt;
         }
     }
-    if (S == 0)
-        tpos = 1;
+    // thread packing of the forward kernel (the states of one branch never
+    // straddle a warp): same routine as K1
+    tpos = (S == 0) ? 1 : awb_pack_branches(bcnt.data(), V, 0, 0, 0);
     return true;
 }
 

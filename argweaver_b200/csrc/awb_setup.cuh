@@ -370,20 +370,11 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             ch.iperm[row0] = 0;
             ch.st_age[row0] = 0;
         } else {
-            int tpos = 0;
-            for (int i = 0; i < V; i++) {
-                const int cnt = ncnt[i];
-                if (cnt <= 0) continue;
-                if ((tpos & 31) + cnt > 32)
-                    tpos = (tpos + 31) & ~31;
-                for (int t = 0; t < cnt; t++) {
-                    if (tpos + t < NSb)
-                        ch.tmap[tr0 + tpos + t] = (unsigned short) (nfirst[i] + t);
+            for (int i = 0; i < V; i++)
+                for (int t = 0; t < ncnt[i]; t++)
                     ch.st_age[row0 + nfirst[i] + t] = (signed char) age[i];
-                }
-                tpos += cnt;
-            }
-            if (tpos > NSb)
+            // the host sized the map with the same routine
+            if (awb_pack_branches(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb)
                 return 6;
             for (int q = 0; q < S; q++)
                 ch.iperm[row0 + ch.perm[row0 + q]] = (unsigned short) q;
