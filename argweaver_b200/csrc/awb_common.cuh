@@ -135,6 +135,7 @@ struct AwbChain {
     int *path;                // [nsites]
     const int *rand_ints;     // [nsites]
     double *logz;             // [1]
+    double *sink;             // [1024] per-thread dump slot of the forward kernel
     int *status;              // [1] first bad site or -1
     int last_state;           // traceback: -1 = sample last column
 };

@@ -66,10 +66,24 @@
 #define AWB_FWD_HELPERS 96    // F-scribes + norm warp
 
 // shared memory (doubles): zT[NS] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
-// scaleS[2] | invS[4]
+// scaleS[2] | invS[4] | dummy[2]
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX)
 {
-    return (3 * (size_t) NS + 4 * (size_t) (TMAX + 2) + 6) * sizeof(double);
+    return (3 * (size_t) NS + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
+}
+
+template <int N> struct AwbInt { static constexpr int value = N; };
+
+__device__ __forceinline__ void awb_sts(unsigned addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ double awb_lds(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
@@ -101,9 +115,12 @@ awb_forward_fast_kernel(const AwbChain *chains)
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
+    double *dummyS = invS + 4;                 // [2] idle lanes store here
 
-    for (int x = tid; x < 3 * NS + 4 * (TMAX + 2) + 6; x += blockDim.x)
-        smem_f[x] = (x < 3 * NS + 4 * (TMAX + 2)) ? 0.0 : 1.0;
+    for (int x = tid; x < 3 * NS + 4 * (TMAX + 2) + 8; x += blockDim.x) {
+        const int y = x - (3 * NS + 4 * (TMAX + 2));
+        smem_f[x] = (y >= 0 && y < 6) ? 1.0 : 0.0;     // scaleS, invS start at 1
+    }
     __syncthreads();
 
     if (tid >= NB1) {
@@ -244,6 +261,11 @@ awb_forward_fast_kernel(const AwbChain *chains)
     // =====================================================================
     // compute warps
     // =====================================================================
+    // Every instruction of this loop is issued by ~15 warps per site on 4
+    // schedulers, so the loop is written for instruction count: 32-bit shared
+    // addresses with ring offsets kept incrementally, a pointer ring for the
+    // lagged table stores (idle lanes and not-to-be-stored columns point at a
+    // per-thread sink), and a per-warp choice of the number of scan levels.
     const unsigned char *__restrict__ kindg = chg.kind;
     double *__restrict__ fwg = chg.fw;
     const long long *__restrict__ row_offg = chg.row_off;
@@ -261,15 +283,24 @@ awb_forward_fast_kernel(const AwbChain *chains)
     const unsigned short *__restrict__ sw_cntg = chg.sw_cnt;
     const unsigned short *__restrict__ sw_srcg = chg.sw_src;
     const double *__restrict__ sw_probg = chg.sw_prob;
+    double *const sink = chg.sink + tid;
+
+    const unsigned zT_s = (unsigned) __cvta_generic_to_shared(zT);
+    const unsigned col_s = (unsigned) __cvta_generic_to_shared(colS);
+    const unsigned Rs_s = (unsigned) __cvta_generic_to_shared(RsS);
+    const unsigned scale_s = (unsigned) __cvta_generic_to_shared(scaleS);
+    const unsigned inv_s = (unsigned) __cvta_generic_to_shared(invS);
+    const unsigned dummy_s = (unsigned) __cvta_generic_to_shared(dummyS);
+    constexpr unsigned RSTR = (TMAX + 2) * 8;
 
     // ---- my state in the current block
-    int jj = 0, tpos = 0, S = 0, S1 = 1;
+    int jj = 0, S = 0, S1 = 1, nl = 0;
     long long r0 = 0;
     bool active = false, live = false;     // live: active and S > 0
-    int span = 0;
-    double inv_e = 1.0, Da = 0.0, hb = 0.0, A1 = 0.0, A2 = 0.0,
+    unsigned zaddr = dummy_s, raddr = Rs_s;
+    long long step = 0;                    // bytes from my entry of one row to the next
+    double inv_e = 0.0, em = 0.0, Da = 0.0, hb = 0.0, A1 = 0.0, A2 = 0.0,
         A3 = 0.0, nrb = 1.0;
-    int atime = 0;
     double upm[NLEV], dnm[NLEV];
 
     auto load_compute = [&](int bb) {
@@ -284,10 +315,9 @@ awb_forward_fast_kernel(const AwbChain *chains)
         active = (tj != 0xFFFF);
         live = active && S > 0;
         jj = active ? (int) tj : 0;
-        int cage = 0, node = -1;
-        atime = 0;
-        tpos = 0;
-        inv_e = 1.0;
+        int atime = 0, cage = 0, node = -1, tpos = 0;
+        inv_e = active ? 1.0 : 0.0;
+        em = inv_e;
         if (live) {
             atime = st_timeg[r0 + jj];
             cage = st_ageg[r0 + jj];
@@ -295,6 +325,9 @@ awb_forward_fast_kernel(const AwbChain *chains)
             tpos = ipermg[r0 + jj];
             inv_e = inv_emitg[r0 + jj];
         }
+        zaddr = active ? zT_s + 8u * (unsigned) tpos : dummy_s;
+        raddr = Rs_s + 8u * (unsigned) atime;
+        step = active ? 8ll * S1 : 0ll;
         const int key = live ? node : (0x10000 + lane);
         const unsigned m = __match_any_sync(0xffffffffu, key);
         const int seglane = __ffs(m) - 1;
@@ -304,120 +337,133 @@ awb_forward_fast_kernel(const AwbChain *chains)
             upm[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
             dnm[l] = (lane + (1 << l) <= segend) ? 1.0 : 0.0;
         }
-        span = __reduce_max_sync(0xffffffffu, segend - seglane);
+        const int span = __reduce_max_sync(0xffffffffu, segend - seglane);
+        nl = span > 0 ? 32 - __clz(span) : 0;          // scan levels this warp needs
         if (live) {
             const double *lin = ling + (size_t) bb * 7 * T;
-            Da = lin[0 * T + atime];
             const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
+            Da = lin[0 * T + atime];
             hb = lin[1 * T + atime] - Bc;
             A1 = lin[3 * T + atime];
             A2 = lin[4 * T + atime] - A1 * Bc;
             A3 = lin[5 * T + atime] - A1 * Bc;
             nrb = lin[6 * T + atime];
         } else {
-            // idle lane, or the size-1 state space (identity transition)
+            // idle lane (everything 0), or the size-1 state space (identity)
             Da = 0.0; hb = 0.0; A1 = 0.0; A2 = 0.0; A3 = 0.0;
-            nrb = 1.0;
+            nrb = active ? 1.0 : 0.0;
         }
     };
 
     load_compute(0);
-    // columns site, site-1, site-2 of my state and where they go in the table
+    // columns site, site-1, site-2 of my state; w0/w1/w2 = where they go in the
+    // table (the sink for the prior column, which is kept as the caller gave it);
+    // nxt = my entry of the row of the next site (emission in, column out)
     double c = 0.0, c1 = 0.0, c2 = 0.0;
-    double *fw0 = nullptr, *fw1 = nullptr, *fw2 = nullptr;
-    if (active)
+    double *w0 = sink, *w1 = sink, *w2 = sink;
+    double *nxt = sink;
+    if (active) {
         c = fwg[fw_offg[0] + jj];                  // prior column (K1 or caller)
-    unsigned char kind_next = (n > 1) ? kindg[1] : 0;
+        nxt = fwg + fw_offg[0] + S1 + jj;
+    }
+    const unsigned char *kp = kindg + 2;
+    unsigned kind_next = (n > 1) ? kindg[1] : 0;
+    // ring offsets (bytes): iofs = ((site-2)&3)*8 into invS, rofs = (site&1)*RSTR
+    // into Rs, sofs = (((site-2)/RS)&1)*8 into scaleS
+    unsigned iofs = 16, rofs = 0, sofs = 0;
 
-    int site = 0;
+    // one site that is followed by a site of the same block
+    auto site_step = [&](auto nlc) {
+        constexpr int NL = decltype(nlc)::value;
+        awb_sts(zaddr, c);
+        awb_bar_sync(1, NB1);
+
+        // branch scans in registers while the F-scribes sum the rows
+        const double x0 = Da * c;
+        const double y0 = x0 * hb;
+        double py = y0, q = x0;
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            const double ty = __shfl_up_sync(0xffffffffu, py, 1 << l);
+            const double tq = __shfl_down_sync(0xffffffffu, q, 1 << l);
+            py = fma(ty, upm[l], py);
+            q = fma(tq, dnm[l], q);
+        }
+        // exclusive sums: PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a
+        const double PY = py - y0, Q = q - x0;
+        const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
+        // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
+        *w2 = c2 * awb_lds(inv_s + iofs);
+        const unsigned kd = kind_next;
+        kind_next = *kp++;
+        double e = inv_e;
+        if (kd != AWB_SITE_INVARIANT)               // uniform, ~3 % of the sites
+            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;
+        awb_bar_sync(2, NB2);
+
+        // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
+        double cn = (awb_lds(raddr + rofs) + W) * e;
+        if (iofs == 0) {                            // (site & 3) == 2
+            cn *= awb_lds(scale_s + sofs);
+            sofs ^= 8u;
+        }
+        iofs = (iofs + 8u) & 24u;
+        rofs ^= RSTR;
+        c2 = c1; c1 = c; c = cn;
+        w2 = w1; w1 = w0; w0 = nxt;
+        nxt = (double *) ((char *) nxt + step);
+    };
+
     for (int b = 0; b < B; b++) {
         const int blen = blocklensg[b];
 
         // ---------------- sites that are followed by a site of the same block
-        for (int i = 0; i + 1 < blen; i++, site++) {
-            if (active)
-                zT[tpos] = c;
-            awb_bar_sync(1, NB1);
-
-            // branch scans in registers while the F-scribes sum the rows
-            const double x0 = Da * c;
-            const double y0 = x0 * hb;
-            double py = y0, q = x0;
-#if AWB_ABLATE != 4 && AWB_ABLATE != 6
-#pragma unroll
-            for (int l = 0; l < NLEV; l++) {
-                if ((1 << l) <= span) {             // warp-uniform
-                    const double ty = __shfl_up_sync(0xffffffffu, py, 1 << l);
-                    const double tq = __shfl_down_sync(0xffffffffu, q, 1 << l);
-                    py = fma(ty, upm[l], py);
-                    q = fma(tq, dnm[l], q);
-                }
-            }
-#endif
-            // exclusive sums: PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a
-            const double PY = py - y0, Q = q - x0;
-            const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
-            // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
-#if AWB_ABLATE != 1 && AWB_ABLATE != 6
-            if (fw2)
-                *fw2 = c2 * invS[(site - 2) & 3];
-#endif
-            const unsigned char kd = kind_next;
-            if (site + 2 < n)
-                kind_next = kindg[site + 2];
-            double e = 1.0;
-            if (live) {
-                e = inv_e;
-#if AWB_ABLATE != 5 && AWB_ABLATE != 6
-                if (kd == AWB_SITE_VARIANT)
-                    e = fw0 ? fw0[S1] : fwg[fw_offg[b] + (long long) (i + 1) * S1 + jj];
-                else if (kd == AWB_SITE_MASKED)
-                    e = 1.0;
-#endif
-            }
-            awb_bar_sync(2, NB2);
-
-            // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
-            double cn = (RsS[(site & 1) * (TMAX + 2) + atime] + W) * e;
-            if ((site & (AWB_FWD_RS - 1)) == 2)
-                cn *= scaleS[((site - 2) / AWB_FWD_RS) & 1];
-            c2 = c1;
-            fw2 = fw1;
-            c1 = c;
-            fw1 = (site == 0) ? nullptr : fw0;          // the prior is stored as is
-            fw0 = active ? (fw0 ? fw0 + S1 :
-                            fwg + fw_offg[b] + (long long) (i + 1) * S1 + jj)
-                         : nullptr;
-            c = active ? cn : 0.0;
+        switch (nl) {
+        case 0:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<0>());
+            break;
+        case 1:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<1>());
+            break;
+        case 2:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<2>());
+            break;
+        case 3:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<3>());
+            break;
+        case 4:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<(NLEV < 4 ? NLEV : 4)>());
+            break;
+        default:
+            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<NLEV>());
+            break;
         }
 
         // ---------------- last site of the block
         {
-            if (active) {
-                zT[tpos] = c;
-                colS[(b & 1) * NS + jj] = c;
-            }
+            awb_sts(zaddr, c);
+            awb_sts(active ? col_s + 8u * (unsigned) ((b & 1) * NS + jj) : dummy_s, c);
             awb_bar_sync(1, NB1);
-            if (fw2)
-                *fw2 = c2 * invS[(site - 2) & 3];
-            const unsigned char kd = kind_next;
-            if (site + 2 < n)
-                kind_next = kindg[site + 2];
+            *w2 = c2 * awb_lds(inv_s + iofs);
+            const unsigned kd = kind_next;
+            kind_next = *kp++;
             awb_bar_sync(2, NB2);
             if (b == B - 1)
                 break;
 
             // breakpoint: gather through the switch CSR (sample_thread.cpp:345-389)
             double scale = 1.0;
-            if ((site & (AWB_FWD_RS - 1)) == 2)
-                scale = scaleS[((site - 2) / AWB_FWD_RS) & 1];
-            c2 = c1;
-            fw2 = fw1;
-            c1 = c;
-            fw1 = (site == 0) ? nullptr : fw0;
+            if (iofs == 0) {
+                scale = awb_lds(scale_s + sofs);
+                sofs ^= 8u;
+            }
+            iofs = (iofs + 8u) & 24u;
+            rofs ^= RSTR;
+            c2 = c1; c1 = c;
+            w2 = w1; w1 = w0;
             load_compute(b + 1);
             double sum = 0.0;
-            double e = 1.0;
+            double e = em;
             if (active) {
                 const int st = sw_startg[r0 + jj];
                 const int cnt = sw_cntg[r0 + jj];
@@ -428,28 +474,27 @@ awb_forward_fast_kernel(const AwbChain *chains)
                 const double *cold = colS + (b & 1) * NS;
                 for (int x = 0; x < cnt; x++)
                     sum += cold[es[x]] * ep[x];
-                fw0 = fwg + fw_offg[b + 1] + jj;
+                w0 = fwg + fw_offg[b + 1] + jj;
                 if (S > 0) {
                     e = inv_e;
                     if (kd == AWB_SITE_VARIANT)
-                        e = *fw0;
+                        e = *w0;
                     else if (kd == AWB_SITE_MASKED)
                         e = 1.0;
                 }
+                nxt = w0 + S1;
             } else {
-                fw0 = nullptr;
+                w0 = sink;
+                nxt = sink;
             }
             c = sum * e * scale;
-            site++;
         }
     }
 
     // ---- the last two columns: their 1/norm is complete after the final barrier
     __syncthreads();
-    if (fw1 && n > 2)
-        *fw1 = c1 * invS[(n - 2) & 3];
-    if (fw0 && n > 1)
-        *fw0 = c * invS[(n - 1) & 3];
+    *w1 = c1 * invS[(n - 2) & 3];
+    *w0 = c * invS[(n - 1) & 3];
 }
 
 #endif // AWB_FORWARD_FAST_CUH

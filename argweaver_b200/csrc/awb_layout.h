@@ -48,7 +48,7 @@ struct AwbLayout {
         o_order, o_root, o_lineages, o_treelen, o_tm_minage, o_sw_start,
         o_sw_cnt, o_sw_src, o_sw_prob, o_sw_determ, o_sw_determprob,
         o_sw_recombrow, o_sw_recoalrow, o_sw_recombsrc, o_sw_recoalsrc, o_kind,
-        o_fw, o_path, o_rand, o_logz, o_status;
+        o_fw, o_path, o_rand, o_logz, o_status, o_sink;
     bool has_subtree_roots;
     std::vector<AwbCopy> copies;         // inputs taken straight from the caller
 };
@@ -374,11 +374,12 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
         L.o_sw_determprob = L.o_sw_recombrow = 0;
         L.o_sw_recoalrow = L.o_sw_recombsrc = L.o_sw_recoalsrc = 0;
     }
-    AWB_PLACE(o_kind, (size_t) L.n);
+    AWB_PLACE(o_kind, (size_t) L.n + 2);     // the forward kernel prefetches kind[site+2]
     AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
     AWB_PLACE(o_path, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_rand, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_logz, sizeof(double));
+    AWB_PLACE(o_sink, (size_t) 1024 * sizeof(double));   // forward kernel: discarded stores
     AWB_PLACE(o_status, sizeof(int));
 #undef AWB_PLACE
     L.total_bytes = off;
@@ -495,6 +496,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(int *, path, o_path);
     AWB_P(const int *, rand_ints, o_rand);
     AWB_P(double *, logz, o_logz);
+    AWB_P(double *, sink, o_sink);
     AWB_P(int *, status, o_status);
 #undef AWB_P
 }
