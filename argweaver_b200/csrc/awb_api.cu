@@ -492,10 +492,22 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
                                 sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice,
                                 st));
-    int NS = ((b->maxS + 31) / 32) * 32;
-    if (NS < 512) NS = 512;            // >= 16 warps: 32-site speculative waves
+    const int maxS1 = b->maxS > 0 ? b->maxS : 1;
+    const int maxent = maxS1 + b->maxT + 4;        // capacity per block (awb_layout.h)
+    const size_t smem = awb_tb_smem_bytes(maxS1, b->maxT, maxent);
+    if (smem > 220 * 1024)
+        return fail("state space too large for the traceback kernel's shared memory");
     CUDA_OK(cudaEventRecord(b->ctx->ev[4], st));
-    awb_traceback_kernel<<<b->C, NS, 0, st>>>(b->d_chains, rand_max);
+#define AWB_LAUNCH_TB(NV, SPW, VPT) do { \
+        CUDA_OK(cudaFuncSetAttribute(awb_traceback_kernel<NV, SPW, VPT>, \
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        awb_traceback_kernel<NV, SPW, VPT><<<b->C, AWB_TB_THREADS, smem, st>>>( \
+            b->d_chains, rand_max, maxS1, b->maxT, maxent); } while (0)
+    if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
+    else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
+    else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
+    else AWB_LAUNCH_TB(32, 1, 2);
+#undef AWB_LAUNCH_TB
     b->launches++;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[5], st));

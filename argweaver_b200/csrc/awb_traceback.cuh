@@ -23,29 +23,148 @@
 // of the wave before the first failure keep k; the failing site is sampled in
 // full with a block-wide scan, k changes, the transition column is rebuilt and
 // the walk continues from there.  One CTA per chain.
+//
+// Latency.  A block (one local tree, ~30 sites) is a chain of dependent phases,
+// so every global load that sits between two phases costs a full DRAM round
+// trip.  Nothing but the forward rows themselves is read from global memory on
+// that chain: the per-block tables (transition vectors, the time-by-time
+// matrix, per-state node/time/age, the switch CSR of the block and the last
+// forward row of the block before it) are copied into shared memory with
+// cp.async ONE BLOCK AHEAD, double buffered; the block scalars are fetched two
+// blocks ahead; the forward rows of the next block's first wave are prefetched
+// into L2; and a warp issues all loads of its rows before it consumes any.
 #ifndef AWB_TRACEBACK_CUH
 #define AWB_TRACEBACK_CUH
 
 #include "awb_common.cuh"
 
-#define AWB_TB_SPW 2          // sites per warp in one speculative wave
+#define AWB_TB_THREADS 512
 
 struct AwbTbSmem {
     double wsum[32];
     int kmin;
     int kcur;
-    int fail;
+    unsigned failmask[3];
 };
 
-// block-wide sample() over one value per thread: returns the chosen index
-__device__ inline int awb_block_sample(double A, bool valid, int S1, int r,
+// scalars of one block
+struct AwbTbBlk {
+    int S, S1, blen, pos, minage, nent, n1;
+    long long r0, fwoff, entoff;
+};
+
+__device__ inline AwbTbBlk awb_tb_blk(const AwbChain &ch, int bb)
+{
+    AwbTbBlk m;
+    if (bb < 0) {
+        m.S = 0; m.S1 = 1; m.blen = 0; m.pos = 0; m.minage = 0; m.nent = 0;
+        m.n1 = 0; m.r0 = 0; m.fwoff = 0; m.entoff = 0;
+        return m;
+    }
+    m.S = ch.nstates[bb];
+    m.S1 = m.S > 0 ? m.S : 1;
+    m.blen = ch.blocklens[bb];
+    m.pos = ch.block_start[bb];
+    // TransMatrix::get uses minage = age[subtree_root] (trans.h:67-74)
+    m.minage = (ch.internal && m.S > 0) ? ch.tm_minage[bb] : 0;
+    m.r0 = ch.row_off[bb];
+    m.fwoff = ch.fw_off[bb];
+    m.entoff = ch.ent_off[bb];
+    m.nent = (int) (ch.ent_off[bb + 1] - m.entoff);
+    const int sp = bb > 0 ? ch.nstates[bb - 1] : 0;
+    m.n1 = bb > 0 ? (sp > 0 ? sp : 1) : 0;
+    return m;
+}
+
+// per-block tables in shared memory (one of two buffers); byte offsets
+struct AwbTbBuf {
+    unsigned tv, tm, last, ep;          // doubles
+    unsigned es, sws, swc, stn;         // 16-bit
+    unsigned stt, sta;                  // 8-bit
+    unsigned bytes;
+};
+
+__host__ __device__ inline AwbTbBuf awb_tb_buf_layout(int maxS1, int maxT, int maxent)
+{
+    AwbTbBuf L;
+    unsigned o = 0;
+    L.tv = o;   o += (unsigned) (AWB_TM_NVEC * maxT) * 8u;
+    L.tm = o;   o += (unsigned) (maxT * maxT) * 8u;
+    L.last = o; o += (unsigned) maxS1 * 8u;
+    L.ep = o;   o += (unsigned) (maxent + 1) * 8u;
+    // 16-/8-bit arrays keep the source's offset within a 4-byte word (cp.async
+    // moves aligned words), hence the slack
+    L.es = o;   o += (((unsigned) maxent * 2u + 8u) + 7u) & ~7u;
+    L.sws = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
+    L.swc = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
+    L.stn = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
+    L.stt = o;  o += (((unsigned) maxS1 + 8u) + 7u) & ~7u;
+    L.sta = o;  o += (((unsigned) maxS1 + 8u) + 7u) & ~7u;
+    L.bytes = (o + 15u) & ~15u;
+    return L;
+}
+
+// dynamic shared memory of the kernel
+__host__ __device__ inline size_t awb_tb_smem_bytes(int maxS1, int maxT, int maxent)
+{
+    const AwbTbBuf L = awb_tb_buf_layout(maxS1, maxT, maxent);
+    size_t n = 2 * (size_t) L.bytes;
+    n += (size_t) maxS1 * 8;                       // transS
+    n += (size_t) (maxent + 1) * 8;                // swA
+    n += (((size_t) (maxent + 1) * 2) + 15) & ~(size_t) 15;   // swJ
+    return n + 16;
+}
+
+__device__ __forceinline__ void awb_cp_async4(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src)
+                 : "memory");
+}
+
+__device__ __forceinline__ void awb_cp_async8(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src)
+                 : "memory");
+}
+
+// copy n doubles (8-byte aligned source)
+__device__ inline void awb_tb_copy8(unsigned dst, const double *src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        awb_cp_async8(dst + 8u * (unsigned) i, src + i);
+}
+
+// copy nbytes from an arbitrarily aligned source as aligned 4-byte words;
+// element 0 lands at dst + (src & 3).  Returns that skew.
+__device__ inline unsigned awb_tb_copy_bytes(unsigned dst, const void *src, int nbytes)
+{
+    const unsigned long long a = (unsigned long long) src;
+    const unsigned skew = (unsigned) (a & 3ull);
+    const char *base = (const char *) (a - skew);
+    const int nw = (int) ((skew + (unsigned) nbytes + 3u) >> 2);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x)
+        awb_cp_async4(dst + 4u * (unsigned) i, base + 4 * i);
+    return skew;
+}
+
+// Block-wide sample() over the S1 weights held VPT per thread (thread t holds
+// indices t*VPT .. t*VPT+VPT-1): returns the chosen index.
+template <int VPT>
+__device__ inline int awb_block_sample(const double (&A)[VPT], int S1, int r,
                                        int rand_max, AwbTbSmem *sm)
 {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    double x = valid ? A : 0.0;
+    double loc[VPT];
+    double x = 0.0;
+#pragma unroll
+    for (int v = 0; v < VPT; v++) {
+        x += A[v];
+        loc[v] = x;                     // inclusive within the thread
+    }
+    const double mine = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const double t = __shfl_up_sync(0xffffffffu, x, d);
@@ -64,96 +183,164 @@ __device__ inline int awb_block_sample(double A, bool valid, int S1, int r,
             off += s;
         total += s;
     }
-    x += off;
+    const double before = off + (x - mine);     // sum of everything before my chunk
     const double pick = (double) r / (double) rand_max * total;
-    const bool hit = valid && (x >= pick);
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m != 0 && lane == 0)
-        atomicMin(&sm->kmin, warp * 32 + __ffs(m) - 1);
+    int hitidx = 0x7fffffff;
+#pragma unroll
+    for (int v = VPT - 1; v >= 0; v--) {
+        const int j = tid * VPT + v;
+        if (j < S1 && before + loc[v] >= pick)
+            hitidx = j;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hitidx != 0x7fffffff);
+    if (m != 0) {
+        const int first = __shfl_sync(0xffffffffu, hitidx, __ffs(m) - 1);
+        if (lane == 0)
+            atomicMin(&sm->kmin, first);
+    }
     __syncthreads();
     const int k = sm->kmin;
     __syncthreads();                // kmin / wsum are reused by the next call
     return k;
 }
 
-__global__ void __launch_bounds__(1024)
-awb_traceback_kernel(const AwbChain *chains, int rand_max)
+// NV = ceil(max states / 32) values per lane and row, SPW = rows per warp and
+// wave, VPT = ceil(max states / threads)
+template <int NV, int SPW, int VPT>
+__global__ void __launch_bounds__(AWB_TB_THREADS, 1)
+awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
+                     int maxent)
 {
+    extern __shared__ __align__(16) unsigned char tb_smem[];
     const AwbChain &ch = chains[blockIdx.x];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int NW = blockDim.x >> 5;
+    const int NW = AWB_TB_THREADS >> 5;
     const int T = ch.model.ntimes;
-    const int V = ch.nnodes;
     const int n = ch.nsites;
     const int B = ch.ntrees;
-    const bool internal = ch.internal != 0;
     const double *__restrict__ fwg = ch.fw;
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
-    const double inv_rand_max = 1.0;   // (division kept literal below)
-    (void) inv_rand_max;
 
     __shared__ AwbTbSmem sm;
-    __shared__ double tvS[AWB_TM_NVEC * AWB_MAXT];
-    __shared__ double transS[AWB_MAXS];
-    __shared__ double swA[AWB_MAXS];          // switch step scratch (thread 0)
-    __shared__ unsigned short swJ[AWB_MAXS];
-    __shared__ int flagS[32 * AWB_TB_SPW];
+    const AwbTbBuf BL = awb_tb_buf_layout(maxS1, maxT, maxent);
+    unsigned char *bufp[2] = { tb_smem, tb_smem + BL.bytes };
+    double *transS = (double *) (tb_smem + 2 * (size_t) BL.bytes);
+    double *swA = transS + maxS1;
+    unsigned short *swJ = (unsigned short *) (swA + (maxent + 1));
+    const unsigned smem_s = (unsigned) __cvta_generic_to_shared(tb_smem);
+
+    // skews of the 16-/8-bit arrays of each buffer (source alignment)
+    unsigned sk_es[2], sk_sws[2], sk_swc[2], sk_stn[2], sk_stt[2], sk_sta[2];
+
+    // issue the asynchronous copy of block bb's tables into buffer q
+    auto preload = [&](const AwbTbBlk &m, int bb, int q) {
+        const unsigned base = smem_s + (unsigned) q * BL.bytes;
+        sk_es[q] = sk_sws[q] = sk_swc[q] = sk_stn[q] = sk_stt[q] = sk_sta[q] = 0;
+        if (bb < 0)
+            return;
+        if (m.S > 0) {
+            awb_tb_copy8(base + BL.tv, ch.tmvec + (size_t) bb * AWB_TM_NVEC * T,
+                         AWB_TM_NVEC * T);
+            awb_tb_copy8(base + BL.tm, ch.tmatrix + (size_t) bb * T * T, T * T);
+            sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, ch.st_node + m.r0, 2 * m.S);
+            sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, ch.st_time + m.r0, m.S);
+            sk_sta[q] = awb_tb_copy_bytes(base + BL.sta, ch.st_age + m.r0, m.S);
+        }
+        if (bb > 0) {
+            awb_tb_copy8(base + BL.last, fwg + m.fwoff - m.n1, m.n1);
+            awb_tb_copy8(base + BL.ep, ch.sw_prob + m.entoff, m.nent);
+            sk_es[q] = awb_tb_copy_bytes(base + BL.es, ch.sw_src + m.entoff, 2 * m.nent);
+            sk_sws[q] = awb_tb_copy_bytes(base + BL.sws, ch.sw_start + m.r0, 2 * m.S1);
+            sk_swc[q] = awb_tb_copy_bytes(base + BL.swc, ch.sw_cnt + m.r0, 2 * m.S1);
+        }
+    };
+    // forward rows of the first wave of block m into L2
+    auto prefetch_rows = [&](const AwbTbBlk &m) {
+        const int nrows = m.blen - 1 < NW * SPW ? m.blen - 1 : NW * SPW;
+        if (nrows <= 0)
+            return;
+        const char *p0 = (const char *) (fwg + m.fwoff +
+                                         (long long) (m.blen - 1 - nrows) * m.S1);
+        const long long nbytes = (long long) nrows * m.S1 * 8;
+        for (long long o = (long long) tid * 128; o < nbytes; o += 128ll * AWB_TB_THREADS)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
+    };
 
     // draw used for site s: the reference consumes one rand() per sampled site,
     // last site first
     const int roff = (ch.last_state < 0) ? (n - 1) : (n - 2);
     int k;
 
+    AwbTbBlk mC = awb_tb_blk(ch, B - 1);
+    AwbTbBlk mN = awb_tb_blk(ch, B - 2);
+    if (tid == 0) {
+        sm.failmask[0] = 0;
+        sm.failmask[1] = 0;
+        sm.failmask[2] = 0;
+    }
+    preload(mC, B - 1, (B - 1) & 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
     // ---- last column (sample_thread.cpp:534-539)
     {
-        const int S1 = ch.nstates[B - 1] > 0 ? ch.nstates[B - 1] : 1;
+        const int S1 = mC.S1;
         if (ch.last_state < 0) {
-            const bool valid = tid < S1;
-            const double A = valid ? fwg[ch.fw_off[B] - S1 + tid] : 0.0;
-            k = awb_block_sample(A, valid, S1, randg[0], rand_max, &sm);
+            double A[VPT];
+#pragma unroll
+            for (int v = 0; v < VPT; v++) {
+                const int j = tid * VPT + v;
+                A[v] = j < S1 ? fwg[ch.fw_off[B] - S1 + j] : 0.0;
+            }
+            k = awb_block_sample<VPT>(A, S1, randg[0], rand_max, &sm);
         } else {
             k = ch.last_state;
         }
         if (tid == 0)
             pathg[n - 1] = k;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 
+    int par = 0;
     for (int b = B - 1; b >= 0; b--) {
-        const int S = ch.nstates[b];
-        const int S1 = S > 0 ? S : 1;
-        const long long r0 = ch.row_off[b];
-        const int pos = ch.block_start[b];
-        const int blen = ch.blocklens[b];
-        const double *fw = fwg + ch.fw_off[b];
-        const int *age = ch.ages + (size_t) b * V;
-        const short *st_node = ch.st_node + r0;
-        const signed char *st_time = ch.st_time + r0;
+        const int q = b & 1;
+        // ---- one block ahead: tables of block b-1; two ahead: scalars of b-2
+        preload(mN, b - 1, q ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const AwbTbBlk mNN = awb_tb_blk(ch, b - 2);
+        if (b > 0)
+            prefetch_rows(mN);
 
-        // TransMatrix::get uses minage = age[subtree_root] (trans.h:67-74)
-        int minage = 0;
-        if (internal && S > 0)
-            minage = age[ch.child0[(size_t) b * V + ch.root[b]]];
-        __syncthreads();
-        for (int x = tid; x < AWB_TM_NVEC * T; x += blockDim.x)
-            tvS[x] = ch.tmvec[(size_t) b * AWB_TM_NVEC * T + x];
-        __syncthreads();
+        const int S = mC.S, S1 = mC.S1, blen = mC.blen, pos = mC.pos;
+        const double *fw = fwg + mC.fwoff;
+        const unsigned char *bp = bufp[q];
+        const double *tvS = (const double *) (bp + BL.tv);
+        const double *tmS = (const double *) (bp + BL.tm);
+        const short *stN = (const short *) (bp + BL.stn + sk_stn[q]);
+        const signed char *stT = (const signed char *) (bp + BL.stt + sk_stt[q]);
+        const signed char *stA = (const signed char *) (bp + BL.sta + sk_sta[q]);
 
         // ---- sample_hmm_posterior (sample_thread.cpp:470-503), speculative
         int i_hi = blen - 2;
         int trans_k = -1;
         while (i_hi >= 0) {
             if (trans_k != k) {
-                // transition column into k (recomputed only when k changes)
+                // transition column into k (recomputed only when k changes):
+                // other branches read the time-by-time matrix, the branch of k
+                // itself uses the closed form
                 if (S > 0) {
-                    const int node_k = st_node[k];
-                    const int b_k = st_time[k];
-                    const int c_k = age[node_k];
-                    for (int j = tid; j < S; j += blockDim.x)
-                        transS[j] = awb_get_time(tvS, T, st_time[j], b_k, c_k,
-                                                 minage, st_node[j] == node_k);
+                    const int node_k = stN[k];
+                    const int b_k = stT[k];
+                    const int c_k = stA[k];
+                    for (int j = tid; j < S; j += AWB_TB_THREADS) {
+                        const int a_j = stT[j];
+                        transS[j] = (stN[j] == node_k) ?
+                            awb_get_time(tvS, T, a_j, b_k, c_k, mC.minage, true) :
+                            tmS[a_j * T + b_k];
+                    }
                 } else if (tid == 0) {
                     transS[0] = 1.0;
                 }
@@ -162,65 +349,71 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max)
             }
 
             // ---- one wave: NW * SPW sites tested for "stays in k"
+            {
+                int r[SPW];
+                double v[SPW][NV];
 #pragma unroll
-            for (int u = 0; u < AWB_TB_SPW; u++) {
-                const int w = warp * AWB_TB_SPW + u;       // w-th site of the wave
-                const int i = i_hi - w;
-                if (i >= 0) {
-                    const double *row = fw + (long long) i * S1;
-                    double tot0 = 0.0, tot1 = 0.0, pre0 = 0.0, pre1 = 0.0;
-                    int j = lane;
-                    for (; j + 32 < S1; j += 64) {
-                        const double v0 = row[j] * transS[j];
-                        const double v1 = row[j + 32] * transS[j + 32];
-                        tot0 += v0;
-                        tot1 += v1;
-                        if (j < k) pre0 += v0;
-                        if (j + 32 < k) pre1 += v1;
+                for (int u = 0; u < SPW; u++) {
+                    const int i = i_hi - (warp * SPW + u);
+                    r[u] = (i >= 0 && lane == 0) ? randg[roff - (pos + i)] : 0;
+                    const double *row = fw + (long long) (i >= 0 ? i : 0) * S1;
+#pragma unroll
+                    for (int x = 0; x < NV; x++) {
+                        const int j = lane + 32 * x;
+                        v[u][x] = (i >= 0 && j < S1) ? row[j] : 0.0;
                     }
-                    if (j < S1) {
-                        const double v0 = row[j] * transS[j];
-                        tot0 += v0;
-                        if (j < k) pre0 += v0;
+                }
+#pragma unroll
+                for (int u = 0; u < SPW; u++) {
+                    const int w = warp * SPW + u;          // w-th site of the wave
+                    const int i = i_hi - w;
+                    double tot = 0.0, pre = 0.0, ak = 0.0;
+#pragma unroll
+                    for (int x = 0; x < NV; x++) {
+                        const int j = lane + 32 * x;
+                        const double t = (j < S1) ? v[u][x] * transS[j] : 0.0;
+                        tot += t;
+                        if (j < k) pre += t;
+                        if (j == k) ak = t;
                     }
-                    double tot = tot0 + tot1, pre = pre0 + pre1;
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) {
                         tot += __shfl_xor_sync(0xffffffffu, tot, d);
                         pre += __shfl_xor_sync(0xffffffffu, pre, d);
                     }
-                    if (lane == 0) {
-                        const double Ak = row[k] * transS[k];
-                        const double pick = (double) randg[roff - (pos + i)] /
-                            (double) rand_max * tot;
-                        flagS[w] = (pre < pick) && (pre + Ak >= pick);
+                    ak = __shfl_sync(0xffffffffu, ak, k & 31);
+                    if (lane == 0 && i >= 0) {
+                        const double pick = (double) r[u] / (double) rand_max * tot;
+                        if (!((pre < pick) && (pre + ak >= pick)))
+                            atomicOr(&sm.failmask[par], 1u << w);
                     }
-                } else if (lane == 0) {
-                    flagS[w] = 1;
                 }
             }
             __syncthreads();
 
             // first site of the wave (highest i) that leaves k
-            int fail = -1;
-            const int wave = NW * AWB_TB_SPW;
-            for (int w = 0; w < wave; w++) {
-                if (!flagS[w]) { fail = w; break; }
-            }
+            // three masks in rotation: the one reset here is used two waves
+            // from now, i.e. after the next barrier
+            const unsigned fm = sm.failmask[par];
+            if (tid == 0)
+                sm.failmask[par == 0 ? 2 : par - 1] = 0;
+            par = (par == 2) ? 0 : par + 1;
+            const int wave = NW * SPW;
+            const int fail = fm ? __ffs(fm) - 1 : -1;
             const int nkeep = (fail < 0) ? wave : fail;
-            for (int w = tid; w < nkeep; w += blockDim.x) {
-                const int i = i_hi - w;
-                if (i >= 0)
-                    pathg[pos + i] = k;
-            }
+            if (tid < nkeep && i_hi - tid >= 0)
+                pathg[pos + i_hi - tid] = k;
             if (fail >= 0) {
                 // sample the failing site in full
                 const int i = i_hi - fail;
-                const bool valid = tid < S1;
-                const double A = valid ? fw[(long long) i * S1 + tid] * transS[tid] : 0.0;
-                const int knew = awb_block_sample(A, valid, S1,
-                                                  randg[roff - (pos + i)],
-                                                  rand_max, &sm);
+                double A[VPT];
+#pragma unroll
+                for (int x = 0; x < VPT; x++) {
+                    const int j = tid * VPT + x;
+                    A[x] = j < S1 ? fw[(long long) i * S1 + j] * transS[j] : 0.0;
+                }
+                const int knew = awb_block_sample<VPT>(A, S1, randg[roff - (pos + i)],
+                                                       rand_max, &sm);
                 if (tid == 0)
                     pathg[pos + i] = knew;
                 k = knew;
@@ -228,23 +421,25 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max)
             } else {
                 i_hi -= wave;
             }
-            __syncthreads();
         }
 
         // ---- sample_hmm_posterior_step through the switch matrix (:506-519)
         if (b > 0) {
             if (tid == 0) {
-                const int n1 = ch.nstates[b - 1] > 0 ? ch.nstates[b - 1] : 1;
-                const double *col1 = fwg + ch.fw_off[b] - n1;
-                const int st = ch.sw_start[r0 + k];
-                const int cn = ch.sw_cnt[r0 + k];
-                const unsigned short *es = ch.sw_src + ch.ent_off[b] + st;
-                const double *ep = ch.sw_prob + ch.ent_off[b] + st;
+                const int n1 = mC.n1;
+                const double *col1 = (const double *) (bp + BL.last);
+                const unsigned short *sws = (const unsigned short *) (bp + BL.sws + sk_sws[q]);
+                const unsigned short *swc = (const unsigned short *) (bp + BL.swc + sk_swc[q]);
+                const int st = sws[k];
+                const int cn = swc[k];
+                const unsigned short *es =
+                    (const unsigned short *) (bp + BL.es + sk_es[q]) + st;
+                const double *ep = (const double *) (bp + BL.ep) + st;
                 // entries sorted by source index = the order sample() walks A[]
-                for (int q = 0; q < cn; q++) {
-                    const unsigned short jj = es[q];
-                    const double val = col1[jj] * ep[q];
-                    int w = q;
+                for (int x = 0; x < cn; x++) {
+                    const unsigned short jj = es[x];
+                    const double val = col1[jj] * ep[x];
+                    int w = x;
                     while (w > 0 && swJ[w - 1] > jj) {
                         swJ[w] = swJ[w - 1];
                         swA[w] = swA[w - 1];
@@ -254,8 +449,8 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max)
                     swA[w] = val;
                 }
                 double total = 0.0;
-                for (int q = 0; q < cn; q++)
-                    total += swA[q];
+                for (int x = 0; x < cn; x++)
+                    total += swA[x];
                 const double pick = (double) randg[roff - (pos - 1)] /
                     (double) rand_max * total;
                 // zero-weight states before the first entry win when pick == 0
@@ -264,9 +459,9 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max)
                 if (0.0 >= pick && (cn == 0 || swJ[0] > 0)) {
                     kk = 0;
                 } else {
-                    for (int q = 0; q < cn; q++) {
-                        x += swA[q];
-                        if (x >= pick) { kk = swJ[q]; break; }
+                    for (int y = 0; y < cn; y++) {
+                        x += swA[y];
+                        if (x >= pick) { kk = swJ[y]; break; }
                     }
                 }
                 sm.kcur = kk;
@@ -274,8 +469,13 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max)
             }
             __syncthreads();
             k = sm.kcur;
-            __syncthreads();
         }
+
+        // ---- the tables of block b-1 have landed; everyone is done with buffer q
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        mC = mN;
+        mN = mNN;
     }
 }
 
