@@ -505,7 +505,11 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
             b->d_chains, rand_max, maxS1, b->maxT, maxent); } while (0)
     if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
     else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
+#ifdef AWB_TB_SPW1
+    else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 1, 1);
+#else
     else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
+#endif
     else AWB_LAUNCH_TB(32, 1, 2);
 #undef AWB_LAUNCH_TB
     b->launches++;

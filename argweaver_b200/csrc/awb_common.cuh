@@ -136,6 +136,7 @@ struct AwbChain {
     const int *rand_ints;     // [nsites]
     double *logz;             // [1]
     double *sink;             // [1024] per-thread dump slot of the forward kernel
+    double *fsum;             // [n][T-1] per-time sums of the stored forward columns
     int *status;              // [1] first bad site or -1
     int last_state;           // traceback: -1 = sample last column
 };

@@ -172,6 +172,10 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
                     sm.scal[0] = 1.0 / nrm;
                     sm.scal[1] = nrm;
                 }
+                // per-time sums of the column as stored (used by the traceback)
+                for (int a = lane; a < T - 1; a += 32)
+                    ch.fsum[(size_t) site * (T - 1) + a] =
+                        sm.Fs[a] * (site == 0 ? 1.0 : 1.0 / nrm);
             } else if (lane == 0) {
                 const double nrm = sm.part[0];
                 sm.scal[0] = 1.0 / nrm;

@@ -129,6 +129,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
         // =================================================================
         double lprod = 1.0, lacc = 0.0;
         int nprod = 0;
+        double *__restrict__ fsumg = chg.fsum;
         int bad_site = -1;
         for (int site = 0; site < n; site++) {
             const double *Fs = FsS + (site & 1) * (TMAX + 2);
@@ -143,6 +144,10 @@ awb_forward_fast_kernel(const AwbChain *chains)
             const double inv = 1.0 / nrm;
             if (lane == 0)
                 invS[site & 3] = inv;
+            // per-time sums of the column as it is stored (the traceback forms
+            // its row totals from these); the prior column is stored unscaled
+            for (int a = lane; a < T - 1; a += 32)
+                fsumg[(size_t) site * (T - 1) + a] = Fs[a] * (site == 0 ? 1.0 : inv);
             if (!(nrm > 0.0) && bad_site < 0)
                 bad_site = site;
             if ((site & (AWB_FWD_RS - 1)) == 0) {

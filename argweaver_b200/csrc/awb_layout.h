@@ -48,7 +48,7 @@ struct AwbLayout {
         o_order, o_root, o_lineages, o_treelen, o_tm_minage, o_sw_start,
         o_sw_cnt, o_sw_src, o_sw_prob, o_sw_determ, o_sw_determprob,
         o_sw_recombrow, o_sw_recoalrow, o_sw_recombsrc, o_sw_recoalsrc, o_kind,
-        o_fw, o_path, o_rand, o_logz, o_status, o_sink;
+        o_fw, o_path, o_rand, o_logz, o_status, o_sink, o_fsum;
     bool has_subtree_roots;
     std::vector<AwbCopy> copies;         // inputs taken straight from the caller
 };
@@ -376,6 +376,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     }
     AWB_PLACE(o_kind, (size_t) L.n + 2);     // the forward kernel prefetches kind[site+2]
     AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
+    // per-site, per-time sums of the stored forward column (traceback)
+    AWB_PLACE(o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * sizeof(double));
     AWB_PLACE(o_path, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_rand, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_logz, sizeof(double));
@@ -497,6 +499,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(const int *, rand_ints, o_rand);
     AWB_P(double *, logz, o_logz);
     AWB_P(double *, sink, o_sink);
+    AWB_P(double *, fsum, o_fsum);
     AWB_P(int *, status, o_status);
 #undef AWB_P
 }
@@ -550,6 +553,7 @@ inline bool awb_layout_find(const AwbLayout &L, const char *name, size_t &off,
         { "kind", L.o_kind, (size_t) L.n, false },
         { "fw", L.o_fw, (size_t) L.fw_off[L.B] * 8, false },
         { "path", L.o_path, (size_t) L.n * 4, false },
+        { "fsum", L.o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * 8, false },
         { "ent_off", L.o_ent_off, (B + 1) * 8, false },
         { "band_off", L.o_band_off, (B + 1) * 8, false },
     };

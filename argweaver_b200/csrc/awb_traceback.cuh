@@ -44,35 +44,43 @@ struct AwbTbSmem {
     double wsum[32];
     int kmin;
     int kcur;
+    int br_first, br_cnt;           // states of the branch of k: [first, end)
     unsigned failmask[3];
 };
 
-// scalars of one block
+// scalars of one block.  awb_tb_blk only LOADS (two blocks ahead of use, so no
+// instruction waits on the loads); the derived values come from the accessors.
 struct AwbTbBlk {
-    int S, S1, blen, pos, minage, nent, n1;
-    long long r0, fwoff, entoff;
+    int S, blen, pos, minage_raw, Sprev;
+    long long r0, fwoff, entoff, entend;
+    __device__ int S1() const { return S > 0 ? S : 1; }
+    __device__ int n1() const { return Sprev > 0 ? Sprev : 1; }
+    __device__ int nent() const { return (int) (entend - entoff); }
 };
 
-__device__ inline AwbTbBlk awb_tb_blk(const AwbChain &ch, int bb)
+// pointers of the chain the kernel walks (read once from the chain record)
+struct AwbTbPtrs {
+    const int *nstates, *blocklens, *block_start, *tm_minage;
+    const long long *row_off, *fw_off, *ent_off;
+};
+
+__device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb)
 {
     AwbTbBlk m;
     if (bb < 0) {
-        m.S = 0; m.S1 = 1; m.blen = 0; m.pos = 0; m.minage = 0; m.nent = 0;
-        m.n1 = 0; m.r0 = 0; m.fwoff = 0; m.entoff = 0;
+        m.S = 0; m.blen = 0; m.pos = 0; m.minage_raw = 0; m.Sprev = 0;
+        m.r0 = 0; m.fwoff = 0; m.entoff = 0; m.entend = 0;
         return m;
     }
-    m.S = ch.nstates[bb];
-    m.S1 = m.S > 0 ? m.S : 1;
-    m.blen = ch.blocklens[bb];
-    m.pos = ch.block_start[bb];
-    // TransMatrix::get uses minage = age[subtree_root] (trans.h:67-74)
-    m.minage = (ch.internal && m.S > 0) ? ch.tm_minage[bb] : 0;
-    m.r0 = ch.row_off[bb];
-    m.fwoff = ch.fw_off[bb];
-    m.entoff = ch.ent_off[bb];
-    m.nent = (int) (ch.ent_off[bb + 1] - m.entoff);
-    const int sp = bb > 0 ? ch.nstates[bb - 1] : 0;
-    m.n1 = bb > 0 ? (sp > 0 ? sp : 1) : 0;
+    m.S = p.nstates[bb];
+    m.blen = p.blocklens[bb];
+    m.pos = p.block_start[bb];
+    m.minage_raw = p.tm_minage[bb];
+    m.r0 = p.row_off[bb];
+    m.fwoff = p.fw_off[bb];
+    m.entoff = p.ent_off[bb];
+    m.entend = p.ent_off[bb + 1];
+    m.Sprev = bb > 0 ? p.nstates[bb - 1] : 0;
     return m;
 }
 
@@ -109,7 +117,8 @@ __host__ __device__ inline size_t awb_tb_smem_bytes(int maxS1, int maxT, int max
 {
     const AwbTbBuf L = awb_tb_buf_layout(maxS1, maxT, maxent);
     size_t n = 2 * (size_t) L.bytes;
-    n += (size_t) maxS1 * 8;                       // transS
+    n += 2 * (size_t) maxS1 * 8;                   // transS, corrS
+    n += (size_t) AWB_MAXT * 8;                    // tmcolS
     n += (size_t) (maxent + 1) * 8;                // swA
     n += (((size_t) (maxent + 1) * 2) + 15) & ~(size_t) 15;   // swJ
     return n + 16;
@@ -217,18 +226,34 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int NW = AWB_TB_THREADS >> 5;
+    constexpr int NVH = (NV + 1) / 2;      // the shorter side of a row, per lane
     const int T = ch.model.ntimes;
     const int n = ch.nsites;
     const int B = ch.ntrees;
     const double *__restrict__ fwg = ch.fw;
+    const double *__restrict__ fsumg = ch.fsum;
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
+    const bool internal = ch.internal != 0;
+    const AwbTbPtrs P = { ch.nstates, ch.blocklens, ch.block_start, ch.tm_minage,
+                          ch.row_off, ch.fw_off, ch.ent_off };
+    const double *__restrict__ tmvecg = ch.tmvec;
+    const double *__restrict__ tmatrixg = ch.tmatrix;
+    const short *__restrict__ st_nodeg = ch.st_node;
+    const signed char *__restrict__ st_timeg = ch.st_time;
+    const signed char *__restrict__ st_ageg = ch.st_age;
+    const double *__restrict__ sw_probg = ch.sw_prob;
+    const unsigned short *__restrict__ sw_srcg = ch.sw_src;
+    const unsigned short *__restrict__ sw_startg = ch.sw_start;
+    const unsigned short *__restrict__ sw_cntg = ch.sw_cnt;
 
     __shared__ AwbTbSmem sm;
     const AwbTbBuf BL = awb_tb_buf_layout(maxS1, maxT, maxent);
     unsigned char *bufp[2] = { tb_smem, tb_smem + BL.bytes };
     double *transS = (double *) (tb_smem + 2 * (size_t) BL.bytes);
-    double *swA = transS + maxS1;
+    double *corrS = transS + maxS1;         // transS[j] - tm[a_j][b_k] (branch of k)
+    double *tmcolS = corrS + maxS1;         // tm[.][b_k]
+    double *swA = tmcolS + AWB_MAXT;
     unsigned short *swJ = (unsigned short *) (swA + (maxent + 1));
     const unsigned smem_s = (unsigned) __cvta_generic_to_shared(tb_smem);
 
@@ -242,29 +267,35 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         if (bb < 0)
             return;
         if (m.S > 0) {
-            awb_tb_copy8(base + BL.tv, ch.tmvec + (size_t) bb * AWB_TM_NVEC * T,
+            awb_tb_copy8(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
                          AWB_TM_NVEC * T);
-            awb_tb_copy8(base + BL.tm, ch.tmatrix + (size_t) bb * T * T, T * T);
-            sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, ch.st_node + m.r0, 2 * m.S);
-            sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, ch.st_time + m.r0, m.S);
-            sk_sta[q] = awb_tb_copy_bytes(base + BL.sta, ch.st_age + m.r0, m.S);
+            awb_tb_copy8(base + BL.tm, tmatrixg + (size_t) bb * T * T, T * T);
+            sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, st_nodeg + m.r0, 2 * m.S);
+            sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, st_timeg + m.r0, m.S);
+            sk_sta[q] = awb_tb_copy_bytes(base + BL.sta, st_ageg + m.r0, m.S);
         }
         if (bb > 0) {
-            awb_tb_copy8(base + BL.last, fwg + m.fwoff - m.n1, m.n1);
-            awb_tb_copy8(base + BL.ep, ch.sw_prob + m.entoff, m.nent);
-            sk_es[q] = awb_tb_copy_bytes(base + BL.es, ch.sw_src + m.entoff, 2 * m.nent);
-            sk_sws[q] = awb_tb_copy_bytes(base + BL.sws, ch.sw_start + m.r0, 2 * m.S1);
-            sk_swc[q] = awb_tb_copy_bytes(base + BL.swc, ch.sw_cnt + m.r0, 2 * m.S1);
+            awb_tb_copy8(base + BL.last, fwg + m.fwoff - m.n1(), m.n1());
+            awb_tb_copy8(base + BL.ep, sw_probg + m.entoff, m.nent());
+            sk_es[q] = awb_tb_copy_bytes(base + BL.es, sw_srcg + m.entoff, 2 * m.nent());
+            sk_sws[q] = awb_tb_copy_bytes(base + BL.sws, sw_startg + m.r0, 2 * m.S1());
+            sk_swc[q] = awb_tb_copy_bytes(base + BL.swc, sw_cntg + m.r0, 2 * m.S1());
         }
     };
     // forward rows of the first wave of block m into L2
     auto prefetch_rows = [&](const AwbTbBlk &m) {
+#if defined(AWB_TB_PF) && AWB_TB_PF == 0
+        const int nrows = 0;
+#elif defined(AWB_TB_PF) && AWB_TB_PF == 2
+        const int nrows = m.blen - 1;
+#else
         const int nrows = m.blen - 1 < NW * SPW ? m.blen - 1 : NW * SPW;
+#endif
         if (nrows <= 0)
             return;
         const char *p0 = (const char *) (fwg + m.fwoff +
-                                         (long long) (m.blen - 1 - nrows) * m.S1);
-        const long long nbytes = (long long) nrows * m.S1 * 8;
+                                         (long long) (m.blen - 1 - nrows) * m.S1());
+        const long long nbytes = (long long) nrows * m.S1() * 8;
         for (long long o = (long long) tid * 128; o < nbytes; o += 128ll * AWB_TB_THREADS)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
     };
@@ -273,9 +304,15 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     // last site first
     const int roff = (ch.last_state < 0) ? (n - 1) : (n - 2);
     int k;
+#ifdef AWB_TB_STATS
+    long long tk[8] = {0,0,0,0,0,0,0,0}; long long t_last = clock64();
+#define TB_MARK(i) do { long long t_now = clock64(); tk[i] += t_now - t_last; t_last = t_now; } while (0)
+#else
+#define TB_MARK(i)
+#endif
 
-    AwbTbBlk mC = awb_tb_blk(ch, B - 1);
-    AwbTbBlk mN = awb_tb_blk(ch, B - 2);
+    AwbTbBlk mC = awb_tb_blk(P, B - 1);
+    AwbTbBlk mN = awb_tb_blk(P, B - 2);
     if (tid == 0) {
         sm.failmask[0] = 0;
         sm.failmask[1] = 0;
@@ -286,7 +323,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
 
     // ---- last column (sample_thread.cpp:534-539)
     {
-        const int S1 = mC.S1;
+        const int S1 = mC.S1();
         if (ch.last_state < 0) {
             double A[VPT];
 #pragma unroll
@@ -310,12 +347,16 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         // ---- one block ahead: tables of block b-1; two ahead: scalars of b-2
         preload(mN, b - 1, q ^ 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const AwbTbBlk mNN = awb_tb_blk(ch, b - 2);
+        const AwbTbBlk mNN = awb_tb_blk(P, b - 2);
         if (b > 0)
             prefetch_rows(mN);
 
-        const int S = mC.S, S1 = mC.S1, blen = mC.blen, pos = mC.pos;
+        const int S = mC.S, S1 = mC.S1(), blen = mC.blen, pos = mC.pos;
+        // TransMatrix::get uses minage = age[subtree_root] (trans.h:67-74)
+        const int minage = (internal && S > 0) ? mC.minage_raw : 0;
         const double *fw = fwg + mC.fwoff;
+        // draw of the switch step, fetched now so that it is there when needed
+        const int r_sw = (b > 0) ? randg[roff - (pos - 1)] : 0;
         const unsigned char *bp = bufp[q];
         const double *tvS = (const double *) (bp + BL.tv);
         const double *tmS = (const double *) (bp + BL.tm);
@@ -323,9 +364,17 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         const signed char *stT = (const signed char *) (bp + BL.stt + sk_stt[q]);
         const signed char *stA = (const signed char *) (bp + BL.sta + sk_sta[q]);
 
+        TB_MARK(0);
         // ---- sample_hmm_posterior (sample_thread.cpp:470-503), speculative
         int i_hi = blen - 2;
         int trans_k = -1;
+        if (S == 0) {
+            // one-state space: every site keeps state 0 (its draw is skipped,
+            // the draws are indexed by position)
+            for (int i = tid; i <= i_hi; i += AWB_TB_THREADS)
+                pathg[pos + i] = 0;
+            i_hi = -1;
+        }
         while (i_hi >= 0) {
             if (trans_k != k) {
                 // transition column into k (recomputed only when k changes):
@@ -337,10 +386,20 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                     const int c_k = stA[k];
                     for (int j = tid; j < S; j += AWB_TB_THREADS) {
                         const int a_j = stT[j];
-                        transS[j] = (stN[j] == node_k) ?
-                            awb_get_time(tvS, T, a_j, b_k, c_k, mC.minage, true) :
-                            tmS[a_j * T + b_k];
+                        const double other = tmS[a_j * T + b_k];
+                        const bool same = stN[j] == node_k;
+                        const double tr = same ?
+                            awb_get_time(tvS, T, a_j, b_k, c_k, minage, true) : other;
+                        transS[j] = tr;
+                        corrS[j] = tr - other;
+                        // the states of a node are contiguous in state order
+                        if (same && (j == 0 || stN[j - 1] != node_k))
+                            sm.br_first = j;
+                        if (same && (j == S - 1 || stN[j + 1] != node_k))
+                            sm.br_cnt = j + 1;          // end of the branch
                     }
+                    if (tid < T - 1)
+                        tmcolS[tid] = tmS[tid * T + b_k];
                 } else if (tid == 0) {
                     transS[0] = 1.0;
                 }
@@ -348,43 +407,67 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                 __syncthreads();
             }
 
-            // ---- one wave: NW * SPW sites tested for "stays in k"
+            TB_MARK(1);
+            // ---- one wave: NW * SPW sites tested for "stays in k".  The row
+            // total comes from the per-time sums the forward kernel stored
+            // (tot = sum_a Fn[a] tm[a][b_k] + correction on the branch of k), so
+            // only the shorter side of the row is read: the states before k
+            // (pre directly) or the states after k (pre = tot - A_k - suffix).
             {
+                const int fk = sm.br_first;
+                const int ck = sm.br_cnt - fk;
+                const bool lower = (k <= S1 - 1 - k);
+                const int scnt = lower ? k : S1 - 1 - k;
+                const int sbase = lower ? 0 : k + 1;
                 int r[SPW];
-                double v[SPW][NV];
+                double v[SPW][NVH], f[SPW][2], br[SPW][2], rk[SPW];
 #pragma unroll
                 for (int u = 0; u < SPW; u++) {
                     const int i = i_hi - (warp * SPW + u);
-                    r[u] = (i >= 0 && lane == 0) ? randg[roff - (pos + i)] : 0;
-                    const double *row = fw + (long long) (i >= 0 ? i : 0) * S1;
+                    const bool ok = i >= 0;
+                    r[u] = (ok && lane == 0) ? randg[roff - (pos + i)] : 0;
+                    const double *row = fw + (long long) (ok ? i : 0) * S1;
+                    const double *Fn = fsumg + (size_t) (pos + (ok ? i : 0)) * (T - 1);
+                    rk[u] = (ok && lane == 0) ? row[k] : 0.0;
 #pragma unroll
-                    for (int x = 0; x < NV; x++) {
+                    for (int x = 0; x < 2; x++) {
+                        const int a = lane + 32 * x;
+                        f[u][x] = (ok && a < T - 1) ? Fn[a] : 0.0;
+                        br[u][x] = (ok && a < ck) ? row[fk + a] : 0.0;
+                    }
+#pragma unroll
+                    for (int x = 0; x < NVH; x++) {
                         const int j = lane + 32 * x;
-                        v[u][x] = (i >= 0 && j < S1) ? row[j] : 0.0;
+                        v[u][x] = (ok && j < scnt) ? row[sbase + j] : 0.0;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < SPW; u++) {
                     const int w = warp * SPW + u;          // w-th site of the wave
                     const int i = i_hi - w;
-                    double tot = 0.0, pre = 0.0, ak = 0.0;
+                    double tot = 0.0, side = 0.0;
 #pragma unroll
-                    for (int x = 0; x < NV; x++) {
+                    for (int x = 0; x < 2; x++) {
+                        const int a = lane + 32 * x;
+                        if (a < T - 1) tot = fma(f[u][x], tmcolS[a], tot);
+                        if (a < ck) tot = fma(br[u][x], corrS[fk + a], tot);
+                    }
+#pragma unroll
+                    for (int x = 0; x < NVH; x++) {
                         const int j = lane + 32 * x;
-                        const double t = (j < S1) ? v[u][x] * transS[j] : 0.0;
-                        tot += t;
-                        if (j < k) pre += t;
-                        if (j == k) ak = t;
+                        if (j < scnt) side = fma(v[u][x], transS[sbase + j], side);
                     }
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) {
                         tot += __shfl_xor_sync(0xffffffffu, tot, d);
-                        pre += __shfl_xor_sync(0xffffffffu, pre, d);
+                        side += __shfl_xor_sync(0xffffffffu, side, d);
                     }
-                    ak = __shfl_sync(0xffffffffu, ak, k & 31);
                     if (lane == 0 && i >= 0) {
+                        const double ak = rk[u] * transS[k];
                         const double pick = (double) r[u] / (double) rand_max * tot;
-                        if (!((pre < pick) && (pre + ak >= pick)))
+                        const double hi = lower ? side + ak : tot - side;
+                        const double lo = lower ? side : hi - ak;
+                        if (!((lo < pick) && (hi >= pick)))
                             atomicOr(&sm.failmask[par], 1u << w);
                     }
                 }
@@ -392,6 +475,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             __syncthreads();
 
             // first site of the wave (highest i) that leaves k
+            TB_MARK(2);
             // three masks in rotation: the one reset here is used two waves
             // from now, i.e. after the next barrier
             const unsigned fm = sm.failmask[par];
@@ -423,10 +507,11 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             }
         }
 
+        TB_MARK(3);
         // ---- sample_hmm_posterior_step through the switch matrix (:506-519)
         if (b > 0) {
             if (tid == 0) {
-                const int n1 = mC.n1;
+                const int n1 = mC.n1();
                 const double *col1 = (const double *) (bp + BL.last);
                 const unsigned short *sws = (const unsigned short *) (bp + BL.sws + sk_sws[q]);
                 const unsigned short *swc = (const unsigned short *) (bp + BL.swc + sk_swc[q]);
@@ -451,8 +536,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                 double total = 0.0;
                 for (int x = 0; x < cn; x++)
                     total += swA[x];
-                const double pick = (double) randg[roff - (pos - 1)] /
-                    (double) rand_max * total;
+                const double pick = (double) r_sw / (double) rand_max * total;
                 // zero-weight states before the first entry win when pick == 0
                 int kk = n1 - 1;
                 double x = 0.0;
@@ -471,12 +555,18 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             k = sm.kcur;
         }
 
+        TB_MARK(4);
         // ---- the tables of block b-1 have landed; everyone is done with buffer q
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         mC = mN;
         mN = mNN;
+        TB_MARK(5);
     }
+#ifdef AWB_TB_STATS
+    if (tid == 0 && blockIdx.x == 0)
+        printf("tb cycles/block: top %lld trans %lld wave %lld flags+sample %lld switch %lld wait %lld\n", tk[0]/B, tk[1]/B, tk[2]/B, tk[3]/B, tk[4]/B, tk[5]/B);
+#endif
 }
 
 #endif // AWB_TRACEBACK_CUH
