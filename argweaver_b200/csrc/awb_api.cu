@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -144,6 +145,11 @@ struct awb_ctx {
     cudaEvent_t ev[6];
     cudaEvent_t user_ev[8];
     int sm_count;
+    // device arena kept across batches (cudaMalloc / cudaFree of a table-sized
+    // arena cost tens to hundreds of milliseconds); lent to one batch at a time
+    char *arena_cache;
+    size_t arena_cap;
+    bool arena_busy;
 };
 
 struct awb_batch {
@@ -183,6 +189,9 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->arena_cache = NULL;
+    ctx->arena_cap = 0;
+    ctx->arena_busy = false;
     CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
@@ -202,6 +211,7 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
     for (int i = 0; i < 8; i++)
         cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->arena_cache) cudaFree(ctx->arena_cache);
     delete ctx;
 }
 
@@ -234,9 +244,14 @@ extern "C" void awb_batch_destroy(awb_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    if (b->arena) cudaFree(b->arena);
-    if (b->d_chains) cudaFree(b->d_chains);
-    if (b->d_err) cudaFree(b->d_err);
+    if (b->arena) {
+        // work queued on the stream may still touch the arena
+        cudaStreamSynchronize(b->ctx->stream);
+        if (b->arena == b->ctx->arena_cache)
+            b->ctx->arena_busy = false;
+        else
+            cudaFree(b->arena);
+    }
     delete b;
 }
 
@@ -277,6 +292,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->uploaded = b->setup_done = b->forward_done = false;
     b->rand_uploaded = false;
 
+    const auto t_create0 = std::chrono::steady_clock::now();
     // host layout of every problem (integer work), one host thread per problem
     {
         std::vector<std::string> errs(nproblems);
@@ -319,21 +335,53 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
     }
+    const auto t_create1 = std::chrono::steady_clock::now();
+    // chain records and the error word live at the tail of the arena
+    const size_t chains_off = total;
+    total += awb_align(sizeof(AwbChain) * nproblems);
+    const size_t err_off = total;
+    total += awb_align(sizeof(int));
     b->arena_bytes = total;
-    cudaError_t e = cudaMalloc((void **) &b->arena, total);
-    if (e != cudaSuccess) {
-        std::string msg = std::string("cudaMalloc of ") + std::to_string(total) +
-            " bytes failed: " + cudaGetErrorString(e);
-        delete b;
-        return fail(msg);
+    if (!ctx->arena_busy) {
+        if (ctx->arena_cap < total) {
+            if (ctx->arena_cache) cudaFree(ctx->arena_cache);
+            ctx->arena_cache = NULL;
+            ctx->arena_cap = 0;
+            cudaError_t e = cudaMalloc((void **) &ctx->arena_cache, total);
+            if (e != cudaSuccess) {
+                std::string msg = std::string("cudaMalloc of ") +
+                    std::to_string(total) + " bytes failed: " + cudaGetErrorString(e);
+                delete b;
+                return fail(msg);
+            }
+            ctx->arena_cap = total;
+        }
+        b->arena = ctx->arena_cache;
+        ctx->arena_busy = true;
+    } else {
+        cudaError_t e = cudaMalloc((void **) &b->arena, total);
+        if (e != cudaSuccess) {
+            std::string msg = std::string("cudaMalloc of ") + std::to_string(total) +
+                " bytes failed: " + cudaGetErrorString(e);
+            b->arena = NULL;
+            delete b;
+            return fail(msg);
+        }
     }
-    CUDA_OK(cudaMalloc((void **) &b->d_chains, sizeof(AwbChain) * nproblems));
-    CUDA_OK(cudaMalloc((void **) &b->d_err, sizeof(int)));
+    b->d_chains = (AwbChain *) (b->arena + chains_off);
+    b->d_err = (int *) (b->arena + err_off);
     for (int c = 0; c < nproblems; c++) {
         awb_layout_bind(b->L[c], b->P[c], b->arena + b->arena_off[c],
                         b->h_chains[c]);
         // the tmatrix2 band is only read by the generic forward kernel
         b->h_chains[c].need_band = batch_fast_path(b) ? 0 : 1;
+    }
+    if (getenv("AWB_VERBOSE")) {
+        const auto t_create2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "awb_batch_create: layout %.1f ms, arena (%.2f GB) + bind %.1f ms\n",
+                std::chrono::duration<double, std::milli>(t_create1 - t_create0).count(),
+                total / 1e9,
+                std::chrono::duration<double, std::milli>(t_create2 - t_create1).count());
     }
     *out = b;
     return 0;
@@ -351,6 +399,10 @@ extern "C" int awb_batch_upload(awb_batch *b)
     for (int c = 0; c < b->C; c++) {
         const AwbLayout &L = b->L[c];
         char *base = b->arena + b->arena_off[c];
+        // debug arrays are compared entry by entry, including the entries no
+        // kernel writes (block 0 has no switch matrix): start them from zero
+        if (L.keep_debug)
+            CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));
         for (size_t i = 0; i < L.copies.size(); i++)
             CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
                                     L.copies[i].bytes, cudaMemcpyHostToDevice,

@@ -172,6 +172,10 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     }
     std::vector<short> &bcnt = awb_pack_scratch();
     bcnt.assign(V, 0);
+    // tpos: thread slots of the forward kernel when the branches are laid out in
+    // node order, none straddling a warp ("next fit") -- the capacity reserved
+    // for this block's thread map; K1 packs tighter when it can (see below)
+    tpos = 0;
     for (int i = 0; i < V; i++) {
         if (ignore[i]) continue;
         const int pa = parent[i];
@@ -183,11 +187,17 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
             band += cnt * cnt;
             bcnt[i] = (short) cnt;
             if (cnt > maxcnt) maxcnt = cnt;
+            if (cnt > 32) {
+                tpos = ((tpos + 31) & ~31) + ((cnt + 31) & ~31);
+            } else {
+                if ((tpos & 31) + cnt > 32)
+                    tpos = (tpos + 31) & ~31;
+                tpos += cnt;
+            }
         }
     }
-    // thread packing of the forward kernel (the states of one branch never
-    // straddle a warp): same routine as K1
-    tpos = (S == 0) ? 1 : awb_pack_branches(bcnt.data(), V, 0, 0, 0);
+    if (S == 0)
+        tpos = 1;
     return true;
 }
 
@@ -247,7 +257,14 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             return false;
         const int NSb = (tpos + 31) & ~31;
         L.trow_off[b + 1] = L.trow_off[b] + NSb;
-        if (NSb > L.maxNS) L.maxNS = NSb;
+        if (NSb > L.maxNS) {
+            // K1 packs first-fit-decreasing when that is tighter; the exact
+            // count only matters for a block that could raise the maximum
+            const int ffd = S > 0 ?
+                awb_pack_branches(awb_pack_scratch().data(), V, 0, 0, 0) : 32;
+            const int used = ffd < NSb ? ffd : NSb;
+            if (used > L.maxNS) L.maxNS = used;
+        }
         if (S > AWB_MAXS) {
             err = "block with more than 1024 states is not supported by this build";
             return false;

@@ -373,9 +373,30 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             for (int i = 0; i < V; i++)
                 for (int t = 0; t < ncnt[i]; t++)
                     ch.st_age[row0 + nfirst[i] + t] = (signed char) age[i];
-            // the host sized the map with the same routine
-            if (awb_pack_branches(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb)
-                return 6;
+            // first-fit-decreasing packing when it fits the reserved slots (it
+            // nearly always does, and is tighter); else node order, which is
+            // what the host reserved (awb_count_states)
+            if (awb_pack_branches(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb) {
+                for (int t = 0; t < NSb; t++)
+                    ch.tmap[tr0 + t] = 0xFFFF;
+                int tpos = 0;
+                for (int i = 0; i < V; i++) {
+                    const int cnt = ncnt[i];
+                    if (cnt <= 0) continue;
+                    if (cnt > 32)
+                        tpos = (tpos + 31) & ~31;
+                    else if ((tpos & 31) + cnt > 32)
+                        tpos = (tpos + 31) & ~31;
+                    for (int t = 0; t < cnt; t++)
+                        if (tpos + t < NSb)
+                            ch.tmap[tr0 + tpos + t] = (unsigned short) (nfirst[i] + t);
+                    tpos += cnt;
+                    if (cnt > 32)
+                        tpos = (tpos + 31) & ~31;
+                }
+                if (tpos > NSb)
+                    return 6;
+            }
             for (int q = 0; q < S; q++)
                 ch.iperm[row0 + ch.perm[row0 + q]] = (unsigned short) q;
         }

@@ -424,7 +424,11 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
 #pragma unroll
                 for (int u = 0; u < SPW; u++) {
                     const int i = i_hi - (warp * SPW + u);
+#ifdef AWB_TB_NOLOAD
+                    const bool ok = false;
+#else
                     const bool ok = i >= 0;
+#endif
                     r[u] = (ok && lane == 0) ? randg[roff - (pos + i)] : 0;
                     const double *row = fw + (long long) (ok ? i : 0) * S1;
                     const double *Fn = fsumg + (size_t) (pos + (ok ? i : 0)) * (T - 1);
