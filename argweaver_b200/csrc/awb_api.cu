@@ -319,11 +319,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
             }
         }
     }
-    size_t total = 0;
     for (int c = 0; c < nproblems; c++) {
         const AwbLayout &L = b->L[c];
-        b->arena_off[c] = total;
-        total += awb_align(L.total_bytes);
         if (L.B > b->maxB) b->maxB = L.B;
         if (L.n > b->maxn) b->maxn = L.n;
         if (L.maxS > b->maxS) b->maxS = L.maxS;
@@ -334,6 +331,13 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
+    }
+    // the tmatrix2 band is only read by the generic forward kernel
+    const bool with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
+    size_t total = 0;
+    for (int c = 0; c < nproblems; c++) {
+        b->arena_off[c] = total;
+        total += awb_align(with_band ? b->L[c].total_bytes : b->L[c].bytes_before_band);
     }
     const auto t_create1 = std::chrono::steady_clock::now();
     // chain records and the error word live at the tail of the arena
@@ -373,7 +377,6 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     for (int c = 0; c < nproblems; c++) {
         awb_layout_bind(b->L[c], b->P[c], b->arena + b->arena_off[c],
                         b->h_chains[c]);
-        // the tmatrix2 band is only read by the generic forward kernel
         b->h_chains[c].need_band = batch_fast_path(b) ? 0 : 1;
     }
     if (getenv("AWB_VERBOSE")) {
@@ -402,7 +405,7 @@ extern "C" int awb_batch_upload(awb_batch *b)
         // debug arrays are compared entry by entry, including the entries no
         // kernel writes (block 0 has no switch matrix): start them from zero
         if (L.keep_debug)
-            CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));
+            CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));   // (band included)
         for (size_t i = 0; i < L.copies.size(); i++)
             CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
                                     L.copies[i].bytes, cudaMemcpyHostToDevice,

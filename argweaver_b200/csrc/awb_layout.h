@@ -38,6 +38,7 @@ struct AwbLayout {
 
     // arena
     size_t total_bytes;
+    size_t bytes_before_band;       // arena size when the band is left out
     size_t o_mappings, o_slotrow, o_trow_off, o_tmap, o_iperm, o_st_age, o_lin,
         o_sc_start, o_sc_cnt, o_sc_row;
     size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
@@ -361,7 +362,6 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_band_len, rows);
     AWB_PLACE(o_band_boff, rows * sizeof(int));
     AWB_PLACE(o_inv_emit, rows * sizeof(double));
-    AWB_PLACE(o_band, (size_t) L.band_off[B] * sizeof(double) + 8);
     AWB_PLACE(o_tmatrix, (size_t) B * T * T * sizeof(double));
     AWB_PLACE(o_tmvec, (size_t) B * AWB_TM_NVEC * T * sizeof(double));
     AWB_PLACE(o_rowstart, (size_t) B * (T + 1) * sizeof(short));
@@ -400,6 +400,10 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_logz, sizeof(double));
     AWB_PLACE(o_sink, (size_t) 1024 * sizeof(double));   // forward kernel: discarded stores
     AWB_PLACE(o_status, sizeof(int));
+    // the tmatrix2 band is only read by the generic forward kernel: it comes
+    // last so that a batch on the fast path can leave it out of its arena
+    L.bytes_before_band = off;
+    AWB_PLACE(o_band, (size_t) L.band_off[B] * sizeof(double) + 8);
 #undef AWB_PLACE
     L.total_bytes = off;
 

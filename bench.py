@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--sites", type=int, default=1000000,
                     help="compressed sites per window (L/c)")
     ap.add_argument("--ntimes", type=int, default=20)
-    ap.add_argument("--windows", type=int, default=32,
+    ap.add_argument("--windows", type=int, default=38,
                     help="independent windows per GPU")
     ap.add_argument("--cpu-sample-sites", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

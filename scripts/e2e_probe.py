@@ -16,6 +16,7 @@ def pinned(a):
 
 def main():
     W = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    print("free/total GB:", [x / 1e9 for x in torch.cuda.mem_get_info()], flush=True)
     sites = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
     keep, problems, rands = [], [], []
     for w in range(W):
