@@ -3,6 +3,7 @@
 // Kernels launched per batch (one launch each, all chains of the batch):
 //   awb_kind_kernel          thread per site     site classification
 //   awb_block_setup_kernel   thread per block    K1 (awb_setup.cuh)
+//   awb_tmatrix_kernel       thread per entry    time-by-time matrices of K1
 //   awb_switch_setup_kernel  warp per breakpoint K2 (awb_setup.cuh)
 //   awb_emit_kernel          warp per site       K3 (awb_emit.cuh), variant sites
 //   awb_forward_kernel       CTA per chain       K4 (awb_forward.cuh)
@@ -76,6 +77,16 @@ __global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
     const int rc = awb_block_setup(ch, b);
     if (rc)
         atomicMax(err, 100 + rc);
+}
+
+// time-by-time matrix of every block, one thread per entry
+__global__ void awb_tmatrix_kernel(const AwbChain *chains)
+{
+    const AwbChain &ch = chains[blockIdx.y];
+    const int b = blockIdx.x;
+    if (b >= ch.ntrees)
+        return;
+    awb_tmatrix_fill(ch, b, threadIdx.x, blockDim.x);
 }
 
 // one warp per breakpoint
@@ -434,6 +445,9 @@ extern "C" int awb_batch_setup(awb_batch *b)
     {
         dim3 grid((b->maxB + 63) / 64, b->C);
         awb_block_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
+        dim3 grid2(b->maxB, b->C);
+        awb_tmatrix_kernel<<<grid2, 128, 0, st>>>(b->d_chains);
+        b->launches++;
     }
     if (b->maxB > 1) {
         const int wpc = 8;

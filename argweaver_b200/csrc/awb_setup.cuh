@@ -48,6 +48,23 @@ AWB_HD inline double awb_state_prior(int b, const int *nbranches,
 }
 
 // Returns 0 on success, a positive code on a layout mismatch.
+// (T x T) time matrix of block b (sample_thread.cpp:212-216): entries
+// first, first+step, ... (one thread per entry on the GPU).  Needs tmvec and
+// tm_minage of the block (awb_block_setup).
+AWB_HD inline void awb_tmatrix_fill(const AwbChain &ch, int b, int first, int step)
+{
+    const int T = ch.model.ntimes;
+    if (ch.nstates[b] == 0)
+        return;
+    const double *tv = ch.tmvec + (size_t) b * AWB_TM_NVEC * T;
+    const int minage = ch.tm_minage[b];
+    double *tm = ch.tmatrix + (size_t) b * T * T;
+    for (int x = first; x < (T - 1) * (T - 1); x += step) {
+        const int a = x / (T - 1), bb = x - a * (T - 1);
+        tm[a * T + bb] = awb_get_time(tv, T, a, bb, 0, minage, false);
+    }
+}
+
 AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 {
     const AwbModel &m = ch.model;
@@ -479,41 +496,47 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         return 0;
     }
 
-    // ---- (T x T) time matrix (sample_thread.cpp:212-216)
-    double *tm = ch.tmatrix + (size_t) b * T * T;
-    for (int a = 0; a < T - 1; a++)
-        for (int bb = 0; bb < T - 1; bb++)
-            tm[a * T + bb] = awb_get_time(tv, T, a, bb, 0, minage, false);
+    // ---- (T x T) time matrix (sample_thread.cpp:212-216): on the GPU a kernel
+    //      of its own fills it, one thread per entry (awb_tmatrix_fill)
+#if !defined(__CUDA_ARCH__)
+    awb_tmatrix_fill(ch, b, 0, 1);
+#endif
 
     // ---- same-branch band (tmatrix2, sample_thread.cpp:218-225, :282-286),
     //      invariant-site emission (emit.cpp:786-819)
     double *band = ch.band + ch.band_off[b];
     int boff = 0;
     const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
+    // the invariant-site emission depends on the coalescence time and on
+    // whether the branch is the main tree's root branch: 2(T-1) values
+    double ie[2][AWB_MAXT];
+    for (int bt = 0; bt < T - 1; bt++) {
+        const double coal_time = m.times[bt];
+        const double tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime);
+        const double tl2r = tl2 + fmax(coal_time - m.times[age[maintree_root]], m.mintime);
+        ie[0][bt] = .25 * exp(-m.mu * fmax(tl2, m.mintime));
+        ie[1][bt] = .25 * exp(-m.mu * fmax(tl2r, m.mintime));
+    }
     for (int k = 0; k < S; k++) {
         const int node = ch.st_node[row0 + k];
         const int bt = ch.st_time[row0 + k];
+        ch.inv_emit[row0 + k] = ie[node == maintree_root ? 1 : 0][bt];
+        if (!ch.need_band)
+            continue;
         const int c = age[node];
         const int lo = awb_imax(c, minage);
         const int len = ncnt[node];
         ch.band_j1[row0 + k] = (unsigned short) nfirst[node];
         ch.band_len[row0 + k] = (unsigned char) len;
         ch.band_boff[row0 + k] = boff;
-        for (int i = 0; i < len && ch.need_band; i++) {
+        for (int i = 0; i < len; i++) {
             const int a = lo + i;
             band[boff + i] = awb_get_time(tv, T, a, bt, c, minage, true) -
                 awb_get_time(tv, T, a, bt, 0, minage, false);
         }
         boff += len;
-
-        const double coal_time = m.times[bt];
-        double tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime);
-        if (node == maintree_root)
-            tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime)
-                + fmax(coal_time - m.times[age[maintree_root]], m.mintime);
-        ch.inv_emit[row0 + k] = .25 * exp(-m.mu * fmax(tl2, m.mintime));
     }
-    if ((long long) boff != ch.band_off[b + 1] - ch.band_off[b])
+    if (ch.need_band && (long long) boff != ch.band_off[b + 1] - ch.band_off[b])
         return 2;
 
     // ---- prior column of the first block (sample_thread.cpp:425-429)
