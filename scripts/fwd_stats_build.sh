@@ -1,0 +1,38 @@
+#!/bin/bash
+# Builds scripts/abl/lib_fwdstats.so: the forward kernel with clock64 phase counters
+# (a copy of csrc is patched; the tree is not touched).
+set -e
+rm -rf /tmp/csrc_stats && cp -r argweaver_b200/csrc /tmp/csrc_stats
+python - <<'PY'
+p='/tmp/csrc_stats/awb_forward_fast.cuh'
+s=open(p).read()
+def rep(a,b,cnt=1):
+    global s
+    assert a in s, a[:60]
+    s=s.replace(a,b,cnt)
+rep("template <int N> struct AwbInt","__device__ __forceinline__ long long awb_clk() { long long t; asm volatile(\"mov.u64 %0, %%clock64;\" : \"=l\"(t) :: \"memory\"); return t; }\n#define FT_DECL long long ft[10] = {0,0,0,0,0,0,0,0,0,0}; long long ft_last = awb_clk();\n#define FT(i) do { long long t_ = awb_clk(); ft[i] += t_ - ft_last; ft_last = t_; } while (0)\n\ntemplate <int N> struct AwbInt")
+rep('''    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+}''','''    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+    unsigned dummy;
+    asm volatile("ld.shared.u32 %0, [%1];\\n\\tmov.u32 %0, %0;" : "=r"(dummy) : "r"(0u) : "memory");
+    if (dummy == 0x12345678u) asm volatile("trap;");
+}''')
+# norm
+rep("        int bad_site = -1;\n        for (int site = 0; site < n; site++) {\n            const double *Fs = FsS + (site & 1) * (TMAX + 2);\n            awb_bar_sync(2, NB2);","        int bad_site = -1;\n        FT_DECL\n        for (int site = 0; site < n; site++) {\n            const double *Fs = FsS + (site & 1) * (TMAX + 2);\n            FT(0);\n            awb_bar_sync(2, NB2);\n            FT(1);")
+rep("            if (site == n - 1 && lane == 0) {\n                chg.logz[0]","            if (site == n - 1 && lane == 0 && blockIdx.x == 0)\n                printf(\"norm cycles/site: work %lld bar2wait %lld\\n\", ft[0]/n, ft[1]/n);\n            if (site == n - 1 && lane == 0) {\n                chg.logz[0]")
+# scribe
+rep("        int site = 0;\n        for (int b = 0; b < B; b++) {\n            const int blen = blocklensg[b];\n            const int sc_start","        int site = 0;\n        FT_DECL\n        for (int b = 0; b < B; b++) {\n            const int blen = blocklensg[b];\n            const int sc_start")
+rep("                double *Fs = FsS + (site & 1) * (TMAX + 2);\n                awb_bar_sync(1, NB1);","                double *Fs = FsS + (site & 1) * (TMAX + 2);\n                FT(0);\n                awb_bar_sync(1, NB1);\n                FT(1);")
+rep("                double v = v0 + v1;","                double v = v0 + v1;\n                if (v == 1.2345e300) printf(\"x\");\n                FT(6);")
+rep("                if (sc_last)\n                    Fs[sc_row] = v;\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);","                if (v == 1.2345e300) printf(\"x\");\n                FT(7);\n                if (sc_last)\n                    Fs[sc_row] = v;\n                FT(2);\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);\n                FT(3);")
+rep("                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);\n                }\n                awb_bar_sync(2, NB2);","                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);\n                }\n                FT(4);\n                awb_bar_sync(2, NB2);\n                FT(5);")
+rep("        __syncthreads();                                   // final barrier\n        return;\n    }\n\n    // =====================================================================\n    // compute warps","        if ((sl == 0 || sl == 32) && blockIdx.x == 0)\n            printf(\"scribe %d cycles/site: misc %lld bar1wait %lld sum %lld scan %lld store %lld bar3wait %lld R %lld bar2wait %lld\\n\", sl, ft[0]/n, ft[1]/n, ft[6]/n, ft[7]/n, ft[2]/n, ft[3]/n, ft[4]/n, ft[5]/n);\n        __syncthreads();                                   // final barrier\n        return;\n    }\n\n    // =====================================================================\n    // compute warps")
+# compute
+rep("    unsigned iofs = 16, rofs = 0, sofs = 0;\n","    unsigned iofs = 16, rofs = 0, sofs = 0;\n    FT_DECL\n")
+rep("        awb_sts(zaddr, c);\n        awb_bar_sync(1, NB1);\n\n        // branch scans","        awb_sts(zaddr, c);\n        FT(0);\n        awb_bar_sync(1, NB1);\n        FT(1);\n\n        // branch scans")
+rep("            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        awb_bar_sync(2, NB2);","            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        FT(2);\n        awb_bar_sync(2, NB2);\n        FT(3);")
+rep("    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();","    if ((tid == 0 || tid == NS - 32) && blockIdx.x == 0)\n        printf(\"compute tid %d cycles/site: A-phase %lld bar1wait %lld B-phase %lld bar2wait %lld\\n\", tid, ft[0]/n, ft[1]/n, ft[2]/n, ft[3]/n);\n    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();")
+open(p,'w').write(s)
+PY
+mkdir -p scripts/abl
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared --fmad=true -I include -I /tmp/csrc_stats -o scripts/abl/lib_fwdstats.so /tmp/csrc_stats/awb_api.cu /tmp/csrc_stats/awb_compat.cu -lcudart 2>&1 | grep -i "error" || true
