@@ -203,7 +203,13 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     ctx->arena_cache = NULL;
     ctx->arena_cap = 0;
     ctx->arena_busy = false;
-    CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel,
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel<1>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel<2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(awb_switch_setup_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
     CUDA_OK(cudaFuncSetAttribute(awb_emit_kernel,
@@ -450,8 +456,10 @@ extern "C" int awb_batch_setup(awb_batch *b)
         b->launches++;
     }
     if (b->maxB > 1) {
-        const int wpc = 8;
+        int wpc = 8;
         const int scratch = (int) awb_sw_warp_scratch_bytes(b->maxS, b->maxT);
+        while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
+            wpc >>= 1;
         dim3 grid((b->maxB - 1 + wpc - 1) / wpc, b->C);
         awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
             b->d_chains, b->d_err, scratch);
@@ -524,11 +532,23 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
         }
 #undef AWB_LAUNCH_FAST
     } else {
-        const size_t smem = awb_fwd_smem_bytes(NS, b->maxT, b->maxband);
-        if (smem > 200 * 1024)
+        // generic kernel: up to 1024 threads, 1 or 2 states per thread; the
+        // band goes to shared memory when it fits, else it is read in place
+        const int GNS = NS < 1024 ? NS : 1024;
+        const int npt = (NS + GNS - 1) / GNS;
+        int bandcap = b->maxband;
+        size_t smem = awb_fwd_smem_bytes(npt * GNS, b->maxT, bandcap);
+        if (smem > 200 * 1024) {
+            bandcap = 0;
+            smem = awb_fwd_smem_bytes(npt * GNS, b->maxT, 0);
+        }
+        if (smem > 200 * 1024 || npt > 2)
             return fail("forward kernel needs " + std::to_string(smem) +
                         " bytes of shared memory (limit 200 KiB)");
-        awb_forward_kernel<<<b->C, NS, smem, st>>>(b->d_chains, b->maxband);
+        if (npt == 1)
+            awb_forward_kernel<1><<<b->C, GNS, smem, st>>>(b->d_chains, bandcap);
+        else
+            awb_forward_kernel<2><<<b->C, GNS, smem, st>>>(b->d_chains, bandcap);
     }
     b->launches++;
     CUDA_OK(cudaGetLastError());
@@ -574,12 +594,9 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
             b->d_chains, rand_max, maxS1, b->maxT, maxent); } while (0)
     if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
     else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
-#ifdef AWB_TB_SPW1
-    else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 1, 1);
-#else
     else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
-#endif
-    else AWB_LAUNCH_TB(32, 1, 2);
+    else if (maxS1 <= 1024) AWB_LAUNCH_TB(32, 1, 2);
+    else AWB_LAUNCH_TB(64, 1, 4);
 #undef AWB_LAUNCH_TB
     b->launches++;
     CUDA_OK(cudaGetLastError());

@@ -31,7 +31,7 @@
 
 #define AWB_MAXT 64      // == AWB_MAX_NTIMES
 #define AWB_MAXV 1024    // == AWB_MAX_NNODES
-#define AWB_MAXS 1024    // == AWB_MAX_NSTATES
+#define AWB_MAXS 2048    // == AWB_MAX_NSTATES
 
 enum { AWB_TM_D = 0, AWB_TM_E, AWB_TM_LNB, AWB_TM_LNE2, AWB_TM_LNNEGG1,
        AWB_TM_G2, AWB_TM_G3, AWB_TM_LNG4, AWB_TM_NORECOMBS, AWB_TM_NVEC };

@@ -35,23 +35,26 @@
 #include "awb_common.cuh"
 
 struct AwbFwdSmem {
-    double *colS;      // [2][NS]
+    double *colS;      // [2][NPT*NS]
     double *part;      // [NP]
     double *Fs;        // [AWB_MAXT]
     double *Rs;        // [AWB_MAXT]
     double *tmS;       // [T*T]
-    double *bandS;     // [bandcap]
+    double *bandS;     // [bandcap] (0: the band is read from global memory)
     double *scal;      // [2] inv, norm
     unsigned short *pstartS; // [AWB_MAXT+1]
 };
 
-__host__ __device__ inline size_t awb_fwd_smem_bytes(int NS, int T, int bandcap)
+// ncol = NPT * NS state slots; bandcap = 0 leaves the band in global memory
+__host__ __device__ inline size_t awb_fwd_smem_bytes(int ncol, int T, int bandcap)
 {
-    size_t nd = 2 * (size_t) NS + (AWB_MAXT + NS / 32 + 2) + AWB_MAXT + AWB_MAXT +
+    size_t nd = 2 * (size_t) ncol + (AWB_MAXT + ncol / 32 + 2) + AWB_MAXT + AWB_MAXT +
         (size_t) T * T + (size_t) bandcap + 2;
     return nd * sizeof(double) + (AWB_MAXT + 1 + 3) * sizeof(unsigned short);
 }
 
+// NPT = states per thread: thread t owns the time-major positions t, t+NS, ...
+template <int NPT>
 __global__ void __launch_bounds__(1024)
 awb_forward_kernel(const AwbChain *chains, int bandcap)
 {
@@ -60,6 +63,7 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int NS = blockDim.x;
+    const int NC = NPT * NS;
     const int T = ch.model.ntimes;
     const int n = ch.nsites;
     const int B = ch.ntrees;
@@ -67,20 +71,21 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
     extern __shared__ double smem_d[];
     AwbFwdSmem sm;
     sm.colS = smem_d;
-    sm.part = sm.colS + 2 * NS;
-    sm.Fs = sm.part + (AWB_MAXT + NS / 32 + 2);
+    sm.part = sm.colS + 2 * NC;
+    sm.Fs = sm.part + (AWB_MAXT + NC / 32 + 2);
     sm.Rs = sm.Fs + AWB_MAXT;
     sm.tmS = sm.Rs + AWB_MAXT;
     sm.bandS = sm.tmS + T * T;
     sm.scal = sm.bandS + bandcap;
     sm.pstartS = (unsigned short *) (sm.scal + 2);
 
-    // ---- per-thread description of "my" state in the current block
+    // ---- per-thread description of "my" states in the current block
     int b = 0, S = 0, S1 = 1, blen = 0, ib = 0;
     long long r0 = 0, fwbase = 0;
-    int j = 0, atime = 0, myslot = 0, seglane = 0, j1 = 0, len = 0, boff = 0;
-    bool active = false, seg_last = false;
-    double inv_e = 1.0;
+    int j[NPT], atime[NPT], myslot[NPT], seglane[NPT], j1[NPT], len[NPT], boff[NPT];
+    bool active[NPT], seg_last[NPT];
+    double inv_e[NPT];
+    const double *bandp = sm.bandS;
 
     auto load_block = [&](int bb) {
         S = ch.nstates[bb];
@@ -88,29 +93,38 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
         r0 = ch.row_off[bb];
         fwbase = ch.fw_off[bb];
         blen = ch.blocklens[bb];
-        active = tid < S1;
-        j = 0; atime = 0; myslot = 0; j1 = 0; len = 0; boff = 0; inv_e = 1.0;
-        if (active && S > 0) {
-            j = ch.perm[r0 + tid];
-            atime = ch.st_time[r0 + j];
-            myslot = ch.pslot[r0 + tid];
-            j1 = ch.band_j1[r0 + j];
-            len = ch.band_len[r0 + j];
-            boff = ch.band_boff[r0 + j];
-            inv_e = ch.inv_emit[r0 + j];
+#pragma unroll
+        for (int q = 0; q < NPT; q++) {
+            const int p = tid + q * NS;
+            active[q] = p < S1;
+            j[q] = 0; atime[q] = 0; myslot[q] = 0; j1[q] = 0; len[q] = 0; boff[q] = 0;
+            inv_e[q] = 1.0;
+            if (active[q] && S > 0) {
+                j[q] = ch.perm[r0 + p];
+                atime[q] = ch.st_time[r0 + j[q]];
+                myslot[q] = ch.pslot[r0 + p];
+                j1[q] = ch.band_j1[r0 + j[q]];
+                len[q] = ch.band_len[r0 + j[q]];
+                boff[q] = ch.band_boff[r0 + j[q]];
+                inv_e[q] = ch.inv_emit[r0 + j[q]];
+            }
+            const int key = active[q] ? myslot[q] : (0x10000 + lane);
+            const unsigned m = __match_any_sync(0xffffffffu, key);
+            seglane[q] = __ffs(m) - 1;
+            seg_last[q] = (lane == 31 - __clz(m));
         }
-        const int key = active ? myslot : (0x10000 + lane);
-        const unsigned m = __match_any_sync(0xffffffffu, key);
-        seglane = __ffs(m) - 1;
-        seg_last = (lane == 31 - __clz(m));
         if (S > 0) {
             const double *tmg = ch.tmatrix + (size_t) bb * T * T;
             for (int x = tid; x < T * T; x += NS)
                 sm.tmS[x] = tmg[x];
             const double *bg = ch.band + ch.band_off[bb];
-            const int bl = (int) (ch.band_off[bb + 1] - ch.band_off[bb]);
-            for (int x = tid; x < bl; x += NS)
-                sm.bandS[x] = bg[x];
+            if (bandcap > 0) {
+                const int bl = (int) (ch.band_off[bb + 1] - ch.band_off[bb]);
+                for (int x = tid; x < bl; x += NS)
+                    sm.bandS[x] = bg[x];
+            } else {
+                bandp = bg;
+            }
             const unsigned short *pg = ch.pstart + (size_t) bb * (T + 1);
             for (int x = tid; x <= T; x += NS)
                 sm.pstartS[x] = pg[x];
@@ -118,36 +132,46 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
     };
 
     load_block(0);
-    double c = active ? ch.fw[fwbase + j] : 0.0;   // prior column (K1 or caller)
+    double c[NPT];
+#pragma unroll
+    for (int q = 0; q < NPT; q++)
+        c[q] = active[q] ? ch.fw[fwbase + j[q]] : 0.0;   // prior column (K1 or caller)
     double logz = 0.0;
     int bad_site = -1;
     int buf = 0;
     unsigned char kind_next = (n > 1) ? ch.kind[1] : 0;
 
     for (int site = 0; site < n; site++) {
-        double *col = sm.colS + buf * NS;
+        double *col = sm.colS + buf * NC;
 
         // ---- 1. publish
-        double v = active ? c : 0.0;
-        if (active)
-            col[j] = c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane - d >= seglane)
-                v += t;
+        for (int q = 0; q < NPT; q++) {
+            double v = active[q] ? c[q] : 0.0;
+            if (active[q])
+                col[j[q]] = c[q];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane - d >= seglane[q])
+                    v += t;
+            }
+            if (active[q] && seg_last[q])
+                sm.part[myslot[q]] = v;
         }
-        if (active && seg_last)
-            sm.part[myslot] = v;
         __syncthreads();
 
         // ---- 2. band term (all warps) and the T-vector R (warp 0)
-        double W = 0.0;
-        if (active && S > 0) {
-            const double *cf = sm.bandS + boff;
-            const double *cj = col + j1;
-            for (int q = 0; q < len; q++)
-                W += cf[q] * cj[q];
+        double W[NPT];
+#pragma unroll
+        for (int q = 0; q < NPT; q++) {
+            W[q] = 0.0;
+            if (active[q] && S > 0) {
+                const double *cf = bandp + boff[q];
+                const double *cj = col + j1[q];
+                for (int x = 0; x < len[q]; x++)
+                    W[q] += cf[x] * cj[x];
+            }
         }
         if (warp == 0) {
             if (S > 0) {
@@ -186,8 +210,9 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
 
         // ---- 3. stream the finished column, form the next one
         const double inv = sm.scal[0];
-        if (site > 0 && tid < S1)
-            ch.fw[fwbase + (long long) ib * S1 + tid] = col[tid] * inv;
+        if (site > 0)
+            for (int x = tid; x < S1; x += NS)
+                ch.fw[fwbase + (long long) ib * S1 + x] = col[x] * inv;
         if (tid == NS - 32) {
             const double nrm = sm.scal[1];
             logz += log(nrm);
@@ -206,33 +231,39 @@ awb_forward_kernel(const AwbChain *chains, int bandcap)
             b++;
             ib = 0;
             load_block(b);
-            double sum = 0.0;
-            if (active) {
-                const int st = ch.sw_start[r0 + j];
-                const int cn = ch.sw_cnt[r0 + j];
-                const unsigned short *es = ch.sw_src + ch.ent_off[b] + st;
-                const double *ep = ch.sw_prob + ch.ent_off[b] + st;
-                for (int q = 0; q < cn; q++)
-                    sum += col[es[q]] * ep[q];
+#pragma unroll
+            for (int q = 0; q < NPT; q++) {
+                double sum = 0.0;
+                if (active[q]) {
+                    const int st = ch.sw_start[r0 + j[q]];
+                    const int cn = ch.sw_cnt[r0 + j[q]];
+                    const unsigned short *es = ch.sw_src + ch.ent_off[b] + st;
+                    const double *ep = ch.sw_prob + ch.ent_off[b] + st;
+                    for (int x = 0; x < cn; x++)
+                        sum += col[es[x]] * ep[x];
+                }
+                double e = 1.0;
+                if (active[q] && S > 0) {
+                    if (kd == AWB_SITE_VARIANT)
+                        e = ch.fw[fwbase + j[q]];
+                    else if (kd == AWB_SITE_INVARIANT)
+                        e = inv_e[q];
+                }
+                c[q] = sum * e * inv;
             }
-            double e = 1.0;
-            if (active && S > 0) {
-                if (kd == AWB_SITE_VARIANT)
-                    e = ch.fw[fwbase + j];
-                else if (kd == AWB_SITE_INVARIANT)
-                    e = inv_e;
-            }
-            c = sum * e * inv;
         } else {
-            double e = 1.0;
-            if (active && S > 0) {
-                if (kd == AWB_SITE_VARIANT)
-                    e = ch.fw[fwbase + (long long) ib * S + j];
-                else if (kd == AWB_SITE_INVARIANT)
-                    e = inv_e;
-                c = (sm.Rs[atime] + W) * e * inv;
-            } else {
-                c = c * inv;
+#pragma unroll
+            for (int q = 0; q < NPT; q++) {
+                double e = 1.0;
+                if (active[q] && S > 0) {
+                    if (kd == AWB_SITE_VARIANT)
+                        e = ch.fw[fwbase + (long long) ib * S + j[q]];
+                    else if (kd == AWB_SITE_INVARIANT)
+                        e = inv_e[q];
+                    c[q] = (sm.Rs[atime[q]] + W[q]) * e * inv;
+                } else {
+                    c[q] = c[q] * inv;
+                }
             }
         }
         buf ^= 1;

@@ -267,7 +267,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             if (used > L.maxNS) L.maxNS = used;
         }
         if (S > AWB_MAXS) {
-            err = "block with more than 1024 states is not supported by this build";
+            err = "block with more than 2048 states is not supported by this build";
             return false;
         }
         if (p.blocklens[b] < 1) { err = "blocklen must be >= 1"; return false; }

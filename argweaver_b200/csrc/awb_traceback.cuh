@@ -227,6 +227,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const int warp = tid >> 5;
     const int NW = AWB_TB_THREADS >> 5;
     constexpr int NVH = (NV + 1) / 2;      // the shorter side of a row, per lane
+    constexpr int NVC = NVH < 16 ? NVH : 16;   // ... read NVC values per lane and pass
     const int T = ch.model.ntimes;
     const int n = ch.nsites;
     const int B = ch.ntrees;
@@ -420,15 +421,12 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                 const int scnt = lower ? k : S1 - 1 - k;
                 const int sbase = lower ? 0 : k + 1;
                 int r[SPW];
-                double v[SPW][NVH], f[SPW][2], br[SPW][2], rk[SPW];
+                double v[SPW][NVC], f[SPW][2], br[SPW][2], rk[SPW];
+                double tot[SPW], side[SPW];
 #pragma unroll
                 for (int u = 0; u < SPW; u++) {
                     const int i = i_hi - (warp * SPW + u);
-#ifdef AWB_TB_NOLOAD
-                    const bool ok = false;
-#else
                     const bool ok = i >= 0;
-#endif
                     r[u] = (ok && lane == 0) ? randg[roff - (pos + i)] : 0;
                     const double *row = fw + (long long) (ok ? i : 0) * S1;
                     const double *Fn = fsumg + (size_t) (pos + (ok ? i : 0)) * (T - 1);
@@ -440,37 +438,65 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                         br[u][x] = (ok && a < ck) ? row[fk + a] : 0.0;
                     }
 #pragma unroll
-                    for (int x = 0; x < NVH; x++) {
+                    for (int x = 0; x < NVC; x++) {
                         const int j = lane + 32 * x;
                         v[u][x] = (ok && j < scnt) ? row[sbase + j] : 0.0;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < SPW; u++) {
-                    const int w = warp * SPW + u;          // w-th site of the wave
-                    const int i = i_hi - w;
-                    double tot = 0.0, side = 0.0;
+                    tot[u] = 0.0;
+                    side[u] = 0.0;
 #pragma unroll
                     for (int x = 0; x < 2; x++) {
                         const int a = lane + 32 * x;
-                        if (a < T - 1) tot = fma(f[u][x], tmcolS[a], tot);
-                        if (a < ck) tot = fma(br[u][x], corrS[fk + a], tot);
+                        if (a < T - 1) tot[u] = fma(f[u][x], tmcolS[a], tot[u]);
+                        if (a < ck) tot[u] = fma(br[u][x], corrS[fk + a], tot[u]);
                     }
 #pragma unroll
-                    for (int x = 0; x < NVH; x++) {
+                    for (int x = 0; x < NVC; x++) {
                         const int j = lane + 32 * x;
-                        if (j < scnt) side = fma(v[u][x], transS[sbase + j], side);
+                        if (j < scnt) side[u] = fma(v[u][x], transS[sbase + j], side[u]);
                     }
+                }
+                if (NVH > NVC) {
+                    // state spaces beyond 1024: the rest of the side in more passes
+                    for (int base = 32 * NVC; base < scnt; base += 32 * NVC) {
+#pragma unroll
+                        for (int u = 0; u < SPW; u++) {
+                            const int i = i_hi - (warp * SPW + u);
+                            const double *row = fw + (long long) (i >= 0 ? i : 0) * S1;
+#pragma unroll
+                            for (int x = 0; x < NVC; x++) {
+                                const int j = base + lane + 32 * x;
+                                v[u][x] = (i >= 0 && j < scnt) ? row[sbase + j] : 0.0;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < SPW; u++)
+#pragma unroll
+                            for (int x = 0; x < NVC; x++) {
+                                const int j = base + lane + 32 * x;
+                                if (j < scnt)
+                                    side[u] = fma(v[u][x], transS[sbase + j], side[u]);
+                            }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SPW; u++) {
+                    const int w = warp * SPW + u;          // w-th site of the wave
+                    const int i = i_hi - w;
+                    double tt = tot[u], ss = side[u];
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) {
-                        tot += __shfl_xor_sync(0xffffffffu, tot, d);
-                        side += __shfl_xor_sync(0xffffffffu, side, d);
+                        tt += __shfl_xor_sync(0xffffffffu, tt, d);
+                        ss += __shfl_xor_sync(0xffffffffu, ss, d);
                     }
                     if (lane == 0 && i >= 0) {
                         const double ak = rk[u] * transS[k];
-                        const double pick = (double) r[u] / (double) rand_max * tot;
-                        const double hi = lower ? side + ak : tot - side;
-                        const double lo = lower ? side : hi - ak;
+                        const double pick = (double) r[u] / (double) rand_max * tt;
+                        const double hi = lower ? ss + ak : tt - ss;
+                        const double lo = lower ? ss : hi - ak;
                         if (!((lo < pick) && (hi >= pick)))
                             atomicOr(&sm.failmask[par], 1u << w);
                     }

@@ -37,7 +37,7 @@ extern "C" {
 
 #define AWB_MAX_NTIMES 64     /* model time points supported by this build */
 #define AWB_MAX_NNODES 1024   /* nodes per local tree (k <= 512 sequences)  */
-#define AWB_MAX_NSTATES 1024  /* HMM states per block (one CUDA thread each) */
+#define AWB_MAX_NSTATES 2048  /* HMM states per block                        */
 
 /* One thread-sampling problem ("chain"): the flattened arguments of
  * arghmm_forward_alg(trees, model, sequences, matrix_iter, ...) and

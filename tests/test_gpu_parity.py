@@ -78,13 +78,24 @@ def test_golden_vectors(path):
 CASES = [(8, 2000, 20, False, 1), (8, 2000, 20, True, 2), (20, 5000, 20, False, 3),
          (20, 5000, 20, True, 4), (12, 3000, 30, False, 5), (6, 1500, 10, True, 6),
          (2, 500, 20, False, 7), (3, 500, 20, True, 8), (40, 3000, 40, False, 9),
-         (50, 4000, 20, True, 10)]
+         (50, 4000, 20, True, 10),
+         # BASELINE config 4 shape: > 1024 states per block (two states per thread
+         # in the generic forward kernel, multi-pass rows in the traceback)
+         (100, 1500, 40, False, 11), (100, 1200, 40, True, 12)]
 
 
 @pytest.mark.parametrize("k,n,T,internal,seed", CASES)
 def test_generated_problems(k, n, T, internal, seed, libc_rand):
     d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
     compare_with_oracle(d, libc_rand(100 + seed, n))
+
+
+def test_generic_forward_kernel_forced(libc_rand, monkeypatch):
+    """The generic kernel (normally only used for state spaces the fast kernel
+    does not cover) on a shape the fast kernel would take."""
+    monkeypatch.setenv("AWB_FORCE_GENERIC", "1")
+    d = sim.simulate_problem(20, 3000, ntimes=20, seed=21, internal=True)
+    compare_with_oracle(d, libc_rand(121, 3000))
 
 
 def test_masked_and_missing_data(libc_rand):
