@@ -169,3 +169,70 @@ def test_full_size_properties(libc_rand):
     assert np.array_equal(b.fw(), fw)
     assert np.array_equal(b.path(), p1)
     b.close()
+
+
+def _truncate(d, nblocks=None, blocklens=None):
+    """The first blocks of a generated problem, optionally with new block lengths."""
+    q = dict(d)
+    B = len(d["blocklens"]) if nblocks is None else nblocks
+    for key in ("ptrees", "ages", "sprs", "mappings", "subtree_roots"):
+        if key in q:
+            q[key] = np.ascontiguousarray(d[key][:B])
+    bl = np.asarray(d["blocklens"][:B] if blocklens is None else blocklens, np.int32)
+    q["blocklens"] = bl
+    return q
+
+
+@pytest.mark.parametrize("internal", [False, True])
+def test_degenerate_shapes(libc_rand, internal):
+    """ragged / minimal inputs: a one-site window, a window of one block, runs of
+    one-site blocks (every site is a breakpoint)"""
+    d = sim.simulate_problem(9, 4000, ntimes=12, seed=61, internal=internal)
+    B = len(d["blocklens"])
+    assert B >= 6
+    # one site, one block
+    compare_with_oracle(_truncate(d, 1, [1]), libc_rand(1, 1))
+    # one block, many sites
+    compare_with_oracle(_truncate(d, 1, [257]), libc_rand(2, 257))
+    # two sites in two blocks
+    compare_with_oracle(_truncate(d, 2, [1, 1]), libc_rand(3, 2))
+    # every block one site long, then a long one
+    nb = min(B, 40)
+    bl = [1] * (nb - 1) + [70]
+    compare_with_oracle(_truncate(d, nb, bl), libc_rand(4, sum(bl)))
+
+
+def test_window_inside_longer_sequences(libc_rand):
+    """start_coord > 0: the window is a slice of longer sequence rows
+    (arg-sample --region, sequences.cpp:218-247)"""
+    d = sim.simulate_problem(7, 900, ntimes=16, seed=71)
+    pad = 123
+    q = dict(d)
+    rng = np.random.default_rng(5)
+    left = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(d["seqs"].shape[0], pad))
+    q["seqs"] = np.ascontiguousarray(np.concatenate([left, d["seqs"], left], axis=1))
+    q["start_coord"] = np.int32(pad)
+    o = ol.run_oracle(d, libc_rand(6, 900))
+    b = run_gpu(q, libc_rand(6, 900))
+    assert_close(b.fw(), o["fw"], "fw", RTOL)
+    assert np.array_equal(b.path(), o["path"])
+    b.close()
+
+
+def test_errors_are_reported_not_computed(libc_rand):
+    """malformed inputs fail at the ABI with a message (no partial results)"""
+    d = sim.simulate_problem(6, 300, seed=81)
+    bad = dict(d)
+    bad["blocklens"] = d["blocklens"].copy()
+    bad["blocklens"][-1] += 50                       # blocks run past the sequences
+    with pytest.raises(api.AwbError):
+        api.Batch([bad])
+    bad = dict(d)
+    bad["ages"] = d["ages"].copy()
+    bad["ages"][0, -1] = 0                           # root younger than its children
+    with pytest.raises(api.AwbError):
+        api.Batch([bad])
+    b = api.Batch([d])
+    with pytest.raises(api.AwbError):
+        b.forward()                                  # setup has not run
+    b.close()
