@@ -86,6 +86,14 @@ __device__ __forceinline__ double awb_lds(unsigned addr)
     return v;
 }
 
+__device__ __forceinline__ double2 awb_lds2(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)
+                 : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
@@ -123,6 +131,18 @@ awb_forward_fast_kernel(const AwbChain *chains)
     }
     __syncthreads();
 
+    // 32-bit shared-memory addresses: generic pointers into dynamic shared
+    // memory make the compiler rebuild the shared window (S2UR SR_CgaCtaId)
+    // in front of every access, which is slow on the per-site critical path
+    const unsigned zT_s = (unsigned) __cvta_generic_to_shared(zT);
+    const unsigned col_s = (unsigned) __cvta_generic_to_shared(colS);
+    const unsigned Fs_s = (unsigned) __cvta_generic_to_shared(FsS);
+    const unsigned Rs_s = (unsigned) __cvta_generic_to_shared(RsS);
+    const unsigned scale_s = (unsigned) __cvta_generic_to_shared(scaleS);
+    const unsigned inv_s = (unsigned) __cvta_generic_to_shared(invS);
+    const unsigned dummy_s = (unsigned) __cvta_generic_to_shared(dummyS);
+    constexpr unsigned RSTR = (TMAX + 2) * 8;
+
     if (tid >= NB1) {
         // =================================================================
         // norm warp: waits on barrier 2 only
@@ -132,28 +152,34 @@ awb_forward_fast_kernel(const AwbChain *chains)
         double *__restrict__ fsumg = chg.fsum;
         int bad_site = -1;
         for (int site = 0; site < n; site++) {
-            const double *Fs = FsS + (site & 1) * (TMAX + 2);
+            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;
             awb_bar_sync(2, NB2);
-            double x = 0.0;
-            for (int a = lane; a < T - 1; a += 32)
-                x += Fs[a];
+            // (T - 1 <= 63: at most two rows per lane)
+            const double f0 = (lane < T - 1) ? awb_lds(Fa_s) : 0.0;
+            const double f1 = (lane + 32 < T - 1) ? awb_lds(Fa_s + 256u) : 0.0;
+            double x = f0 + f1;
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1)
                 x += __shfl_xor_sync(0xffffffffu, x, d);
             const double nrm = x;
             const double inv = 1.0 / nrm;
             if (lane == 0)
-                invS[site & 3] = inv;
+                awb_sts(inv_s + 8u * (site & 3), inv);
             // per-time sums of the column as it is stored (the traceback forms
             // its row totals from these); the prior column is stored unscaled
-            for (int a = lane; a < T - 1; a += 32)
-                fsumg[(size_t) site * (T - 1) + a] = Fs[a] * (site == 0 ? 1.0 : inv);
+            {
+                const double sc = (site == 0) ? 1.0 : inv;
+                if (lane < T - 1)
+                    fsumg[(size_t) site * (T - 1) + lane] = f0 * sc;
+                if (lane + 32 < T - 1)
+                    fsumg[(size_t) site * (T - 1) + lane + 32] = f1 * sc;
+            }
             if (!(nrm > 0.0) && bad_site < 0)
                 bad_site = site;
             if ((site & (AWB_FWD_RS - 1)) == 0) {
                 // this factor is applied when column site+3 is formed
                 if (lane == 0)
-                    scaleS[(site / AWB_FWD_RS) & 1] = inv;
+                    awb_sts(scale_s + 8u * ((site / AWB_FWD_RS) & 1), inv);
                 if (site + 3 <= n - 1) {
                     lprod *= nrm;
                     if (++nprod == 8) {
@@ -197,7 +223,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
 #pragma unroll
             for (int l = 0; l < 5; l++)
                 um[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
-            const double *z = zT + sc_start;
+            const unsigned z_s = zT_s + 8u * (unsigned) sc_start;
+            const unsigned last_q = sc_cnt > 0 ? (unsigned) (sc_cnt - 1) : 0u;
             // column `sl` of the block's time-by-time matrix: this lane turns
             // the per-time sums F into R[sl] for the compute warps
             double tmc[TMAX];
@@ -210,22 +237,27 @@ awb_forward_fast_kernel(const AwbChain *chains)
             }
 
             for (int i = 0; i < blen; i++, site++) {
-                double *Fs = FsS + (site & 1) * (TMAX + 2);
+                const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
                 awb_bar_sync(1, NB1);
-                // each lane sums its chunk of one row; the lanes of a row
+                // each lane sums its chunk of one row (loads issued eight at a
+                // time, clamped to the chunk and masked); the lanes of a row
                 // combine with a segmented scan
                 double v0 = 0.0, v1 = 0.0;
-                int q = 0;
-#if AWB_ABLATE != 2 && AWB_ABLATE != 6
-                for (; q + 2 <= sc_cnt; q += 2) {
-                    v0 += z[q];
-                    v1 += z[q + 1];
+                for (int q0 = 0; q0 < sc_cnt; q0 += 8) {
+                    double t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const unsigned q = (unsigned) (q0 + u);
+                        t[u] = awb_lds(z_s + 8u * (q < last_q ? q : last_q));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (q0 + u >= sc_cnt)
+                            t[u] = 0.0;
+                    v0 += (t[0] + t[1]) + (t[2] + t[3]);
+                    v1 += (t[4] + t[5]) + (t[6] + t[7]);
                 }
-                if (q < sc_cnt)
-                    v0 += z[q];
-#endif
                 double v = v0 + v1;
-#if AWB_ABLATE != 2 && AWB_ABLATE != 6 && AWB_ABLATE != 7
 #pragma unroll
                 for (int l = 0; l < 5; l++) {
                     if ((1 << l) <= span) {
@@ -233,16 +265,14 @@ awb_forward_fast_kernel(const AwbChain *chains)
                         v = fma(t, um[l], v);
                     }
                 }
-#endif
                 if (sc_last)
-                    Fs[sc_row] = v;
+                    awb_sts(Fp_s + 8u * (unsigned) sc_row, v);
                 awb_bar_sync(3, AWB_FWD_FSCRIBES);
                 if (i + 1 < blen && sl < T - 1) {
-                    const double2 *F2 = reinterpret_cast<const double2 *>(Fs);
                     double2 f[(TMAX + 1) / 2];
 #pragma unroll
                     for (int a = 0; a < (TMAX + 1) / 2; a++)
-                        f[a] = F2[a];
+                        f[a] = awb_lds2(Fp_s + 16u * a);
                     double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
 #pragma unroll
                     for (int a = 0; a + 3 < TMAX; a += 4) {
@@ -254,7 +284,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
 #pragma unroll
                     for (int a = TMAX - (TMAX % 4); a < TMAX; a++)
                         ra = fma(tmc[a], (a & 1) ? f[a / 2].y : f[a / 2].x, ra);
-                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);
+                    awb_sts(Rs_s + (site & 1) * RSTR + 8u * (unsigned) sl,
+                            (ra + rb) + (rc + rd));
                 }
                 awb_bar_sync(2, NB2);
             }
@@ -289,14 +320,6 @@ awb_forward_fast_kernel(const AwbChain *chains)
     const unsigned short *__restrict__ sw_srcg = chg.sw_src;
     const double *__restrict__ sw_probg = chg.sw_prob;
     double *const sink = chg.sink + tid;
-
-    const unsigned zT_s = (unsigned) __cvta_generic_to_shared(zT);
-    const unsigned col_s = (unsigned) __cvta_generic_to_shared(colS);
-    const unsigned Rs_s = (unsigned) __cvta_generic_to_shared(RsS);
-    const unsigned scale_s = (unsigned) __cvta_generic_to_shared(scaleS);
-    const unsigned inv_s = (unsigned) __cvta_generic_to_shared(invS);
-    const unsigned dummy_s = (unsigned) __cvta_generic_to_shared(dummyS);
-    constexpr unsigned RSTR = (TMAX + 2) * 8;
 
     // ---- my state in the current block
     int jj = 0, S = 0, S1 = 1, nl = 0;

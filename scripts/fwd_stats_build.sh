@@ -32,7 +32,11 @@ rep("    unsigned iofs = 16, rofs = 0, sofs = 0;\n","    unsigned iofs = 16, rof
 rep("        awb_sts(zaddr, c);\n        awb_bar_sync(1, NB1);\n\n        // branch scans","        awb_sts(zaddr, c);\n        FT(0);\n        awb_bar_sync(1, NB1);\n        FT(1);\n\n        // branch scans")
 rep("            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        awb_bar_sync(2, NB2);","            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        FT(2);\n        awb_bar_sync(2, NB2);\n        FT(3);")
 rep("    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();","    if ((tid == 0 || tid == NS - 32) && blockIdx.x == 0)\n        printf(\"compute tid %d cycles/site: A-phase %lld bar1wait %lld B-phase %lld bar2wait %lld\\n\", tid, ft[0]/n, ft[1]/n, ft[2]/n, ft[3]/n);\n    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();")
-open(p,'w').write(s)
+import os
+if os.environ.get("FWD_NOSCAN"):
+    import re
+    s=re.sub(r"site_step\(AwbInt<[^;]*>\(\)\);", "site_step(AwbInt<0>());", s)
+open(p,"w").write(s)
 PY
 mkdir -p scripts/abl
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared --fmad=true -I include -I /tmp/csrc_stats -o scripts/abl/lib_fwdstats.so /tmp/csrc_stats/awb_api.cu /tmp/csrc_stats/awb_compat.cu -lcudart 2>&1 | grep -i "error" || true
