@@ -16,6 +16,7 @@ from . import build as _build
 from .problem import AwbProblem, make_problem
 
 KEEP_DEBUG = 1
+CHECKPOINT = 2      # AWB_CHECKPOINT: segment-wise forward table (see the header)
 RAND_MAX = 2147483647
 
 _lib = None
@@ -144,7 +145,7 @@ class Batch(object):
     """A set of independent thread-sampling problems on one device
     (``awb_batch``).  ``problems`` is a list of problem dicts (see sim.py)."""
 
-    def __init__(self, problems, ctx=None, keep_debug=False):
+    def __init__(self, problems, ctx=None, keep_debug=False, checkpoint=False):
         self.ctx = ctx or default_context()
         self.n = len(problems)
         arr = (AwbProblem * self.n)()
@@ -156,7 +157,8 @@ class Batch(object):
         self._arr = arr
         self.h = C.c_void_p()
         _check(lib().awb_batch_create(self.ctx.h, self.n, arr,
-                                      KEEP_DEBUG if keep_debug else 0,
+                                      (KEEP_DEBUG if keep_debug else 0) |
+                                      (CHECKPOINT if checkpoint else 0),
                                       C.byref(self.h)))
         self.ntrees = [arr[i].ntrees for i in range(self.n)]
 

@@ -109,7 +109,7 @@ __global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err,
 
 // one warp per site; invariant / masked sites exit at once.  The warp stages
 // the block's tree arrays in shared memory before the pruning passes.
-__global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
+__global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int seg)
 {
     extern __shared__ unsigned char emit_smem[];
     const AwbChain &ch = chains[blockIdx.y];
@@ -125,11 +125,15 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
     short *sc1 = sc0 + V;
     short *sorder = sc1 + V;
     int staged = -1;
-    for (int i = blockIdx.x * wpc + warp; i < ch.nsites; i += gridDim.x * wpc) {
+    const AwbSeg g = awb_seg(ch, seg);
+    if (!g.valid)
+        return;
+    // (the first column of a table is the prior / the stored first column of
+    // the segment: no emission applied)
+    for (int i = g.site0 + 1 + blockIdx.x * wpc + warp; i < g.site0 + g.nsites;
+         i += gridDim.x * wpc) {
         if (ch.kind[i] != AWB_SITE_VARIANT)
             continue;
-        if (i == 0)
-            continue;       // the first column is the prior; no emission applied
         const int b = awb_find_block(ch, i);
         if (b != staged) {
             const size_t o = (size_t) b * V;
@@ -143,7 +147,8 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes)
             staged = b;
             __syncwarp();
         }
-        awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder);
+        awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder,
+                      g.fwbias);
         __syncwarp();
     }
 }
@@ -179,6 +184,9 @@ struct awb_batch {
     int launches;
     int64_t h2d_bytes;
     bool uploaded, setup_done, forward_done, rand_uploaded;
+    bool ckpt;                 // checkpointed forward table (AWB_CHECKPOINT)
+    int maxseg;                // most segments of any problem
+    int maxsegsites;           // most sites of any segment
 };
 
 extern "C" int awb_ctx_create(int device, awb_ctx **out)
@@ -315,11 +323,16 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         std::vector<std::string> errs(nproblems);
         std::vector<char> ok(nproblems, 0);
         const int keep = (flags & AWB_KEEP_DEBUG) ? 1 : 0;
+        // checkpointed table: segments of at most 2^21 doubles (16 MiB) per problem
+        long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 21) : 0;
+        if (seg_cap && getenv("AWB_SEG_DOUBLES"))
+            seg_cap = atoll(getenv("AWB_SEG_DOUBLES"));
         unsigned hw = std::thread::hardware_concurrency();
         const int nthreads = (int) std::min<unsigned>(hw ? hw : 1, (unsigned) nproblems);
         auto work = [&](int t) {
             for (int c = t; c < nproblems; c += nthreads)
-                ok[c] = awb_layout_build(problems[c], keep, b->L[c], errs[c]) ? 1 : 0;
+                ok[c] = awb_layout_build(problems[c], keep, b->L[c], errs[c],
+                                         seg_cap) ? 1 : 0;
         };
         if (nthreads <= 1) {
             work(0);
@@ -348,6 +361,20 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
+    }
+    b->ckpt = (flags & AWB_CHECKPOINT) != 0;
+    b->maxseg = 1;
+    b->maxsegsites = b->maxn;
+    if (b->ckpt) {
+        if (!batch_fast_path(b)) {
+            delete b;
+            return fail("AWB_CHECKPOINT needs a state space the fast forward kernel covers");
+        }
+        b->maxsegsites = 1;
+        for (int c = 0; c < nproblems; c++) {
+            if (b->L[c].nseg > b->maxseg) b->maxseg = b->L[c].nseg;
+            if (b->L[c].seg_sites > b->maxsegsites) b->maxsegsites = b->L[c].seg_sites;
+        }
     }
     // the tmatrix2 band is only read by the generic forward kernel
     const bool with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
@@ -436,6 +463,84 @@ extern "C" int awb_batch_upload(awb_batch *b)
     return 0;
 }
 
+// ---- kernel launchers (seg: segment of a checkpointed table, else 0)
+
+static int launch_emit(awb_batch *b, int seg)
+{
+    cudaStream_t st = b->ctx->stream;
+    const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
+                               (((size_t) b->maxV * 14 + 15) & ~(size_t) 15));
+    int wpc = 8;
+    while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
+        wpc >>= 1;
+    if ((size_t) wpc * scratch > 200 * 1024)
+        return fail("tree too large for the emission kernel's shared memory");
+    int gx = (b->maxsegsites + wpc - 1) / wpc;
+    const int cap = b->ctx->sm_count * 16;
+    if (gx > cap) gx = cap;
+    if (b->ckpt && gx * b->C > cap)
+        gx = (cap + b->C - 1) / b->C;
+    dim3 grid(gx, b->C);
+    awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
+        b->d_chains, scratch, seg);
+    b->launches++;
+    return 0;
+}
+
+static int launch_forward_fast(awb_batch *b, int seg, int pass)
+{
+    cudaStream_t st = b->ctx->stream;
+    const int Tm1 = b->maxT - 1;
+    const int FNS = b->maxNS;
+    const int threads = FNS + AWB_FWD_HELPERS;
+    int maxd = 1;
+    while (maxd < b->maxcnt) maxd <<= 1;
+    const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
+    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax);
+#define AWB_LAUNCH_FAST(TM, NL, MT)                                              \
+    awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(b->d_chains, \
+                                                                      seg, pass)
+    const bool lev4 = maxd <= 16;
+    if (tmax == 20) {
+        if (threads <= 384) { if (lev4) AWB_LAUNCH_FAST(20, 4, 384); else AWB_LAUNCH_FAST(20, 5, 384); }
+        else if (threads <= 512) { if (lev4) AWB_LAUNCH_FAST(20, 4, 512); else AWB_LAUNCH_FAST(20, 5, 512); }
+        else if (threads <= 640) { if (lev4) AWB_LAUNCH_FAST(20, 4, 640); else AWB_LAUNCH_FAST(20, 5, 640); }
+        else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768);
+        else AWB_LAUNCH_FAST(20, 5, 1024);
+    } else if (tmax == 40) {
+        if (threads <= 512) AWB_LAUNCH_FAST(40, 5, 512);
+        else AWB_LAUNCH_FAST(40, 5, 1024);
+    } else {
+        AWB_LAUNCH_FAST(64, 5, 384);
+    }
+#undef AWB_LAUNCH_FAST
+    b->launches++;
+    return 0;
+}
+
+static int launch_traceback(awb_batch *b, int rand_max, int seg)
+{
+    cudaStream_t st = b->ctx->stream;
+    const int maxS1 = b->maxS > 0 ? b->maxS : 1;
+    const int maxent = maxS1 + b->maxT + 4;        // capacity per block (awb_layout.h)
+    const size_t smem = awb_tb_smem_bytes(maxS1, b->maxT, maxent);
+    if (smem > 220 * 1024)
+        return fail("state space too large for the traceback kernel's shared memory");
+#define AWB_LAUNCH_TB(NV, SPW, VPT) do { \
+        CUDA_OK(cudaFuncSetAttribute(awb_traceback_kernel<NV, SPW, VPT>, \
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        awb_traceback_kernel<NV, SPW, VPT><<<b->C, AWB_TB_THREADS, smem, st>>>( \
+            b->d_chains, rand_max, maxS1, b->maxT, maxent, seg); } while (0)
+    if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
+    else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
+    else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
+    else if (maxS1 <= 1024) AWB_LAUNCH_TB(32, 1, 2);
+    else AWB_LAUNCH_TB(64, 1, 4);
+#undef AWB_LAUNCH_TB
+    b->launches++;
+    return 0;
+}
+
 extern "C" int awb_batch_setup(awb_batch *b)
 {
     if (!b->uploaded) return fail("awb_batch_setup: inputs not uploaded");
@@ -465,22 +570,13 @@ extern "C" int awb_batch_setup(awb_batch *b)
             b->d_chains, b->d_err, scratch);
         b->launches++;
     }
-    {
-        const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
-                                   (((size_t) b->maxV * 14 + 15) & ~(size_t) 15));
-        int wpc = 8;
-        while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
-            wpc >>= 1;
-        if ((size_t) wpc * scratch > 200 * 1024)
-            return fail("tree too large for the emission kernel's shared memory");
-        int gx = (b->maxn + wpc - 1) / wpc;
-        const int cap = b->ctx->sm_count * 16;
-        if (gx > cap) gx = cap;
-        dim3 grid(gx, b->C);
-        awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
-            b->d_chains, scratch);
+    // variant-site emissions go into the forward table; with a checkpointed
+    // table they are recomputed per segment, right before its forward pass
+    if (!b->ckpt) {
+        if (launch_emit(b, 0))
+            return 1;
     }
-    b->launches += 3;
+    b->launches += 2;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[1], st));
     b->setup_done = true;
@@ -503,34 +599,21 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
         }
     }
     const int NS = ((b->maxS + 31) / 32) * 32;
-    // fast path (awb_forward_fast.cuh): node-major threads + 2 scribe warps,
-    // time-matrix column in registers (T-1 <= 20 / 40 / 63); else generic
-    const int Tm1 = b->maxT - 1;
-    const int FNS = b->maxNS;
-    const int threads = FNS + AWB_FWD_HELPERS;
-    int maxd = 1;
-    while (maxd < b->maxcnt) maxd <<= 1;
-    int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
-    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax);
+    // fast path (awb_forward_fast.cuh): node-major threads + scribe warps; else
+    // the generic kernel
     const bool fast = batch_fast_path(b);
     CUDA_OK(cudaEventRecord(b->ctx->ev[2], st));
-    if (fast) {
-#define AWB_LAUNCH_FAST(TM, NL, MT)                                              \
-    awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(b->d_chains)
-        const bool lev4 = maxd <= 16;
-        if (tmax == 20) {
-            if (threads <= 384) { if (lev4) AWB_LAUNCH_FAST(20, 4, 384); else AWB_LAUNCH_FAST(20, 5, 384); }
-            else if (threads <= 512) { if (lev4) AWB_LAUNCH_FAST(20, 4, 512); else AWB_LAUNCH_FAST(20, 5, 512); }
-            else if (threads <= 640) { if (lev4) AWB_LAUNCH_FAST(20, 4, 640); else AWB_LAUNCH_FAST(20, 5, 640); }
-            else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768);
-            else AWB_LAUNCH_FAST(20, 5, 1024);
-        } else if (tmax == 40) {
-            if (threads <= 512) AWB_LAUNCH_FAST(40, 5, 512);
-            else AWB_LAUNCH_FAST(40, 5, 1024);
-        } else {
-            AWB_LAUNCH_FAST(64, 5, 384);
+    if (b->ckpt) {
+        // checkpointed table, first pass: segment by segment (emissions, then
+        // the forward pass of the segment); every segment leaves its last
+        // column -- the first of the next segment -- in ckptcol
+        for (int s = 0; s < b->maxseg; s++) {
+            if (launch_emit(b, s) || launch_forward_fast(b, s, 0))
+                return 1;
         }
-#undef AWB_LAUNCH_FAST
+    } else if (fast) {
+        if (launch_forward_fast(b, 0, 0))
+            return 1;
     } else {
         // generic kernel: up to 1024 threads, 1 or 2 states per thread; the
         // band goes to shared memory when it fits, else it is read in place
@@ -549,8 +632,8 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
             awb_forward_kernel<1><<<b->C, GNS, smem, st>>>(b->d_chains, bandcap);
         else
             awb_forward_kernel<2><<<b->C, GNS, smem, st>>>(b->d_chains, bandcap);
+        b->launches++;
     }
-    b->launches++;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[3], st));
     b->forward_done = true;
@@ -581,24 +664,20 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
                                 sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice,
                                 st));
-    const int maxS1 = b->maxS > 0 ? b->maxS : 1;
-    const int maxent = maxS1 + b->maxT + 4;        // capacity per block (awb_layout.h)
-    const size_t smem = awb_tb_smem_bytes(maxS1, b->maxT, maxent);
-    if (smem > 220 * 1024)
-        return fail("state space too large for the traceback kernel's shared memory");
     CUDA_OK(cudaEventRecord(b->ctx->ev[4], st));
-#define AWB_LAUNCH_TB(NV, SPW, VPT) do { \
-        CUDA_OK(cudaFuncSetAttribute(awb_traceback_kernel<NV, SPW, VPT>, \
-            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-        awb_traceback_kernel<NV, SPW, VPT><<<b->C, AWB_TB_THREADS, smem, st>>>( \
-            b->d_chains, rand_max, maxS1, b->maxT, maxent); } while (0)
-    if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
-    else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
-    else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
-    else if (maxS1 <= 1024) AWB_LAUNCH_TB(32, 1, 2);
-    else AWB_LAUNCH_TB(64, 1, 4);
-#undef AWB_LAUNCH_TB
-    b->launches++;
+    if (b->ckpt) {
+        // checkpointed table, second pass: from the last segment to the first,
+        // rebuild the segment's table from its stored first column, then walk
+        // back through it
+        for (int s = b->maxseg - 1; s >= 0; s--) {
+            if (launch_emit(b, s) || launch_forward_fast(b, s, 1) ||
+                launch_traceback(b, rand_max, s))
+                return 1;
+        }
+    } else {
+        if (launch_traceback(b, rand_max, 0))
+            return 1;
+    }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[5], st));
     return 0;
@@ -694,6 +773,8 @@ extern "C" int awb_batch_get_status(awb_batch *b, int i, int *first_bad_site)
 
 extern "C" int awb_batch_get_fw(awb_batch *b, int i, double *fw)
 {
+    if (b->ckpt)
+        return fail("awb_batch_get_fw: the forward table is not kept with AWB_CHECKPOINT");
     CUDA_OK(cudaSetDevice(b->ctx->device));
     CUDA_OK(cudaMemcpyAsync(fw, b->h_chains[i].fw,
                             sizeof(double) * b->L[i].fw_off[b->L[i].B],

@@ -60,6 +60,12 @@ struct AwbChain {
     int maxcnt;               // longest branch (states)
     int keep_debug;
     int need_band;            // compute the tmatrix2 band (generic forward kernel only)
+    // checkpointed table: `fw` / `fsum` hold ONE segment (blocks
+    // [seg_start[s], seg_start[s+1]) plus the first row of the next block);
+    // ckptcol[s] is the stored first column of segment s (s >= 1)
+    int ckpt, nseg;
+    const int *seg_start;     // [nseg + 1]
+    double *ckptcol;          // [nseg + 1][maxS]
 
     // ---- inputs
     const int *ptrees;        // [B][V]
@@ -149,6 +155,40 @@ AWB_HD inline double awb_logadd(double lna, double lnb)
     if (lna == -INFINITY) return lnb;
     if (lnb == -INFINITY) return lna;
     return fmax(lna, lnb) + log1p(exp(-fabs(lna - lnb)));
+}
+
+// The part of a chain one kernel launch works on.  Whole table: everything.
+// Checkpointed table (ch.ckpt): segment s = blocks [b0, b1) plus, when there is
+// a next block, its first site ("extra": it yields the first column of segment
+// s+1 and lets the traceback step through the breakpoint between the segments).
+// fw / fsum then hold that segment only; fwbias / site0 turn whole-table
+// offsets into offsets of the segment's table.
+struct AwbSeg {
+    int b0, b1, extra, site0, nsites;
+    long long fwbias;
+    bool valid;
+};
+
+AWB_HD inline AwbSeg awb_seg(const AwbChain &ch, int s)
+{
+    AwbSeg g;
+    if (!ch.ckpt) {
+        g.b0 = 0; g.b1 = ch.ntrees; g.extra = 0; g.site0 = 0; g.nsites = ch.nsites;
+        g.fwbias = 0; g.valid = true;
+        return g;
+    }
+    g.valid = s >= 0 && s < ch.nseg;
+    if (!g.valid) {
+        g.b0 = g.b1 = 0; g.extra = 0; g.site0 = 0; g.nsites = 0; g.fwbias = 0;
+        return g;
+    }
+    g.b0 = ch.seg_start[s];
+    g.b1 = ch.seg_start[s + 1];
+    g.extra = g.b1 < ch.ntrees ? 1 : 0;
+    g.site0 = ch.block_start[g.b0];
+    g.nsites = ch.block_start[g.b1] - g.site0 + g.extra;
+    g.fwbias = ch.fw_off[g.b0];
+    return g;
 }
 
 // trans.h:89-128 TransMatrix::get_time.  v points at 9 vectors of stride T.

@@ -82,7 +82,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                                  int nlanes, unsigned char *scratch,
                                  const int *parent, const int *age,
                                  const short *c0, const short *c1,
-                                 const short *order)
+                                 const short *order, long long fwbias = 0)
 {
     const AwbModel &m = ch.model;
     const int V = ch.nnodes;
@@ -192,7 +192,9 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
 
     // per-state emission (emit.cpp:778-805, calc_emit :620-645)
     const long long row0 = ch.row_off[b];
-    double *out = ch.fw + ch.fw_off[b] + (long long) (i - ch.block_start[b]) * S;
+    // (fwbias: first table offset of the resident segment, checkpointed table)
+    double *out = ch.fw + (ch.fw_off[b] - fwbias) +
+        (long long) (i - ch.block_start[b]) * S;
     for (int k = lane; k < S; k += nlanes) {
         const int node2 = ch.st_node[row0 + k];
         const int p = parent[node2];

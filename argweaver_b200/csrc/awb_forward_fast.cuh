@@ -101,7 +101,7 @@ __device__ __forceinline__ void awb_bar_sync(int id, int count)
 
 template <int TMAX, int NLEV, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1)
-awb_forward_fast_kernel(const AwbChain *chains)
+awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
 {
     const AwbChain &chg = chains[blockIdx.x];
     const int tid = threadIdx.x;
@@ -110,8 +110,13 @@ awb_forward_fast_kernel(const AwbChain *chains)
     const int NB1 = NS + AWB_FWD_FSCRIBES;           // barrier 1 participants
     const int NB2 = NS + AWB_FWD_HELPERS;            // barrier 2 participants
     const int T = chg.model.ntimes;
-    const int n = chg.nsites;
-    const int B = chg.ntrees;
+    // the blocks / sites of this launch (checkpointed table: one segment)
+    const AwbSeg g = awb_seg(chg, seg);
+    if (!g.valid)
+        return;
+    const int n = g.nsites;
+    const int bbeg = g.b0, bend = g.b1 + g.extra;
+    const int bextra = g.extra ? g.b1 : -1;     // block of which only the first site is done
     const int *__restrict__ nstatesg = chg.nstates;
     const int *__restrict__ blocklensg = chg.blocklens;
 
@@ -168,7 +173,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
             // per-time sums of the column as it is stored (the traceback forms
             // its row totals from these); the prior column is stored unscaled
             {
-                const double sc = (site == 0) ? 1.0 : inv;
+                const double sc = (site == 0 && !(chg.ckpt && seg > 0)) ? 1.0 : inv;
                 if (lane < T - 1)
                     fsumg[(size_t) site * (T - 1) + lane] = f0 * sc;
                 if (lane + 32 < T - 1)
@@ -190,8 +195,20 @@ awb_forward_fast_kernel(const AwbChain *chains)
                 }
             }
             if (site == n - 1 && lane == 0) {
-                chg.logz[0] = log(nrm) + log(lprod) + lacc;
-                chg.status[0] = bad_site;
+                // (a segment that starts from a stored, normalised column adds
+                // the log-likelihood of its own sites; the recompute pass adds
+                // nothing)
+                const double lz = log(nrm) + log(lprod) + lacc;
+                if (pass == 0) {
+                    if (seg <= 0 || !chg.ckpt) {
+                        chg.logz[0] = lz;
+                        chg.status[0] = bad_site < 0 ? -1 : g.site0 + bad_site;
+                    } else {
+                        chg.logz[0] += lz;
+                        if (bad_site >= 0 && chg.status[0] < 0)
+                            chg.status[0] = g.site0 + bad_site;
+                    }
+                }
             }
         }
         __syncthreads();                                   // final barrier
@@ -208,8 +225,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
         const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
         const unsigned char *__restrict__ sc_rowg = chg.sc_row;
         int site = 0;
-        for (int b = 0; b < B; b++) {
-            const int blen = blocklensg[b];
+        for (int b = bbeg; b < bend; b++) {
+            const int blen = (b == bextra) ? 1 : blocklensg[b];
             const int sc_start = sc_startg[(size_t) b * 64 + sl];
             const int sc_cnt = sc_cntg[(size_t) b * 64 + sl];
             const int sc_row = sc_rowg[(size_t) b * 64 + sl];
@@ -302,8 +319,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
     // addresses with ring offsets kept incrementally, a pointer ring for the
     // lagged table stores (idle lanes and not-to-be-stored columns point at a
     // per-thread sink), and a per-warp choice of the number of scan levels.
-    const unsigned char *__restrict__ kindg = chg.kind;
-    double *__restrict__ fwg = chg.fw;
+    const unsigned char *__restrict__ kindg = chg.kind + g.site0;
+    double *__restrict__ fwg = chg.fw - g.fwbias;
     const long long *__restrict__ row_offg = chg.row_off;
     const long long *__restrict__ fw_offg = chg.fw_off;
     const long long *__restrict__ trow_offg = chg.trow_off;
@@ -383,7 +400,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
         }
     };
 
-    load_compute(0);
+    load_compute(bbeg);
     // columns site, site-1, site-2 of my state; w0/w1/w2 = where they go in the
     // table (the sink for the prior column, which is kept as the caller gave it);
     // nxt = my entry of the row of the next site (emission in, column out)
@@ -391,8 +408,27 @@ awb_forward_fast_kernel(const AwbChain *chains)
     double *w0 = sink, *w1 = sink, *w2 = sink;
     double *nxt = sink;
     if (active) {
-        c = fwg[fw_offg[0] + jj];                  // prior column (K1 or caller)
-        nxt = fwg + fw_offg[0] + S1 + jj;
+        // first column: the prior (K1 or caller), kept as given.  With a
+        // checkpointed table the prior is saved aside on the first pass (the
+        // table memory is reused by the other segments) and put back for the
+        // second; a later segment starts from its stored first column, which
+        // goes into the table like any other column.
+        double *row0 = fwg + fw_offg[bbeg] + jj;
+        if (!chg.ckpt) {
+            c = *row0;
+        } else if (seg == 0) {
+            if (pass == 0) {
+                c = *row0;
+                chg.ckptcol[jj] = c;
+            } else {
+                c = chg.ckptcol[jj];
+                *row0 = c;
+            }
+        } else {
+            c = chg.ckptcol[(size_t) seg * chg.maxS + jj];
+            w0 = row0;
+        }
+        nxt = fwg + fw_offg[bbeg] + S1 + jj;
     }
     const unsigned char *kp = kindg + 2;
     unsigned kind_next = (n > 1) ? kindg[1] : 0;
@@ -442,8 +478,8 @@ awb_forward_fast_kernel(const AwbChain *chains)
         nxt = (double *) ((char *) nxt + step);
     };
 
-    for (int b = 0; b < B; b++) {
-        const int blen = blocklensg[b];
+    for (int b = bbeg; b < bend; b++) {
+        const int blen = (b == bextra) ? 1 : blocklensg[b];
 
         // ---------------- sites that are followed by a site of the same block
         switch (nl) {
@@ -476,7 +512,7 @@ awb_forward_fast_kernel(const AwbChain *chains)
             const unsigned kd = kind_next;
             kind_next = *kp++;
             awb_bar_sync(2, NB2);
-            if (b == B - 1)
+            if (b == bend - 1)
                 break;
 
             // breakpoint: gather through the switch CSR (sample_thread.cpp:345-389)
@@ -523,6 +559,9 @@ awb_forward_fast_kernel(const AwbChain *chains)
     __syncthreads();
     *w1 = c1 * invS[(n - 2) & 3];
     *w0 = c * invS[(n - 1) & 3];
+    // the column of the extra site is the first column of the next segment
+    if (g.extra && pass == 0 && active)
+        chg.ckptcol[(size_t) (seg + 1) * chg.maxS + jj] = c * invS[(n - 1) & 3];
 }
 
 #endif // AWB_FORWARD_FAST_CUH

@@ -39,6 +39,12 @@ struct AwbLayout {
     // arena
     size_t total_bytes;
     size_t bytes_before_band;       // arena size when the band is left out
+    // checkpointed table (seg_start.size() == nseg + 1, block indices)
+    int ckpt, nseg;
+    std::vector<int> seg_start;
+    long long seg_doubles;          // largest segment table (+ one extra row)
+    int seg_sites;                  // most sites in a segment (+ 1)
+    size_t o_seg_start, o_ckptcol;
     size_t o_mappings, o_slotrow, o_trow_off, o_tmap, o_iperm, o_st_age, o_lin,
         o_sc_start, o_sc_cnt, o_sc_row;
     size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
@@ -205,8 +211,12 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
 inline size_t awb_align(size_t x) { return (x + 255) & ~(size_t) 255; }
 
 // Build the layout.  Returns false and sets err on invalid input.
+// seg_cap > 0 selects the checkpointed table: the forward table is not kept
+// whole; the window is cut into segments of whole blocks whose tables hold at
+// most seg_cap doubles, and only one segment's table is resident at a time
+// (see awb_api.cu).
 inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
-                             std::string &err)
+                             std::string &err, long long seg_cap = 0)
 {
     const int B = p.ntrees, V = p.nnodes, T = p.ntimes;
     if (T < 3 || T > AWB_MAXT) { err = "ntimes must be in [3, 64]"; return false; }
@@ -326,6 +336,31 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
         }
     }
 
+    // ---- segments of the checkpointed table
+    L.ckpt = seg_cap > 0 ? 1 : 0;
+    L.nseg = 0;
+    L.seg_start.clear();
+    L.seg_doubles = 0;
+    L.seg_sites = 0;
+    if (L.ckpt) {
+        int b0 = 0;
+        while (b0 < B) {
+            int b1 = b0 + 1;
+            // a segment holds blocks [b0, b1) plus the first row of block b1
+            while (b1 < B &&
+                   (L.fw_off[b1 + 1] - L.fw_off[b0]) + L.maxS <= seg_cap)
+                b1++;
+            L.seg_start.push_back(b0);
+            const long long d = (L.fw_off[b1] - L.fw_off[b0]) + L.maxS;
+            const int ns = (L.block_start[b1] - L.block_start[b0]) + 1;
+            if (d > L.seg_doubles) L.seg_doubles = d;
+            if (ns > L.seg_sites) L.seg_sites = ns;
+            b0 = b1;
+        }
+        L.nseg = (int) L.seg_start.size();
+        L.seg_start.push_back(B);
+    }
+
     // ---- arena
     size_t off = 0;
     const size_t rows = (size_t) L.row_off[B];
@@ -392,9 +427,19 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
         L.o_sw_recoalrow = L.o_sw_recombsrc = L.o_sw_recoalsrc = 0;
     }
     AWB_PLACE(o_kind, (size_t) L.n + 2);     // the forward kernel prefetches kind[site+2]
-    AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
-    // per-site, per-time sums of the stored forward column (traceback)
-    AWB_PLACE(o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * sizeof(double));
+    if (L.ckpt) {
+        // one segment's table and per-time sums, the first column of every
+        // segment, the segment list
+        AWB_PLACE(o_fw, (size_t) L.seg_doubles * sizeof(double));
+        AWB_PLACE(o_fsum, (size_t) L.seg_sites * (T > 1 ? T - 1 : 1) * sizeof(double));
+        AWB_PLACE(o_ckptcol, (size_t) (L.nseg + 1) * L.maxS * sizeof(double));
+        AWB_PLACE(o_seg_start, (size_t) (L.nseg + 1) * sizeof(int));
+    } else {
+        AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
+        // per-site, per-time sums of the stored forward column (traceback)
+        AWB_PLACE(o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * sizeof(double));
+        L.o_ckptcol = L.o_seg_start = 0;
+    }
     AWB_PLACE(o_path, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_rand, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_logz, sizeof(double));
@@ -409,6 +454,9 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
 
     // ---- input copies
     L.copies.clear();
+    if (L.ckpt)
+        L.copies.push_back({ L.o_seg_start, L.seg_start.data(),
+                             (size_t) (L.nseg + 1) * sizeof(int) });
     L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int) });
     L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int) });
     L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int) });
@@ -452,6 +500,10 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.maxcnt = L.maxcnt;
     ch.keep_debug = L.keep_debug;
     ch.need_band = 1;
+    ch.ckpt = L.ckpt;
+    ch.nseg = L.nseg;
+    ch.seg_start = L.ckpt ? (const int *) (base + L.o_seg_start) : 0;
+    ch.ckptcol = L.ckpt ? (double *) (base + L.o_ckptcol) : 0;
     ch.last_state = -1;
 #define AWB_P(type, field, off) ch.field = (type) (base + L.off)
     AWB_P(const int *, ptrees, o_ptrees);

@@ -64,23 +64,25 @@ struct AwbTbPtrs {
     const long long *row_off, *fw_off, *ent_off;
 };
 
-__device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb)
+// (bb below the first block of the launch, or the block of which a segment
+// only holds the first site, are handled through bmin / bextra)
+__device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb, int bmin, int bextra)
 {
     AwbTbBlk m;
-    if (bb < 0) {
+    if (bb < bmin) {
         m.S = 0; m.blen = 0; m.pos = 0; m.minage_raw = 0; m.Sprev = 0;
         m.r0 = 0; m.fwoff = 0; m.entoff = 0; m.entend = 0;
         return m;
     }
     m.S = p.nstates[bb];
-    m.blen = p.blocklens[bb];
+    m.blen = (bb == bextra) ? 1 : p.blocklens[bb];
     m.pos = p.block_start[bb];
     m.minage_raw = p.tm_minage[bb];
     m.r0 = p.row_off[bb];
     m.fwoff = p.fw_off[bb];
     m.entoff = p.ent_off[bb];
     m.entend = p.ent_off[bb + 1];
-    m.Sprev = bb > 0 ? p.nstates[bb - 1] : 0;
+    m.Sprev = bb > bmin ? p.nstates[bb - 1] : 0;
     return m;
 }
 
@@ -218,7 +220,7 @@ __device__ inline int awb_block_sample(const double (&A)[VPT], int S1, int r,
 template <int NV, int SPW, int VPT>
 __global__ void __launch_bounds__(AWB_TB_THREADS, 1)
 awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
-                     int maxent)
+                     int maxent, int seg)
 {
     extern __shared__ __align__(16) unsigned char tb_smem[];
     const AwbChain &ch = chains[blockIdx.x];
@@ -231,8 +233,14 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const int T = ch.model.ntimes;
     const int n = ch.nsites;
     const int B = ch.ntrees;
-    const double *__restrict__ fwg = ch.fw;
-    const double *__restrict__ fsumg = ch.fsum;
+    // the blocks of this launch (checkpointed table: one segment, see AwbSeg)
+    const AwbSeg g = awb_seg(ch, seg);
+    if (!g.valid)
+        return;
+    const int bmin = g.b0, btop = g.b1 - 1 + g.extra;
+    const int bextra = g.extra ? g.b1 : -1;
+    const double *__restrict__ fwg = ch.fw - g.fwbias;
+    const double *__restrict__ fsumg = ch.fsum - (size_t) g.site0 * (T - 1);
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
     const bool internal = ch.internal != 0;
@@ -265,7 +273,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     auto preload = [&](const AwbTbBlk &m, int bb, int q) {
         const unsigned base = smem_s + (unsigned) q * BL.bytes;
         sk_es[q] = sk_sws[q] = sk_swc[q] = sk_stn[q] = sk_stt[q] = sk_sta[q] = 0;
-        if (bb < 0)
+        if (bb < bmin)
             return;
         if (m.S > 0) {
             awb_tb_copy8(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
@@ -275,7 +283,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, st_timeg + m.r0, m.S);
             sk_sta[q] = awb_tb_copy_bytes(base + BL.sta, st_ageg + m.r0, m.S);
         }
-        if (bb > 0) {
+        if (bb > bmin) {
             awb_tb_copy8(base + BL.last, fwg + m.fwoff - m.n1(), m.n1());
             awb_tb_copy8(base + BL.ep, sw_probg + m.entoff, m.nent());
             sk_es[q] = awb_tb_copy_bytes(base + BL.es, sw_srcg + m.entoff, 2 * m.nent());
@@ -312,20 +320,23 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
 #define TB_MARK(i)
 #endif
 
-    AwbTbBlk mC = awb_tb_blk(P, B - 1);
-    AwbTbBlk mN = awb_tb_blk(P, B - 2);
+    AwbTbBlk mC = awb_tb_blk(P, btop, bmin, bextra);
+    AwbTbBlk mN = awb_tb_blk(P, btop - 1, bmin, bextra);
     if (tid == 0) {
         sm.failmask[0] = 0;
         sm.failmask[1] = 0;
         sm.failmask[2] = 0;
     }
-    preload(mC, B - 1, (B - 1) & 1);
+    preload(mC, btop, btop & 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- last column (sample_thread.cpp:534-539)
     {
         const int S1 = mC.S1();
-        if (ch.last_state < 0) {
+        if (g.extra) {
+            // the state at the extra site was sampled with the segment after this one
+            k = pathg[ch.block_start[g.b1]];
+        } else if (ch.last_state < 0) {
             double A[VPT];
 #pragma unroll
             for (int v = 0; v < VPT; v++) {
@@ -336,20 +347,20 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         } else {
             k = ch.last_state;
         }
-        if (tid == 0)
+        if (tid == 0 && !g.extra)
             pathg[n - 1] = k;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     int par = 0;
-    for (int b = B - 1; b >= 0; b--) {
+    for (int b = btop; b >= bmin; b--) {
         const int q = b & 1;
         // ---- one block ahead: tables of block b-1; two ahead: scalars of b-2
         preload(mN, b - 1, q ^ 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const AwbTbBlk mNN = awb_tb_blk(P, b - 2);
-        if (b > 0)
+        const AwbTbBlk mNN = awb_tb_blk(P, b - 2, bmin, bextra);
+        if (b > bmin)
             prefetch_rows(mN);
 
         const int S = mC.S, S1 = mC.S1(), blen = mC.blen, pos = mC.pos;
@@ -357,7 +368,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         const int minage = (internal && S > 0) ? mC.minage_raw : 0;
         const double *fw = fwg + mC.fwoff;
         // draw of the switch step, fetched now so that it is there when needed
-        const int r_sw = (b > 0) ? randg[roff - (pos - 1)] : 0;
+        const int r_sw = (b > bmin) ? randg[roff - (pos - 1)] : 0;
         const unsigned char *bp = bufp[q];
         const double *tvS = (const double *) (bp + BL.tv);
         const double *tmS = (const double *) (bp + BL.tm);
@@ -539,7 +550,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
 
         TB_MARK(3);
         // ---- sample_hmm_posterior_step through the switch matrix (:506-519)
-        if (b > 0) {
+        if (b > bmin) {
             if (tid == 0) {
                 const int n1 = mC.n1();
                 const double *col1 = (const double *) (bp + BL.last);

@@ -77,6 +77,12 @@ typedef struct awb_batch awb_batch;   /* a set of independent problems        */
 
 /* flags for awb_batch_create */
 #define AWB_KEEP_DEBUG 1   /* keep per-block setup arrays readable (tests)   */
+/* Do not keep the forward table: the window is cut into segments, the forward
+ * pass stores the first column of every segment, and the traceback rebuilds one
+ * segment's table at a time (the forward recursion runs twice).  Memory per
+ * problem drops from 8 B per site*state to one segment, so several times more
+ * problems fit a batch.  awb_batch_get_fw is not available in this mode. */
+#define AWB_CHECKPOINT 2
 
 const char *awb_last_error(void);
 int awb_device_count(void);

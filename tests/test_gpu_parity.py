@@ -236,3 +236,51 @@ def test_errors_are_reported_not_computed(libc_rand):
     with pytest.raises(api.AwbError):
         b.forward()                                  # setup has not run
     b.close()
+
+
+@pytest.mark.parametrize("k,n,T,internal,seed,segd",
+                         [(8, 3000, 20, False, 91, 20000), (20, 4000, 20, True, 92, 60000),
+                          (12, 1500, 30, False, 93, 4000), (50, 3000, 20, True, 94, 200000),
+                          (6, 800, 10, True, 95, 1 << 21)])
+def test_checkpointed_table(k, n, T, internal, seed, segd, libc_rand, monkeypatch):
+    """AWB_CHECKPOINT: the forward table is rebuilt segment by segment from
+    stored columns; path and logZ must equal the oracle's (and the whole-table
+    mode's)."""
+    monkeypatch.setenv("AWB_SEG_DOUBLES", str(segd))
+    d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
+    r = libc_rand(200 + seed, n)
+    o = ol.run_oracle(d, r)
+    b = api.Batch([d], checkpoint=True)
+    b.upload().setup().forward().traceback([r]).sync()
+    assert b.status() == -1
+    assert abs(b.logz() - o["logZ"]) <= RTOL * abs(o["logZ"])
+    div = first_divergence(b.path(), o["path"])
+    assert div is None, "path diverges from the oracle at site %d" % div
+    with pytest.raises(api.AwbError):
+        b.fw()
+    b.close()
+
+
+def test_checkpointed_batch_with_given_prior_and_last_state(libc_rand, monkeypatch):
+    monkeypatch.setenv("AWB_SEG_DOUBLES", "30000")
+    specs = [(8, 900, 20, False, 41), (12, 1300, 20, True, 42), (5, 300, 20, False, 43)]
+    ds = [sim.simulate_problem(k, n, ntimes=T, seed=s, internal=i)
+          for (k, n, T, i, s) in specs]
+    rs = [libc_rand(s, n) for (k, n, T, i, s) in specs]
+    full = api.Batch(ds)
+    S0 = [int(full.nstates(c)[0]) for c in range(len(ds))]
+    SL = [int(full.nstates(c)[-1]) for c in range(len(ds))]
+    priors = []
+    for s0 in S0:
+        p = np.zeros(max(s0, 1))
+        p[max(s0, 1) // 2] = 1.0
+        priors.append(p)
+    last = [max(s, 1) // 3 for s in SL]
+    full.upload().setup().forward(priors).traceback(rs, last_states=last).sync()
+    ck = api.Batch(ds, checkpoint=True)
+    ck.upload().setup().forward(priors).traceback(rs, last_states=last).sync()
+    for c in range(len(ds)):
+        assert np.array_equal(ck.path(c), full.path(c))
+        assert abs(ck.logz(c) - full.logz(c)) <= RTOL * abs(full.logz(c))
+    full.close()
+    ck.close()
