@@ -243,8 +243,10 @@ class Batch(object):
         return dict(setup_ms=a.value, forward_ms=b.value, traceback_ms=c.value)
 
     # ---- results
-    def path(self, i=0):
-        out = np.empty(self.nsites(i), np.int32)
+    def path(self, i=0, out=None):
+        """Sampled state path of problem i; `out`: a caller buffer (e.g. pinned)."""
+        if out is None:
+            out = np.empty(self.nsites(i), np.int32)
         _check(lib().awb_batch_get_path(self.h, i, out.ctypes.data))
         return out
 

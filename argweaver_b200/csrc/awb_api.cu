@@ -109,7 +109,8 @@ __global__ void awb_switch_setup_kernel(const AwbChain *chains, int *err,
 
 // one warp per site; invariant / masked sites exit at once.  The warp stages
 // the block's tree arrays in shared memory before the pruning passes.
-__global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int seg)
+__global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int seg,
+                                int pass)
 {
     extern __shared__ unsigned char emit_smem[];
     const AwbChain &ch = chains[blockIdx.y];
@@ -127,6 +128,10 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     int staged = -1;
     const AwbSeg g = awb_seg(ch, seg);
     if (!g.valid)
+        return;
+    // second pass of a checkpointed table: the last segment's table is still
+    // resident from the first pass
+    if (pass == 1 && seg == ch.nseg - 1)
         return;
     // (the first column of a table is the prior / the stored first column of
     // the segment: no emission applied)
@@ -323,8 +328,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         std::vector<std::string> errs(nproblems);
         std::vector<char> ok(nproblems, 0);
         const int keep = (flags & AWB_KEEP_DEBUG) ? 1 : 0;
-        // checkpointed table: segments of at most 2^21 doubles (16 MiB) per problem
-        long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 21) : 0;
+        // checkpointed table: segments of at most 2^24 doubles (128 MiB) per problem
+        long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 24) : 0;
         if (seg_cap && getenv("AWB_SEG_DOUBLES"))
             seg_cap = atoll(getenv("AWB_SEG_DOUBLES"));
         unsigned hw = std::thread::hardware_concurrency();
@@ -465,7 +470,7 @@ extern "C" int awb_batch_upload(awb_batch *b)
 
 // ---- kernel launchers (seg: segment of a checkpointed table, else 0)
 
-static int launch_emit(awb_batch *b, int seg)
+static int launch_emit(awb_batch *b, int seg, int pass)
 {
     cudaStream_t st = b->ctx->stream;
     const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
@@ -482,7 +487,7 @@ static int launch_emit(awb_batch *b, int seg)
         gx = (cap + b->C - 1) / b->C;
     dim3 grid(gx, b->C);
     awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
-        b->d_chains, scratch, seg);
+        b->d_chains, scratch, seg, pass);
     b->launches++;
     return 0;
 }
@@ -573,7 +578,7 @@ extern "C" int awb_batch_setup(awb_batch *b)
     // variant-site emissions go into the forward table; with a checkpointed
     // table they are recomputed per segment, right before its forward pass
     if (!b->ckpt) {
-        if (launch_emit(b, 0))
+        if (launch_emit(b, 0, 0))
             return 1;
     }
     b->launches += 2;
@@ -608,7 +613,7 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
         // the forward pass of the segment); every segment leaves its last
         // column -- the first of the next segment -- in ckptcol
         for (int s = 0; s < b->maxseg; s++) {
-            if (launch_emit(b, s) || launch_forward_fast(b, s, 0))
+            if (launch_emit(b, s, 0) || launch_forward_fast(b, s, 0))
                 return 1;
         }
     } else if (fast) {
@@ -670,7 +675,7 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         // rebuild the segment's table from its stored first column, then walk
         // back through it
         for (int s = b->maxseg - 1; s >= 0; s--) {
-            if (launch_emit(b, s) || launch_forward_fast(b, s, 1) ||
+            if (launch_emit(b, s, 1) || launch_forward_fast(b, s, 1) ||
                 launch_traceback(b, rand_max, s))
                 return 1;
         }

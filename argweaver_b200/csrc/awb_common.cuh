@@ -60,6 +60,7 @@ struct AwbChain {
     int maxcnt;               // longest branch (states)
     int keep_debug;
     int need_band;            // compute the tmatrix2 band (generic forward kernel only)
+    int gen_mappings;         // no node mappings given: identity except the broken node
     // checkpointed table: `fw` / `fsum` hold ONE segment (blocks
     // [seg_start[s], seg_start[s+1]) plus the first row of the next block);
     // ckptcol[s] is the stored first column of segment s (s >= 1)
@@ -71,7 +72,7 @@ struct AwbChain {
     const int *ptrees;        // [B][V]
     const int *ages;          // [B][V]
     const int *sprs;          // [B][4]
-    const int *mappings;      // [B][V] previous-tree node -> this tree, -1 = broken
+    int *mappings;            // [B][V] old node -> new node (-1: broken), caller's or K1's
     const int *blocklens;     // [B]
     const int *subtree_roots; // [B] (internal) or NULL
     const int *rowidx;        // [nrows] rows of seqs compared for invariance:

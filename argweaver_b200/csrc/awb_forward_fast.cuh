@@ -114,6 +114,10 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     const AwbSeg g = awb_seg(chg, seg);
     if (!g.valid)
         return;
+    // second pass of a checkpointed table: the last segment's table is still
+    // resident from the first pass
+    if (pass == 1 && seg == chg.nseg - 1)
+        return;
     const int n = g.nsites;
     const int bbeg = g.b0, bend = g.b1 + g.extra;
     const int bextra = g.extra ? g.b1 : -1;     // block of which only the first site is done

@@ -32,7 +32,8 @@ struct AwbLayout {
     int maxcnt;                          // longest branch (states)
     int keep_debug;
     double states_sites;                 // sum blocklen * nstates
-    std::vector<int> nstates, block_start, rowidx, mappings;
+    std::vector<int> nstates, block_start, rowidx;
+    int gen_mappings;                    // no mappings given: K1 makes them
     std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off, trow_off;
     AwbModel model;
 
@@ -324,17 +325,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.has_subtree_roots = p.internal && p.subtree_roots;
 
     // node mappings: the caller's, or identity except the broken node
-    // (make_node_mapping, local_tree.h:767-776)
-    L.mappings.clear();
-    if (!p.mappings) {
-        L.mappings.resize((size_t) B * V);
-        for (int b = 0; b < B; b++) {
-            int *mp = L.mappings.data() + (size_t) b * V;
-            for (int x = 0; x < V; x++) mp[x] = x;
-            if (b > 0)
-                mp[p.ptrees[(size_t) (b - 1) * V + p.sprs[4 * (size_t) b]]] = -1;
-        }
-    }
+    // (make_node_mapping, local_tree.h:767-776), which K1 writes on the device
+    L.gen_mappings = p.mappings ? 0 : 1;
 
     // ---- segments of the checkpointed table
     L.ckpt = seg_cap > 0 ? 1 : 0;
@@ -460,8 +452,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int) });
     L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int) });
     L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int) });
-    L.copies.push_back({ L.o_mappings, p.mappings ? (const void *) p.mappings :
-                         (const void *) L.mappings.data(), BV * sizeof(int) });
+    if (p.mappings)
+        L.copies.push_back({ L.o_mappings, p.mappings, BV * sizeof(int) });
     L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int) });
     if (L.has_subtree_roots)
         L.copies.push_back({ L.o_subtree_roots, p.subtree_roots, (size_t) B * sizeof(int) });
@@ -500,6 +492,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.maxcnt = L.maxcnt;
     ch.keep_debug = L.keep_debug;
     ch.need_band = 1;
+    ch.gen_mappings = L.gen_mappings;
     ch.ckpt = L.ckpt;
     ch.nseg = L.nseg;
     ch.seg_start = L.ckpt ? (const int *) (base + L.o_seg_start) : 0;
@@ -509,7 +502,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(const int *, ptrees, o_ptrees);
     AWB_P(const int *, ages, o_ages);
     AWB_P(const int *, sprs, o_sprs);
-    AWB_P(const int *, mappings, o_mappings);
+    AWB_P(int *, mappings, o_mappings);
     AWB_P(const int *, blocklens, o_blocklens);
     ch.subtree_roots = L.has_subtree_roots ?
         (const int *) (base + L.o_subtree_roots) : 0;

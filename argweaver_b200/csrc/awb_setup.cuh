@@ -78,6 +78,15 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     short *nfirst = ch.node_first + (size_t) b * V;
     short *ncnt = ch.node_cnt + (size_t) b * V;
     const long long row0 = ch.row_off[b];
+    if (ch.gen_mappings) {
+        // make_node_mapping (local_tree.h:767-776): identity, except that the
+        // parent of the SPR's recombination node (in the previous tree) is gone
+        int *mp = ch.mappings + (size_t) b * V;
+        for (int x = 0; x < V; x++)
+            mp[x] = x;
+        if (b > 0)
+            mp[ch.ptrees[(size_t) (b - 1) * V + ch.sprs[4 * (size_t) b]]] = -1;
+    }
     const int S = ch.nstates[b];
 
     // ---- children in node-index order (local_tree.h:188-229)

@@ -59,12 +59,19 @@ def parse_args():
     ap.add_argument("--sites", type=int, default=1000000,
                     help="compressed sites per window (L/c)")
     ap.add_argument("--ntimes", type=int, default=20)
-    ap.add_argument("--windows", type=int, default=38,
-                    help="independent windows per GPU")
+    ap.add_argument("--windows", type=int, default=0,
+                    help="independent windows per GPU (default: 148 with the "
+                         "checkpointed table, 38 with the whole table)")
+    ap.add_argument("--checkpoint", type=int, default=1,
+                    help="1: AWB_CHECKPOINT (forward table kept one segment at a "
+                         "time, forward recursion run twice); 0: whole table")
     ap.add_argument("--cpu-sample-sites", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.windows <= 0:
+        a.windows = 148 if a.checkpoint else 38
+    return a
 
 
 def workload_name(a):
@@ -261,7 +268,10 @@ def bench_b200(a, rank, world, local_rank):
         seed = 1000 + shard.my_windows(W * world, rank, world)[w]
         d = sim.simulate_problem(a.k, a.sites, ntimes=a.ntimes, seed=seed,
                                  internal=(w % 2 == 1))
-        for key in ("seqs", "ptrees", "ages", "mappings", "sprs", "blocklens"):
+        # the simulator's SPRs keep node indices stable, i.e. the default node
+        # mapping (identity except the broken node): not passed, made on device
+        d.pop("mappings", None)
+        for key in ("seqs", "ptrees", "ages", "sprs", "blocklens"):
             d[key], t = pinned_like(np.ascontiguousarray(d[key]))
             keep.append(t)
         r = np.random.RandomState(seed).randint(0, 2**31 - 1, a.sites)
@@ -279,7 +289,7 @@ def bench_b200(a, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident measurement (`value`)
-    batch = api.Batch(problems, ctx)
+    batch = api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
     batch.upload().upload_rand(rands).sync()
     ss_local = batch.total_states_sites()
     fw_bytes = sum(8.0 * batch.states_sites(i) for i in range(W))
@@ -319,10 +329,16 @@ def bench_b200(a, rank, world, local_rank):
     # ---- end to end through the public API, host buffers in pinned memory
     e2e_ms_local = None
     if not a.no_e2e:
+        path_bufs = []
+        for w in range(W):
+            pb, t = pinned_like(np.zeros(a.sites, np.int32))
+            keep.append(t)
+            path_bufs.append(pb)
+
         def e2e_step():
-            b = api.Batch(problems, ctx)
+            b = api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
             b.upload().setup().forward().traceback(rands).sync()
-            paths = [b.path(i) for i in range(W)]
+            paths = [b.path(i, out=path_bufs[i]) for i in range(W)]
             b.close()
             return paths
         e2e_step()
@@ -359,8 +375,9 @@ def bench_b200(a, rank, world, local_rank):
             tj = json.load(open(os.path.join(ROOT, "profiles",
                                              "r1_forward_traffic.json")))
             c = tj["config"]
-            if (c["k"], c["ntimes"], c["sites_per_window"], c["windows_per_gpu"]) \
-                    == (a.k, a.ntimes, a.sites, W):
+            if (c["k"], c["ntimes"], c["sites_per_window"], c["windows_per_gpu"],
+                    c.get("checkpoint", 0)) == (a.k, a.ntimes, a.sites, W,
+                                                a.checkpoint):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             pass
@@ -377,6 +394,10 @@ def bench_b200(a, rank, world, local_rank):
                 "l2": "inputs larger than L2: %.1f GB of forward table per GPU "
                       "streamed per step" % (fw_bytes / 1e9),
                 "parallelism": "windows sharded across GPUs, one CTA per window",
+                "table": ("checkpointed: the forward table is kept one 128 MiB "
+                          "segment per window at a time and rebuilt for the "
+                          "traceback (forward recursion runs twice per step)"
+                          if a.checkpoint else "whole forward table resident"),
             },
             "clocks": clocks,
             "e2e": None if e2e_ms is None else {
@@ -390,7 +411,10 @@ def bench_b200(a, rank, world, local_rank):
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fw_bytes,
-                "note": "8 B per site*state (FP64 forward-table store)"},
+                "note": "8 B per site*state (FP64 forward-table store) over the "
+                        "forward stage of the step (per-segment emission + forward "
+                        "kernels); with the checkpointed table the traceback stage "
+                        "runs the same kernels once more"},
             "logz_mean": float(np.mean(logz_all)),
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -21,24 +21,30 @@ def main():
     keep, problems, rands = [], [], []
     for w in range(W):
         d = sim.simulate_problem(50, sites, ntimes=20, seed=1000 + w, internal=(w % 2 == 1))
-        for key in ("seqs", "ptrees", "ages", "mappings", "sprs", "blocklens"):
+        d.pop("mappings", None)
+        for key in ("seqs", "ptrees", "ages", "sprs", "blocklens"):
             d[key], t = pinned(d[key])
             keep.append(t)
         r, t = pinned(np.random.RandomState(w).randint(0, 2**31 - 1, sites).astype(np.int32))
         keep.append(t)
         problems.append(d)
         rands.append(r)
+    pbuf = []
+    for w in range(W):
+        pb, t = pinned(np.zeros(sites, np.int32))
+        keep.append(t)
+        pbuf.append(pb)
     ctx = api.Context(0)
     for rep in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        b = api.Batch(problems, ctx)
+        b = api.Batch(problems, ctx, checkpoint=True)
         t1 = time.perf_counter()
         b.upload().sync()
         t2 = time.perf_counter()
         b.setup().forward().traceback(rands).sync()
         t3 = time.perf_counter()
-        paths = [b.path(i) for i in range(W)]
+        paths = [b.path(i, out=pbuf[i]) for i in range(W)]
         t4 = time.perf_counter()
         b.close()
         torch.cuda.synchronize()

@@ -13,7 +13,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-    --clock-control none -k regex:awb_forward_fast -c 1 --csv \
+    --clock-control none -k regex:awb_forward_fast -c 60 --csv \
     --log-file gpurun_out/traffic_fwd_$TAG.csv \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_traffic_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--chains", type=str, default="1")
     ap.add_argument("--internal", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--checkpoint", type=int, default=0)
     a = ap.parse_args()
     for C in [int(x) for x in a.chains.split(",")]:
         t0 = time.time()
@@ -26,7 +27,7 @@ def main():
               for c in range(C)]
         tg = time.time() - t0
         t0 = time.time()
-        b = api.Batch(ds)
+        b = api.Batch(ds, checkpoint=bool(a.checkpoint))
         tc = time.time() - t0
         for rep in range(a.reps):
             t0 = time.time()
