@@ -135,10 +135,17 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
         return;
     // (the first column of a table is the prior / the stored first column of
     // the segment: no emission applied)
-    for (int i = g.site0 + 1 + blockIdx.x * wpc + warp; i < g.site0 + g.nsites;
-         i += gridDim.x * wpc) {
-        if (ch.kind[i] != AWB_SITE_VARIANT)
-            continue;
+    // a warp scans 32 sites at a time for variant ones (one coalesced load and a
+    // ballot; ~97 % of the sites are skipped) and then works through them
+    const int first = g.site0 + 1, last = g.site0 + g.nsites;
+    for (int base = first + 32 * (blockIdx.x * wpc + warp); base < last;
+         base += 32 * gridDim.x * wpc) {
+      const int mine = base + lane;
+      unsigned vm = __ballot_sync(0xffffffffu, mine < last &&
+                                  ch.kind[mine] == AWB_SITE_VARIANT);
+      while (vm) {
+        const int i = base + __ffs(vm) - 1;
+        vm &= vm - 1;
         const int b = awb_find_block(ch, i);
         if (b != staged) {
             const size_t o = (size_t) b * V;
@@ -155,6 +162,7 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
         awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder,
                       g.fwbias);
         __syncwarp();
+      }
     }
 }
 

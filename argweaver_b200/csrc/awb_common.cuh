@@ -73,6 +73,7 @@ struct AwbChain {
     const int *ages;          // [B][V]
     const int *sprs;          // [B][4]
     int *mappings;            // [B][V] old node -> new node (-1: broken), caller's or K1's
+    const double *ptab;       // [(T*T + T)][2] branch probabilities by time-index pair
     const int *blocklens;     // [B]
     const int *subtree_roots; // [B] (internal) or NULL
     const int *rowidx;        // [nrows] rows of seqs compared for invariance:

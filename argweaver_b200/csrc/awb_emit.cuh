@@ -108,9 +108,10 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         if (j != root) {
             const int pa = age[parent[j]];
             if (pa != m.removed_root_time) {
-                const double t = fmax(m.times[pa] - m.times[age[j]], m.mintime);
-                mu_j = awb_prob_branch(t, m.mu, true);
-                nomu_j = awb_prob_branch(t, m.mu, false);
+                // prob_branch(max(times[pa] - times[age[j]], mintime)), tabulated
+                const double *pt = ch.ptab + ((size_t) age[j] * T + pa) * 2;
+                mu_j = pt[0];
+                nomu_j = pt[1];
             }
         }
         mut[j] = mu_j;
@@ -188,29 +189,29 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         awb_leaf_row(ch.seqs[(size_t) ch.rowidx[ch.nrows - 1] * ch.seqlen + col],
                      in2);
     }
-    const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
+    // branch of the threaded lineage below the coalescence point: from the
+    // subtree root's time (internal) or from time 0.0 (external) up to the
+    // state's time; tabulated like every other branch probability
+    const double *tab0 = internal ?
+        ch.ptab + (size_t) age[subtree_root] * T * 2 : ch.ptab + (size_t) T * T * 2;
 
     // per-state emission (emit.cpp:778-805, calc_emit :620-645)
     const long long row0 = ch.row_off[b];
-    // (fwbias: first table offset of the resident segment, checkpointed table)
     double *out = ch.fw + (ch.fw_off[b] - fwbias) +
         (long long) (i - ch.block_start[b]) * S;
     for (int k = lane; k < S; k += nlanes) {
         const int node2 = ch.st_node[row0 + k];
         const int p = parent[node2];
-        const double time2 = m.times[age[node2]];
-        const double parent_time = (p != -1) ?
-            m.times[awb_imin(age[p], T - 1)] : 0.0;
-        const double coal_time = m.times[ch.st_time[row0 + k]];
-        const double d0 = fmax(coal_time - time1, m.mintime);
-        const double d1 = fmax(coal_time - time2, m.mintime);
-        const double d2 = fmax(parent_time - coal_time, m.mintime);
-        const double mu0 = awb_prob_branch(d0, m.mu, true);
-        const double mu1 = awb_prob_branch(d1, m.mu, true);
-        const double mu2 = awb_prob_branch(d2, m.mu, true);
-        const double no0 = awb_prob_branch(d0, m.mu, false);
-        const double no1 = awb_prob_branch(d1, m.mu, false);
-        const double no2 = awb_prob_branch(d2, m.mu, false);
+        const int bt = ch.st_time[row0 + k];
+        // d0 = coal - time1, d1 = coal - times[age[node2]], d2 = parent - coal
+        // (each floored at mintime; the root branch's d2 is not used)
+        const double *t0 = tab0 + (size_t) bt * 2;
+        const double *t1 = ch.ptab + ((size_t) age[node2] * T + bt) * 2;
+        const double *t2 = ch.ptab +
+            ((size_t) bt * T + (p != -1 ? awb_imin(age[p], T - 1) : bt)) * 2;
+        const double mu0 = t0[0], no0 = t0[1];
+        const double mu1 = t1[0], no1 = t1[1];
+        const double mu2 = t2[0], no2 = t2[1];
         const double *in_n = inner + 4 * node2;
         const double *out_n = outer + 4 * node2;
         double emit = 0.0;

@@ -34,6 +34,11 @@ struct AwbLayout {
     double states_sites;                 // sum blocklen * nstates
     std::vector<int> nstates, block_start, rowidx;
     int gen_mappings;                    // no mappings given: K1 makes them
+    // Jukes-Cantor branch probabilities by time-index pair (emission kernel):
+    // ptab[(y*T + x)*2 + {0: mutation, 1: none}] for a branch from time y up to
+    // time x, and p0tab[x*2 + ..] for a branch from time 0.0 up to time x
+    std::vector<double> ptab;
+    size_t o_ptab;
     std::vector<long long> row_off, fw_off, band_off, ent_off, sw1_off, trow_off;
     AwbModel model;
 
@@ -378,6 +383,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_iperm, rows * sizeof(short));
     AWB_PLACE(o_st_age, rows);
     AWB_PLACE(o_lin, (size_t) B * 7 * T * sizeof(double));
+    AWB_PLACE(o_ptab, (size_t) (T * T + T) * 2 * sizeof(double));
     AWB_PLACE(o_sc_start, (size_t) B * 64 * sizeof(short));
     AWB_PLACE(o_sc_cnt, (size_t) B * 64 * sizeof(short));
     AWB_PLACE(o_sc_row, (size_t) B * 64);
@@ -444,8 +450,23 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
 #undef AWB_PLACE
     L.total_bytes = off;
 
+    // ---- branch-probability table of the emission kernel (emit.cpp:86-116)
+    L.ptab.assign((size_t) (T * T + T) * 2, 0.0);
+    for (int y = 0; y < T; y++)
+        for (int x = 0; x < T; x++) {
+            const double t = fmax(p.times[x] - p.times[y], L.model.mintime);
+            L.ptab[((size_t) y * T + x) * 2 + 0] = awb_prob_branch(t, L.model.mu, true);
+            L.ptab[((size_t) y * T + x) * 2 + 1] = awb_prob_branch(t, L.model.mu, false);
+        }
+    for (int x = 0; x < T; x++) {
+        const double t = fmax(p.times[x] - 0.0, L.model.mintime);
+        L.ptab[((size_t) T * T + x) * 2 + 0] = awb_prob_branch(t, L.model.mu, true);
+        L.ptab[((size_t) T * T + x) * 2 + 1] = awb_prob_branch(t, L.model.mu, false);
+    }
+
     // ---- input copies
     L.copies.clear();
+    L.copies.push_back({ L.o_ptab, L.ptab.data(), L.ptab.size() * sizeof(double) });
     if (L.ckpt)
         L.copies.push_back({ L.o_seg_start, L.seg_start.data(),
                              (size_t) (L.nseg + 1) * sizeof(int) });
@@ -520,6 +541,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(unsigned short *, iperm, o_iperm);
     AWB_P(signed char *, st_age, o_st_age);
     AWB_P(double *, lin, o_lin);
+    AWB_P(const double *, ptab, o_ptab);
     AWB_P(unsigned short *, sc_start, o_sc_start);
     AWB_P(unsigned short *, sc_cnt, o_sc_cnt);
     AWB_P(unsigned char *, sc_row, o_sc_row);
