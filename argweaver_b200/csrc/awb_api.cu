@@ -168,9 +168,15 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
 
 // ---------------------------------------------------------------- host side
 
+#define AWB_UPLOAD_GROUPS 4
+
 struct awb_ctx {
     int device;
     cudaStream_t stream;
+    // inputs go up on their own stream, in groups of problems, so that the
+    // setup kernels of one group overlap with the copies of the next
+    cudaStream_t copy_stream;
+    cudaEvent_t up_ev[AWB_UPLOAD_GROUPS], order_ev;
     cudaEvent_t ev[6];
     cudaEvent_t user_ev[8];
     int sm_count;
@@ -214,6 +220,10 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     awb_ctx *ctx = new awb_ctx;
     ctx->device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
+        CUDA_OK(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
     for (int i = 0; i < 6; i++)
         CUDA_OK(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < 8; i++)
@@ -249,6 +259,10 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
     for (int i = 0; i < 8; i++)
         cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
+        cudaEventDestroy(ctx->up_ev[i]);
+    cudaEventDestroy(ctx->order_ev);
     if (ctx->arena_cache) cudaFree(ctx->arena_cache);
     delete ctx;
 }
@@ -283,7 +297,9 @@ extern "C" void awb_batch_destroy(awb_batch *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     if (b->arena) {
-        // work queued on the stream may still touch the arena
+        // work queued on the streams may still touch the arena (and the copies
+        // read host arrays owned by this batch)
+        cudaStreamSynchronize(b->ctx->copy_stream);
         cudaStreamSynchronize(b->ctx->stream);
         if (b->arena == b->ctx->arena_cache)
             b->ctx->arena_busy = false;
@@ -452,25 +468,42 @@ extern "C" int64_t awb_batch_h2d_bytes(const awb_batch *b)
     return b->h2d_bytes + (int64_t) sizeof(AwbChain) * b->C;
 }
 
+// problems [g0, g1) of upload group g
+static void upload_group(const awb_batch *b, int g, int &g0, int &g1)
+{
+    const int ng = b->C >= 2 * AWB_UPLOAD_GROUPS ? AWB_UPLOAD_GROUPS : 1;
+    if (g >= ng) { g0 = g1 = b->C; return; }
+    g0 = (int) ((long long) b->C * g / ng);
+    g1 = (int) ((long long) b->C * (g + 1) / ng);
+}
+
 extern "C" int awb_batch_upload(awb_batch *b)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
-    cudaStream_t st = b->ctx->stream;
-    for (int c = 0; c < b->C; c++) {
-        const AwbLayout &L = b->L[c];
-        char *base = b->arena + b->arena_off[c];
-        // debug arrays are compared entry by entry, including the entries no
-        // kernel writes (block 0 has no switch matrix): start them from zero
-        if (L.keep_debug)
-            CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));   // (band included)
-        for (size_t i = 0; i < L.copies.size(); i++)
-            CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
-                                    L.copies[i].bytes, cudaMemcpyHostToDevice,
-                                    st));
-    }
+    cudaStream_t st = b->ctx->copy_stream;
+    // after whatever the compute stream still has queued on this arena
+    CUDA_OK(cudaEventRecord(b->ctx->order_ev, b->ctx->stream));
+    CUDA_OK(cudaStreamWaitEvent(st, b->ctx->order_ev, 0));
     CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
                             sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+    for (int g = 0; g < AWB_UPLOAD_GROUPS; g++) {
+        int g0, g1;
+        upload_group(b, g, g0, g1);
+        for (int c = g0; c < g1; c++) {
+            const AwbLayout &L = b->L[c];
+            char *base = b->arena + b->arena_off[c];
+            // debug arrays are compared entry by entry, including the entries no
+            // kernel writes (block 0 has no switch matrix): start them from zero
+            if (L.keep_debug)
+                CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));   // (band included)
+            for (size_t i = 0; i < L.copies.size(); i++)
+                CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
+                                        L.copies[i].bytes, cudaMemcpyHostToDevice,
+                                        st));
+        }
+        CUDA_OK(cudaEventRecord(b->ctx->up_ev[g], st));
+    }
     b->uploaded = true;
     b->setup_done = b->forward_done = false;
     return 0;
@@ -561,35 +594,43 @@ extern "C" int awb_batch_setup(awb_batch *b)
     cudaStream_t st = b->ctx->stream;
     CUDA_OK(cudaEventRecord(b->ctx->ev[0], st));
 
-    {
-        dim3 grid((b->maxn + 255) / 256, b->C);
-        if (grid.x > 4096) grid.x = 4096;
-        awb_kind_kernel<<<grid, 256, 0, st>>>(b->d_chains);
+    int wpc = 8;
+    const int sw_scratch = (int) awb_sw_warp_scratch_bytes(b->maxS, b->maxT);
+    while (wpc > 1 && (size_t) wpc * sw_scratch > 160 * 1024)
+        wpc >>= 1;
+    for (int g = 0; g < AWB_UPLOAD_GROUPS; g++) {
+        int g0, g1;
+        upload_group(b, g, g0, g1);
+        if (g1 <= g0)
+            continue;
+        // the group's inputs have arrived
+        CUDA_OK(cudaStreamWaitEvent(st, b->ctx->up_ev[g], 0));
+        const AwbChain *chains = b->d_chains + g0;
+        const int Cg = g1 - g0;
+        {
+            dim3 grid((b->maxn + 255) / 256, Cg);
+            if (grid.x > 4096) grid.x = 4096;
+            awb_kind_kernel<<<grid, 256, 0, st>>>(chains);
+        }
+        {
+            dim3 grid((b->maxB + 63) / 64, Cg);
+            awb_block_setup_kernel<<<grid, 64, 0, st>>>(chains, b->d_err);
+            dim3 grid2(b->maxB, Cg);
+            awb_tmatrix_kernel<<<grid2, 128, 0, st>>>(chains);
+        }
+        if (b->maxB > 1) {
+            dim3 grid((b->maxB - 1 + wpc - 1) / wpc, Cg);
+            awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * sw_scratch, st>>>(
+                chains, b->d_err, sw_scratch);
+        }
     }
-    {
-        dim3 grid((b->maxB + 63) / 64, b->C);
-        awb_block_setup_kernel<<<grid, 64, 0, st>>>(b->d_chains, b->d_err);
-        dim3 grid2(b->maxB, b->C);
-        awb_tmatrix_kernel<<<grid2, 128, 0, st>>>(b->d_chains);
-        b->launches++;
-    }
-    if (b->maxB > 1) {
-        int wpc = 8;
-        const int scratch = (int) awb_sw_warp_scratch_bytes(b->maxS, b->maxT);
-        while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
-            wpc >>= 1;
-        dim3 grid((b->maxB - 1 + wpc - 1) / wpc, b->C);
-        awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
-            b->d_chains, b->d_err, scratch);
-        b->launches++;
-    }
+    b->launches += b->maxB > 1 ? 4 : 3;
     // variant-site emissions go into the forward table; with a checkpointed
     // table they are recomputed per segment, right before its forward pass
     if (!b->ckpt) {
         if (launch_emit(b, 0, 0))
             return 1;
     }
-    b->launches += 2;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[1], st));
     b->setup_done = true;
@@ -710,6 +751,7 @@ extern "C" int awb_batch_upload_rand(awb_batch *b, const int *const *rand_ints)
 extern "C" int awb_batch_sync(awb_batch *b)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->copy_stream));
     CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
     int err = 0;
     CUDA_OK(cudaMemcpy(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost));
