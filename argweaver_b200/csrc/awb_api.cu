@@ -125,6 +125,7 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     short *sc0 = (short *) (sage + V);
     short *sc1 = sc0 + V;
     short *sorder = sc1 + V;
+    short *slstart = sorder + V;        // [V + 2]
     int staged = -1;
     const AwbSeg g = awb_seg(ch, seg);
     if (!g.valid)
@@ -156,11 +157,13 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
                 sc1[x] = ch.child1[o + x];
                 sorder[x] = ch.order[o + x];
             }
+            for (int x = lane; x < V + 2; x += 32)
+                slstart[x] = ch.lstart[(size_t) b * (V + 2) + x];
             staged = b;
             __syncwarp();
         }
         awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder,
-                      g.fwbias);
+                      slstart, g.fwbias);
         __syncwarp();
       }
     }
@@ -515,7 +518,7 @@ static int launch_emit(awb_batch *b, int seg, int pass)
 {
     cudaStream_t st = b->ctx->stream;
     const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
-                               (((size_t) b->maxV * 14 + 15) & ~(size_t) 15));
+                               (((size_t) b->maxV * 16 + 4 + 15) & ~(size_t) 15));
     int wpc = 8;
     while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
         wpc >>= 1;

@@ -119,6 +119,8 @@ struct AwbChain {
     short *node_cnt;          // [B][V]
     short *child0, *child1;   // [B][V]
     short *order;             // [B][V] post-order (local_tree.h:274-304)
+    short *lstart;            // [B][V+2] order[] is sorted by height above the leaves:
+                              //   level L = order[lstart[L] .. lstart[L+1]); [V+1] = #levels
     short *root;              // [B]
     int *lineages;            // [B][3][T] nbranches, nrecombs, ncoals
     double *treelen;          // [B] get_treelen / get_treelen_internal

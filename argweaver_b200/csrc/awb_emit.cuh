@@ -82,7 +82,8 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                                  int nlanes, unsigned char *scratch,
                                  const int *parent, const int *age,
                                  const short *c0, const short *c1,
-                                 const short *order, long long fwbias = 0)
+                                 const short *order, const short *lstart,
+                                 long long fwbias = 0)
 {
     const AwbModel &m = ch.model;
     const int V = ch.nnodes;
@@ -123,43 +124,50 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
     }
     AWB_LANESYNC();
 
-    // inner partials, post-order (emit.cpp:175-194)
-    for (int q = 0; q < V; q++) {
-        const int j = order[q];
-        if (c0[j] != -1) {
+    // `order` is sorted by height above the leaves and lstart[] gives the level
+    // boundaries (awb_block_setup): the nodes of a level only depend on lower
+    // levels (inner pass) or higher levels (outer pass), so a level is worked
+    // through in parallel, one lane per (node, base).
+    const int nlev = lstart[V + 1];
+
+    // inner partials, children before parents (emit.cpp:175-194)
+    for (int L = 1; L < nlev; L++) {
+        const int q0 = lstart[L], cntL = lstart[L + 1] - q0;
+        for (int idx = lane; idx < 4 * cntL; idx += nlanes) {
+            const int j = order[q0 + (idx >> 2)];
+            const int a = idx & 3;
             const int k1 = c0[j], k2 = c1[j];
-            for (int a = lane; a < 4; a += nlanes) {
-                double p1 = 0.0, p2 = 0.0;
-                for (int x = 0; x < 4; x++) {
-                    if (a == x) {
-                        p1 += inner[4 * k1 + x] * nomut[k1];
-                        p2 += inner[4 * k2 + x] * nomut[k2];
-                    } else {
-                        p1 += inner[4 * k1 + x] * mut[k1];
-                        p2 += inner[4 * k2 + x] * mut[k2];
-                    }
+            double p1 = 0.0, p2 = 0.0;
+            for (int x = 0; x < 4; x++) {
+                if (a == x) {
+                    p1 += inner[4 * k1 + x] * nomut[k1];
+                    p2 += inner[4 * k2 + x] * nomut[k2];
+                } else {
+                    p1 += inner[4 * k1 + x] * mut[k1];
+                    p2 += inner[4 * k2 + x] * mut[k2];
                 }
-                inner[4 * j + a] = p1 * p2;
             }
-            AWB_LANESYNC();
+            inner[4 * j + a] = p1 * p2;
         }
+        AWB_LANESYNC();
     }
 
-    // outer partials, parents before children = reverse post-order
-    // (emit.cpp:200-296); only nodes of the main tree
-    for (int q = V - 1; q >= 0; q--) {
-        const int j = order[q];
-        bool in;
-        if (j == maintree_root) {
-            in = true;
-            for (int a = lane; a < 4; a += nlanes)
+    // outer partials, parents before children (emit.cpp:200-296); only nodes
+    // of the main tree
+    for (int L = nlev - 1; L >= 0; L--) {
+        const int q0 = lstart[L], cntL = lstart[L + 1] - q0;
+        for (int idx = lane; idx < 4 * cntL; idx += nlanes) {
+            const int j = order[q0 + (idx >> 2)];
+            const int a = idx & 3;
+            bool in;
+            if (j == maintree_root) {
+                in = true;
                 outer[4 * j + a] = 1.0;
-        } else {
-            const int p = parent[j];
-            in = (p != -1) && inmain[p];
-            if (in) {
-                const int sib = (c0[p] == j) ? c1[p] : c0[p];
-                for (int a = lane; a < 4; a += nlanes) {
+            } else {
+                const int p = parent[j];
+                in = (p != -1) && inmain[p];
+                if (in) {
+                    const int sib = (c0[p] == j) ? c1[p] : c0[p];
                     double p1 = 0.0, p2 = 0.0;
                     for (int x = 0; x < 4; x++) {
                         if (a == x) {
@@ -173,10 +181,9 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                     outer[4 * j + a] = (p != maintree_root) ? p1 * p2 : p1;
                 }
             }
+            if (a == 0)
+                inmain[j] = in ? 1 : 0;
         }
-        AWB_LANESYNC();
-        if (lane == 0)
-            inmain[j] = in ? 1 : 0;
         AWB_LANESYNC();
     }
 

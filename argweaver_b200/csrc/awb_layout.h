@@ -58,7 +58,7 @@ struct AwbLayout {
         o_ent_off, o_sw1_off, o_st_node, o_st_time, o_perm, o_pslot, o_band_j1,
         o_band_len, o_band_boff, o_inv_emit, o_band, o_tmatrix, o_tmvec,
         o_rowstart, o_pstart, o_node_first, o_node_cnt, o_child0, o_child1,
-        o_order, o_root, o_lineages, o_treelen, o_tm_minage, o_sw_start,
+        o_order, o_lstart, o_root, o_lineages, o_treelen, o_tm_minage, o_sw_start,
         o_sw_cnt, o_sw_src, o_sw_prob, o_sw_determ, o_sw_determprob,
         o_sw_recombrow, o_sw_recoalrow, o_sw_recombsrc, o_sw_recoalsrc, o_kind,
         o_fw, o_path, o_rand, o_logz, o_status, o_sink, o_fsum;
@@ -405,6 +405,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_child0, BV * sizeof(short));
     AWB_PLACE(o_child1, BV * sizeof(short));
     AWB_PLACE(o_order, BV * sizeof(short));
+    AWB_PLACE(o_lstart, (size_t) B * (V + 2) * sizeof(short));
     AWB_PLACE(o_root, (size_t) B * sizeof(short));
     AWB_PLACE(o_lineages, (size_t) B * 3 * T * sizeof(int));
     AWB_PLACE(o_treelen, (size_t) B * sizeof(double));
@@ -565,6 +566,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(short *, child0, o_child0);
     AWB_P(short *, child1, o_child1);
     AWB_P(short *, order, o_order);
+    AWB_P(short *, lstart, o_lstart);
     AWB_P(short *, root, o_root);
     AWB_P(int *, lineages, o_lineages);
     AWB_P(double *, treelen, o_treelen);

@@ -114,9 +114,14 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     }
     ch.root[b] = (short) root;
 
-    // ---- post-order (local_tree.h:274-304); ncnt doubles as the visit counter
+    // ---- post-order (local_tree.h:274-304); ncnt doubles as the visit counter.
+    //      Leaves first, a parent as soon as both children are placed: the order
+    //      is sorted by height above the leaves, and the level boundaries let
+    //      the emission kernel work through a level in parallel (nfirst holds
+    //      the heights here; it is filled with its real content further down).
     {
         short *order = ch.order + (size_t) b * V;
+        short *lstart = ch.lstart + (size_t) b * (V + 2);
         int i;
         for (i = 0; i < V; i++)
             ncnt[i] = 0;
@@ -124,18 +129,30 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             if (c0[i] != -1)
                 break;
             order[i] = (short) i;
+            nfirst[i] = 0;
         }
         int end = i;
+        int nlev = 1;
+        lstart[0] = 0;
         for (i = 0; i < V && i < end; i++) {
             const int p = parent[order[i]];
             if (p != -1) {
                 ncnt[p]++;
-                if (ncnt[p] == 2)
+                if (ncnt[p] == 2) {
+                    const int h = nfirst[order[i]] + 1;   // the later child is the higher
+                    nfirst[p] = (short) h;
+                    if (h == nlev) {
+                        lstart[nlev] = (short) end;
+                        nlev++;
+                    }
                     order[end++] = (short) p;
+                }
             }
         }
         if (end != V)
             return 5;   // not a binary tree with leaves listed first
+        lstart[nlev] = (short) V;
+        lstart[V + 1] = (short) nlev;
     }
 
     const int subtree_root = internal ? c0[root] : root;

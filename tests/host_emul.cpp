@@ -71,7 +71,8 @@ int emul_setup(void *h)
             const int b = awb_find_block(ch, i);
             const size_t o = (size_t) b * ch.nnodes;
             awb_emit_site(ch, i, b, 0, 1, e->scratch.data(), ch.ptrees + o,
-                          ch.ages + o, ch.child0 + o, ch.child1 + o, ch.order + o);
+                          ch.ages + o, ch.child0 + o, ch.child1 + o, ch.order + o,
+                          ch.lstart + (size_t) b * (ch.nnodes + 2));
         }
     return 0;
 }
