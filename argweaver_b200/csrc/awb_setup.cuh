@@ -358,22 +358,48 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     unsigned short *rowstart = ch.rowstart + (size_t) b * (T + 1);
     unsigned short *pstart = ch.pstart + (size_t) b * (T + 1);
     {
-        int q = 0;
+        // states per time row (difference array over the branches), row starts,
+        // then one pass over the branches fills the time-major permutation and
+        // its inverse; within a row the states keep node order
+        int rowpos[AWB_MAXT + 1];
+        for (int t = 0; t <= T; t++)
+            rowpos[t] = 0;
+        if (S > 0) {
+            for (int i = 0; i < V; i++) {
+                const int cnt = ncnt[i];
+                if (cnt <= 0) continue;
+                const int lo = awb_imax(age[i], minage);
+                rowpos[lo]++;
+                rowpos[lo + cnt]--;
+            }
+        }
+        int q = 0, run = 0;
         for (int t = 0; t < T; t++) {
+            run += rowpos[t];
             rowstart[t] = (unsigned short) q;
-            if (S > 0 && t < T - 1) {
-                for (int i = 0; i < V; i++) {
-                    const int cnt = ncnt[i];
-                    if (cnt <= 0) continue;
-                    const int lo = awb_imax(age[i], minage);
-                    if (t >= lo && t < lo + cnt)
-                        ch.perm[row0 + q++] = (unsigned short) (nfirst[i] + (t - lo));
+            rowpos[t] = q;
+            if (t < T - 1)
+                q += run;
+        }
+        rowstart[T] = (unsigned short) q;
+        if (S > 0) {
+            for (int i = 0; i < V; i++) {
+                const int cnt = ncnt[i];
+                if (cnt <= 0) continue;
+                const int lo = awb_imax(age[i], minage);
+                for (int x = 0; x < cnt; x++) {
+                    const int pos = rowpos[lo + x]++;
+                    const int st = nfirst[i] + x;
+                    ch.perm[row0 + pos] = (unsigned short) st;
+                    ch.iperm[row0 + st] = (unsigned short) pos;
                 }
             }
         }
-        rowstart[T] = (unsigned short) q;
         if (S == 0)
             ch.perm[row0] = 0;
+    }
+    // (the generic forward kernel's slot tables)
+    if (ch.need_band) {
         // partial slots: a new slot starts at each warp boundary and each new row
         int slot = -1;
         int t = 0;
@@ -440,8 +466,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 if (tpos > NSb)
                     return 6;
             }
-            for (int q = 0; q < S; q++)
-                ch.iperm[row0 + ch.perm[row0 + q]] = (unsigned short) q;
         }
 
         // scribe lanes: each of 64 lanes sums a chunk of one time row
