@@ -1,13 +1,17 @@
 // awb_api.cu -- the flat C ABI (include/argweaver_b200.h) over the CUDA kernels.
 //
-// Kernels launched per batch (one launch each, all chains of the batch):
+// Kernels (every launch covers all chains of the batch, or one upload group
+// of them during setup):
 //   awb_kind_kernel          thread per site     site classification
 //   awb_block_setup_kernel   thread per block    K1 (awb_setup.cuh)
 //   awb_tmatrix_kernel       thread per entry    time-by-time matrices of K1
 //   awb_switch_setup_kernel  warp per breakpoint K2 (awb_setup.cuh)
 //   awb_emit_kernel          warp per site       K3 (awb_emit.cuh), variant sites
-//   awb_forward_kernel       CTA per chain       K4 (awb_forward.cuh)
+//   awb_forward_fast_kernel  CTA per chain       K4 (awb_forward_fast.cuh);
+//   awb_forward_kernel                           generic K4 (awb_forward.cuh)
 //   awb_traceback_kernel     CTA per chain       K5 (awb_traceback.cuh)
+// With AWB_CHECKPOINT the last three run once per segment of the window, and
+// the forward table holds one segment at a time.
 //
 // There is no CPU fallback: without a usable CUDA device every entry point
 // returns an error.

@@ -17,50 +17,54 @@
 //   W_k = E e2[b] * PY + x_b * A2 + A3 * Q + norecombs[b]*col[k]
 //   PY = sum_{a<b} x_a (h[a] - Bc)   Q = sum_{a>b} x_a
 //
-// (Bc, A2, A3 per-state constants, see load_compute).  P0, P1, Q are exclusive
-// prefix / suffix sums along one branch; the two forms agree to ~4e-15
-// relative (checked against the literal band on random columns).
+// (Bc, A2, A3 per-state constants, see load_compute).  PY and Q are exclusive
+// prefix / suffix sums along one branch; the separable form agrees with the
+// literal band to ~4e-15 relative (checked on random columns).
 //
 // Mapping to the SM (numbers measured on B200, scripts/microbench.cu:
 // dependent DFMA 8.4 cycles, 64-bit SHFL+DADD 35, LDS 33, bar.sync 33,
-// DDIV 130).  A site step is latency- and issue-bound, not bandwidth-bound, so
-// the kernel minimises the dependent chain of one site:
+// DDIV 130).  A site step is a chain of ~30 dependent shared-memory / shuffle /
+// FP64 operations, not a bandwidth problem, so the kernel is organised around
+// that chain:
 //
-//   compute warps   one thread per state in NODE-MAJOR order, packed so that
-//                   the states of a branch never straddle a warp: P0/P1/Q are
-//                   segmented warp-shuffle scans in registers, branch-free
-//                   (0/1 multipliers, one DFMA per level and quantity).  The
-//                   time-matrix column a state needs sits in registers.
-//   F-scribes       two warps owning no state: between the two barriers of a
-//                   step their 64 lanes turn the column (staged in shared
-//                   memory in TIME-MAJOR order) into the per-time sums F[a].
+//   compute warps   one thread per state in NODE-MAJOR order, packed
+//                   (first-fit decreasing, K1) so that the states of a branch
+//                   never straddle a warp: PY and Q are segmented warp-shuffle
+//                   scans in registers, branch-free (0/1 multipliers, one DFMA
+//                   per level and quantity); a warp runs only the levels its
+//                   longest branch needs.
+//   F-scribes       two warps owning no state: between barrier 1 and barrier 2
+//                   their 64 lanes turn the column (staged in shared memory in
+//                   TIME-MAJOR order) into the per-time sums F[a] and then,
+//                   one lane per b with the matrix column in registers, into
+//                   R[b]; a compute thread reads a single value.
 //   norm warp       one warp that only waits on barrier 2: column norm, 1/norm,
-//                   logZ, rescale factor.  Its division and log() are off the
-//                   critical cycle; consumers pick the results up two steps
-//                   later.
+//                   logZ, rescale factor, and the per-time sums of the stored
+//                   column (fsum) for the traceback.  Its division and log()
+//                   are off the critical cycle; consumers pick the results up
+//                   two steps later.
 //
 //   step(site):  STS value (time-major slot)
 //                B1 (compute + F-scribes)
-//                    compute:  branch scans -> W ; store column site-2 to HBM
-//                              scaled by its 1/norm ; fetch next emission
-//                    F-scribes: F[a]
+//                    compute:  store column site-2 to HBM scaled by its 1/norm ;
+//                              fetch next emission ; branch scans -> W
+//                    F-scribes: F[a] ; B3 (scribes) ; R[b]
 //                B2 (everybody)
-//                    compute:  R = sum_a tmc[a]*F[a]  (10 LDS.128 + 19 DFMA)
-//                              col(site+1) = (R + W) * emission
+//                    compute:  col(site+1) = (R[b] + W) * emission
 //                    norm warp: norm(site) ...
 //
 // The forward table is written once, 8 B per site*state, in the reference's
 // state order.  Columns are carried unnormalised; a factor published for
 // column s is applied when column s+3 is formed (every AWB_FWD_RS = 4 sites),
 // which bounds the magnitude by the product of at most RS+2 one-step norms.
+//
+// A launch works on one AwbSeg: the whole window, or one segment of a
+// checkpointed table (awb_common.cuh, awb_api.cu).
 #ifndef AWB_FORWARD_FAST_CUH
 #define AWB_FORWARD_FAST_CUH
 
 #include "awb_common.cuh"
 
-#ifndef AWB_ABLATE
-#define AWB_ABLATE 0
-#endif
 #define AWB_FWD_RS 4          // rescale period (sites); power of two, >= 4
 #define AWB_FWD_FSCRIBES 64   // F-scribe lanes (2 warps)
 #define AWB_FWD_HELPERS 96    // F-scribes + norm warp

@@ -293,13 +293,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     };
     // forward rows of the first wave of block m into L2
     auto prefetch_rows = [&](const AwbTbBlk &m) {
-#if defined(AWB_TB_PF) && AWB_TB_PF == 0
-        const int nrows = 0;
-#elif defined(AWB_TB_PF) && AWB_TB_PF == 2
-        const int nrows = m.blen - 1;
-#else
         const int nrows = m.blen - 1 < NW * SPW ? m.blen - 1 : NW * SPW;
-#endif
         if (nrows <= 0)
             return;
         const char *p0 = (const char *) (fwg + m.fwoff +
@@ -313,12 +307,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     // last site first
     const int roff = (ch.last_state < 0) ? (n - 1) : (n - 2);
     int k;
-#ifdef AWB_TB_STATS
-    long long tk[8] = {0,0,0,0,0,0,0,0}; long long t_last = clock64();
-#define TB_MARK(i) do { long long t_now = clock64(); tk[i] += t_now - t_last; t_last = t_now; } while (0)
-#else
-#define TB_MARK(i)
-#endif
 
     AwbTbBlk mC = awb_tb_blk(P, btop, bmin, bextra);
     AwbTbBlk mN = awb_tb_blk(P, btop - 1, bmin, bextra);
@@ -376,7 +364,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         const signed char *stT = (const signed char *) (bp + BL.stt + sk_stt[q]);
         const signed char *stA = (const signed char *) (bp + BL.sta + sk_sta[q]);
 
-        TB_MARK(0);
         // ---- sample_hmm_posterior (sample_thread.cpp:470-503), speculative
         int i_hi = blen - 2;
         int trans_k = -1;
@@ -419,7 +406,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                 __syncthreads();
             }
 
-            TB_MARK(1);
             // ---- one wave: NW * SPW sites tested for "stays in k".  The row
             // total comes from the per-time sums the forward kernel stored
             // (tot = sum_a Fn[a] tm[a][b_k] + correction on the branch of k), so
@@ -516,7 +502,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             __syncthreads();
 
             // first site of the wave (highest i) that leaves k
-            TB_MARK(2);
             // three masks in rotation: the one reset here is used two waves
             // from now, i.e. after the next barrier
             const unsigned fm = sm.failmask[par];
@@ -548,7 +533,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             }
         }
 
-        TB_MARK(3);
         // ---- sample_hmm_posterior_step through the switch matrix (:506-519)
         if (b > bmin) {
             if (tid == 0) {
@@ -596,18 +580,12 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             k = sm.kcur;
         }
 
-        TB_MARK(4);
         // ---- the tables of block b-1 have landed; everyone is done with buffer q
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         mC = mN;
         mN = mNN;
-        TB_MARK(5);
     }
-#ifdef AWB_TB_STATS
-    if (tid == 0 && blockIdx.x == 0)
-        printf("tb cycles/block: top %lld trans %lld wave %lld flags+sample %lld switch %lld wait %lld\n", tk[0]/B, tk[1]/B, tk[2]/B, tk[3]/B, tk[4]/B, tk[5]/B);
-#endif
 }
 
 #endif // AWB_TRACEBACK_CUH
