@@ -340,12 +340,20 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.seg_doubles = 0;
     L.seg_sites = 0;
     if (L.ckpt) {
+        // the fewest segments the capacity allows, then cut by SITES (a
+        // segment's run time is proportional to its sites, and every launch
+        // waits for the slowest window), never exceeding the capacity
+        const long long total = L.fw_off[B] + L.maxS;
+        long long want = (total + seg_cap - 1) / seg_cap;
+        if (want < 1) want = 1;
+        const int target = (int) ((L.n + want - 1) / want);
         int b0 = 0;
         while (b0 < B) {
             int b1 = b0 + 1;
             // a segment holds blocks [b0, b1) plus the first row of block b1
             while (b1 < B &&
-                   (L.fw_off[b1 + 1] - L.fw_off[b0]) + L.maxS <= seg_cap)
+                   (L.fw_off[b1 + 1] - L.fw_off[b0]) + L.maxS <= seg_cap &&
+                   L.block_start[b1] - L.block_start[b0] < target)
                 b1++;
             L.seg_start.push_back(b0);
             const long long d = (L.fw_off[b1] - L.fw_off[b0]) + L.maxS;

@@ -284,3 +284,22 @@ def test_checkpointed_batch_with_given_prior_and_last_state(libc_rand, monkeypat
         assert abs(ck.logz(c) - full.logz(c)) <= RTOL * abs(full.logz(c))
     full.close()
     ck.close()
+
+
+def test_checkpointed_equals_whole_table_at_size(libc_rand):
+    """BASELINE config 3 shape (k=50, T=20), 3e5 sites, leaf and subtree
+    threading: the checkpointed table (several 128 MiB segments) gives the same
+    paths and logZ as the whole table."""
+    n = 300000
+    ds = [sim.simulate_problem(50, n, seed=71 + i, internal=bool(i)) for i in range(2)]
+    rs = [libc_rand(300 + i, n) for i in range(2)]
+    full = api.Batch(ds)
+    full.upload().setup().forward().traceback(rs).sync()
+    ck = api.Batch(ds, checkpoint=True)
+    ck.upload().setup().forward().traceback(rs).sync()
+    for c in range(2):
+        assert full.status(c) == -1 and ck.status(c) == -1
+        assert np.array_equal(ck.path(c), full.path(c))
+        assert abs(ck.logz(c) - full.logz(c)) <= RTOL * abs(full.logz(c))
+    full.close()
+    ck.close()
