@@ -51,7 +51,7 @@ struct AwbTbSmem {
 // scalars of one block.  awb_tb_blk only LOADS (two blocks ahead of use, so no
 // instruction waits on the loads); the derived values come from the accessors.
 struct AwbTbBlk {
-    int S, blen, pos, minage_raw, Sprev;
+    int S, blen, pos, Sprev;
     long long r0, fwoff, entoff, entend;
     __device__ int S1() const { return S > 0 ? S : 1; }
     __device__ int n1() const { return Sprev > 0 ? Sprev : 1; }
@@ -60,7 +60,7 @@ struct AwbTbBlk {
 
 // pointers of the chain the kernel walks (read once from the chain record)
 struct AwbTbPtrs {
-    const int *nstates, *blocklens, *block_start, *tm_minage;
+    const int *nstates, *blocklens, *block_start;
     const long long *row_off, *fw_off, *ent_off;
 };
 
@@ -70,14 +70,13 @@ __device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb, int bmin, int 
 {
     AwbTbBlk m;
     if (bb < bmin) {
-        m.S = 0; m.blen = 0; m.pos = 0; m.minage_raw = 0; m.Sprev = 0;
+        m.S = 0; m.blen = 0; m.pos = 0; m.Sprev = 0;
         m.r0 = 0; m.fwoff = 0; m.entoff = 0; m.entend = 0;
         return m;
     }
     m.S = p.nstates[bb];
     m.blen = (bb == bextra) ? 1 : p.blocklens[bb];
     m.pos = p.block_start[bb];
-    m.minage_raw = p.tm_minage[bb];
     m.r0 = p.row_off[bb];
     m.fwoff = p.fw_off[bb];
     m.entoff = p.ent_off[bb];
@@ -243,10 +242,9 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const double *__restrict__ fsumg = ch.fsum - (size_t) g.site0 * (T - 1);
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
-    const bool internal = ch.internal != 0;
-    const AwbTbPtrs P = { ch.nstates, ch.blocklens, ch.block_start, ch.tm_minage,
+    const AwbTbPtrs P = { ch.nstates, ch.blocklens, ch.block_start,
                           ch.row_off, ch.fw_off, ch.ent_off };
-    const double *__restrict__ tmvecg = ch.tmvec;
+    const double *__restrict__ ling = ch.lin;
     const double *__restrict__ tmatrixg = ch.tmatrix;
     const short *__restrict__ st_nodeg = ch.st_node;
     const signed char *__restrict__ st_timeg = ch.st_time;
@@ -276,8 +274,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         if (bb < bmin)
             return;
         if (m.S > 0) {
-            awb_tb_copy8(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
-                         AWB_TM_NVEC * T);
+            awb_tb_copy8(base + BL.tv, ling + (size_t) bb * 7 * T, 7 * T);
             awb_tb_copy8(base + BL.tm, tmatrixg + (size_t) bb * T * T, T * T);
             sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, st_nodeg + m.r0, 2 * m.S);
             sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, st_timeg + m.r0, m.S);
@@ -352,13 +349,11 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
             prefetch_rows(mN);
 
         const int S = mC.S, S1 = mC.S1(), blen = mC.blen, pos = mC.pos;
-        // TransMatrix::get uses minage = age[subtree_root] (trans.h:67-74)
-        const int minage = (internal && S > 0) ? mC.minage_raw : 0;
         const double *fw = fwg + mC.fwoff;
         // draw of the switch step, fetched now so that it is there when needed
         const int r_sw = (b > bmin) ? randg[roff - (pos - 1)] : 0;
         const unsigned char *bp = bufp[q];
-        const double *tvS = (const double *) (bp + BL.tv);
+        const double *linS = (const double *) (bp + BL.tv);   // lin[7][T] (K1)
         const double *tmS = (const double *) (bp + BL.tm);
         const short *stN = (const short *) (bp + BL.stn + sk_stn[q]);
         const signed char *stT = (const signed char *) (bp + BL.stt + sk_stt[q]);
@@ -377,18 +372,32 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         while (i_hi >= 0) {
             if (trans_k != k) {
                 // transition column into k (recomputed only when k changes):
-                // other branches read the time-by-time matrix, the branch of k
-                // itself uses the closed form
+                // other branches read the time-by-time matrix (which already
+                // holds the minage rule), the branch of k adds its band term
                 if (S > 0) {
                     const int node_k = stN[k];
                     const int b_k = stT[k];
                     const int c_k = stA[k];
+                    // same-branch transitions in the separable, linear-domain
+                    // form the forward kernel uses (awb_forward_fast.cuh):
+                    // T[(n,a)->(n,b)] = tm[a][b] + D[a] {A1_b (h[a]-Bc) | A2_b | A3_b}
+                    //                   (+ norecombs[b] when a == b)
+                    const double Bc = c_k > 0 ? linS[2 * T + c_k - 1] : 0.0;
+                    const double A1 = linS[3 * T + b_k];
+                    const double A2 = linS[4 * T + b_k] - A1 * Bc;
+                    const double A3 = linS[5 * T + b_k] - A1 * Bc;
+                    const double nrb = linS[6 * T + b_k];
                     for (int j = tid; j < S; j += AWB_TB_THREADS) {
                         const int a_j = stT[j];
                         const double other = tmS[a_j * T + b_k];
                         const bool same = stN[j] == node_k;
-                        const double tr = same ?
-                            awb_get_time(tvS, T, a_j, b_k, c_k, minage, true) : other;
+                        double tr = other;
+                        if (same) {
+                            const double Da = linS[a_j];
+                            const double co = (a_j < b_k) ? A1 * (linS[T + a_j] - Bc) :
+                                (a_j == b_k ? A2 : A3);
+                            tr = other + (Da * co + (a_j == b_k ? nrb : 0.0));
+                        }
                         transS[j] = tr;
                         corrS[j] = tr - other;
                         // the states of a node are contiguous in state order
