@@ -18,14 +18,14 @@ rep('''    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
     if (dummy == 0x12345678u) asm volatile("trap;");
 }''')
 # norm
-rep("        int bad_site = -1;\n        for (int site = 0; site < n; site++) {\n            const double *Fs = FsS + (site & 1) * (TMAX + 2);\n            awb_bar_sync(2, NB2);","        int bad_site = -1;\n        FT_DECL\n        for (int site = 0; site < n; site++) {\n            const double *Fs = FsS + (site & 1) * (TMAX + 2);\n            FT(0);\n            awb_bar_sync(2, NB2);\n            FT(1);")
-rep("            if (site == n - 1 && lane == 0) {\n                chg.logz[0]","            if (site == n - 1 && lane == 0 && blockIdx.x == 0)\n                printf(\"norm cycles/site: work %lld bar2wait %lld\\n\", ft[0]/n, ft[1]/n);\n            if (site == n - 1 && lane == 0) {\n                chg.logz[0]")
+rep("        int bad_site = -1;\n        for (int site = 0; site < n; site++) {\n            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            awb_bar_sync(2, NB2);","        int bad_site = -1;\n        FT_DECL\n        for (int site = 0; site < n; site++) {\n            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            FT(0);\n            awb_bar_sync(2, NB2);\n            FT(1);")
+rep("            if (site == n - 1 && lane == 0) {\n                // (a segment","            if (site == n - 1 && lane == 0 && blockIdx.x == 0)\n                printf(\"norm cycles/site: work %lld bar2wait %lld\\n\", ft[0]/n, ft[1]/n);\n            if (site == n - 1 && lane == 0) {\n                // (a segment")
 # scribe
-rep("        int site = 0;\n        for (int b = 0; b < B; b++) {\n            const int blen = blocklensg[b];\n            const int sc_start","        int site = 0;\n        FT_DECL\n        for (int b = 0; b < B; b++) {\n            const int blen = blocklensg[b];\n            const int sc_start")
-rep("                double *Fs = FsS + (site & 1) * (TMAX + 2);\n                awb_bar_sync(1, NB1);","                double *Fs = FsS + (site & 1) * (TMAX + 2);\n                FT(0);\n                awb_bar_sync(1, NB1);\n                FT(1);")
+rep("        int site = 0;\n        for (int b = bbeg; b < bend; b++) {\n            const int blen = (b == bextra) ? 1 : blocklensg[b];\n            const int sc_start","        int site = 0;\n        FT_DECL\n        for (int b = bbeg; b < bend; b++) {\n            const int blen = (b == bextra) ? 1 : blocklensg[b];\n            const int sc_start")
+rep("                const unsigned Fp_s = Fs_s + (site & 1) * RSTR;\n                awb_bar_sync(1, NB1);","                const unsigned Fp_s = Fs_s + (site & 1) * RSTR;\n                FT(0);\n                awb_bar_sync(1, NB1);\n                FT(1);")
 rep("                double v = v0 + v1;","                double v = v0 + v1;\n                if (v == 1.2345e300) printf(\"x\");\n                FT(6);")
-rep("                if (sc_last)\n                    Fs[sc_row] = v;\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);","                if (v == 1.2345e300) printf(\"x\");\n                FT(7);\n                if (sc_last)\n                    Fs[sc_row] = v;\n                FT(2);\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);\n                FT(3);")
-rep("                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);\n                }\n                awb_bar_sync(2, NB2);","                    RsS[(site & 1) * (TMAX + 2) + sl] = (ra + rb) + (rc + rd);\n                }\n                FT(4);\n                awb_bar_sync(2, NB2);\n                FT(5);")
+rep("                if (sc_last)\n                    awb_sts(Fp_s + 8u * (unsigned) sc_row, v);\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);","                if (v == 1.2345e300) printf(\"x\");\n                FT(7);\n                if (sc_last)\n                    awb_sts(Fp_s + 8u * (unsigned) sc_row, v);\n                FT(2);\n                awb_bar_sync(3, AWB_FWD_FSCRIBES);\n                FT(3);")
+rep("                            (ra + rb) + (rc + rd));\n                }\n                awb_bar_sync(2, NB2);","                            (ra + rb) + (rc + rd));\n                }\n                FT(4);\n                awb_bar_sync(2, NB2);\n                FT(5);")
 rep("        __syncthreads();                                   // final barrier\n        return;\n    }\n\n    // =====================================================================\n    // compute warps","        if ((sl == 0 || sl == 32) && blockIdx.x == 0)\n            printf(\"scribe %d cycles/site: misc %lld bar1wait %lld sum %lld scan %lld store %lld bar3wait %lld R %lld bar2wait %lld\\n\", sl, ft[0]/n, ft[1]/n, ft[6]/n, ft[7]/n, ft[2]/n, ft[3]/n, ft[4]/n, ft[5]/n);\n        __syncthreads();                                   // final barrier\n        return;\n    }\n\n    // =====================================================================\n    // compute warps")
 # compute
 rep("    unsigned iofs = 16, rofs = 0, sofs = 0;\n","    unsigned iofs = 16, rofs = 0, sofs = 0;\n    FT_DECL\n")
