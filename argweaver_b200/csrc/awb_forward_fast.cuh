@@ -232,12 +232,16 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
         const unsigned short *__restrict__ sc_startg = chg.sc_start;
         const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
         const unsigned char *__restrict__ sc_rowg = chg.sc_row;
+        const unsigned char *__restrict__ sc_strideg = chg.sc_stride;
         int site = 0;
         for (int b = bbeg; b < bend; b++) {
             const int blen = (b == bextra) ? 1 : blocklensg[b];
             const int sc_start = sc_startg[(size_t) b * 64 + sl];
             const int sc_cnt = sc_cntg[(size_t) b * 64 + sl];
             const int sc_row = sc_rowg[(size_t) b * 64 + sl];
+            // the lanes of a row read it interleaved: element q of this lane is
+            // zstep bytes after element q-1
+            const unsigned zstep = 8u * sc_strideg[(size_t) b * 64 + sl];
             const int key = (sc_row != 255) ? sc_row : (0x100 + lane);
             const unsigned m = __match_any_sync(0xffffffffu, key);
             const int seglane = __ffs(m) - 1;
@@ -264,16 +268,16 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
                 awb_bar_sync(1, NB1);
-                // each lane sums its chunk of one row (loads issued eight at a
-                // time, clamped to the chunk and masked); the lanes of a row
-                // combine with a segmented scan
+                // each lane sums its share of one row (loads issued eight at a
+                // time, clamped and masked); the lanes of a row combine with a
+                // segmented scan
                 double v0 = 0.0, v1 = 0.0;
                 for (int q0 = 0; q0 < sc_cnt; q0 += 8) {
                     double t[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const unsigned q = (unsigned) (q0 + u);
-                        t[u] = awb_lds(z_s + 8u * (q < last_q ? q : last_q));
+                        t[u] = awb_lds(z_s + zstep * (q < last_q ? q : last_q));
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++)

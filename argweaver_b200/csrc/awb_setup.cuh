@@ -468,14 +468,19 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             }
         }
 
-        // scribe lanes: each of 64 lanes sums a chunk of one time row
+        // scribe lanes: the lanes of a time row sum it INTERLEAVED (lane i of nl
+        // takes elements i, i+nl, ...): consecutive lanes read consecutive
+        // shared-memory words, so the row reads have no bank conflicts (a
+        // contiguous chunk per lane made a stride of ~8 doubles: 16-way conflicts)
         unsigned short *scs = ch.sc_start + (size_t) b * 64;
         unsigned short *scc = ch.sc_cnt + (size_t) b * 64;
         unsigned char *scr = ch.sc_row + (size_t) b * 64;
+        unsigned char *sct = ch.sc_stride + (size_t) b * 64;
         for (int l = 0; l < 64; l++) {
             scs[l] = 0;
             scc[l] = 0;
             scr[l] = 255;
+            sct[l] = 1;
         }
         if (S == 0) {
             scs[0] = 0;
@@ -508,9 +513,10 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
                 if ((l & 31) + nl > 32) l = (l + 31) & ~31;
                 for (int i = 0; i < nl; i++) {
-                    scs[l] = (unsigned short) (w == 0 ? 0 : rowstart[t] + i * CH);
-                    scc[l] = (unsigned short) (w == 0 ? 0 : awb_imin(CH, w - i * CH));
+                    scs[l] = (unsigned short) (w == 0 ? 0 : rowstart[t] + i);
+                    scc[l] = (unsigned short) (w == 0 ? 0 : (w - i + nl - 1) / nl);
                     scr[l] = (unsigned char) t;
+                    sct[l] = (unsigned char) nl;
                     l++;
                 }
             }

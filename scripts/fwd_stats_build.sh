@@ -33,6 +33,9 @@ rep("        awb_sts(zaddr, c);\n        awb_bar_sync(1, NB1);\n\n        // bra
 rep("            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        awb_bar_sync(2, NB2);","            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;\n        FT(2);\n        awb_bar_sync(2, NB2);\n        FT(3);")
 rep("    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();","    if ((tid == 0 || tid == NS - 32) && blockIdx.x == 0)\n        printf(\"compute tid %d cycles/site: A-phase %lld bar1wait %lld B-phase %lld bar2wait %lld\\n\", tid, ft[0]/n, ft[1]/n, ft[2]/n, ft[3]/n);\n    // ---- the last two columns: their 1/norm is complete after the final barrier\n    __syncthreads();")
 import os
+if os.environ.get("FWD_SUMSRC"):
+    # scribes sum from a region nobody writes in the site loop (timing experiment only)
+    s=s.replace("const unsigned z_s = zT_s + 8u * (unsigned) sc_start;","const unsigned z_s = col_s + 8u * (unsigned) sc_start;")
 if os.environ.get("FWD_NOSCAN"):
     import re
     s=re.sub(r"site_step\(AwbInt<[^;]*>\(\)\);", "site_step(AwbInt<0>());", s)
