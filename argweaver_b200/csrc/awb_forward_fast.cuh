@@ -136,11 +136,11 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
-    double *dummyS = invS + 4;                 // [2] idle lanes store here
+    double *dummyS = invS + 4;                 // [2] [0]: idle lanes store here; [1] = 1.0
 
     for (int x = tid; x < 3 * NS + 4 * (TMAX + 2) + 8; x += blockDim.x) {
         const int y = x - (3 * NS + 4 * (TMAX + 2));
-        smem_f[x] = (y >= 0 && y < 6) ? 1.0 : 0.0;     // scaleS, invS start at 1
+        smem_f[x] = ((y >= 0 && y < 6) || y == 7) ? 1.0 : 0.0;   // scaleS, invS, one
     }
     __syncthreads();
 
@@ -478,11 +478,13 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
         awb_bar_sync(2, NB2);
 
         // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
-        double cn = (awb_lds(raddr + rofs) + W) * e;
-        if (iofs == 0) {                            // (site & 3) == 2
-            cn *= awb_lds(scale_s + sofs);
-            sofs ^= 8u;
-        }
+        // the lagged rescale factor every fourth site ((site & 3) == 2), the
+        // constant 1.0 otherwise: branch-free (a branch around a volatile load
+        // costs a branch resolution per warp and site)
+        const bool resc = iofs == 0;
+        const double sc = awb_lds(resc ? scale_s + sofs : dummy_s + 8u);
+        double cn = (awb_lds(raddr + rofs) + W) * (e * sc);
+        sofs ^= resc ? 8u : 0u;
         iofs = (iofs + 8u) & 24u;
         rofs ^= RSTR;
         c2 = c1; c1 = c; c = cn;

@@ -17,7 +17,7 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
     --log-file gpurun_out/traffic_fwd_$TAG.csv \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_traffic_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'awb_forward_fast|awb_traceback|awb_switch_setup|awb_block_setup|awb_emit' -c 5 \
+    -k regex:'awb_forward_fast|awb_traceback|awb_emit' -c 6 \
     -o gpurun_out/full_$TAG -f \
     python bench.py --steps 1 --warmup 0 --windows 8 --sites 100000 --no-cpu-baseline --no-e2e \
     > gpurun_out/ncu_full_$TAG.log 2>&1
