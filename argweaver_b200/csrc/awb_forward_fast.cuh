@@ -90,6 +90,14 @@ __device__ __forceinline__ double awb_lds(unsigned addr)
     return v;
 }
 
+// prefetch [p, p + bytes) into L1, one 128-byte line per lane and step
+__device__ __forceinline__ void awb_prefetch_range(const void *p, long long bytes, int lane)
+{
+    const char *q = (const char *) p;
+    for (long long o = 128ll * lane; o < bytes; o += 128ll * 32)
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(q + o));
+}
+
 __device__ __forceinline__ double2 awb_lds2(unsigned addr)
 {
     double2 v;
@@ -164,7 +172,78 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
         int nprod = 0;
         double *__restrict__ fsumg = chg.fsum;
         int bad_site = -1;
+        // This warp has slack, so it also warms the cache for the others: when
+        // a block starts, the per-block tables of the NEXT block (what
+        // load_compute, the switch gather and the scribes read in dependent
+        // chains at the block boundary) are prefetched into L1.
+        int pb = bbeg, pnext = 0;
+        // ... and the emission rows of the variant sites a few sites ahead
+        // (K3 left them in the table; a compute thread reads its entry right
+        // before it needs it).  Cursor (ab, ai) = block / offset of site + LA.
+        constexpr int LA = 6;
+        const unsigned char *__restrict__ kindn = chg.kind + g.site0;
+        const double *fwn = chg.fw - g.fwbias;
+        int ab = bbeg, ai = 0, ablen = (ab == bextra) ? 1 : blocklensg[ab];
+        for (int x = 0; x < LA && ab < bend; x++) {
+            if (++ai == ablen) {
+                ab++;
+                ai = 0;
+                ablen = (ab < bend) ? ((ab == bextra) ? 1 : blocklensg[ab]) : 0;
+            }
+        }
+        int aS1 = 1;
+        long long arow = 0;
+        if (ab < bend) {
+            aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+            arow = chg.fw_off[ab] + (long long) ai * aS1;
+        }
         for (int site = 0; site < n; site++) {
+            if (ab < bend) {
+                if (kindn[site + LA] == AWB_SITE_VARIANT)
+                    awb_prefetch_range(fwn + arow, 8ll * aS1, lane);
+                arow += aS1;
+                if (++ai == ablen) {
+                    ab++;
+                    ai = 0;
+                    if (ab < bend) {
+                        ablen = (ab == bextra) ? 1 : blocklensg[ab];
+                        aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+                        arow = chg.fw_off[ab];
+                    }
+                }
+            }
+            if (site == pnext) {
+                pnext += (pb == bextra) ? 1 : blocklensg[pb];
+                const int nb = ++pb;
+                if (nb < bend) {
+                    const long long r0n = chg.row_off[nb];
+                    const long long S1n = chg.row_off[nb + 1] - r0n;
+                    const long long tr0n = chg.trow_off[nb];
+                    const long long e0n = chg.ent_off[nb];
+                    const long long nen = chg.ent_off[nb + 1] - e0n;
+                    awb_prefetch_range(chg.tmap + tr0n, 2 * (chg.trow_off[nb + 1] - tr0n), lane);
+                    awb_prefetch_range(chg.st_node + r0n, 2 * S1n, lane);
+                    awb_prefetch_range(chg.st_time + r0n, S1n, lane);
+                    awb_prefetch_range(chg.st_age + r0n, S1n, lane);
+                    awb_prefetch_range(chg.iperm + r0n, 2 * S1n, lane);
+                    awb_prefetch_range(chg.inv_emit + r0n, 8 * S1n, lane);
+                    awb_prefetch_range(chg.sw_start + r0n, 2 * S1n, lane);
+                    awb_prefetch_range(chg.sw_cnt + r0n, 2 * S1n, lane);
+                    awb_prefetch_range(chg.sw_src + e0n, 2 * nen, lane);
+                    awb_prefetch_range(chg.sw_prob + e0n, 8 * nen, lane);
+                    awb_prefetch_range(chg.lin + (size_t) nb * 7 * T, 56ll * T, lane);
+                    awb_prefetch_range(chg.tmatrix + (size_t) nb * T * T, 8ll * T * T, lane);
+                    awb_prefetch_range(chg.sc_start + (size_t) nb * 64, 128, lane);
+                    awb_prefetch_range(chg.sc_cnt + (size_t) nb * 64, 128, lane);
+                    awb_prefetch_range(chg.sc_row + (size_t) nb * 64, 64, lane);
+                    awb_prefetch_range(chg.sc_stride + (size_t) nb * 64, 64, lane);
+                    if (lane == 0) {
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
+                    }
+                }
+            }
             const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;
             awb_bar_sync(2, NB2);
             // (T - 1 <= 63: at most two rows per lane)

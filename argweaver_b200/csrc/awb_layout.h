@@ -434,7 +434,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
         L.o_sw_determprob = L.o_sw_recombrow = 0;
         L.o_sw_recoalrow = L.o_sw_recombsrc = L.o_sw_recoalsrc = 0;
     }
-    AWB_PLACE(o_kind, (size_t) L.n + 2);     // the forward kernel prefetches kind[site+2]
+    AWB_PLACE(o_kind, (size_t) L.n + 8);     // the forward kernel reads a few sites ahead
     if (L.ckpt) {
         // one segment's table and per-time sums, the first column of every
         // segment, the segment list
