@@ -140,18 +140,29 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
         return;
     // (the first column of a table is the prior / the stored first column of
     // the segment: no emission applied)
-    // a warp scans 32 sites at a time for variant ones (one coalesced load and a
-    // ballot; ~97 % of the sites are skipped) and then works through them
+    // every warp takes a contiguous range of sites (consecutive variant sites
+    // mostly share their block: the tree stays staged, and the block index only
+    // moves forward), scans it 32 sites at a time for variant ones (one
+    // coalesced load and a ballot; ~97 % of the sites are skipped) and works
+    // through those
     const int first = g.site0 + 1, last = g.site0 + g.nsites;
-    for (int base = first + 32 * (blockIdx.x * wpc + warp); base < last;
-         base += 32 * gridDim.x * wpc) {
+    const int nw = gridDim.x * wpc;
+    const int per = (((last - first) + nw - 1) / nw + 31) & ~31;
+    const int w0 = first + (blockIdx.x * wpc + warp) * per;
+    const int w1 = w0 + per < last ? w0 + per : last;
+    int b = -1;
+    for (int base = w0; base < w1; base += 32) {
       const int mine = base + lane;
-      unsigned vm = __ballot_sync(0xffffffffu, mine < last &&
+      unsigned vm = __ballot_sync(0xffffffffu, mine < w1 &&
                                   ch.kind[mine] == AWB_SITE_VARIANT);
       while (vm) {
         const int i = base + __ffs(vm) - 1;
         vm &= vm - 1;
-        const int b = awb_find_block(ch, i);
+        if (b < 0)
+            b = awb_find_block(ch, i);
+        else
+            while (ch.block_start[b + 1] <= i)
+                b++;
         if (b != staged) {
             const size_t o = (size_t) b * V;
             for (int x = lane; x < V; x += 32) {
