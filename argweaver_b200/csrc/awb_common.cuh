@@ -114,7 +114,8 @@ struct AwbChain {
     unsigned short *sc_start; // [B][64] scribe lane -> first time-major slot
     unsigned short *sc_cnt;   // [B][64] scribe lane -> number of slots
     unsigned char *sc_row;    // [B][64] scribe lane -> time row (255 idle)
-    unsigned char *sc_stride; // [B][64] lanes sharing the row: lane i sums elements i, i+stride, ...
+    unsigned char *sc_stride; // [B][64] lanes sharing the row: lane i sums slots i, i+stride, ...
+    unsigned char *sc_ch;     // [B] slots every scribe lane sums (rows are zero-padded)
     int slotcap;              // ntimes + 32
     short *node_first;        // [B][V] first state index of node (or -1)
     short *node_cnt;          // [B][V]

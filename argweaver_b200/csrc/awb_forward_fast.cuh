@@ -69,11 +69,11 @@
 #define AWB_FWD_FSCRIBES 64   // F-scribe lanes (2 warps)
 #define AWB_FWD_HELPERS 96    // F-scribes + norm warp
 
-// shared memory (doubles): zT[NS] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
+// shared memory (doubles): zT[2 NS + 64] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
 // scaleS[2] | invS[4] | dummy[2]
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX)
 {
-    return (3 * (size_t) NS + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
+    return (4 * (size_t) NS + 64 + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
 }
 
 template <int N> struct AwbInt { static constexpr int value = N; };
@@ -137,8 +137,9 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     const int *__restrict__ blocklensg = chg.blocklens;
 
     extern __shared__ double smem_f[];
-    double *zT = smem_f;                       // [NS] column, time-major slots
-    double *colS = zT + NS;                    // [2][NS] last column of a block in
+    double *zT = smem_f;                       // [2 NS + 64] column, time-major rows,
+                                               //   zero-padded for the scribes (K1)
+    double *colS = zT + 2 * NS + 64;                    // [2][NS] last column of a block in
                                                //   state order, by block parity
     double *FsS = colS + 2 * NS;               // [2][TMAX+2] per-time sums
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
@@ -146,8 +147,8 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
     double *dummyS = invS + 4;                 // [2] [0]: idle lanes store here; [1] = 1.0
 
-    for (int x = tid; x < 3 * NS + 4 * (TMAX + 2) + 8; x += blockDim.x) {
-        const int y = x - (3 * NS + 4 * (TMAX + 2));
+    for (int x = tid; x < 4 * NS + 64 + 4 * (TMAX + 2) + 8; x += blockDim.x) {
+        const int y = x - (4 * NS + 64 + 4 * (TMAX + 2));
         smem_f[x] = ((y >= 0 && y < 6) || y == 7) ? 1.0 : 0.0;   // scaleS, invS, one
     }
     __syncthreads();
@@ -321,6 +322,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
             // the lanes of a row read it interleaved: element q of this lane is
             // zstep bytes after element q-1
             const unsigned zstep = 8u * sc_strideg[(size_t) b * 64 + sl];
+            const int CH = chg.sc_ch[b];            // slots every lane sums (even)
             const int key = (sc_row != 255) ? sc_row : (0x100 + lane);
             const unsigned m = __match_any_sync(0xffffffffu, key);
             const int seglane = __ffs(m) - 1;
@@ -332,7 +334,11 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
             for (int l = 0; l < 5; l++)
                 um[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
             const unsigned z_s = zT_s + 8u * (unsigned) sc_start;
-            const unsigned last_q = sc_cnt > 0 ? (unsigned) (sc_cnt - 1) : 0u;
+            // the slots of this lane beyond its real ones are padding: zero them
+            // for this block (the compute warps only write real slots; the
+            // previous block is past its last barrier 2)
+            for (int q = sc_cnt; q < CH; q++)
+                awb_sts(z_s + zstep * (unsigned) q, 0.0);
             // column `sl` of the block's time-by-time matrix: this lane turns
             // the per-time sums F into R[sl] for the compute warps
             double tmc[TMAX];
@@ -347,23 +353,17 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
                 awb_bar_sync(1, NB1);
-                // each lane sums its share of one row (loads issued eight at a
-                // time, clamped and masked); the lanes of a row combine with a
-                // segmented scan
+                // each lane sums its CH slots of one (zero-padded) row; the lanes of
+                // a row combine with a segmented scan
                 double v0 = 0.0, v1 = 0.0;
-                for (int q0 = 0; q0 < sc_cnt; q0 += 8) {
-                    double t[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const unsigned q = (unsigned) (q0 + u);
-                        t[u] = awb_lds(z_s + zstep * (q < last_q ? q : last_q));
+                {
+                    unsigned a = z_s;
+#pragma unroll 4
+                    for (int q = 0; q < CH; q += 2) {
+                        v0 += awb_lds(a);
+                        v1 += awb_lds(a + zstep);
+                        a += 2u * zstep;
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (q0 + u >= sc_cnt)
-                            t[u] = 0.0;
-                    v0 += (t[0] + t[1]) + (t[2] + t[3]);
-                    v1 += (t[4] + t[5]) + (t[6] + t[7]);
                 }
                 double v = v0 + v1;
 #pragma unroll

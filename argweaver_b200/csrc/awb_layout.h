@@ -52,7 +52,7 @@ struct AwbLayout {
     int seg_sites;                  // most sites in a segment (+ 1)
     size_t o_seg_start, o_ckptcol;
     size_t o_mappings, o_slotrow, o_trow_off, o_tmap, o_iperm, o_st_age, o_lin,
-        o_sc_start, o_sc_cnt, o_sc_row, o_sc_stride;
+        o_sc_start, o_sc_cnt, o_sc_row, o_sc_stride, o_sc_ch;
     size_t o_ptrees, o_ages, o_sprs, o_blocklens, o_subtree_roots, o_rowidx,
         o_seqs, o_block_start, o_nstates, o_row_off, o_fw_off, o_band_off,
         o_ent_off, o_sw1_off, o_st_node, o_st_time, o_perm, o_pslot, o_band_j1,
@@ -396,6 +396,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_sc_cnt, (size_t) B * 64 * sizeof(short));
     AWB_PLACE(o_sc_row, (size_t) B * 64);
     AWB_PLACE(o_sc_stride, (size_t) B * 64);
+    AWB_PLACE(o_sc_ch, (size_t) B);
     AWB_PLACE(o_st_node, rows * sizeof(short));
     AWB_PLACE(o_st_time, rows);
     AWB_PLACE(o_perm, rows * sizeof(short));
@@ -556,6 +557,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(unsigned short *, sc_cnt, o_sc_cnt);
     AWB_P(unsigned char *, sc_row, o_sc_row);
     AWB_P(unsigned char *, sc_stride, o_sc_stride);
+    AWB_P(unsigned char *, sc_ch, o_sc_ch);
     AWB_P(short *, st_node, o_st_node);
     AWB_P(signed char *, st_time, o_st_time);
     AWB_P(unsigned short *, perm, o_perm);

@@ -382,16 +382,74 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 q += run;
         }
         rowstart[T] = (unsigned short) q;
+
+        // ---- the F-scribes' view of the column (awb_forward_fast.cuh).  The 64
+        // scribe lanes are shared out over the T-1 time rows, nl lanes for a row
+        // of w states with nl = ceil(w / CH) and CH the smallest (even) count
+        // that makes all rows fit (a row stays inside one warp).  In shared
+        // memory every row is PADDED to nl*CH slots, the lanes of a row read it
+        // interleaved (lane i: slots i, i+nl, ...; consecutive lanes, consecutive
+        // words, no bank conflicts), and EVERY lane reads exactly CH slots -- the
+        // padding holds zeros -- so the summation loop has no clamps or masks.
+        // iperm[state] is the state's padded slot.
+        unsigned short *scs = ch.sc_start + (size_t) b * 64;
+        unsigned short *scc = ch.sc_cnt + (size_t) b * 64;
+        unsigned char *scr = ch.sc_row + (size_t) b * 64;
+        unsigned char *sct = ch.sc_stride + (size_t) b * 64;
+        int zbase[AWB_MAXT];
+        {
+            for (int l = 0; l < 64; l++) {
+                scs[l] = 0;
+                scc[l] = 0;
+                scr[l] = 255;
+                sct[l] = 1;
+            }
+            int CH = 2;
+            for (;; CH += 2) {
+                int l = 0;
+                bool fits = true;
+                for (int t = 0; t < T - 1 && fits; t++) {
+                    const int w = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
+                    const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
+                    if (nl > 32) { fits = false; break; }
+                    if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+                    l += nl;
+                    if (l > 64) fits = false;
+                }
+                if (fits) break;
+            }
+            ch.sc_ch[b] = (unsigned char) CH;
+            int l = 0, zb = 0;
+            for (int t = 0; t < T - 1; t++) {
+                // every row gets at least one lane: an empty row sums zeros
+                const int w = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
+                const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
+                if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+                zbase[t] = zb;
+                for (int i = 0; i < nl; i++) {
+                    scs[l] = (unsigned short) (zb + i);
+                    scc[l] = (unsigned short) (w > i ? (w - i + nl - 1) / nl : 0);   // real slots
+                    scr[l] = (unsigned char) t;
+                    sct[l] = (unsigned char) nl;
+                    l++;
+                }
+                zb += nl * CH;
+            }
+            if (zb > 2 * ch.maxNS + 64)
+                return 7;       // padded column larger than the kernel's buffer
+        }
+
         if (S > 0) {
             for (int i = 0; i < V; i++) {
                 const int cnt = ncnt[i];
                 if (cnt <= 0) continue;
                 const int lo = awb_imax(age[i], minage);
                 for (int x = 0; x < cnt; x++) {
-                    const int pos = rowpos[lo + x]++;
+                    const int tt = lo + x;
+                    const int pos = rowpos[tt]++;
                     const int st = nfirst[i] + x;
                     ch.perm[row0 + pos] = (unsigned short) st;
-                    ch.iperm[row0 + st] = (unsigned short) pos;
+                    ch.iperm[row0 + st] = (unsigned short) (zbase[tt] + (pos - rowstart[tt]));
                 }
             }
         }
@@ -465,60 +523,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 }
                 if (tpos > NSb)
                     return 6;
-            }
-        }
-
-        // scribe lanes: the lanes of a time row sum it INTERLEAVED (lane i of nl
-        // takes elements i, i+nl, ...): consecutive lanes read consecutive
-        // shared-memory words, so the row reads have no bank conflicts (a
-        // contiguous chunk per lane made a stride of ~8 doubles: 16-way conflicts)
-        unsigned short *scs = ch.sc_start + (size_t) b * 64;
-        unsigned short *scc = ch.sc_cnt + (size_t) b * 64;
-        unsigned char *scr = ch.sc_row + (size_t) b * 64;
-        unsigned char *sct = ch.sc_stride + (size_t) b * 64;
-        for (int l = 0; l < 64; l++) {
-            scs[l] = 0;
-            scc[l] = 0;
-            scr[l] = 255;
-            sct[l] = 1;
-        }
-        if (S == 0) {
-            scs[0] = 0;
-            scc[0] = 1;
-            scr[0] = 0;
-            for (int t = 1; t < T - 1; t++) {
-                scs[t] = 0;
-                scc[t] = 0;
-                scr[t] = (unsigned char) t;
-            }
-        } else {
-            int CH = 1;
-            for (;; CH++) {
-                int l = 0;
-                bool fits = true;
-                for (int t = 0; t < T - 1 && fits; t++) {
-                    const int w = rowstart[t + 1] - rowstart[t];
-                    const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
-                    if (nl > 32) { fits = false; break; }
-                    if ((l & 31) + nl > 32) l = (l + 31) & ~31;
-                    l += nl;
-                    if (l > 64) fits = false;
-                }
-                if (fits) break;
-            }
-            int l = 0;
-            for (int t = 0; t < T - 1; t++) {
-                // every row gets at least one lane: an empty row is written as 0
-                const int w = rowstart[t + 1] - rowstart[t];
-                const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
-                if ((l & 31) + nl > 32) l = (l + 31) & ~31;
-                for (int i = 0; i < nl; i++) {
-                    scs[l] = (unsigned short) (w == 0 ? 0 : rowstart[t] + i);
-                    scc[l] = (unsigned short) (w == 0 ? 0 : (w - i + nl - 1) / nl);
-                    scr[l] = (unsigned char) t;
-                    sct[l] = (unsigned char) nl;
-                    l++;
-                }
             }
         }
 
