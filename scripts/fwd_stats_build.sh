@@ -18,7 +18,8 @@ rep('''    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
     if (dummy == 0x12345678u) asm volatile("trap;");
 }''')
 # norm
-rep("        int bad_site = -1;\n        for (int site = 0; site < n; site++) {\n            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            awb_bar_sync(2, NB2);","        int bad_site = -1;\n        FT_DECL\n        for (int site = 0; site < n; site++) {\n            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            FT(0);\n            awb_bar_sync(2, NB2);\n            FT(1);")
+rep("        int bad_site = -1;\n","        int bad_site = -1;\n        FT_DECL\n")
+rep("            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            awb_bar_sync(2, NB2);","            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;\n            FT(0);\n            awb_bar_sync(2, NB2);\n            FT(1);")
 rep("            if (site == n - 1 && lane == 0) {\n                // (a segment","            if (site == n - 1 && lane == 0 && blockIdx.x == 0)\n                printf(\"norm cycles/site: work %lld bar2wait %lld\\n\", ft[0]/n, ft[1]/n);\n            if (site == n - 1 && lane == 0) {\n                // (a segment")
 # scribe
 rep("        int site = 0;\n        for (int b = bbeg; b < bend; b++) {\n            const int blen = (b == bextra) ? 1 : blocklensg[b];\n            const int sc_start","        int site = 0;\n        FT_DECL\n        for (int b = bbeg; b < bend; b++) {\n            const int blen = (b == bextra) ? 1 : blocklensg[b];\n            const int sc_start")
@@ -35,7 +36,7 @@ rep("    // ---- the last two columns: their 1/norm is complete after the final 
 import os
 if os.environ.get("FWD_SUMSRC"):
     # scribes sum from a region nobody writes in the site loop (timing experiment only)
-    s=s.replace("const unsigned z_s = zT_s + 8u * (unsigned) sc_start;","const unsigned z_s = col_s + 8u * (unsigned) sc_start;")
+    s=s.replace("const unsigned z_s = zT_s + 8u * (unsigned) sc_start;","const unsigned z_s = col_s + 8u * (unsigned) (sc_start % 64);")
 if os.environ.get("FWD_NOSCAN"):
     import re
     s=re.sub(r"site_step\(AwbInt<[^;]*>\(\)\);", "site_step(AwbInt<0>());", s)
