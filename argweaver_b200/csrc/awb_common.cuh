@@ -32,6 +32,9 @@
 #define AWB_MAXT 64      // == AWB_MAX_NTIMES
 #define AWB_MAXV 1024    // == AWB_MAX_NNODES
 #define AWB_MAXS 2048    // == AWB_MAX_NSTATES
+#ifndef AWB_NSCRIBE
+#define AWB_NSCRIBE 64    // F-scribe lanes of the fast forward kernel
+#endif
 
 enum { AWB_TM_D = 0, AWB_TM_E, AWB_TM_LNB, AWB_TM_LNE2, AWB_TM_LNNEGG1,
        AWB_TM_G2, AWB_TM_G3, AWB_TM_LNG4, AWB_TM_NORECOMBS, AWB_TM_NVEC };
@@ -111,10 +114,10 @@ struct AwbChain {
     signed char *st_age;      // [rows] age of the state's node
     double *lin;              // [B][7][T] linear-domain transition vectors:
                               //   D, h=B-NegG1, B, E*E2, E*(pre+G3), E*(pre+G2), norecombs
-    unsigned short *sc_start; // [B][64] scribe lane -> first time-major slot
-    unsigned short *sc_cnt;   // [B][64] scribe lane -> number of slots
-    unsigned char *sc_row;    // [B][64] scribe lane -> time row (255 idle)
-    unsigned char *sc_stride; // [B][64] lanes sharing the row: lane i sums slots i, i+stride, ...
+    unsigned short *sc_start; // [B][AWB_NSCRIBE] scribe lane -> first time-major slot
+    unsigned short *sc_cnt;   // [B][AWB_NSCRIBE] scribe lane -> number of slots
+    unsigned char *sc_row;    // [B][AWB_NSCRIBE] scribe lane -> time row (255 idle)
+    unsigned char *sc_stride; // [B][AWB_NSCRIBE] lanes sharing the row: lane i sums slots i, i+stride, ...
     unsigned char *sc_ch;     // [B] slots every scribe lane sums (rows are zero-padded)
     int slotcap;              // ntimes + 32
     short *node_first;        // [B][V] first state index of node (or -1)

@@ -66,8 +66,8 @@
 #include "awb_common.cuh"
 
 #define AWB_FWD_RS 4          // rescale period (sites); power of two, >= 4
-#define AWB_FWD_FSCRIBES 64   // F-scribe lanes (2 warps)
-#define AWB_FWD_HELPERS 96    // F-scribes + norm warp
+#define AWB_FWD_FSCRIBES AWB_NSCRIBE          // F-scribe lanes
+#define AWB_FWD_HELPERS (AWB_NSCRIBE + 32)    // F-scribes + norm warp
 
 // shared memory (doubles): zT[2 NS + 64] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
 // scaleS[2] | invS[4] | dummy[2]
@@ -234,10 +234,10 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
                     awb_prefetch_range(chg.sw_prob + e0n, 8 * nen, lane);
                     awb_prefetch_range(chg.lin + (size_t) nb * 7 * T, 56ll * T, lane);
                     awb_prefetch_range(chg.tmatrix + (size_t) nb * T * T, 8ll * T * T, lane);
-                    awb_prefetch_range(chg.sc_start + (size_t) nb * 64, 128, lane);
-                    awb_prefetch_range(chg.sc_cnt + (size_t) nb * 64, 128, lane);
-                    awb_prefetch_range(chg.sc_row + (size_t) nb * 64, 64, lane);
-                    awb_prefetch_range(chg.sc_stride + (size_t) nb * 64, 64, lane);
+                    awb_prefetch_range(chg.sc_start + (size_t) nb * AWB_NSCRIBE, 2 * AWB_NSCRIBE, lane);
+                    awb_prefetch_range(chg.sc_cnt + (size_t) nb * AWB_NSCRIBE, 2 * AWB_NSCRIBE, lane);
+                    awb_prefetch_range(chg.sc_row + (size_t) nb * AWB_NSCRIBE, AWB_NSCRIBE, lane);
+                    awb_prefetch_range(chg.sc_stride + (size_t) nb * AWB_NSCRIBE, AWB_NSCRIBE, lane);
                     if (lane == 0) {
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
@@ -316,12 +316,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
         int site = 0;
         for (int b = bbeg; b < bend; b++) {
             const int blen = (b == bextra) ? 1 : blocklensg[b];
-            const int sc_start = sc_startg[(size_t) b * 64 + sl];
-            const int sc_cnt = sc_cntg[(size_t) b * 64 + sl];
-            const int sc_row = sc_rowg[(size_t) b * 64 + sl];
+            const int sc_start = sc_startg[(size_t) b * AWB_NSCRIBE + sl];
+            const int sc_cnt = sc_cntg[(size_t) b * AWB_NSCRIBE + sl];
+            const int sc_row = sc_rowg[(size_t) b * AWB_NSCRIBE + sl];
             // the lanes of a row read it interleaved: element q of this lane is
             // zstep bytes after element q-1
-            const unsigned zstep = 8u * sc_strideg[(size_t) b * 64 + sl];
+            const unsigned zstep = 8u * sc_strideg[(size_t) b * AWB_NSCRIBE + sl];
             const int CH = chg.sc_ch[b];            // slots every lane sums (even)
             const int key = (sc_row != 255) ? sc_row : (0x100 + lane);
             const unsigned m = __match_any_sync(0xffffffffu, key);

@@ -392,10 +392,10 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_st_age, rows);
     AWB_PLACE(o_lin, (size_t) B * 7 * T * sizeof(double));
     AWB_PLACE(o_ptab, (size_t) (T * T + T) * 2 * sizeof(double));
-    AWB_PLACE(o_sc_start, (size_t) B * 64 * sizeof(short));
-    AWB_PLACE(o_sc_cnt, (size_t) B * 64 * sizeof(short));
-    AWB_PLACE(o_sc_row, (size_t) B * 64);
-    AWB_PLACE(o_sc_stride, (size_t) B * 64);
+    AWB_PLACE(o_sc_start, (size_t) B * AWB_NSCRIBE * sizeof(short));
+    AWB_PLACE(o_sc_cnt, (size_t) B * AWB_NSCRIBE * sizeof(short));
+    AWB_PLACE(o_sc_row, (size_t) B * AWB_NSCRIBE);
+    AWB_PLACE(o_sc_stride, (size_t) B * AWB_NSCRIBE);
     AWB_PLACE(o_sc_ch, (size_t) B);
     AWB_PLACE(o_st_node, rows * sizeof(short));
     AWB_PLACE(o_st_time, rows);

@@ -392,13 +392,13 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         // words, no bank conflicts), and EVERY lane reads exactly CH slots -- the
         // padding holds zeros -- so the summation loop has no clamps or masks.
         // iperm[state] is the state's padded slot.
-        unsigned short *scs = ch.sc_start + (size_t) b * 64;
-        unsigned short *scc = ch.sc_cnt + (size_t) b * 64;
-        unsigned char *scr = ch.sc_row + (size_t) b * 64;
-        unsigned char *sct = ch.sc_stride + (size_t) b * 64;
+        unsigned short *scs = ch.sc_start + (size_t) b * AWB_NSCRIBE;
+        unsigned short *scc = ch.sc_cnt + (size_t) b * AWB_NSCRIBE;
+        unsigned char *scr = ch.sc_row + (size_t) b * AWB_NSCRIBE;
+        unsigned char *sct = ch.sc_stride + (size_t) b * AWB_NSCRIBE;
         int zbase[AWB_MAXT];
         {
-            for (int l = 0; l < 64; l++) {
+            for (int l = 0; l < AWB_NSCRIBE; l++) {
                 scs[l] = 0;
                 scc[l] = 0;
                 scr[l] = 255;
@@ -414,7 +414,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                     if (nl > 32) { fits = false; break; }
                     if ((l & 31) + nl > 32) l = (l + 31) & ~31;
                     l += nl;
-                    if (l > 64) fits = false;
+                    if (l > AWB_NSCRIBE) fits = false;
                 }
                 if (fits) break;
             }
