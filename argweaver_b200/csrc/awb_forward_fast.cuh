@@ -69,8 +69,8 @@
 #define AWB_FWD_FSCRIBES AWB_NSCRIBE          // F-scribe lanes
 #define AWB_FWD_HELPERS (AWB_NSCRIBE + 32)    // F-scribes + norm warp
 
-// shared memory (doubles): zT[2 NS + 64] | colS[2][NS] | Fs[2][TMAX+2] | Rs[2][TMAX+2] |
-// scaleS[2] | invS[4] | dummy[2]
+// shared memory (doubles): Fs[2][TMAX+2] | Rs[2][TMAX+2] | scaleS[2] | invS[4] |
+// dummy[2] | zT[2 NS + 64] | colS[2][NS]
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX)
 {
     return (4 * (size_t) NS + 64 + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
@@ -136,19 +136,22 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     const int *__restrict__ nstatesg = chg.nstates;
     const int *__restrict__ blocklensg = chg.blocklens;
 
+    // the small arrays come first, at compile-time offsets from the start of
+    // shared memory (the site loops address them every site; offsets that
+    // depend on the CTA size were being recomputed from blockDim there)
     extern __shared__ double smem_f[];
-    double *zT = smem_f;                       // [2 NS + 64] column, time-major rows,
-                                               //   zero-padded for the scribes (K1)
-    double *colS = zT + 2 * NS + 64;                    // [2][NS] last column of a block in
-                                               //   state order, by block parity
-    double *FsS = colS + 2 * NS;               // [2][TMAX+2] per-time sums
+    double *FsS = smem_f;                      // [2][TMAX+2] per-time sums
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
     double *dummyS = invS + 4;                 // [2] [0]: idle lanes store here; [1] = 1.0
+    double *zT = dummyS + 2;                   // [2 NS + 64] column, time-major rows,
+                                               //   zero-padded for the scribes (K1)
+    double *colS = zT + 2 * NS + 64;           // [2][NS] last column of a block in
+                                               //   state order, by block parity
 
     for (int x = tid; x < 4 * NS + 64 + 4 * (TMAX + 2) + 8; x += blockDim.x) {
-        const int y = x - (4 * NS + 64 + 4 * (TMAX + 2));
+        const int y = x - 4 * (TMAX + 2);
         smem_f[x] = ((y >= 0 && y < 6) || y == 7) ? 1.0 : 0.0;   // scaleS, invS, one
     }
     __syncthreads();
