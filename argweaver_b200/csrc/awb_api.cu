@@ -216,7 +216,7 @@ struct awb_batch {
     size_t arena_bytes;
     AwbChain *d_chains;
     int *d_err;
-    int maxB, maxn, maxS, maxV, maxT, maxband, maxNS, maxcnt;
+    int maxB, maxn, maxS, maxV, maxT, maxband, maxNS, maxcnt, zcap;
     float ms[3];
     int launches;
     int64_t h2d_bytes;
@@ -335,7 +335,8 @@ static bool batch_fast_path(const awb_batch *b)
     const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
     // (a branch longer than a warp would need a cross-warp carry in the scans)
     return !getenv("AWB_FORCE_GENERIC") && threads <= 1024 && b->maxcnt <= 32 &&
-        !(tmax == 64 && threads > 384);
+        !(tmax == 64 && threads > 384) &&
+        awb_fwd_fast_smem_bytes(b->maxNS, tmax, b->zcap) <= 200 * 1024;
 }
 
 extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
@@ -357,6 +358,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->h_chains.resize(nproblems);
     b->maxB = b->maxn = b->maxS = b->maxV = b->maxT = b->maxband = 0;
     b->maxNS = 32;
+    b->zcap = 64;
     b->maxcnt = 1;
     b->ms[0] = b->ms[1] = b->ms[2] = 0;
     b->launches = 0;
@@ -405,6 +407,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.T > b->maxT) b->maxT = L.T;
         if (L.maxband > b->maxband) b->maxband = L.maxband;
         if (L.maxNS > b->maxNS) b->maxNS = L.maxNS;
+        if (L.zcap > b->zcap) b->zcap = L.zcap;
         if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
@@ -560,10 +563,15 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass)
     int maxd = 1;
     while (maxd < b->maxcnt) maxd <<= 1;
     const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
-    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax);
+    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax, b->zcap);
 #define AWB_LAUNCH_FAST(TM, NL, MT)                                              \
-    awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(b->d_chains, \
-                                                                      seg, pass)
+    do {                                                                         \
+        if (fsmem > 48 * 1024)                                                   \
+            CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT>,    \
+                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));      \
+        awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(       \
+            b->d_chains, seg, pass, b->zcap);                                    \
+    } while (0)
     const bool lev4 = maxd <= 16;
     if (tmax == 20) {
         if (threads <= 384) { if (lev4) AWB_LAUNCH_FAST(20, 4, 384); else AWB_LAUNCH_FAST(20, 5, 384); }

@@ -60,6 +60,7 @@ struct AwbChain {
     int maxS;                 // max over blocks of max(S_b, 1)
     int maxband;              // max over blocks of the band size (doubles)
     int maxNS;                // max over blocks of the padded thread count
+    int zcap;                 // max over blocks of the scribes' padded column (awb_scribe_plan)
     int maxcnt;               // longest branch (states)
     int keep_debug;
     int need_band;            // compute the tmatrix2 band (generic forward kernel only)
@@ -118,7 +119,7 @@ struct AwbChain {
     unsigned short *sc_cnt;   // [B][AWB_NSCRIBE] scribe lane -> number of slots
     unsigned char *sc_row;    // [B][AWB_NSCRIBE] scribe lane -> time row (255 idle)
     unsigned char *sc_stride; // [B][AWB_NSCRIBE] lanes sharing the row: lane i sums slots i, i+stride, ...
-    unsigned char *sc_ch;     // [B] slots every scribe lane sums (rows are zero-padded)
+    unsigned short *sc_ch;    // [B] slots every scribe lane sums (rows are zero-padded)
     int slotcap;              // ntimes + 32
     short *node_first;        // [B][V] first state index of node (or -1)
     short *node_cnt;          // [B][V]
@@ -301,6 +302,35 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
         }
     }
     return 32 * (nw > 0 ? nw : 1);
+}
+
+// The F-scribes' plan of one block (awb_setup.cuh K1 fills it in,
+// awb_forward_fast.cuh reads it): the AWB_NSCRIBE lanes are shared out over the
+// time rows, nl = ceil(w / CH) lanes for a row of w states (at least one, a row
+// never straddles a warp), with CH the smallest even slot count per lane for
+// which all rows fit.  Every row is padded to nl*CH slots.  Returns the padded
+// size of the column; the host layout runs the same code to size the kernel's
+// buffer.  w[0..nrows) are the row widths.
+AWB_HD inline int awb_scribe_plan(const int *w, int nrows, int &CHout)
+{
+    int CH = 2;
+    for (;; CH += 2) {
+        int l = 0;
+        bool fits = true;
+        for (int t = 0; t < nrows && fits; t++) {
+            const int nl = w[t] == 0 ? 1 : (w[t] + CH - 1) / CH;
+            if (nl > 32) { fits = false; break; }
+            if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+            l += nl;
+            if (l > AWB_NSCRIBE) fits = false;
+        }
+        if (fits) break;
+    }
+    int zb = 0;
+    for (int t = 0; t < nrows; t++)
+        zb += (w[t] == 0 ? 1 : (w[t] + CH - 1) / CH) * CH;
+    CHout = CH;
+    return zb;
 }
 
 #endif // AWB_COMMON_CUH

@@ -70,10 +70,10 @@
 #define AWB_FWD_HELPERS (AWB_NSCRIBE + 32)    // F-scribes + norm warp
 
 // shared memory (doubles): Fs[2][TMAX+2] | Rs[2][TMAX+2] | scaleS[2] | invS[4] |
-// dummy[2] | zT[2 NS + 64] | colS[2][NS]
-__host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX)
+// dummy[2] | colS[2][NS] | zT[zcap]
+__host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX, int zcap)
 {
-    return (4 * (size_t) NS + 64 + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
+    return (2 * (size_t) NS + (size_t) zcap + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
 }
 
 template <int N> struct AwbInt { static constexpr int value = N; };
@@ -113,7 +113,7 @@ __device__ __forceinline__ void awb_bar_sync(int id, int count)
 
 template <int TMAX, int NLEV, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1)
-awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
+awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
 {
     const AwbChain &chg = chains[blockIdx.x];
     const int tid = threadIdx.x;
@@ -145,12 +145,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass)
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
     double *dummyS = invS + 4;                 // [2] [0]: idle lanes store here; [1] = 1.0
-    double *zT = dummyS + 2;                   // [2 NS + 64] column, time-major rows,
-                                               //   zero-padded for the scribes (K1)
-    double *colS = zT + 2 * NS + 64;           // [2][NS] last column of a block in
+    double *colS = dummyS + 2;                 // [2][NS] last column of a block in
                                                //   state order, by block parity
+    double *zT = colS + 2 * NS;                // [zcap] column, time-major rows,
+                                               //   zero-padded for the scribes (K1)
 
-    for (int x = tid; x < 4 * NS + 64 + 4 * (TMAX + 2) + 8; x += blockDim.x) {
+    for (int x = tid; x < 2 * NS + zcap + 4 * (TMAX + 2) + 8; x += blockDim.x) {
         const int y = x - 4 * (TMAX + 2);
         smem_f[x] = ((y >= 0 && y < 6) || y == 7) ? 1.0 : 0.0;   // scaleS, invS, one
     }

@@ -29,6 +29,7 @@ struct AwbLayout {
     int B, V, T, n, nrows;
     int maxS, maxband;
     int maxNS;                           // forward kernel: padded threads per block
+    int zcap;                            // forward kernel: padded time-major column (slots)
     int maxcnt;                          // longest branch (states)
     int keep_debug;
     double states_sites;                 // sum blocklen * nstates
@@ -105,7 +106,8 @@ inline std::vector<short> &awb_pack_scratch()
 inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
                              std::vector<int> &c1, std::vector<int> &stack,
                              std::vector<char> &ignore, int &S, int &band,
-                             int &tpos, int &maxcnt, std::string &err)
+                             int &tpos, int &maxcnt, std::string &err,
+                             int *wrow = NULL)
 {
     const int V = p.nnodes, T = p.ntimes;
     const int *parent = p.ptrees + (size_t) b * V;
@@ -153,6 +155,10 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     S = 0;
     band = 0;
     tpos = 1;
+    if (wrow) {
+        for (int t = 0; t < T; t++) wrow[t] = 0;
+        wrow[0] = 1;                        // (a block without states: one dummy slot)
+    }
     int minage = p.minage;
     if (internal) {
         if (V < 3 || c0[root] == -1) {
@@ -185,6 +191,8 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     }
     std::vector<short> &bcnt = awb_pack_scratch();
     bcnt.assign(V, 0);
+    if (wrow) wrow[0] = 0;
+
     // tpos: thread slots of the forward kernel when the branches are laid out in
     // node order, none straddling a warp ("next fit") -- the capacity reserved
     // for this block's thread map; K1 packs tighter when it can (see below)
@@ -199,6 +207,10 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
             S += cnt;
             band += cnt * cnt;
             bcnt[i] = (short) cnt;
+            if (wrow) {             // states per time row, as differences
+                wrow[lo]++;
+                wrow[hi + 1]--;
+            }
             if (cnt > maxcnt) maxcnt = cnt;
             if (cnt > 32) {
                 tpos = ((tpos + 31) & ~31) + ((cnt + 31) & ~31);
@@ -211,6 +223,10 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     }
     if (S == 0)
         tpos = 1;
+    if (wrow) {
+        for (int t = 1; t < T; t++) wrow[t] += wrow[t - 1];
+        if (S == 0) wrow[0] = 1;
+    }
     return true;
 }
 
@@ -262,6 +278,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.trow_off.assign(B + 1, 0);
     L.maxS = 1;
     L.maxNS = 32;
+    L.zcap = 64;
     L.maxcnt = 1;
     L.maxband = 0;
     L.states_sites = 0;
@@ -269,9 +286,33 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     std::vector<char> ignore(V);
     for (int b = 0; b < B; b++) {
         int S = 0, band = 0, tpos = 1;
+        int wrow[AWB_MAXT + 1];
         if (!awb_count_states(p, b, c0, c1, stack, ignore, S, band, tpos,
-                              L.maxcnt, err))
+                              L.maxcnt, err, wrow))
             return false;
+        {
+            // the scribes' padded column (awb_scribe_plan): the slots per lane
+            // are at most CHub = the even count for which the rows surely fit
+            // (lanes <= S/CH + rows + a warp-boundary gap), hence the column is
+            // at most S + rows*CHub; the exact plan only for a block that
+            // could raise the maximum
+            const int rows = T - 1;
+            int maxw = 1;
+            for (int t = 0; t < rows; t++)
+                if (wrow[t] > maxw) maxw = wrow[t];
+            const int spare = AWB_NSCRIBE - rows - 1;
+            long long chub = spare > 0 ? (S + 2 * maxw + spare - 1) / spare : maxw;
+            if (chub * 32 < maxw) chub = (maxw + 31) / 32;
+            if (chub > maxw) chub = maxw;
+            chub = (chub + 1) & ~1ll;
+            if (chub < 2) chub = 2;
+            if (S + rows * chub > L.zcap) {
+                int CH;
+                const int z = awb_scribe_plan(wrow, rows, CH);
+                if (CH > 65535) { err = "block too wide for the forward kernel"; return false; }
+                if (z > L.zcap) L.zcap = z;
+            }
+        }
         const int NSb = (tpos + 31) & ~31;
         L.trow_off[b + 1] = L.trow_off[b] + NSb;
         if (NSb > L.maxNS) {
@@ -396,7 +437,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_sc_cnt, (size_t) B * AWB_NSCRIBE * sizeof(short));
     AWB_PLACE(o_sc_row, (size_t) B * AWB_NSCRIBE);
     AWB_PLACE(o_sc_stride, (size_t) B * AWB_NSCRIBE);
-    AWB_PLACE(o_sc_ch, (size_t) B);
+    AWB_PLACE(o_sc_ch, (size_t) B * 2);
     AWB_PLACE(o_st_node, rows * sizeof(short));
     AWB_PLACE(o_st_time, rows);
     AWB_PLACE(o_perm, rows * sizeof(short));
@@ -521,6 +562,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.maxS = L.maxS;
     ch.maxband = L.maxband;
     ch.maxNS = L.maxNS;
+    ch.zcap = L.zcap;
     ch.maxcnt = L.maxcnt;
     ch.keep_debug = L.keep_debug;
     ch.need_band = 1;
@@ -557,7 +599,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     AWB_P(unsigned short *, sc_cnt, o_sc_cnt);
     AWB_P(unsigned char *, sc_row, o_sc_row);
     AWB_P(unsigned char *, sc_stride, o_sc_stride);
-    AWB_P(unsigned char *, sc_ch, o_sc_ch);
+    AWB_P(unsigned short *, sc_ch, o_sc_ch);
     AWB_P(short *, st_node, o_st_node);
     AWB_P(signed char *, st_time, o_st_time);
     AWB_P(unsigned short *, perm, o_perm);

@@ -404,21 +404,13 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 scr[l] = 255;
                 sct[l] = 1;
             }
-            int CH = 2;
-            for (;; CH += 2) {
-                int l = 0;
-                bool fits = true;
-                for (int t = 0; t < T - 1 && fits; t++) {
-                    const int w = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
-                    const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
-                    if (nl > 32) { fits = false; break; }
-                    if ((l & 31) + nl > 32) l = (l + 31) & ~31;
-                    l += nl;
-                    if (l > AWB_NSCRIBE) fits = false;
-                }
-                if (fits) break;
-            }
-            ch.sc_ch[b] = (unsigned char) CH;
+            int wrow[AWB_MAXT];
+            for (int t = 0; t < T - 1; t++)
+                wrow[t] = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
+            int CH;
+            if (awb_scribe_plan(wrow, T - 1, CH) > ch.zcap)
+                return 7;       // the host layout sized the buffer with the same code
+            ch.sc_ch[b] = (unsigned short) CH;
             int l = 0, zb = 0;
             for (int t = 0; t < T - 1; t++) {
                 // every row gets at least one lane: an empty row sums zeros
@@ -435,8 +427,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 }
                 zb += nl * CH;
             }
-            if (zb > 2 * ch.maxNS + 64)
-                return 7;       // padded column larger than the kernel's buffer
         }
 
         if (S > 0) {

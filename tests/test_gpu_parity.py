@@ -81,13 +81,25 @@ CASES = [(8, 2000, 20, False, 1), (8, 2000, 20, True, 2), (20, 5000, 20, False, 
          (50, 4000, 20, True, 10),
          # BASELINE config 4 shape: > 1024 states per block (two states per thread
          # in the generic forward kernel, multi-pass rows in the traceback)
-         (100, 1500, 40, False, 11), (100, 1200, 40, True, 12)]
+         (100, 1500, 40, False, 11), (100, 1200, 40, True, 12),
+         # few states spread over many time rows (the forward kernel's padded
+         # time-major column is sized by the host layout)
+         (4, 800, 40, False, 13), (6, 800, 64, True, 14), (3, 600, 64, False, 15),
+         (12, 800, 64, False, 16)]
 
 
 @pytest.mark.parametrize("k,n,T,internal,seed", CASES)
 def test_generated_problems(k, n, T, internal, seed, libc_rand):
     d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
     compare_with_oracle(d, libc_rand(100 + seed, n))
+
+
+@pytest.mark.parametrize("k,T,popsize", [(30, 64, 200.), (24, 64, 100.)])
+def test_skewed_time_rows(k, T, popsize, libc_rand):
+    # all lineages coalesce in the first few of 63 time rows (see
+    # test_host_logic.test_setup_workers_skewed_time_rows)
+    d = sim.simulate_problem(k, 1000, ntimes=T, seed=5, popsize=popsize)
+    compare_with_oracle(d, libc_rand(77, 1000))
 
 
 def test_generic_forward_kernel_forced(libc_rand, monkeypatch):

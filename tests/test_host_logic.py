@@ -14,7 +14,10 @@ from helpers import assert_close, block_starts
 
 CASES = [(8, 600, 20, False, 1), (8, 600, 20, True, 2), (20, 1500, 20, False, 3),
          (20, 1500, 20, True, 4), (12, 800, 30, False, 5), (6, 500, 10, True, 6),
-         (2, 200, 20, False, 7), (3, 200, 20, True, 8), (30, 800, 40, False, 9)]
+         (2, 200, 20, False, 7), (3, 200, 20, True, 8), (30, 800, 40, False, 9),
+         # few states spread over many time rows (the forward kernel's padded
+         # time-major column is sized by the host layout)
+         (4, 400, 40, False, 13), (6, 400, 64, True, 14), (3, 300, 64, False, 15)]
 
 
 def check_problem(d):
@@ -88,6 +91,14 @@ def check_problem(d):
 def test_setup_workers_generated(k, n, T, internal, seed):
     check_problem(sim.simulate_problem(k, n, ntimes=T, seed=seed,
                                        internal=internal))
+
+
+@pytest.mark.parametrize("k,T,popsize", [(30, 64, 200.), (24, 64, 100.)])
+def test_setup_workers_skewed_time_rows(k, T, popsize):
+    # all lineages coalesce in the first few of 63 time rows: one wide row and
+    # many one-state rows, the worst case for the forward kernel's padded
+    # time-major column (awb_scribe_plan sizes it on the host)
+    check_problem(sim.simulate_problem(k, 300, ntimes=T, seed=5, popsize=popsize))
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1])
