@@ -194,7 +194,7 @@ struct awb_ctx {
     // inputs go up on their own stream, in groups of problems, so that the
     // setup kernels of one group overlap with the copies of the next
     cudaStream_t copy_stream;
-    cudaEvent_t up_ev[AWB_UPLOAD_GROUPS], order_ev;
+    cudaEvent_t up_ev[AWB_UPLOAD_GROUPS], seq_ev, order_ev;
     cudaEvent_t ev[6];
     cudaEvent_t user_ev[8];
     int sm_count;
@@ -242,6 +242,7 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
         CUDA_OK(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->seq_ev, cudaEventDisableTiming));
     for (int i = 0; i < 6; i++)
         CUDA_OK(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < 8; i++)
@@ -281,6 +282,7 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
     for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
         cudaEventDestroy(ctx->up_ev[i]);
     cudaEventDestroy(ctx->order_ev);
+    cudaEventDestroy(ctx->seq_ev);
     if (ctx->arena_cache) cudaFree(ctx->arena_cache);
     delete ctx;
 }
@@ -508,6 +510,9 @@ extern "C" int awb_batch_upload(awb_batch *b)
     CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
                             sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
+    // the trees first, group by group (the per-block setup kernels start on a
+    // group as soon as its trees are there), then the sequences, which are 2/3
+    // of the bytes and are not read before the site-kind kernel
     for (int g = 0; g < AWB_UPLOAD_GROUPS; g++) {
         int g0, g1;
         upload_group(b, g, g0, g1);
@@ -519,12 +524,23 @@ extern "C" int awb_batch_upload(awb_batch *b)
             if (L.keep_debug)
                 CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));   // (band included)
             for (size_t i = 0; i < L.copies.size(); i++)
-                CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
-                                        L.copies[i].bytes, cudaMemcpyHostToDevice,
-                                        st));
+                if (L.copies[i].dst_off != L.o_seqs)
+                    CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
+                                            L.copies[i].bytes, cudaMemcpyHostToDevice,
+                                            st));
         }
         CUDA_OK(cudaEventRecord(b->ctx->up_ev[g], st));
     }
+    for (int c = 0; c < b->C; c++) {
+        const AwbLayout &L = b->L[c];
+        char *base = b->arena + b->arena_off[c];
+        for (size_t i = 0; i < L.copies.size(); i++)
+            if (L.copies[i].dst_off == L.o_seqs)
+                CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
+                                        L.copies[i].bytes, cudaMemcpyHostToDevice,
+                                        st));
+    }
+    CUDA_OK(cudaEventRecord(b->ctx->seq_ev, st));
     b->uploaded = true;
     b->setup_done = b->forward_done = false;
     return 0;
@@ -634,11 +650,6 @@ extern "C" int awb_batch_setup(awb_batch *b)
         const AwbChain *chains = b->d_chains + g0;
         const int Cg = g1 - g0;
         {
-            dim3 grid((b->maxn + 255) / 256, Cg);
-            if (grid.x > 4096) grid.x = 4096;
-            awb_kind_kernel<<<grid, 256, 0, st>>>(chains);
-        }
-        {
             dim3 grid((b->maxB + 63) / 64, Cg);
             awb_block_setup_kernel<<<grid, 64, 0, st>>>(chains, b->d_err);
             dim3 grid2(b->maxB, Cg);
@@ -649,6 +660,13 @@ extern "C" int awb_batch_setup(awb_batch *b)
             awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * sw_scratch, st>>>(
                 chains, b->d_err, sw_scratch);
         }
+    }
+    {
+        // site kinds: the first kernel that reads the sequences
+        CUDA_OK(cudaStreamWaitEvent(st, b->ctx->seq_ev, 0));
+        dim3 grid((b->maxn + 255) / 256, b->C);
+        if (grid.x > 4096) grid.x = 4096;
+        awb_kind_kernel<<<grid, 256, 0, st>>>(b->d_chains);
     }
     b->launches += b->maxB > 1 ? 4 : 3;
     // variant-site emissions go into the forward table; with a checkpointed

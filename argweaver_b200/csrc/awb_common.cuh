@@ -269,19 +269,22 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
 {
     unsigned char fill[AWB_MAXS / 32 + 2];
     int nw = 0;
-    unsigned long long present = 0;
-    for (int i = 0; i < V; i++) {
+    // the branches of each length, in node order: one pass over cnt (K1 reads
+    // it from global memory), linked through nxt
+    unsigned short head[64], nxt[AWB_MAXV];
+    for (int l = 0; l < 64; l++)
+        head[l] = 0xFFFF;
+    for (int i = V - 1; i >= 0; i--) {
         const int c = cnt[i];
-        if (c > 0)
-            present |= 1ull << (c > 63 ? 63 : c - 1);
+        if (c > 0) {
+            const int l = c > 63 ? 63 : c - 1;
+            nxt[i] = head[l];
+            head[l] = (unsigned short) i;
+        }
     }
     for (int len = 63; len >= 0; len--) {
-        if (!((present >> len) & 1ull))
-            continue;
-        for (int i = 0; i < V; i++) {
-            const int c = cnt[i];
-            if (c <= 0 || (c > 63 ? 63 : c - 1) != len)
-                continue;
+        for (int i = head[len]; i != 0xFFFF; i = nxt[i]) {
+            const int c = len == 63 ? cnt[i] : len + 1;
             int slot;
             if (c > 32) {
                 slot = 32 * nw;

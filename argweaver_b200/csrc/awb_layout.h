@@ -103,7 +103,7 @@ inline std::vector<short> &awb_pack_scratch()
 
 // Number of states of one tree and the sum of squared branch state counts.
 // Returns false on a malformed tree.
-inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
+inline bool awb_count_states_checked(const awb_problem &p, int b, std::vector<int> &c0,
                              std::vector<int> &c1, std::vector<int> &stack,
                              std::vector<char> &ignore, int &S, int &band,
                              int &tpos, int &maxcnt, std::string &err,
@@ -113,44 +113,50 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     const int *parent = p.ptrees + (size_t) b * V;
     const int *age = p.ages + (size_t) b * V;
     int root = -1, nroots = 0;
+    const bool internal = p.internal != 0;
+    int *c0p = c0.data(), *c1p = c1.data();
+    memset(c0p, 0xFF, (size_t) V * sizeof(int));       // -1
+    memset(c1p, 0xFF, (size_t) V * sizeof(int));
+    memset(ignore.data(), 0, (size_t) V);
+    // one pass: children in node-index order (no data-dependent branches: which
+    // child slot is free is a coin flip to the branch predictor) and the checks
+    unsigned three = 0, young = 0, badage = 0;
     for (int i = 0; i < V; i++) {
-        c0[i] = c1[i] = -1;
-        ignore[i] = 0;
-    }
-    for (int i = 0; i < V; i++) {
-        const int pa = parent[i];
+        const int pa = parent[i], a = age[i];
         if (pa == -1) {
             root = i;
             nroots++;
+            const bool vroot = internal && a == T + 1;
+            if (!vroot && (a < 0 || a > T - 2)) badage = 1;
             continue;
         }
         if (pa < 0 || pa >= V || pa == i) {
             err = "tree " + std::to_string(b) + ": bad parent index";
             return false;
         }
-        if (c0[pa] == -1) c0[pa] = i;
-        else if (c1[pa] == -1) c1[pa] = i;
-        else {
-            err = "tree " + std::to_string(b) + ": node with three children";
-            return false;
-        }
+        badage |= (unsigned) (a < 0) | (unsigned) (a > T - 2);
+        young |= (unsigned) (age[pa] < a);
+        const int f = c0p[pa];
+        const bool has0 = f != -1;
+        three |= (unsigned) (has0 & (c1p[pa] != -1));
+        c0p[pa] = has0 ? f : i;
+        c1p[pa] = has0 ? i : -1;
+    }
+    if (three) {
+        err = "tree " + std::to_string(b) + ": node with three children";
+        return false;
     }
     if (nroots != 1) {
         err = "tree " + std::to_string(b) + ": expected exactly one root";
         return false;
     }
-    const bool internal = p.internal != 0;
-    for (int i = 0; i < V; i++) {
-        const int a = age[i];
-        const bool vroot = internal && i == root && a == T + 1;
-        if (!vroot && (a < 0 || a > T - 2)) {
-            err = "tree " + std::to_string(b) + ": node age out of range";
-            return false;
-        }
-        if (parent[i] != -1 && age[parent[i]] < a) {
-            err = "tree " + std::to_string(b) + ": parent younger than child";
-            return false;
-        }
+    if (badage) {
+        err = "tree " + std::to_string(b) + ": node age out of range";
+        return false;
+    }
+    if (young) {
+        err = "tree " + std::to_string(b) + ": parent younger than child";
+        return false;
     }
     S = 0;
     band = 0;
@@ -230,6 +236,73 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
     return true;
 }
 
+// The same, with the common case (a new leaf is threaded: every branch carries
+// states) done in ONE branch-light pass over the nodes -- the layout of a
+// genome-scale batch visits ~5*10^8 nodes on the host.  Anything unusual (an
+// invalid tree included) is left to the checked version above, which also
+// words the error.
+inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
+                             std::vector<int> &c1, std::vector<int> &stack,
+                             std::vector<char> &ignore, int &S, int &band,
+                             int &tpos, int &maxcnt, std::string &err,
+                             int *wrow)
+{
+    const int V = p.nnodes, T = p.ntimes;
+    if (!p.internal) {
+        const int *parent = p.ptrees + (size_t) b * V;
+        const int *age = p.ages + (size_t) b * V;
+        const int minage = p.minage;
+        std::vector<short> &bcnt = awb_pack_scratch();
+        bcnt.resize(V);
+        short *bc = bcnt.data();
+        unsigned char nch[AWB_MAXV];
+        memset(nch, 0, (size_t) V);
+        for (int t = 0; t < T; t++) wrow[t] = 0;
+        int S_ = 0, band_ = 0, tp = 0, mc = maxcnt, nroots = 0;
+        unsigned bad = 0;
+        bool odd = false;
+        for (int i = 0; i < V; i++) {
+            const int pa = parent[i], a = age[i];
+            const bool isroot = pa == -1;
+            const int pidx = isroot ? i : pa;
+            if ((unsigned) pidx >= (unsigned) V) { odd = true; break; }
+            const int pa_age = age[pidx];
+            if (((unsigned) a > (unsigned) (T - 2)) | ((unsigned) pa_age > (unsigned) (T - 2))) {
+                odd = true;
+                break;
+            }
+            nroots += isroot;
+            nch[pidx] = (unsigned char) (nch[pidx] + !isroot);
+            bad |= (unsigned) (!isroot & (pa == i)) | (unsigned) (pa_age < a);
+            const int lo = a > minage ? a : minage;
+            const int hi = isroot ? T - 2 : pa_age;
+            const int cnt = hi - lo + 1;
+            if (cnt <= 0 || cnt > 32) { odd = true; break; }
+            S_ += cnt;
+            band_ += cnt * cnt;
+            bc[i] = (short) cnt;
+            wrow[lo]++;
+            wrow[hi + 1]--;
+            mc = cnt > mc ? cnt : mc;
+            const int tp32 = (tp + 31) & ~31;
+            tp = ((tp & 31) + cnt > 32 ? tp32 : tp) + cnt;
+        }
+        if (!odd) {
+            for (int i = 0; i < V; i++) bad |= (unsigned) (nch[i] > 2);
+        }
+        if (!odd && !bad && nroots == 1) {
+            S = S_;
+            band = band_;
+            tpos = tp;
+            maxcnt = mc;
+            for (int t = 1; t < T; t++) wrow[t] += wrow[t - 1];
+            return true;
+        }
+    }
+    return awb_count_states_checked(p, b, c0, c1, stack, ignore, S, band, tpos,
+                                    maxcnt, err, wrow);
+}
+
 inline size_t awb_align(size_t x) { return (x + 255) & ~(size_t) 255; }
 
 // Build the layout.  Returns false and sets err on invalid input.
@@ -294,8 +367,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             // the scribes' padded column (awb_scribe_plan): the slots per lane
             // are at most CHub = the even count for which the rows surely fit
             // (lanes <= S/CH + rows + a warp-boundary gap), hence the column is
-            // at most S + rows*CHub; the exact plan only for a block that
-            // could raise the maximum
+            // at most S + rows*CHub; the exact plan only for a block whose
+            // bound is large and could raise the maximum
             const int rows = T - 1;
             int maxw = 1;
             for (int t = 0; t < rows; t++)
@@ -306,11 +379,16 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             if (chub > maxw) chub = maxw;
             chub = (chub + 1) & ~1ll;
             if (chub < 2) chub = 2;
-            if (S + rows * chub > L.zcap) {
-                int CH;
-                const int z = awb_scribe_plan(wrow, rows, CH);
-                if (CH > 65535) { err = "block too wide for the forward kernel"; return false; }
-                if (z > L.zcap) L.zcap = z;
+            const long long zub = S + rows * chub;
+            if (zub > L.zcap) {
+                if (zub <= 2 * (long long) ((tpos + 31) & ~31) + 64) {
+                    L.zcap = (int) zub;     // a modest buffer: the bound will do
+                } else {
+                    int CH;
+                    const int z = awb_scribe_plan(wrow, rows, CH);
+                    if (CH > 65535) { err = "block too wide for the forward kernel"; return false; }
+                    if (z > L.zcap) L.zcap = z;
+                }
             }
         }
         const int NSb = (tpos + 31) & ~31;

@@ -254,9 +254,9 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     }
 
     // ---- lineage counts (local_tree.cpp:34-69 / :82-131)
-    int *nbranches = ch.lineages + (size_t) b * 3 * T;
-    int *nrecombs = nbranches + T;
-    int *ncoals = nrecombs + T;
+    //      counted in thread-local arrays (one thread per block on the GPU: the
+    //      increments would be scattered read-modify-writes in global memory)
+    int nbranches[AWB_MAXT], nrecombs[AWB_MAXT], ncoals[AWB_MAXT];
     for (int i = 0; i < T; i++)
         nbranches[i] = nrecombs[i] = ncoals[i] = 0;
     for (int i = 0; i < V; i++) {
@@ -284,6 +284,14 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         }
     }
     nbranches[T - 1] = 1;
+    {
+        int *lg = ch.lineages + (size_t) b * 3 * T;
+        for (int i = 0; i < T; i++) {
+            lg[i] = nbranches[i];
+            lg[T + i] = nrecombs[i];
+            lg[2 * T + i] = ncoals[i];
+        }
+    }
 
     // ---- tree length (local_tree.cpp:136-176), summed in node order
     double treelen = 0.0;

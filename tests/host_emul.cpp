@@ -189,3 +189,11 @@ void emul_layout(void *h, int *nstates, long long *row_off, long long *fw_off,
 void emul_destroy(void *h) { delete (Emul *) h; }
 
 } // extern "C"
+
+// host layout alone (timed by scripts/layout_time.py); returns 0 on success
+extern "C" int emul_layout_only(const awb_problem *p, int ckpt)
+{
+    AwbLayout L;
+    std::string err;
+    return awb_layout_build(*p, 0, L, err, ckpt ? (1ll << 24) : 0) ? 0 : -1;
+}
