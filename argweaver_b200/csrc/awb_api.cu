@@ -194,7 +194,7 @@ struct awb_ctx {
     // inputs go up on their own stream, in groups of problems, so that the
     // setup kernels of one group overlap with the copies of the next
     cudaStream_t copy_stream;
-    cudaEvent_t up_ev[AWB_UPLOAD_GROUPS], seq_ev, order_ev;
+    cudaEvent_t up_ev[AWB_UPLOAD_GROUPS], seq_ev, rand_ev, order_ev;
     cudaEvent_t ev[6];
     cudaEvent_t user_ev[8];
     int sm_count;
@@ -203,6 +203,11 @@ struct awb_ctx {
     char *arena_cache;
     size_t arena_cap;
     bool arena_busy;
+    // pinned staging buffer for the arrays the host layout makes (a copy from
+    // pageable memory blocks the calling thread until the stream has drained);
+    // lent together with the arena
+    char *stage;
+    size_t stage_cap;
 };
 
 struct awb_batch {
@@ -212,6 +217,9 @@ struct awb_batch {
     std::vector<awb_problem> P;
     std::vector<size_t> arena_off;
     std::vector<AwbChain> h_chains;
+    AwbChain *stage_chains;      // pinned copy of h_chains (or NULL)
+    size_t windows_bytes;        // arena bytes of the windows (before the chain records)
+    bool bound;                  // batch_bind has run
     char *arena;
     size_t arena_bytes;
     AwbChain *d_chains;
@@ -220,7 +228,7 @@ struct awb_batch {
     float ms[3];
     int launches;
     int64_t h2d_bytes;
-    bool uploaded, setup_done, forward_done, rand_uploaded;
+    bool uploaded, setup_done, forward_done, rand_uploaded, rand_in_use;
     bool ckpt;                 // checkpointed forward table (AWB_CHECKPOINT)
     int maxseg;                // most segments of any problem
     int maxsegsites;           // most sites of any segment
@@ -243,6 +251,7 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
         CUDA_OK(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ctx->seq_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->rand_ev, cudaEventDisableTiming));
     for (int i = 0; i < 6; i++)
         CUDA_OK(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < 8; i++)
@@ -253,6 +262,8 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     ctx->arena_cache = NULL;
     ctx->arena_cap = 0;
     ctx->arena_busy = false;
+    ctx->stage = NULL;
+    ctx->stage_cap = 0;
     CUDA_OK(cudaFuncSetAttribute(awb_forward_kernel<1>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
@@ -283,7 +294,9 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
         cudaEventDestroy(ctx->up_ev[i]);
     cudaEventDestroy(ctx->order_ev);
     cudaEventDestroy(ctx->seq_ev);
+    cudaEventDestroy(ctx->rand_ev);
     if (ctx->arena_cache) cudaFree(ctx->arena_cache);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     delete ctx;
 }
 
@@ -367,6 +380,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->h2d_bytes = 0;
     b->uploaded = b->setup_done = b->forward_done = false;
     b->rand_uploaded = false;
+    b->rand_in_use = false;
 
     const auto t_create0 = std::chrono::steady_clock::now();
     // host layout of every problem (integer work), one host thread per problem
@@ -435,7 +449,27 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         b->arena_off[c] = total;
         total += awb_align(with_band ? b->L[c].total_bytes : b->L[c].bytes_before_band);
     }
+    b->windows_bytes = total;
+    b->bound = false;
+    if (getenv("AWB_VERBOSE"))
+        fprintf(stderr, "awb_batch_create: layout %.1f ms\n",
+                std::chrono::duration<double, std::milli>(
+                    std::chrono::steady_clock::now() - t_create0).count());
+    *out = b;
+    return 0;
+}
+
+// Second half of the batch's construction, at the first awb_batch_upload: the
+// device arena (the context's cached one when it is free), the chain records,
+// the pinned staging copies.  awb_batch_create itself is host-only work, so the
+// layout of the next batch can be made while the previous batch still runs on
+// (and owns the arena of) the device.
+static int batch_bind(awb_batch *b)
+{
+    awb_ctx *ctx = b->ctx;
+    const int nproblems = b->C;
     const auto t_create1 = std::chrono::steady_clock::now();
+    size_t total = b->windows_bytes;
     // chain records and the error word live at the tail of the arena
     const size_t chains_off = total;
     total += awb_align(sizeof(AwbChain) * nproblems);
@@ -451,7 +485,6 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
             if (e != cudaSuccess) {
                 std::string msg = std::string("cudaMalloc of ") +
                     std::to_string(total) + " bytes failed: " + cudaGetErrorString(e);
-                delete b;
                 return fail(msg);
             }
             ctx->arena_cap = total;
@@ -464,7 +497,6 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
             std::string msg = std::string("cudaMalloc of ") + std::to_string(total) +
                 " bytes failed: " + cudaGetErrorString(e);
             b->arena = NULL;
-            delete b;
             return fail(msg);
         }
     }
@@ -475,14 +507,76 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
                         b->h_chains[c]);
         b->h_chains[c].need_band = batch_fast_path(b) ? 0 : 1;
     }
+    b->stage_chains = NULL;
+    if (b->arena == ctx->arena_cache) {
+        // stage the layout's own arrays (and the chain records) in pinned memory
+        std::vector<size_t> soff(nproblems + 1, 0);
+        for (int c = 0; c < nproblems; c++) {
+            size_t need = 0;
+            for (size_t i = 0; i < b->L[c].copies.size(); i++)
+                if (b->L[c].copies[i].own)
+                    need += awb_align(b->L[c].copies[i].bytes);
+            soff[c + 1] = soff[c] + need;
+        }
+        const size_t need = soff[nproblems] + awb_align(sizeof(AwbChain) * nproblems);
+        if (ctx->stage_cap < need) {
+            if (ctx->stage) cudaFreeHost(ctx->stage);
+            ctx->stage = NULL;
+            ctx->stage_cap = 0;
+            if (cudaHostAlloc((void **) &ctx->stage, need + need / 8,
+                              cudaHostAllocDefault) == cudaSuccess)
+                ctx->stage_cap = need + need / 8;
+            else
+                cudaGetLastError();     // no staging: the copies work without it
+        }
+        if (ctx->stage) {
+            unsigned hw = std::thread::hardware_concurrency();
+            const int nthreads = (int) std::min<unsigned>(hw ? hw : 1, (unsigned) nproblems);
+            auto work = [&](int t) {
+                for (int c = t; c < nproblems; c += nthreads) {
+                    char *dst = ctx->stage + soff[c];
+                    std::vector<AwbCopy> merged;
+                    for (size_t i = 0; i < b->L[c].copies.size(); i++) {
+                        AwbCopy cp = b->L[c].copies[i];
+                        if (!cp.own) {
+                            merged.push_back(cp);
+                            continue;
+                        }
+                        memcpy(dst, cp.src, cp.bytes);
+                        cp.src = dst;
+                        dst += awb_align(cp.bytes);
+                        // neighbours in the arena are neighbours here: one copy
+                        // (the alignment gaps go along)
+                        if (!merged.empty() && merged.back().own &&
+                            cp.dst_off == awb_align(merged.back().dst_off +
+                                                    merged.back().bytes) &&
+                            (const char *) cp.src == (const char *) merged.back().src +
+                                awb_align(merged.back().bytes))
+                            merged.back().bytes = cp.dst_off - merged.back().dst_off + cp.bytes;
+                        else
+                            merged.push_back(cp);
+                    }
+                    b->L[c].copies.swap(merged);
+                }
+            };
+            if (nthreads <= 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nthreads; t++) pool.emplace_back(work, t);
+                for (auto &th : pool) th.join();
+            }
+            b->stage_chains = (AwbChain *) (ctx->stage + soff[nproblems]);
+            memcpy(b->stage_chains, b->h_chains.data(), sizeof(AwbChain) * nproblems);
+        }
+    }
     if (getenv("AWB_VERBOSE")) {
         const auto t_create2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "awb_batch_create: layout %.1f ms, arena (%.2f GB) + bind %.1f ms\n",
-                std::chrono::duration<double, std::milli>(t_create1 - t_create0).count(),
+        fprintf(stderr, "awb_batch_upload: arena (%.2f GB) + bind + staging %.1f ms\n",
                 total / 1e9,
                 std::chrono::duration<double, std::milli>(t_create2 - t_create1).count());
     }
-    *out = b;
+    b->bound = true;
     return 0;
 }
 
@@ -503,11 +597,14 @@ static void upload_group(const awb_batch *b, int g, int &g0, int &g1)
 extern "C" int awb_batch_upload(awb_batch *b)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    if (!b->bound && batch_bind(b))
+        return 1;
     cudaStream_t st = b->ctx->copy_stream;
     // after whatever the compute stream still has queued on this arena
     CUDA_OK(cudaEventRecord(b->ctx->order_ev, b->ctx->stream));
     CUDA_OK(cudaStreamWaitEvent(st, b->ctx->order_ev, 0));
-    CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
+    CUDA_OK(cudaMemcpyAsync(b->d_chains,
+                            b->stage_chains ? b->stage_chains : b->h_chains.data(),
                             sizeof(AwbChain) * b->C, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(b->d_err, 0, sizeof(int), st));
     // the trees first, group by group (the per-block setup kernels start on a
@@ -738,6 +835,25 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
     return 0;
 }
 
+// The random draws go up on the copy stream, next to whatever the compute
+// stream still has queued (normally the forward pass); the traceback waits for
+// rand_ev.
+static int upload_rand_ints(awb_batch *b, const int *const *rand_ints)
+{
+    cudaStream_t cs = b->ctx->copy_stream;
+    if (b->rand_in_use) {
+        // an earlier traceback of this batch may still be reading the old draws
+        CUDA_OK(cudaEventRecord(b->ctx->order_ev, b->ctx->stream));
+        CUDA_OK(cudaStreamWaitEvent(cs, b->ctx->order_ev, 0));
+    }
+    for (int c = 0; c < b->C; c++)
+        CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints, rand_ints[c],
+                                sizeof(int) * b->L[c].n, cudaMemcpyHostToDevice, cs));
+    CUDA_OK(cudaEventRecord(b->ctx->rand_ev, cs));
+    b->rand_uploaded = true;
+    return 0;
+}
+
 extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
                                    int rand_max, const int *last_states)
 {
@@ -747,16 +863,21 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
     CUDA_OK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     bool chains_dirty = false;
+    if (rand_ints && upload_rand_ints(b, rand_ints))
+        return 1;
+    CUDA_OK(cudaStreamWaitEvent(st, b->ctx->rand_ev, 0));
+    b->rand_in_use = true;
     for (int c = 0; c < b->C; c++) {
-        if (rand_ints)
-            CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints,
-                                    rand_ints[c], sizeof(int) * b->L[c].n,
-                                    cudaMemcpyHostToDevice, st));
         const int ls = last_states ? last_states[c] : -1;
         if (ls != b->h_chains[c].last_state) {
             b->h_chains[c].last_state = ls;
             chains_dirty = true;
         }
+    }
+    if (chains_dirty && b->stage_chains) {
+        // keep the pinned copy (used by a later awb_batch_upload) in step
+        CUDA_OK(cudaStreamSynchronize(b->ctx->copy_stream));
+        memcpy(b->stage_chains, b->h_chains.data(), sizeof(AwbChain) * b->C);
     }
     if (chains_dirty)
         CUDA_OK(cudaMemcpyAsync(b->d_chains, b->h_chains.data(),
@@ -784,12 +905,9 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
 extern "C" int awb_batch_upload_rand(awb_batch *b, const int *const *rand_ints)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
-    for (int c = 0; c < b->C; c++)
-        CUDA_OK(cudaMemcpyAsync((void *) b->h_chains[c].rand_ints, rand_ints[c],
-                                sizeof(int) * b->L[c].n, cudaMemcpyHostToDevice,
-                                b->ctx->stream));
-    b->rand_uploaded = true;
-    return 0;
+    if (!b->bound && batch_bind(b))
+        return 1;
+    return upload_rand_ints(b, rand_ints);
 }
 
 extern "C" int awb_batch_sync(awb_batch *b)
@@ -846,6 +964,7 @@ extern "C" int awb_batch_kernel_launches(const awb_batch *b) { return b->launche
 extern "C" int awb_batch_get_path(awb_batch *b, int i, int *path)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    if (!b->bound) return fail("awb_batch_get_path: nothing has been uploaded or computed");
     CUDA_OK(cudaMemcpyAsync(path, b->h_chains[i].path, sizeof(int) * b->L[i].n,
                             cudaMemcpyDeviceToHost, b->ctx->stream));
     CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
@@ -855,6 +974,7 @@ extern "C" int awb_batch_get_path(awb_batch *b, int i, int *path)
 extern "C" int awb_batch_get_logz(awb_batch *b, int i, double *logz)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    if (!b->bound) return fail("awb_batch_get_logz: nothing has been uploaded or computed");
     CUDA_OK(cudaMemcpyAsync(logz, b->h_chains[i].logz, sizeof(double),
                             cudaMemcpyDeviceToHost, b->ctx->stream));
     CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
@@ -864,6 +984,7 @@ extern "C" int awb_batch_get_logz(awb_batch *b, int i, double *logz)
 extern "C" int awb_batch_get_status(awb_batch *b, int i, int *first_bad_site)
 {
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    if (!b->bound) return fail("awb_batch_get_status: nothing has been uploaded or computed");
     CUDA_OK(cudaMemcpyAsync(first_bad_site, b->h_chains[i].status, sizeof(int),
                             cudaMemcpyDeviceToHost, b->ctx->stream));
     CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
@@ -875,6 +996,7 @@ extern "C" int awb_batch_get_fw(awb_batch *b, int i, double *fw)
     if (b->ckpt)
         return fail("awb_batch_get_fw: the forward table is not kept with AWB_CHECKPOINT");
     CUDA_OK(cudaSetDevice(b->ctx->device));
+    if (!b->bound) return fail("awb_batch_get_fw: nothing has been uploaded or computed");
     CUDA_OK(cudaMemcpyAsync(fw, b->h_chains[i].fw,
                             sizeof(double) * b->L[i].fw_off[b->L[i].B],
                             cudaMemcpyDeviceToHost, b->ctx->stream));

@@ -23,6 +23,7 @@ struct AwbCopy {            // one host -> arena copy of an input array
     size_t dst_off;
     const void *src;
     size_t bytes;
+    int own;                // see awb_layout_build ("input copies")
 };
 
 struct AwbLayout {
@@ -492,12 +493,15 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
 #define AWB_PLACE(name, bytes) do { L.name = off; off = awb_align(off + (bytes)); } while (0)
     AWB_PLACE(o_ptrees, BV * sizeof(int));
     AWB_PLACE(o_ages, BV * sizeof(int));
-    AWB_PLACE(o_sprs, (size_t) B * 4 * sizeof(int));
     AWB_PLACE(o_mappings, BV * sizeof(int));
+    AWB_PLACE(o_seqs, (size_t) p.nseqs * p.seqlen);
+    // the small inputs and the arrays made above, next to each other and in the
+    // order of L.copies: they go up as ONE copy from a pinned staging buffer
+    // (awb_api.cu)
+    AWB_PLACE(o_sprs, (size_t) B * 4 * sizeof(int));
     AWB_PLACE(o_blocklens, (size_t) B * sizeof(int));
     AWB_PLACE(o_subtree_roots, (size_t) B * sizeof(int));
     AWB_PLACE(o_rowidx, (size_t) L.nrows * sizeof(int));
-    AWB_PLACE(o_seqs, (size_t) p.nseqs * p.seqlen);
     AWB_PLACE(o_block_start, (size_t) (B + 1) * sizeof(int));
     AWB_PLACE(o_nstates, (size_t) B * sizeof(int));
     AWB_PLACE(o_row_off, (size_t) (B + 1) * sizeof(long long));
@@ -506,11 +510,15 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_ent_off, (size_t) (B + 1) * sizeof(long long));
     AWB_PLACE(o_sw1_off, (size_t) (B + 1) * sizeof(long long));
     AWB_PLACE(o_trow_off, (size_t) (B + 1) * sizeof(long long));
+    AWB_PLACE(o_ptab, (size_t) (T * T + T) * 2 * sizeof(double));
+    if (L.ckpt)
+        AWB_PLACE(o_seg_start, (size_t) (L.nseg + 1) * sizeof(int));
+    else
+        L.o_seg_start = 0;
     AWB_PLACE(o_tmap, (size_t) L.trow_off[B] * sizeof(short));
     AWB_PLACE(o_iperm, rows * sizeof(short));
     AWB_PLACE(o_st_age, rows);
     AWB_PLACE(o_lin, (size_t) B * 7 * T * sizeof(double));
-    AWB_PLACE(o_ptab, (size_t) (T * T + T) * 2 * sizeof(double));
     AWB_PLACE(o_sc_start, (size_t) B * AWB_NSCRIBE * sizeof(short));
     AWB_PLACE(o_sc_cnt, (size_t) B * AWB_NSCRIBE * sizeof(short));
     AWB_PLACE(o_sc_row, (size_t) B * AWB_NSCRIBE);
@@ -561,12 +569,11 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
         AWB_PLACE(o_fw, (size_t) L.seg_doubles * sizeof(double));
         AWB_PLACE(o_fsum, (size_t) L.seg_sites * (T > 1 ? T - 1 : 1) * sizeof(double));
         AWB_PLACE(o_ckptcol, (size_t) (L.nseg + 1) * L.maxS * sizeof(double));
-        AWB_PLACE(o_seg_start, (size_t) (L.nseg + 1) * sizeof(int));
     } else {
         AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
         // per-site, per-time sums of the stored forward column (traceback)
         AWB_PLACE(o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * sizeof(double));
-        L.o_ckptcol = L.o_seg_start = 0;
+        L.o_ckptcol = 0;
     }
     AWB_PLACE(o_path, (size_t) L.n * sizeof(int));
     AWB_PLACE(o_rand, (size_t) L.n * sizeof(int));
@@ -595,29 +602,32 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     }
 
     // ---- input copies
+    // (own: 0 = a large caller array, copied from where it is; 1 = a small
+    // caller array, 2 = made by the layout -- both staged when the batch has a
+    // pinned staging buffer; the staged ones in arena order)
     L.copies.clear();
-    L.copies.push_back({ L.o_ptab, L.ptab.data(), L.ptab.size() * sizeof(double) });
+    L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int), 0 });
+    L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int), 0 });
+    if (p.mappings)
+        L.copies.push_back({ L.o_mappings, p.mappings, BV * sizeof(int), 0 });
+    L.copies.push_back({ L.o_seqs, p.seqs, (size_t) p.nseqs * p.seqlen, 0 });
+    L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int), 1 });
+    L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int), 1 });
+    if (L.has_subtree_roots)
+        L.copies.push_back({ L.o_subtree_roots, p.subtree_roots, (size_t) B * sizeof(int), 1 });
+    L.copies.push_back({ L.o_rowidx, L.rowidx.data(), (size_t) L.nrows * sizeof(int), 2 });
+    L.copies.push_back({ L.o_block_start, L.block_start.data(), (size_t) (B + 1) * sizeof(int), 2 });
+    L.copies.push_back({ L.o_nstates, L.nstates.data(), (size_t) B * sizeof(int), 2 });
+    L.copies.push_back({ L.o_row_off, L.row_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_fw_off, L.fw_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_band_off, L.band_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_ent_off, L.ent_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_sw1_off, L.sw1_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_trow_off, L.trow_off.data(), (size_t) (B + 1) * sizeof(long long), 2 });
+    L.copies.push_back({ L.o_ptab, L.ptab.data(), L.ptab.size() * sizeof(double), 2 });
     if (L.ckpt)
         L.copies.push_back({ L.o_seg_start, L.seg_start.data(),
-                             (size_t) (L.nseg + 1) * sizeof(int) });
-    L.copies.push_back({ L.o_ptrees, p.ptrees, BV * sizeof(int) });
-    L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int) });
-    L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int) });
-    if (p.mappings)
-        L.copies.push_back({ L.o_mappings, p.mappings, BV * sizeof(int) });
-    L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int) });
-    if (L.has_subtree_roots)
-        L.copies.push_back({ L.o_subtree_roots, p.subtree_roots, (size_t) B * sizeof(int) });
-    L.copies.push_back({ L.o_rowidx, L.rowidx.data(), (size_t) L.nrows * sizeof(int) });
-    L.copies.push_back({ L.o_seqs, p.seqs, (size_t) p.nseqs * p.seqlen });
-    L.copies.push_back({ L.o_block_start, L.block_start.data(), (size_t) (B + 1) * sizeof(int) });
-    L.copies.push_back({ L.o_nstates, L.nstates.data(), (size_t) B * sizeof(int) });
-    L.copies.push_back({ L.o_row_off, L.row_off.data(), (size_t) (B + 1) * sizeof(long long) });
-    L.copies.push_back({ L.o_fw_off, L.fw_off.data(), (size_t) (B + 1) * sizeof(long long) });
-    L.copies.push_back({ L.o_band_off, L.band_off.data(), (size_t) (B + 1) * sizeof(long long) });
-    L.copies.push_back({ L.o_ent_off, L.ent_off.data(), (size_t) (B + 1) * sizeof(long long) });
-    L.copies.push_back({ L.o_sw1_off, L.sw1_off.data(), (size_t) (B + 1) * sizeof(long long) });
-    L.copies.push_back({ L.o_trow_off, L.trow_off.data(), (size_t) (B + 1) * sizeof(long long) });
+                             (size_t) (L.nseg + 1) * sizeof(int), 2 });
     return true;
 }
 

@@ -46,12 +46,31 @@ def main():
         t3 = time.perf_counter()
         paths = [b.path(i, out=pbuf[i]) for i in range(W)]
         t4 = time.perf_counter()
+        tm = b.timings()
         b.close()
         torch.cuda.synchronize()
         t5 = time.perf_counter()
-        print("e2e %.0f ms: create %.0f upload %.0f run %.0f paths %.0f close %.0f | %s"
+        print("serial    e2e %.0f ms: create %.0f upload %.0f run %.0f paths %.0f close %.0f | %s"
               % ((t5 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
-                 (t4 - t3) * 1e3, (t5 - t4) * 1e3, b_t(b)), flush=True)
+                 (t4 - t3) * 1e3, (t5 - t4) * 1e3, tm), flush=True)
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b = api.Batch(problems, ctx, checkpoint=True)
+        t1 = time.perf_counter()
+        b.upload().setup().forward().traceback(rands)
+        t2 = time.perf_counter()
+        b.sync()
+        t3 = time.perf_counter()
+        paths = [b.path(i, out=pbuf[i]) for i in range(W)]
+        t4 = time.perf_counter()
+        tm = b.timings()
+        b.close()
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        print("pipelined e2e %.0f ms: create %.0f enqueue %.0f wait %.0f paths %.0f close %.0f | %s"
+              % ((t5 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
+                 (t4 - t3) * 1e3, (t5 - t4) * 1e3, tm), flush=True)
 
 
 def b_t(b):
