@@ -134,9 +134,9 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     const AwbSeg g = awb_seg(ch, seg);
     if (!g.valid)
         return;
-    // second pass of a checkpointed table: the last segment's table is still
+    // second pass of a checkpointed table: the last segments' tables are still
     // resident from the first pass
-    if (pass == 1 && seg == ch.nseg - 1)
+    if (pass == 1 && g.resident)
         return;
     // (the first column of a table is the prior / the stored first column of
     // the segment: no emission applied)
@@ -219,6 +219,8 @@ struct awb_batch {
     std::vector<AwbChain> h_chains;
     AwbChain *stage_chains;      // pinned copy of h_chains (or NULL)
     size_t windows_bytes;        // arena bytes of the windows (before the chain records)
+    bool with_band;              // the generic kernel's tables are part of the arena
+    int nslots;                  // checkpointed table: segment tables per window
     bool bound;                  // batch_bind has run
     char *arena;
     size_t arena_bytes;
@@ -443,13 +445,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         }
     }
     // the tmatrix2 band is only read by the generic forward kernel
-    const bool with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
-    size_t total = 0;
-    for (int c = 0; c < nproblems; c++) {
-        b->arena_off[c] = total;
-        total += awb_align(with_band ? b->L[c].total_bytes : b->L[c].bytes_before_band);
-    }
-    b->windows_bytes = total;
+    b->with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
+    b->windows_bytes = 0;
     b->bound = false;
     if (getenv("AWB_VERBOSE"))
         fprintf(stderr, "awb_batch_create: layout %.1f ms\n",
@@ -469,36 +466,78 @@ static int batch_bind(awb_batch *b)
     awb_ctx *ctx = b->ctx;
     const int nproblems = b->C;
     const auto t_create1 = std::chrono::steady_clock::now();
-    size_t total = b->windows_bytes;
-    // chain records and the error word live at the tail of the arena
-    const size_t chains_off = total;
-    total += awb_align(sizeof(AwbChain) * nproblems);
-    const size_t err_off = total;
-    total += awb_align(sizeof(int));
-    b->arena_bytes = total;
-    if (!ctx->arena_busy) {
-        if (ctx->arena_cap < total) {
-            if (ctx->arena_cache) cudaFree(ctx->arena_cache);
-            ctx->arena_cache = NULL;
-            ctx->arena_cap = 0;
-            cudaError_t e = cudaMalloc((void **) &ctx->arena_cache, total);
-            if (e != cudaSuccess) {
-                std::string msg = std::string("cudaMalloc of ") +
-                    std::to_string(total) + " bytes failed: " + cudaGetErrorString(e);
-                return fail(msg);
+    // arena bytes of every window.  Checkpointed table: as many segment tables
+    // per window as the device has room for (AWB_RESIDENT_SEGS overrides) --
+    // the traceback then finds the last ones still resident and rebuilds fewer
+    int nslots = 1;
+    if (b->ckpt) {
+        size_t base = 0, slot = 0;
+        for (int c = 0; c < nproblems; c++) {
+            base += awb_align(awb_layout_place_slots(b->L[c], 1, b->with_band));
+            slot += awb_layout_slot_bytes(b->L[c]);
+        }
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            if (!ctx->arena_busy)
+                free_b += ctx->arena_cap;               // ours to re-use or replace
+            const size_t margin = (size_t) 8 << 30;     // kernels' local memory, NCCL, ...
+            if (free_b > base + margin && slot > 0)
+                nslots = 1 + (int) ((free_b - base - margin) / slot);
+        } else {
+            cudaGetLastError();
+        }
+        if (getenv("AWB_RESIDENT_SEGS"))
+            nslots = atoi(getenv("AWB_RESIDENT_SEGS"));
+        if (nslots > b->maxseg) nslots = b->maxseg;
+        if (nslots < 1) nslots = 1;
+    }
+    size_t total = 0, chains_off = 0, err_off = 0;
+    for (;;) {
+        total = 0;
+        for (int c = 0; c < nproblems; c++) {
+            b->arena_off[c] = total;
+            if (b->ckpt)
+                total += awb_align(awb_layout_place_slots(b->L[c], nslots, b->with_band));
+            else
+                total += awb_align(b->with_band ? b->L[c].total_bytes
+                                                : b->L[c].bytes_before_band);
+        }
+        b->windows_bytes = total;
+        b->nslots = nslots;
+        // chain records and the error word live at the tail of the arena
+        chains_off = total;
+        total += awb_align(sizeof(AwbChain) * nproblems);
+        err_off = total;
+        total += awb_align(sizeof(int));
+        b->arena_bytes = total;
+        cudaError_t e = cudaSuccess;
+        if (!ctx->arena_busy) {
+            if (ctx->arena_cap < total) {
+                if (ctx->arena_cache) cudaFree(ctx->arena_cache);
+                ctx->arena_cache = NULL;
+                ctx->arena_cap = 0;
+                e = cudaMalloc((void **) &ctx->arena_cache, total);
+                if (e == cudaSuccess)
+                    ctx->arena_cap = total;
             }
-            ctx->arena_cap = total;
+            if (e == cudaSuccess) {
+                b->arena = ctx->arena_cache;
+                ctx->arena_busy = true;
+            }
+        } else {
+            e = cudaMalloc((void **) &b->arena, total);
+            if (e != cudaSuccess)
+                b->arena = NULL;
         }
-        b->arena = ctx->arena_cache;
-        ctx->arena_busy = true;
-    } else {
-        cudaError_t e = cudaMalloc((void **) &b->arena, total);
-        if (e != cudaSuccess) {
-            std::string msg = std::string("cudaMalloc of ") + std::to_string(total) +
-                " bytes failed: " + cudaGetErrorString(e);
-            b->arena = NULL;
-            return fail(msg);
+        if (e == cudaSuccess)
+            break;
+        cudaGetLastError();
+        if (nslots > 1) {
+            nslots = 1;         // the estimate of the free memory was too generous
+            continue;
         }
+        return fail(std::string("cudaMalloc of ") + std::to_string(total) +
+                    " bytes failed: " + cudaGetErrorString(e));
     }
     b->d_chains = (AwbChain *) (b->arena + chains_off);
     b->d_err = (int *) (b->arena + err_off);
@@ -572,8 +611,8 @@ static int batch_bind(awb_batch *b)
     }
     if (getenv("AWB_VERBOSE")) {
         const auto t_create2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "awb_batch_upload: arena (%.2f GB) + bind + staging %.1f ms\n",
-                total / 1e9,
+        fprintf(stderr, "awb_batch_upload: arena (%.2f GB, %d segment tables per window) + bind + staging %.1f ms\n",
+                total / 1e9, b->nslots,
                 std::chrono::duration<double, std::milli>(t_create2 - t_create1).count());
     }
     b->bound = true;

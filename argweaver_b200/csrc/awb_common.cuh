@@ -69,6 +69,10 @@ struct AwbChain {
     // [seg_start[s], seg_start[s+1]) plus the first row of the next block);
     // ckptcol[s] is the stored first column of segment s (s >= 1)
     int ckpt, nseg;
+    int nslots;               // segment tables in fw / fsum (the last nslots segments
+                              //   of the forward pass stay resident for the traceback)
+    int seg_sites;            // sites per segment table (fsum stride between tables)
+    long long seg_doubles;    // doubles per segment table
     const int *seg_start;     // [nseg + 1]
     double *ckptcol;          // [nseg + 1][maxS]
 
@@ -175,7 +179,9 @@ AWB_HD inline double awb_logadd(double lna, double lnb)
 // offsets into offsets of the segment's table.
 struct AwbSeg {
     int b0, b1, extra, site0, nsites;
-    long long fwbias;
+    long long fwbias;       // fw table of the segment: ch.fw - fwbias + (whole-table offset)
+    long long fsoff;        // fsum of the segment: ch.fsum + fsoff + (site - site0) * (T-1)
+    bool resident;          // the table written by the forward pass is still there
     bool valid;
 };
 
@@ -184,12 +190,13 @@ AWB_HD inline AwbSeg awb_seg(const AwbChain &ch, int s)
     AwbSeg g;
     if (!ch.ckpt) {
         g.b0 = 0; g.b1 = ch.ntrees; g.extra = 0; g.site0 = 0; g.nsites = ch.nsites;
-        g.fwbias = 0; g.valid = true;
+        g.fwbias = 0; g.fsoff = 0; g.resident = true; g.valid = true;
         return g;
     }
     g.valid = s >= 0 && s < ch.nseg;
     if (!g.valid) {
         g.b0 = g.b1 = 0; g.extra = 0; g.site0 = 0; g.nsites = 0; g.fwbias = 0;
+        g.fsoff = 0; g.resident = false;
         return g;
     }
     g.b0 = ch.seg_start[s];
@@ -197,7 +204,13 @@ AWB_HD inline AwbSeg awb_seg(const AwbChain &ch, int s)
     g.extra = g.b1 < ch.ntrees ? 1 : 0;
     g.site0 = ch.block_start[g.b0];
     g.nsites = ch.block_start[g.b1] - g.site0 + g.extra;
-    g.fwbias = ch.fw_off[g.b0];
+    // the last nslots segments have a table of their own (and stay resident
+    // after the forward pass); all earlier ones take turns in table 0
+    const int R = ch.nslots < ch.nseg ? ch.nslots : ch.nseg;
+    g.resident = s >= ch.nseg - R;
+    const int slot = g.resident ? s - (ch.nseg - R) : 0;
+    g.fwbias = ch.fw_off[g.b0] - (long long) slot * ch.seg_doubles;
+    g.fsoff = (long long) slot * ch.seg_sites * (ch.model.ntimes - 1);
     return g;
 }
 

@@ -126,9 +126,9 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const AwbSeg g = awb_seg(chg, seg);
     if (!g.valid)
         return;
-    // second pass of a checkpointed table: the last segment's table is still
+    // second pass of a checkpointed table: the last segments' tables are still
     // resident from the first pass
-    if (pass == 1 && seg == chg.nseg - 1)
+    if (pass == 1 && g.resident)
         return;
     const int n = g.nsites;
     const int bbeg = g.b0, bend = g.b1 + g.extra;
@@ -174,7 +174,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         // =================================================================
         double lprod = 1.0, lacc = 0.0;
         int nprod = 0;
-        double *__restrict__ fsumg = chg.fsum;
+        double *__restrict__ fsumg = chg.fsum + g.fsoff;
         int bad_site = -1;
         // This warp has slack, so it also warms the cache for the others: when
         // a block starts, the per-block tables of the NEXT block (what

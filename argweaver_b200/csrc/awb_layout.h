@@ -46,6 +46,9 @@ struct AwbLayout {
 
     // arena
     size_t total_bytes;
+    size_t total_bytes_noslots;     // checkpointed table: without the segment tables
+    size_t slots_at;                // checkpointed table: where they start
+    int nslots;                     // checkpointed table: resident segment tables
     size_t bytes_before_band;       // arena size when the band is left out
     // checkpointed table (seg_start.size() == nseg + 1, block indices)
     int ckpt, nseg;
@@ -306,6 +309,30 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
 
 inline size_t awb_align(size_t x) { return (x + 255) & ~(size_t) 255; }
 
+// Checkpointed table: the segment tables sit at the end of the window's
+// sub-arena -- `nslots` of them (fw, then fsum).  One is needed; the batch gives
+// more when the device has room, and the last `nslots` segments of the forward
+// pass then stay resident for the traceback instead of being rebuilt
+// (awb_api.cu batch_bind).  Returns the window's arena bytes.
+inline size_t awb_layout_slot_bytes(const AwbLayout &L)
+{
+    const int T = L.T;
+    return awb_align((size_t) L.seg_doubles * sizeof(double)) +
+        awb_align((size_t) L.seg_sites * (T > 1 ? T - 1 : 1) * sizeof(double));
+}
+
+inline size_t awb_layout_place_slots(AwbLayout &L, int nslots, bool with_band)
+{
+    const int T = L.T;
+    const size_t base = with_band ? L.total_bytes_noslots : L.bytes_before_band;
+    L.nslots = nslots;
+    L.o_fw = base;
+    L.o_fsum = base + awb_align((size_t) nslots * L.seg_doubles * sizeof(double));
+    L.slots_at = base;
+    return L.o_fsum +
+        awb_align((size_t) nslots * L.seg_sites * (T > 1 ? T - 1 : 1) * sizeof(double));
+}
+
 // Build the layout.  Returns false and sets err on invalid input.
 // seg_cap > 0 selects the checkpointed table: the forward table is not kept
 // whole; the window is cut into segments of whole blocks whose tables hold at
@@ -527,10 +554,6 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_st_node, rows * sizeof(short));
     AWB_PLACE(o_st_time, rows);
     AWB_PLACE(o_perm, rows * sizeof(short));
-    AWB_PLACE(o_pslot, rows * sizeof(short));
-    AWB_PLACE(o_band_j1, rows * sizeof(short));
-    AWB_PLACE(o_band_len, rows);
-    AWB_PLACE(o_band_boff, rows * sizeof(int));
     AWB_PLACE(o_inv_emit, rows * sizeof(double));
     AWB_PLACE(o_tmatrix, (size_t) B * T * T * sizeof(double));
     AWB_PLACE(o_tmvec, (size_t) B * AWB_TM_NVEC * T * sizeof(double));
@@ -564,11 +587,10 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     }
     AWB_PLACE(o_kind, (size_t) L.n + 8);     // the forward kernel reads a few sites ahead
     if (L.ckpt) {
-        // one segment's table and per-time sums, the first column of every
-        // segment, the segment list
-        AWB_PLACE(o_fw, (size_t) L.seg_doubles * sizeof(double));
-        AWB_PLACE(o_fsum, (size_t) L.seg_sites * (T > 1 ? T - 1 : 1) * sizeof(double));
+        // the first column of every segment; the segment tables themselves
+        // (fw, fsum) are placed behind everything else by awb_layout_place_slots
         AWB_PLACE(o_ckptcol, (size_t) (L.nseg + 1) * L.maxS * sizeof(double));
+        L.o_fw = L.o_fsum = 0;
     } else {
         AWB_PLACE(o_fw, (size_t) L.fw_off[B] * sizeof(double));
         // per-site, per-time sums of the stored forward column (traceback)
@@ -580,12 +602,21 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_logz, sizeof(double));
     AWB_PLACE(o_sink, (size_t) 1024 * sizeof(double));   // forward kernel: discarded stores
     AWB_PLACE(o_status, sizeof(int));
-    // the tmatrix2 band is only read by the generic forward kernel: it comes
-    // last so that a batch on the fast path can leave it out of its arena
+    // the tmatrix2 band and the per-state slot tables are only read by the
+    // generic forward kernel: they come last so that a batch on the fast path
+    // can leave them out of its arena
     L.bytes_before_band = off;
+    AWB_PLACE(o_pslot, rows * sizeof(short));
+    AWB_PLACE(o_band_j1, rows * sizeof(short));
+    AWB_PLACE(o_band_len, rows);
+    AWB_PLACE(o_band_boff, rows * sizeof(int));
     AWB_PLACE(o_band, (size_t) L.band_off[B] * sizeof(double) + 8);
 #undef AWB_PLACE
-    L.total_bytes = off;
+    L.total_bytes = L.total_bytes_noslots = off;
+    L.nslots = 1;
+    L.slots_at = 0;
+    if (L.ckpt)
+        L.total_bytes = awb_layout_place_slots(L, 1, true);
 
     // ---- branch-probability table of the emission kernel (emit.cpp:86-116)
     L.ptab.assign((size_t) (T * T + T) * 2, 0.0);
@@ -657,6 +688,9 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.gen_mappings = L.gen_mappings;
     ch.ckpt = L.ckpt;
     ch.nseg = L.nseg;
+    ch.nslots = L.nslots;
+    ch.seg_doubles = L.seg_doubles;
+    ch.seg_sites = L.seg_sites;
     ch.seg_start = L.ckpt ? (const int *) (base + L.o_seg_start) : 0;
     ch.ckptcol = L.ckpt ? (double *) (base + L.o_ckptcol) : 0;
     ch.last_state = -1;

@@ -219,6 +219,21 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         }
     }
 
+    // ---- invariant-site emission (emit.cpp:786-819): it depends on the
+    //      coalescence time and on whether the branch is the main tree's root
+    //      branch, 2(T-1) values; the states loop below writes them per state
+    double ie[2][AWB_MAXT];
+    {
+        const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
+        for (int bt = 0; bt < T - 1; bt++) {
+            const double coal_time = m.times[bt];
+            const double tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime);
+            const double tl2r = tl2 + fmax(coal_time - m.times[age[maintree_root]], m.mintime);
+            ie[0][bt] = .25 * exp(-m.mu * fmax(tl2, m.mintime));
+            ie[1][bt] = .25 * exp(-m.mu * fmax(tl2r, m.mintime));
+        }
+    }
+
     // ---- states, node-major (states.cpp:53-74 / :146-165)
     int ns = 0;
     for (int i = 0; i < V; i++) {
@@ -239,9 +254,12 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         nfirst[i] = (short) ns;
         ncnt[i] = (short) cnt;
         if (ns + cnt <= S) {
+            const double *iev = ie[i == maintree_root ? 1 : 0];
             for (int t = lo; t <= hi; t++) {
                 ch.st_node[row0 + ns + (t - lo)] = (short) i;
                 ch.st_time[row0 + ns + (t - lo)] = (signed char) t;
+                ch.st_age[row0 + ns + (t - lo)] = (signed char) age[i];
+                ch.inv_emit[row0 + ns + (t - lo)] = iev[t];
             }
         }
         ns += cnt;
@@ -488,16 +506,14 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         // node-major thread map; a branch never straddles a warp
         const long long tr0 = ch.trow_off[b];
         const int NSb = (int) (ch.trow_off[b + 1] - tr0);
-        for (int t = 0; t < NSb; t++)
-            ch.tmap[tr0 + t] = 0xFFFF;
+        // (trow_off and NSb are multiples of 32 slots: 8-byte stores)
+        for (int t = 0; t < NSb / 4; t++)
+            ((unsigned long long *) (ch.tmap + tr0))[t] = 0xFFFFFFFFFFFFFFFFull;
         if (S == 0) {
             ch.tmap[tr0] = 0;
             ch.iperm[row0] = 0;
             ch.st_age[row0] = 0;
         } else {
-            for (int i = 0; i < V; i++)
-                for (int t = 0; t < ncnt[i]; t++)
-                    ch.st_age[row0 + nfirst[i] + t] = (signed char) age[i];
             // first-fit-decreasing packing when it fits the reserved slots (it
             // nearly always does, and is tighter); else node order, which is
             // what the host reserved (awb_count_states)
@@ -546,9 +562,11 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 
     if (S == 0) {
         ch.inv_emit[row0] = 1.0;
-        ch.band_j1[row0] = 0;
-        ch.band_len[row0] = 0;
-        ch.band_boff[row0] = 0;
+        if (ch.need_band) {
+            ch.band_j1[row0] = 0;
+            ch.band_len[row0] = 0;
+            ch.band_boff[row0] = 0;
+        }
         if (b == 0)
             ch.fw[ch.fw_off[0]] = 1.0;        // trans.cpp:822-825
         return 0;
@@ -564,23 +582,9 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     //      invariant-site emission (emit.cpp:786-819)
     double *band = ch.band + ch.band_off[b];
     int boff = 0;
-    const double time1 = internal ? m.times[age[subtree_root]] : 0.0;
-    // the invariant-site emission depends on the coalescence time and on
-    // whether the branch is the main tree's root branch: 2(T-1) values
-    double ie[2][AWB_MAXT];
-    for (int bt = 0; bt < T - 1; bt++) {
-        const double coal_time = m.times[bt];
-        const double tl2 = maintreelen + subtreelen + fmax(coal_time - time1, m.mintime);
-        const double tl2r = tl2 + fmax(coal_time - m.times[age[maintree_root]], m.mintime);
-        ie[0][bt] = .25 * exp(-m.mu * fmax(tl2, m.mintime));
-        ie[1][bt] = .25 * exp(-m.mu * fmax(tl2r, m.mintime));
-    }
-    for (int k = 0; k < S; k++) {
+    for (int k = 0; ch.need_band && k < S; k++) {
         const int node = ch.st_node[row0 + k];
         const int bt = ch.st_time[row0 + k];
-        ch.inv_emit[row0 + k] = ie[node == maintree_root ? 1 : 0][bt];
-        if (!ch.need_band)
-            continue;
         const int c = age[node];
         const int lo = awb_imax(c, minage);
         const int len = ncnt[node];

@@ -239,7 +239,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const int bmin = g.b0, btop = g.b1 - 1 + g.extra;
     const int bextra = g.extra ? g.b1 : -1;
     const double *__restrict__ fwg = ch.fw - g.fwbias;
-    const double *__restrict__ fsumg = ch.fsum - (size_t) g.site0 * (T - 1);
+    const double *__restrict__ fsumg = ch.fsum + g.fsoff - (long long) g.site0 * (T - 1);
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
     const AwbTbPtrs P = { ch.nstates, ch.blocklens, ch.block_start,

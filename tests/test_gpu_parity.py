@@ -254,11 +254,17 @@ def test_errors_are_reported_not_computed(libc_rand):
                          [(8, 3000, 20, False, 91, 20000), (20, 4000, 20, True, 92, 60000),
                           (12, 1500, 30, False, 93, 4000), (50, 3000, 20, True, 94, 200000),
                           (6, 800, 10, True, 95, 1 << 21)])
-def test_checkpointed_table(k, n, T, internal, seed, segd, libc_rand, monkeypatch):
+@pytest.mark.parametrize("resident", ["1", "2", "3", None])
+def test_checkpointed_table(k, n, T, internal, seed, segd, resident, libc_rand,
+                            monkeypatch):
     """AWB_CHECKPOINT: the forward table is rebuilt segment by segment from
     stored columns; path and logZ must equal the oracle's (and the whole-table
-    mode's)."""
+    mode's).  `resident`: segment tables per window -- the last ones of the
+    forward pass stay resident and are not rebuilt (None: as many as fit, here
+    all of them)."""
     monkeypatch.setenv("AWB_SEG_DOUBLES", str(segd))
+    if resident is not None:
+        monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
     d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
     r = libc_rand(200 + seed, n)
     o = ol.run_oracle(d, r)
@@ -275,6 +281,7 @@ def test_checkpointed_table(k, n, T, internal, seed, segd, libc_rand, monkeypatc
 
 def test_checkpointed_batch_with_given_prior_and_last_state(libc_rand, monkeypatch):
     monkeypatch.setenv("AWB_SEG_DOUBLES", "30000")
+    monkeypatch.setenv("AWB_RESIDENT_SEGS", "2")
     specs = [(8, 900, 20, False, 41), (12, 1300, 20, True, 42), (5, 300, 20, False, 43)]
     ds = [sim.simulate_problem(k, n, ntimes=T, seed=s, internal=i)
           for (k, n, T, i, s) in specs]
@@ -298,10 +305,12 @@ def test_checkpointed_batch_with_given_prior_and_last_state(libc_rand, monkeypat
     ck.close()
 
 
-def test_checkpointed_equals_whole_table_at_size(libc_rand):
+@pytest.mark.parametrize("resident", ["1", "3"])
+def test_checkpointed_equals_whole_table_at_size(resident, libc_rand, monkeypatch):
     """BASELINE config 3 shape (k=50, T=20), 3e5 sites, leaf and subtree
-    threading: the checkpointed table (several 128 MiB segments) gives the same
-    paths and logZ as the whole table."""
+    threading: the checkpointed table (several 128 MiB segments, 1 or 3 of them
+    resident) gives the same paths and logZ as the whole table."""
+    monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
     n = 300000
     ds = [sim.simulate_problem(50, n, seed=71 + i, internal=bool(i)) for i in range(2)]
     rs = [libc_rand(300 + i, n) for i in range(2)]
