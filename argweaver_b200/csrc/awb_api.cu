@@ -477,9 +477,9 @@ static int batch_bind(awb_batch *b)
             slot += awb_layout_slot_bytes(b->L[c]);
         }
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            if (!ctx->arena_busy)
-                free_b += ctx->arena_cap;               // ours to re-use or replace
+        // (a batch next to another live one gets a plain allocation: one table)
+        if (!ctx->arena_busy && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += ctx->arena_cap;                   // ours to re-use or replace
             const size_t margin = (size_t) 8 << 30;     // kernels' local memory, NCCL, ...
             if (free_b > base + margin && slot > 0)
                 nslots = 1 + (int) ((free_b - base - margin) / slot);

@@ -312,9 +312,11 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
                 slot = 32 * w + fill[w];
                 fill[w] = (unsigned char) (fill[w] + c);
             }
-            if (tmap && slot + c <= cap)
+            if (tmap && slot + c <= cap) {
+                const int nf = nfirst[i];
                 for (int t = 0; t < c; t++)
-                    tmap[slot + t] = (unsigned short) (nfirst[i] + t);
+                    tmap[slot + t] = (unsigned short) (nf + t);
+            }
         }
     }
     return 32 * (nw > 0 ? nw : 1);

@@ -254,12 +254,16 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         nfirst[i] = (short) ns;
         ncnt[i] = (short) cnt;
         if (ns + cnt <= S) {
+            // (values in registers: the arrays may alias as far as the compiler
+            // knows, and every store would make it read age[i] etc. again)
             const double *iev = ie[i == maintree_root ? 1 : 0];
+            const signed char ag = (signed char) age[i];
+            const long long k0 = row0 + ns - lo;
             for (int t = lo; t <= hi; t++) {
-                ch.st_node[row0 + ns + (t - lo)] = (short) i;
-                ch.st_time[row0 + ns + (t - lo)] = (signed char) t;
-                ch.st_age[row0 + ns + (t - lo)] = (signed char) age[i];
-                ch.inv_emit[row0 + ns + (t - lo)] = iev[t];
+                ch.st_node[k0 + t] = (short) i;
+                ch.st_time[k0 + t] = (signed char) t;
+                ch.st_age[k0 + t] = ag;
+                ch.inv_emit[k0 + t] = iev[t];
             }
         }
         ns += cnt;
@@ -443,7 +447,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 const int w = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
                 const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
                 if ((l & 31) + nl > 32) l = (l + 31) & ~31;
-                zbase[t] = zb;
+                zbase[t] = zb - (S == 0 ? 0 : rowstart[t]);   // padded slot = zbase + time-major position
                 for (int i = 0; i < nl; i++) {
                     scs[l] = (unsigned short) (zb + i);
                     scc[l] = (unsigned short) (w > i ? (w - i + nl - 1) / nl : 0);   // real slots
@@ -460,12 +464,13 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 const int cnt = ncnt[i];
                 if (cnt <= 0) continue;
                 const int lo = awb_imax(age[i], minage);
+                const int nf = nfirst[i];
                 for (int x = 0; x < cnt; x++) {
                     const int tt = lo + x;
                     const int pos = rowpos[tt]++;
-                    const int st = nfirst[i] + x;
+                    const int st = nf + x;
                     ch.perm[row0 + pos] = (unsigned short) st;
-                    ch.iperm[row0 + st] = (unsigned short) (zbase[tt] + (pos - rowstart[tt]));
+                    ch.iperm[row0 + st] = (unsigned short) (zbase[tt] + pos);
                 }
             }
         }
