@@ -58,6 +58,8 @@ def lib():
         L.awb_batch_fw_doubles.argtypes = [C.c_void_p, C.c_int]
         L.awb_batch_nsites.argtypes = [C.c_void_p, C.c_int]
         L.awb_batch_kernel_launches.argtypes = [C.c_void_p]
+        L.awb_batch_segments.argtypes = [C.c_void_p]
+        L.awb_batch_resident_segments.argtypes = [C.c_void_p]
         L.awb_batch_get_path.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.awb_batch_get_logz.argtypes = [C.c_void_p, C.c_int,
                                          C.POINTER(C.c_double)]
@@ -235,6 +237,12 @@ class Batch(object):
 
     def kernel_launches(self):
         return lib().awb_batch_kernel_launches(self.h)
+
+    def segments(self):
+        """Checkpointed table: (segments of the longest window, segment tables
+        kept per window)."""
+        return (lib().awb_batch_segments(self.h),
+                lib().awb_batch_resident_segments(self.h))
 
     def timings(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()

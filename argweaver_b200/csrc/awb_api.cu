@@ -447,6 +447,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     // the tmatrix2 band is only read by the generic forward kernel
     b->with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
     b->windows_bytes = 0;
+    b->nslots = 1;
     b->bound = false;
     if (getenv("AWB_VERBOSE"))
         fprintf(stderr, "awb_batch_create: layout %.1f ms\n",
@@ -999,6 +1000,11 @@ extern "C" int64_t awb_batch_fw_doubles(const awb_batch *b, int i)
 extern "C" int awb_batch_nsites(const awb_batch *b, int i) { return b->L[i].n; }
 
 extern "C" int awb_batch_kernel_launches(const awb_batch *b) { return b->launches; }
+extern "C" int awb_batch_segments(const awb_batch *b) { return b->maxseg; }
+extern "C" int awb_batch_resident_segments(const awb_batch *b)
+{
+    return b->bound ? b->nslots : 1;
+}
 
 extern "C" int awb_batch_get_path(awb_batch *b, int i, int *path)
 {

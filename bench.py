@@ -322,6 +322,7 @@ def bench_b200(a, rank, world, local_rank):
     logz_local = [batch.logz(i) for i in range(W)]
     status = [batch.status(i) for i in range(W)]
     assert all(s == -1 for s in status), "forward hit a non-positive column"
+    nseg, nres = batch.segments()
     h2d = batch.h2d_bytes() + sum(r.nbytes for r in rands)
     d2h = sum(4 * batch.nsites(i) for i in range(W))
     batch.close()
@@ -415,9 +416,12 @@ def bench_b200(a, rank, world, local_rank):
                 "l2": "inputs larger than L2: %.1f GB of forward table per GPU "
                       "streamed per step" % (fw_bytes / 1e9),
                 "parallelism": "windows sharded across GPUs, one CTA per window",
-                "table": ("checkpointed: the forward table is kept one 128 MiB "
-                          "segment per window at a time and rebuilt for the "
-                          "traceback (forward recursion runs twice per step)"
+                "table": ("checkpointed: %d segments of <= 128 MiB per window, "
+                          "%d segment tables kept per window (all the device "
+                          "memory allows); the traceback rebuilds the other "
+                          "%d segments (forward recursion runs %.2f times per "
+                          "step)" % (nseg, nres, nseg - nres,
+                                     1.0 + (nseg - nres) / float(nseg))
                           if a.checkpoint else "whole forward table resident"),
             },
             "clocks": clocks,

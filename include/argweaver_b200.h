@@ -135,6 +135,12 @@ double awb_batch_states_sites(const awb_batch *b, int i);
 int64_t awb_batch_fw_doubles(const awb_batch *b, int i);
 int awb_batch_nsites(const awb_batch *b, int i);
 int awb_batch_kernel_launches(const awb_batch *b);
+/* AWB_CHECKPOINT: segments of the longest window, and segment tables kept per
+ * window (chosen at the first upload from the free device memory; the last
+ * that many segments of the forward pass are not rebuilt for the traceback).
+ * Both 1 without AWB_CHECKPOINT. */
+int awb_batch_segments(const awb_batch *b);
+int awb_batch_resident_segments(const awb_batch *b);
 
 /* results (device -> host) */
 int awb_batch_get_path(awb_batch *b, int i, int *path /*[nsites]*/);
