@@ -93,7 +93,10 @@ __device__ __forceinline__ double awb_lds(unsigned addr)
 // prefetch [p, p + bytes) into L1, one 128-byte line per lane and step
 __device__ __forceinline__ void awb_prefetch_range(const void *p, long long bytes, int lane)
 {
-    const char *q = (const char *) p;
+    // (from the line that holds p[0] to the line that holds the last byte)
+    const unsigned long long a = (unsigned long long) p;
+    const char *q = (const char *) (a & ~127ull);
+    bytes += (long long) (a & 127ull);
     for (long long o = 128ll * lane; o < bytes; o += 128ll * 32)
         asm volatile("prefetch.global.L1 [%0];" :: "l"(q + o));
 }
@@ -266,9 +269,9 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             {
                 const double sc = (site == 0 && !(chg.ckpt && seg > 0)) ? 1.0 : inv;
                 if (lane < T - 1)
-                    fsumg[(size_t) site * (T - 1) + lane] = f0 * sc;
+                    __stcs(fsumg + (size_t) site * (T - 1) + lane, f0 * sc);
                 if (lane + 32 < T - 1)
-                    fsumg[(size_t) site * (T - 1) + lane + 32] = f1 * sc;
+                    __stcs(fsumg + (size_t) site * (T - 1) + lane + 32, f1 * sc);
             }
             if (!(nrm > 0.0) && bad_site < 0)
                 bad_site = site;
@@ -551,7 +554,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         const double PY = py - y0, Q = q - x0;
         const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
         // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
-        *w2 = c2 * awb_lds(inv_s + iofs);
+        __stcs(w2, c2 * awb_lds(inv_s + iofs));      // streaming: L1 is for the block tables
         const unsigned kd = kind_next;
         kind_next = *kp++;
         double e = inv_e;
@@ -604,7 +607,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             awb_sts(zaddr, c);
             awb_sts(active ? col_s + 8u * (unsigned) ((b & 1) * NS + jj) : dummy_s, c);
             awb_bar_sync(1, NB1);
-            *w2 = c2 * awb_lds(inv_s + iofs);
+            __stcs(w2, c2 * awb_lds(inv_s + iofs));      // streaming: L1 is for the block tables
             const unsigned kd = kind_next;
             kind_next = *kp++;
             awb_bar_sync(2, NB2);

@@ -197,3 +197,11 @@ extern "C" int emul_layout_only(const awb_problem *p, int ckpt)
     std::string err;
     return awb_layout_build(*p, 0, L, err, ckpt ? (1ll << 24) : 0) ? 0 : -1;
 }
+
+// thread slots of the fast forward kernel (max over blocks) for a problem
+extern "C" int emul_layout_maxns(const awb_problem *p)
+{
+    AwbLayout L;
+    std::string err;
+    return awb_layout_build(*p, 0, L, err, 0) ? L.maxNS : -1;
+}
