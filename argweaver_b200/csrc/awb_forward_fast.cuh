@@ -101,6 +101,19 @@ __device__ __forceinline__ void awb_prefetch_range(const void *p, long long byte
         asm volatile("prefetch.global.L1 [%0];" :: "l"(q + o));
 }
 
+// First and last lane of the run of equal keys this lane is in (a branch's
+// states, a row's scribe lanes: always consecutive lanes, and no key comes
+// twice in a warp -- what __match_any_sync would give, in a handful of
+// instructions instead of its per-value loop).
+__device__ __forceinline__ void awb_lane_run(int key, int lane, int &first, int &last)
+{
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned starts = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+    first = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+    const unsigned above = (lane == 31) ? 0u : (starts & (0xffffffffu << (lane + 1)));
+    last = above ? (__ffs(above) - 2) : 31;
+}
+
 __device__ __forceinline__ double2 awb_lds2(unsigned addr)
 {
     double2 v;
@@ -248,6 +261,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.sc_ch + nb));
                     }
                 }
             }
@@ -330,9 +344,8 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             const unsigned zstep = 8u * sc_strideg[(size_t) b * AWB_NSCRIBE + sl];
             const int CH = chg.sc_ch[b];            // slots every lane sums (even)
             const int key = (sc_row != 255) ? sc_row : (0x100 + lane);
-            const unsigned m = __match_any_sync(0xffffffffu, key);
-            const int seglane = __ffs(m) - 1;
-            const int segend = 31 - __clz(m);
+            int seglane, segend;
+            awb_lane_run(key, lane, seglane, segend);
             const bool sc_last = (lane == segend) && (sc_row != 255);
             const int span = __reduce_max_sync(0xffffffffu, segend - seglane);
             double um[5];
@@ -471,9 +484,8 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         raddr = Rs_s + 8u * (unsigned) atime;
         step = active ? 8ll * S1 : 0ll;
         const int key = live ? node : (0x10000 + lane);
-        const unsigned m = __match_any_sync(0xffffffffu, key);
-        const int seglane = __ffs(m) - 1;
-        const int segend = 31 - __clz(m);
+        int seglane, segend;
+        awb_lane_run(key, lane, seglane, segend);
 #pragma unroll
         for (int l = 0; l < NLEV; l++) {
             upm[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
