@@ -7,10 +7,12 @@
 //                           gather list over the target states
 //
 // Both are written as __host__ __device__ workers over one block so the same
-// code is unit-tested on the CPU (tests/host_emul.cpp) and launched one CUDA
-// thread per block by the kernels in awb_api.cu: per-block setup is ~0.5 % of
-// the work, embarrassingly parallel over 10^4-10^5 blocks, and off the
-// critical path of the forward recursion.
+// code is unit-tested on the CPU (tests/host_emul.cpp).  On the GPU K1 runs one
+// thread per block (awb_api.cu; it is bound by L1 sector throughput -- every
+// access of a warp goes to 32 different lines -- which is why counters and loop
+// invariants are kept in registers / local memory here) and K2 has a
+// warp-per-breakpoint twin (awb_switch_setup_warp).  Together with the time
+// matrices they are ~17 % of a step at the bench shape.
 //
 // Reference behaviour restated here (file:line in mdrasmus/argweaver):
 //   states.cpp:53-74,109-166          local_tree.cpp:34-219
