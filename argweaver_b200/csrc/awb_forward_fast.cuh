@@ -241,22 +241,30 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     const long long tr0n = chg.trow_off[nb];
                     const long long e0n = chg.ent_off[nb];
                     const long long nen = chg.ent_off[nb + 1] - e0n;
-                    awb_prefetch_range(chg.tmap + tr0n, 2 * (chg.trow_off[nb + 1] - tr0n), lane);
-                    awb_prefetch_range(chg.st_node + r0n, 2 * S1n, lane);
-                    awb_prefetch_range(chg.st_time + r0n, S1n, lane);
-                    awb_prefetch_range(chg.st_age + r0n, S1n, lane);
-                    awb_prefetch_range(chg.iperm + r0n, 2 * S1n, lane);
-                    awb_prefetch_range(chg.inv_emit + r0n, 8 * S1n, lane);
-                    awb_prefetch_range(chg.sw_start + r0n, 2 * S1n, lane);
-                    awb_prefetch_range(chg.sw_cnt + r0n, 2 * S1n, lane);
-                    awb_prefetch_range(chg.sw_src + e0n, 2 * nen, lane);
-                    awb_prefetch_range(chg.sw_prob + e0n, 8 * nen, lane);
-                    awb_prefetch_range(chg.lin + (size_t) nb * 7 * T, 56ll * T, lane);
-                    awb_prefetch_range(chg.tmatrix + (size_t) nb * T * T, 8ll * T * T, lane);
-                    awb_prefetch_range(chg.sc_start + (size_t) nb * AWB_NSCRIBE, 2 * AWB_NSCRIBE, lane);
-                    awb_prefetch_range(chg.sc_cnt + (size_t) nb * AWB_NSCRIBE, 2 * AWB_NSCRIBE, lane);
-                    awb_prefetch_range(chg.sc_row + (size_t) nb * AWB_NSCRIBE, AWB_NSCRIBE, lane);
-                    awb_prefetch_range(chg.sc_stride + (size_t) nb * AWB_NSCRIBE, AWB_NSCRIBE, lane);
+                    // (one compact loop over the 16 tables: this code runs once
+                    // per block, cold in the instruction cache, and inlined
+                    // range by range it was several hundred instructions)
+                    const void *pp[16];
+                    long long pl[16];
+                    pp[0] = chg.tmap + tr0n;      pl[0] = 2 * (chg.trow_off[nb + 1] - tr0n);
+                    pp[1] = chg.st_node + r0n;    pl[1] = 2 * S1n;
+                    pp[2] = chg.st_time + r0n;    pl[2] = S1n;
+                    pp[3] = chg.st_age + r0n;     pl[3] = S1n;
+                    pp[4] = chg.iperm + r0n;      pl[4] = 2 * S1n;
+                    pp[5] = chg.inv_emit + r0n;   pl[5] = 8 * S1n;
+                    pp[6] = chg.sw_start + r0n;   pl[6] = 2 * S1n;
+                    pp[7] = chg.sw_cnt + r0n;     pl[7] = 2 * S1n;
+                    pp[8] = chg.sw_src + e0n;     pl[8] = 2 * nen;
+                    pp[9] = chg.sw_prob + e0n;    pl[9] = 8 * nen;
+                    pp[10] = chg.lin + (size_t) nb * 7 * T;              pl[10] = 56ll * T;
+                    pp[11] = chg.tmatrix + (size_t) nb * T * T;          pl[11] = 8ll * T * T;
+                    pp[12] = chg.sc_start + (size_t) nb * AWB_NSCRIBE;   pl[12] = 2 * AWB_NSCRIBE;
+                    pp[13] = chg.sc_cnt + (size_t) nb * AWB_NSCRIBE;     pl[13] = 2 * AWB_NSCRIBE;
+                    pp[14] = chg.sc_row + (size_t) nb * AWB_NSCRIBE;     pl[14] = AWB_NSCRIBE;
+                    pp[15] = chg.sc_stride + (size_t) nb * AWB_NSCRIBE;  pl[15] = AWB_NSCRIBE;
+#pragma unroll 1
+                    for (int r = 0; r < 16; r++)
+                        awb_prefetch_range(pp[r], pl[r], lane);
                     if (lane == 0) {
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
@@ -428,7 +436,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     // schedulers, so the loop is written for instruction count: 32-bit shared
     // addresses with ring offsets kept incrementally, a pointer ring for the
     // lagged table stores (idle lanes and not-to-be-stored columns point at a
-    // per-thread sink), and a per-warp choice of the number of scan levels.
+    // per-thread sink).
     const unsigned char *__restrict__ kindg = chg.kind + g.site0;
     double *__restrict__ fwg = chg.fw - g.fwbias;
     const long long *__restrict__ row_offg = chg.row_off;
@@ -449,7 +457,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     double *const sink = chg.sink + tid;
 
     // ---- my state in the current block
-    int jj = 0, S = 0, S1 = 1, nl = 0;
+    int jj = 0, S = 0, S1 = 1;
     long long r0 = 0;
     bool active = false, live = false;     // live: active and S > 0
     unsigned zaddr = dummy_s, raddr = Rs_s;
@@ -491,8 +499,6 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             upm[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
             dnm[l] = (lane + (1 << l) <= segend) ? 1.0 : 0.0;
         }
-        const int span = __reduce_max_sync(0xffffffffu, segend - seglane);
-        nl = span > 0 ? 32 - __clz(span) : 0;          // scan levels this warp needs
         if (live) {
             const double *lin = ling + (size_t) bb * 7 * T;
             const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
@@ -593,26 +599,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         const int blen = (b == bextra) ? 1 : blocklensg[b];
 
         // ---------------- sites that are followed by a site of the same block
-        switch (nl) {
-        case 0:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<0>());
-            break;
-        case 1:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<1>());
-            break;
-        case 2:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<2>());
-            break;
-        case 3:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<3>());
-            break;
-        case 4:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<(NLEV < 4 ? NLEV : 4)>());
-            break;
-        default:
-            for (int i = blen - 1; i > 0; i--) site_step(AwbInt<NLEV>());
-            break;
-        }
+        // (ONE scan variant for all warps.  A variant per warp with just the
+        // levels its longest branch needs was no faster per site and cost 0.6 us
+        // per block: a warp changing variant at a block boundary runs cold
+        // instructions, and the variants compete for the instruction cache.)
+        for (int i = blen - 1; i > 0; i--)
+            site_step(AwbInt<NLEV>());
 
         // ---------------- last site of the block
         {
