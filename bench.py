@@ -15,8 +15,11 @@ the data path -- only a small all_gather of per-window logZ at the end).
 
 metric `value`  = sum over windows of (sum_blocks blocklen*nstates) / device time
 `e2e`           = same, through the public API with host (pinned) inputs: batch
-                  creation (host layout + cudaMalloc), H2D of trees/sequences,
-                  all kernels, D2H of the sampled paths, every step.
+                  creation (host layout), H2D of trees/sequences/draws, all
+                  kernels, D2H of the sampled paths, every step -- a stream of
+                  batches: the host-only creation of batch n+1 overlaps the
+                  device work of batch n (`single_batch_latency_ms` is one
+                  batch alone, nothing overlapped).
 `roofline`      = forward kernel: 8 B per site*state (the FP64 forward-table
                   store) / its CUDA-event time, against
                   the measured HBM copy bandwidth in MEASURED_PEAKS.json.
