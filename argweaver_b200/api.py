@@ -319,3 +319,45 @@ def sample_thread(problem, rand_ints, rand_max=RAND_MAX, ctx=None):
         return b.path(0), b.logz(0)
     finally:
         b.close()
+
+
+def sample_thread_stream(batches, ctx=None, checkpoint=True, rand_max=RAND_MAX,
+                         out=None):
+    """Thread sampling over a stream of batches (a genome-wide run: one batch
+    = the windows that fit on the device at once).
+
+    `batches` yields `(problems, rand_ints)` pairs; for each the generator
+    yields `(paths, logz)` -- lists with one entry per problem.  The host-only
+    part of a batch (`awb_batch_create`: validation and layout) is done for
+    batch n+1 while batch n runs on the device, so it is off the critical path;
+    the copies and kernels of every batch are as in `Batch`.  `out(i)`, if
+    given, returns the (e.g. pinned) int32 buffer for the path of problem i.
+    """
+    ctx = ctx or default_context()
+    it = iter(batches)
+
+    def create():
+        try:
+            problems, rands = next(it)
+        except StopIteration:
+            return None
+        return Batch(problems, ctx, checkpoint=checkpoint), rands
+
+    cur = create()
+    try:
+        while cur is not None:
+            b, rands = cur
+            cur = None
+            try:
+                b.upload().setup().forward().traceback(rands, rand_max)   # queued
+                cur = create()                                            # overlaps
+                b.sync()
+                paths = [b.path(i, out=None if out is None else out(i))
+                         for i in range(b.n)]
+                logz = [b.logz(i) for i in range(b.n)]
+            finally:
+                b.close()
+            yield paths, logz
+    finally:
+        if cur is not None:             # the consumer stopped early
+            cur[0].close()

@@ -340,31 +340,27 @@ def bench_b200(a, rank, world, local_rank):
             keep.append(t)
             path_bufs.append(pb)
 
-        # A stream of batches, software-pipelined the way a genome-wide run
-        # would drive the API: awb_batch_create is host-only work (the layout),
-        # so the NEXT batch is created while the current one runs on the device;
-        # every step still pays its own layout, host->device copies of all its
-        # inputs, kernels, and device->host copies of all its paths.
+        # A stream of batches through api.sample_thread_stream, the way a
+        # genome-wide run would drive the library: awb_batch_create is host-only
+        # work (the layout), so the NEXT batch is created while the current one
+        # runs on the device; every step still pays its own layout,
+        # host->device copies of all its inputs, kernels, and device->host
+        # copies of all its paths.
         def create():
             return api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
 
-        def e2e_step(cur):
-            cur.upload().setup().forward().traceback(rands)     # queued, not waited for
-            nxt = create()
-            cur.sync()
-            paths = [cur.path(i, out=path_bufs[i]) for i in range(W)]
-            cur.close()
-            return nxt, paths
         nsteps = max(1, min(a.steps, 3))
-        cur = create()
-        cur, _ = e2e_step(cur)
+        stream = api.sample_thread_stream(
+            ((problems, rands) for _ in range(nsteps + 2)), ctx,
+            checkpoint=bool(a.checkpoint), out=lambda i: path_bufs[i])
+        next(stream)                       # warm-up batch (and batch 1 is created)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(nsteps):
-            cur, _ = e2e_step(cur)
+        for _ in range(nsteps):            # (each of them also creates its successor)
+            next(stream)
         torch.cuda.synchronize()
         e2e_ms_local = (time.perf_counter() - t0) * 1e3 / nsteps
-        cur.close()
+        stream.close()
         # latency of ONE isolated batch (nothing overlapped): create -> paths
         barrier()
         t0 = time.perf_counter()

@@ -324,3 +324,30 @@ def test_checkpointed_equals_whole_table_at_size(resident, libc_rand, monkeypatc
         assert abs(ck.logz(c) - full.logz(c)) <= RTOL * abs(full.logz(c))
     full.close()
     ck.close()
+
+
+def test_sample_thread_stream_equals_single_batches(libc_rand):
+    """api.sample_thread_stream (the next batch's host layout overlaps the
+    device work of the current one) gives what one Batch per batch gives."""
+    specs = [[(8, 1200, 20, False, 51), (12, 900, 20, True, 52)],
+             [(6, 700, 16, True, 53)],
+             [(20, 1500, 20, False, 54), (5, 400, 12, False, 55), (9, 800, 20, True, 56)]]
+    batches = []
+    for group in specs:
+        ds = [sim.simulate_problem(k, n, ntimes=T, seed=s, internal=i)
+              for (k, n, T, i, s) in group]
+        rs = [libc_rand(s, n) for (k, n, T, i, s) in group]
+        batches.append((ds, rs))
+    got = list(api.sample_thread_stream(batches, checkpoint=True))
+    assert len(got) == len(batches)
+    for (ds, rs), (paths, logz) in zip(batches, got):
+        b = api.Batch(ds)
+        b.upload().setup().forward().traceback(rs).sync()
+        for c in range(len(ds)):
+            assert np.array_equal(paths[c], b.path(c))
+            assert abs(logz[c] - b.logz(c)) <= RTOL * abs(b.logz(c))
+        b.close()
+    # a consumer that stops early leaves nothing behind
+    g = api.sample_thread_stream(batches, checkpoint=True)
+    next(g)
+    g.close()
