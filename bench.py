@@ -435,6 +435,10 @@ def bench_b200(a, rank, world, local_rank):
                         "all copies of every batch are inside the timed region"},
             "gpu_launches": int(launches),
             "stage_ms": stage,
+            # SURVEY 8d also asks for the forward-only figure (per-segment
+            # emission + forward kernels of the first pass)
+            "forward_only": {"value": ss / (fwd_ms * 1e-3) if fwd_ms > 0 else None,
+                             "unit": UNIT},
             "roofline": {
                 "kernel": "awb_forward_fast_kernel", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
