@@ -187,8 +187,14 @@ class Batch(object):
     def forward(self, priors=None):
         ptr = None
         if priors is not None:
+            if len(priors) != self.n:
+                raise ValueError("need one prior (or None) per problem")
             self._priors = [None if p is None else
                             np.ascontiguousarray(p, np.float64) for p in priors]
+            for i, p in enumerate(self._priors):
+                if p is not None and p.size < max(int(self.nstates(i)[0]), 1):
+                    raise ValueError("prior of problem %d is shorter than its "
+                                     "first state space" % i)
             pa = (C.c_void_p * self.n)()
             for i, p in enumerate(self._priors):
                 pa[i] = None if p is None else p.ctypes.data
@@ -220,6 +226,16 @@ class Batch(object):
 
     def sync(self):
         _check(lib().awb_batch_sync(self.h))
+        return self
+
+    def check_status(self):
+        """Raise if the forward pass met a column whose norm is not positive
+        (the reference asserts there, sample_thread.cpp:443-444,457-458)."""
+        for i in range(self.n):
+            s = self.status(i)
+            if s >= 0:
+                raise AwbError("problem %d: forward column %d is not positive"
+                               % (i, s))
         return self
 
     # ---- info
@@ -306,6 +322,7 @@ def forward_algorithm(problem, prior=None, ctx=None):
     b = Batch([problem], ctx)
     try:
         b.upload().setup().forward(None if prior is None else [prior]).sync()
+        b.check_status()
         return b.fw(0), b.layout(0), b.logz(0)
     finally:
         b.close()
@@ -316,6 +333,7 @@ def sample_thread(problem, rand_ints, rand_max=RAND_MAX, ctx=None):
     b = Batch([problem], ctx)
     try:
         b.upload().setup().forward().traceback([rand_ints], rand_max).sync()
+        b.check_status()
         return b.path(0), b.logz(0)
     finally:
         b.close()
@@ -352,6 +370,7 @@ def sample_thread_stream(batches, ctx=None, checkpoint=True, rand_max=RAND_MAX,
                 b.upload().setup().forward().traceback(rands, rand_max)   # queued
                 cur = create()                                            # overlaps
                 b.sync()
+                b.check_status()
                 paths = [b.path(i, out=None if out is None else out(i))
                          for i in range(b.n)]
                 logz = [b.logz(i) for i in range(b.n)]

@@ -232,6 +232,11 @@ struct awb_batch {
     int64_t h2d_bytes;
     bool uploaded, setup_done, forward_done, rand_uploaded, rand_in_use;
     bool ckpt;                 // checkpointed forward table (AWB_CHECKPOINT)
+    bool lin_unsafe;           // some problem's linear-domain vectors may overflow
+                               //   (awb_layout.h): generic forward kernel, closed-form
+                               //   transitions in the traceback
+    bool tables_stale;         // checkpointed table: a traceback has rebuilt segments
+                               //   over the tables the forward pass left resident
     int maxseg;                // most segments of any problem
     int maxsegsites;           // most sites of any segment
 };
@@ -351,7 +356,8 @@ static bool batch_fast_path(const awb_batch *b)
     const int threads = b->maxNS + AWB_FWD_HELPERS;
     const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
     // (a branch longer than a warp would need a cross-warp carry in the scans)
-    return !getenv("AWB_FORCE_GENERIC") && threads <= 1024 && b->maxcnt <= 32 &&
+    return !getenv("AWB_FORCE_GENERIC") && !b->lin_unsafe && threads <= 1024 &&
+        b->maxcnt <= 32 &&
         !(tmax == 64 && threads > 384) &&
         awb_fwd_fast_smem_bytes(b->maxNS, tmax, b->zcap) <= 200 * 1024;
 }
@@ -383,6 +389,9 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->uploaded = b->setup_done = b->forward_done = false;
     b->rand_uploaded = false;
     b->rand_in_use = false;
+    b->lin_unsafe = false;
+    b->tables_stale = false;
+    b->ckpt = false;
 
     const auto t_create0 = std::chrono::steady_clock::now();
     // host layout of every problem (integer work), one host thread per problem
@@ -427,6 +436,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.maxNS > b->maxNS) b->maxNS = L.maxNS;
         if (L.zcap > b->zcap) b->zcap = L.zcap;
         if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
+        if (L.lin_unsafe) b->lin_unsafe = true;
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
     }
@@ -658,8 +668,12 @@ extern "C" int awb_batch_upload(awb_batch *b)
             char *base = b->arena + b->arena_off[c];
             // debug arrays are compared entry by entry, including the entries no
             // kernel writes (block 0 has no switch matrix): start them from zero
-            if (L.keep_debug)
-                CUDA_OK(cudaMemsetAsync(base, 0, L.total_bytes, st));   // (band included)
+            // (band included; not the draws, which awb_batch_upload_rand may
+            // already have put there)
+            if (L.keep_debug) {
+                CUDA_OK(cudaMemsetAsync(base, 0, L.o_rand, st));
+                CUDA_OK(cudaMemsetAsync(base + L.o_logz, 0, L.total_bytes - L.o_logz, st));
+            }
             for (size_t i = 0; i < L.copies.size(); i++)
                 if (L.copies[i].dst_off != L.o_seqs)
                     CUDA_OK(cudaMemcpyAsync(base + L.copies[i].dst_off, L.copies[i].src,
@@ -755,7 +769,8 @@ static int launch_traceback(awb_batch *b, int rand_max, int seg)
         CUDA_OK(cudaFuncSetAttribute(awb_traceback_kernel<NV, SPW, VPT>, \
             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
         awb_traceback_kernel<NV, SPW, VPT><<<b->C, AWB_TB_THREADS, smem, st>>>( \
-            b->d_chains, rand_max, maxS1, b->maxT, maxent, seg); } while (0)
+            b->d_chains, rand_max, maxS1, b->maxT, maxent, seg, \
+            b->lin_unsafe ? 1 : 0); } while (0)
     if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
     else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
     else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
@@ -872,6 +887,7 @@ extern "C" int awb_batch_forward(awb_batch *b, const double *const *priors)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(b->ctx->ev[3], st));
     b->forward_done = true;
+    b->tables_stale = false;
     return 0;
 }
 
@@ -928,11 +944,18 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         // checkpointed table, second pass: from the last segment to the first,
         // rebuild the segment's table from its stored first column, then walk
         // back through it
+        // (pass 1: the last segments' tables are still resident from the
+        // forward pass and are not rebuilt; pass 2, a further traceback of the
+        // same forward pass: the rebuilt segments have taken turns in table 0,
+        // which is also the first resident one, so every table is rebuilt)
+        const int pass = b->tables_stale ? 2 : 1;
         for (int s = b->maxseg - 1; s >= 0; s--) {
-            if (launch_emit(b, s, 1) || launch_forward_fast(b, s, 1) ||
+            if (launch_emit(b, s, pass) || launch_forward_fast(b, s, pass) ||
                 launch_traceback(b, rand_max, s))
                 return 1;
         }
+        if (b->maxseg > b->nslots)
+            b->tables_stale = true;
     } else {
         if (launch_traceback(b, rand_max, 0))
             return 1;

@@ -36,6 +36,11 @@ struct AwbLayout {
     double states_sites;                 // sum blocklen * nstates
     std::vector<int> nstates, block_start, rowidx;
     int gen_mappings;                    // no mappings given: K1 makes them
+    // the linear-domain transition vectors (lin: exp(lnB) ...) may overflow for
+    // this problem (cumulative coalescent rate beyond the double exponent
+    // range, e.g. tiny population sizes): the batch then runs the generic
+    // forward kernel and the traceback uses the closed-form transitions
+    int lin_unsafe;
     // Jukes-Cantor branch probabilities by time-index pair (emission kernel):
     // ptab[(y*T + x)*2 + {0: mutation, 1: none}] for a branch from time y up to
     // time x, and p0tab[x*2 + ..] for a branch from time 0.0 up to time x
@@ -105,6 +110,24 @@ inline std::vector<short> &awb_pack_scratch()
     return v;
 }
 
+
+// A parent chain that never reaches the root can only run through nodes of
+// EQUAL age (a parent is never younger than its child, checked by the callers):
+// from every node whose parent has its own age, walk up while the age stays the
+// same; more than V steps means a cycle.
+inline bool awb_parent_cycle(const int *parent, const int *age, int V)
+{
+    for (int i = 0; i < V; i++) {
+        int x = i, steps = 0;
+        while (parent[x] >= 0 && parent[x] < V && age[parent[x]] == age[x]) {
+            x = parent[x];
+            if (++steps > V)
+                return true;
+        }
+    }
+    return false;
+}
+
 // Number of states of one tree and the sum of squared branch state counts.
 // Returns false on a malformed tree.
 inline bool awb_count_states_checked(const awb_problem &p, int b, std::vector<int> &c0,
@@ -160,6 +183,21 @@ inline bool awb_count_states_checked(const awb_problem &p, int b, std::vector<in
     }
     if (young) {
         err = "tree " + std::to_string(b) + ": parent younger than child";
+        return false;
+    }
+    // a binary tree with the leaves listed first: nodes [0, nleaves) have no
+    // children, every other node has exactly two (K1's level order, the subtree
+    // walk below and the emission passes rely on it)
+    for (int i = 0; i < V; i++) {
+        const bool leaf = i < p.nleaves;
+        if (leaf ? (c0p[i] != -1) : (c0p[i] == -1 || c1p[i] == -1)) {
+            err = "tree " + std::to_string(b) +
+                ": not a binary tree with the leaves listed first";
+            return false;
+        }
+    }
+    if (awb_parent_cycle(parent, age, V)) {
+        err = "tree " + std::to_string(b) + ": parent cycle";
         return false;
     }
     S = 0;
@@ -292,7 +330,12 @@ inline bool awb_count_states(const awb_problem &p, int b, std::vector<int> &c0,
             tp = ((tp & 31) + cnt > 32 ? tp32 : tp) + cnt;
         }
         if (!odd) {
-            for (int i = 0; i < V; i++) bad |= (unsigned) (nch[i] > 2);
+            // leaves first, every other node with exactly two children
+            const int nl = p.nleaves;
+            for (int i = 0; i < V; i++)
+                bad |= (unsigned) (nch[i] != (i < nl ? 0 : 2));
+            if (!bad && awb_parent_cycle(parent, age, V))
+                bad = 1;
         }
         if (!odd && !bad && nroots == 1) {
             S = S_;
@@ -385,12 +428,36 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.states_sites = 0;
     std::vector<int> c0(V), c1(V), stack(V + 2);
     std::vector<char> ignore(V);
+    // Upper bound on lnB (trans.cpp:44-71) = cumulative coalescent rate + log of
+    // a time step: K1's linear-domain vectors hold exp(lnB), so beyond ~700
+    // they overflow.  First with every lineage present at every time; only when
+    // that fails, block by block from the states per time row (>= the lineages
+    // of that time).
+    double rate[AWB_MAXT];
+    double gbound = 0.0, maxstep = 0.0;
+    for (int t = 0; t < T - 1; t++) {
+        rate[t] = (L.model.coal_time_steps[2 * t] + L.model.coal_time_steps[2 * t + 1]) /
+            (2.0 * p.popsizes[t]);
+        gbound += rate[t] * (p.nleaves + 1);
+        if (L.model.time_steps[t] > maxstep) maxstep = L.model.time_steps[t];
+    }
+    const double lnslack = log(maxstep * (V + 2.0)) + log((double) T);
+    const double lnlimit = 680.0;
+    const bool block_bound = !(gbound + lnslack <= lnlimit);
+    L.lin_unsafe = 0;
     for (int b = 0; b < B; b++) {
         int S = 0, band = 0, tpos = 1;
         int wrow[AWB_MAXT + 1];
         if (!awb_count_states(p, b, c0, c1, stack, ignore, S, band, tpos,
                               L.maxcnt, err, wrow))
             return false;
+        if (block_bound && !L.lin_unsafe && S > 0) {
+            double c = 0.0;
+            for (int t = 0; t < T - 1; t++)
+                c += rate[t] * (wrow[t] > 0 ? wrow[t] : p.nleaves + 1);
+            if (!(c + lnslack <= lnlimit))
+                L.lin_unsafe = 1;
+        }
         {
             // the scribes' padded column (awb_scribe_plan): the slots per lane
             // are at most CHub = the even count for which the rows surely fit
@@ -452,7 +519,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             const int *spr = p.sprs + 4 * (size_t) b;
             const int *lp = p.ptrees + (size_t) (b - 1) * V;
             if (spr[0] < 0 || spr[0] >= V || spr[2] < 0 || spr[2] >= V ||
-                spr[1] < 0 || spr[3] < spr[1] || lp[spr[0]] < 0) {
+                spr[1] < 0 || spr[3] < spr[1] || spr[3] > T - 1 || lp[spr[0]] < 0) {
                 err = "tree " + std::to_string(b) + ": invalid SPR";
                 return false;
             }

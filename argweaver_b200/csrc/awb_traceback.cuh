@@ -51,7 +51,7 @@ struct AwbTbSmem {
 // scalars of one block.  awb_tb_blk only LOADS (two blocks ahead of use, so no
 // instruction waits on the loads); the derived values come from the accessors.
 struct AwbTbBlk {
-    int S, blen, pos, Sprev;
+    int S, blen, pos, Sprev, minage;
     long long r0, fwoff, entoff, entend;
     __device__ int S1() const { return S > 0 ? S : 1; }
     __device__ int n1() const { return Sprev > 0 ? Sprev : 1; }
@@ -62,6 +62,7 @@ struct AwbTbBlk {
 struct AwbTbPtrs {
     const int *nstates, *blocklens, *block_start;
     const long long *row_off, *fw_off, *ent_off;
+    const int *tm_minage;       // only read for the closed-form transitions
 };
 
 // (bb below the first block of the launch, or the block of which a segment
@@ -70,7 +71,7 @@ __device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb, int bmin, int 
 {
     AwbTbBlk m;
     if (bb < bmin) {
-        m.S = 0; m.blen = 0; m.pos = 0; m.Sprev = 0;
+        m.S = 0; m.blen = 0; m.pos = 0; m.Sprev = 0; m.minage = 0;
         m.r0 = 0; m.fwoff = 0; m.entoff = 0; m.entend = 0;
         return m;
     }
@@ -82,6 +83,7 @@ __device__ inline AwbTbBlk awb_tb_blk(const AwbTbPtrs &p, int bb, int bmin, int 
     m.entoff = p.ent_off[bb];
     m.entend = p.ent_off[bb + 1];
     m.Sprev = bb > bmin ? p.nstates[bb - 1] : 0;
+    m.minage = p.tm_minage ? p.tm_minage[bb] : 0;
     return m;
 }
 
@@ -219,7 +221,7 @@ __device__ inline int awb_block_sample(const double (&A)[VPT], int S1, int r,
 template <int NV, int SPW, int VPT>
 __global__ void __launch_bounds__(AWB_TB_THREADS, 1)
 awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
-                     int maxent, int seg)
+                     int maxent, int seg, int closed_form)
 {
     extern __shared__ __align__(16) unsigned char tb_smem[];
     const AwbChain &ch = chains[blockIdx.x];
@@ -242,8 +244,13 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     const double *__restrict__ fsumg = ch.fsum + g.fsoff - (long long) g.site0 * (T - 1);
     const int *__restrict__ randg = ch.rand_ints;
     int *__restrict__ pathg = ch.path;
+    // closed_form: the batch's linear-domain vectors may overflow (awb_layout.h,
+    // lin_unsafe); same-branch transitions then come from the reference's closed
+    // form (awb_get_time over the 9 log-domain vectors) instead
     const AwbTbPtrs P = { ch.nstates, ch.blocklens, ch.block_start,
-                          ch.row_off, ch.fw_off, ch.ent_off };
+                          ch.row_off, ch.fw_off, ch.ent_off,
+                          closed_form ? ch.tm_minage : (const int *) 0 };
+    const double *__restrict__ tmvecg = ch.tmvec;
     const double *__restrict__ ling = ch.lin;
     const double *__restrict__ tmatrixg = ch.tmatrix;
     const short *__restrict__ st_nodeg = ch.st_node;
@@ -274,7 +281,11 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         if (bb < bmin)
             return;
         if (m.S > 0) {
-            awb_tb_copy8(base + BL.tv, ling + (size_t) bb * 7 * T, 7 * T);
+            if (closed_form)
+                awb_tb_copy8(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
+                             AWB_TM_NVEC * T);
+            else
+                awb_tb_copy8(base + BL.tv, ling + (size_t) bb * 7 * T, 7 * T);
             awb_tb_copy8(base + BL.tm, tmatrixg + (size_t) bb * T * T, T * T);
             sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, st_nodeg + m.r0, 2 * m.S);
             sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, st_timeg + m.r0, m.S);
@@ -392,7 +403,9 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                         const double other = tmS[a_j * T + b_k];
                         const bool same = stN[j] == node_k;
                         double tr = other;
-                        if (same) {
+                        if (same && closed_form) {
+                            tr = awb_get_time(linS, T, a_j, b_k, c_k, mC.minage, true);
+                        } else if (same) {
                             const double Da = linS[a_j];
                             const double co = (a_j < b_k) ? A1 * (linS[T + a_j] - Bc) :
                                 (a_j == b_k ? A2 : A3);

@@ -50,9 +50,23 @@ def normalize(d):
     q["ages"] = np.ascontiguousarray(d["ages"], np.int32)
     q["sprs"] = np.ascontiguousarray(d["sprs"], np.int32)
     q["blocklens"] = np.ascontiguousarray(d["blocklens"], np.int32)
+    if q["ptrees"].ndim != 2:
+        raise ValueError("ptrees must be [ntrees][nnodes]")
     B, V = q["ptrees"].shape
     q["mappings"] = (np.ascontiguousarray(d["mappings"], np.int32)
                      if "mappings" in d else None)
+    # shapes are checked here: past this point only raw pointers reach C
+    T = q["ntimes"]
+    for key, shape in (("times", (T,)), ("popsizes", (T,)), ("ages", (B, V)),
+                       ("sprs", (B, 4)), ("blocklens", (B,)),
+                       ("mappings", (B, V))):
+        if q[key] is not None and q[key].shape != shape:
+            raise ValueError("%s has shape %s, expected %s"
+                             % (key, q[key].shape, shape))
+    if q["seqs"].ndim != 2:
+        raise ValueError("seqs must be [nseqs][seqlen]")
+    if q["seqids"].ndim != 1:
+        raise ValueError("seqids must be one-dimensional")
     if "subtree_roots" in d:
         q["subtree_roots"] = np.ascontiguousarray(d["subtree_roots"], np.int32)
     elif q["internal"] and "child0" in d:
@@ -61,6 +75,9 @@ def normalize(d):
             np.asarray(d["child0"])[np.arange(B), roots], np.int32)
     else:
         q["subtree_roots"] = None
+    if q["subtree_roots"] is not None and q["subtree_roots"].shape != (B,):
+        raise ValueError("subtree_roots has shape %s, expected %s"
+                         % (q["subtree_roots"].shape, (B,)))
     return q
 
 

@@ -94,9 +94,15 @@ int awb_ctx_record(awb_ctx *ctx, int slot);
 int awb_ctx_elapsed_ms(awb_ctx *ctx, int slot0, int slot1, float *ms);
 int awb_ctx_sync(awb_ctx *ctx);
 
-/* Validate the problems, compute the table layout, allocate device memory.
- * The problem structs and the arrays they point to must stay valid until
- * awb_batch_upload() returns. */
+/* Validate the problems and compute the table layout (host-only work; device
+ * memory is taken at the first awb_batch_upload).  The problem structs are
+ * copied; the ARRAYS they point to are read by asynchronous copies
+ * (cudaMemcpyAsync straight from the caller's memory, truly asynchronous when
+ * it is pinned) queued by awb_batch_upload, so they must stay valid and
+ * unchanged until awb_batch_sync() -- or any call that returns results -- has
+ * returned.  The same holds for the rand() draws given to
+ * awb_batch_upload_rand / awb_batch_traceback and the priors given to
+ * awb_batch_forward. */
 int awb_batch_create(awb_ctx *ctx, int nproblems, const awb_problem *problems,
                      int flags, awb_batch **out);
 void awb_batch_destroy(awb_batch *b);

@@ -66,6 +66,9 @@ def lib():
                                   C.c_longlong]
         _lib.emul_layout.argtypes = [C.c_void_p] * 7
         _lib.emul_destroy.argtypes = [C.c_void_p]
+        _lib.emul_lin_unsafe.argtypes = [C.c_void_p]
+        _lib.emul_lin_max.restype = C.c_double
+        _lib.emul_lin_max.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -97,6 +100,12 @@ class Emul(object):
         rc = lib().emul_get(self.h, name.encode(), out.ctypes.data, nb)
         assert rc == 0
         return out
+
+    def lin_unsafe(self):
+        return bool(lib().emul_lin_unsafe(self.h))
+
+    def lin_max(self):
+        return lib().emul_lin_max(self.h)
 
     def layout(self):
         B = self.B

@@ -186,6 +186,23 @@ void emul_layout(void *h, int *nstates, long long *row_off, long long *fw_off,
     *maxband = e->L.maxband;
 }
 
+// 1: the layout found that exp(lnB) may overflow for this problem
+int emul_lin_unsafe(void *h) { return ((Emul *) h)->L.lin_unsafe; }
+
+// largest |value| of K1's linear-domain vectors (inf / nan when they overflow)
+double emul_lin_max(void *h)
+{
+    Emul *e = (Emul *) h;
+    const size_t n = (size_t) e->L.B * 7 * e->L.T;
+    const double *lin = (const double *) &e->arena[e->L.o_lin];
+    double m = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        if (!(lin[i] == lin[i])) return NAN;
+        if (fabs(lin[i]) > m) m = fabs(lin[i]);
+    }
+    return m;
+}
+
 void emul_destroy(void *h) { delete (Emul *) h; }
 
 } // extern "C"

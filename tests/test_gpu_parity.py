@@ -351,3 +351,37 @@ def test_sample_thread_stream_equals_single_batches(libc_rand):
     g = api.sample_thread_stream(batches, checkpoint=True)
     next(g)
     g.close()
+
+
+@pytest.mark.parametrize("popsize", [200., 100., 40.])
+@pytest.mark.parametrize("internal", [False, True])
+def test_small_population_sizes(popsize, internal, libc_rand):
+    """cumulative coalescent rates near and beyond the double exponent range
+    (ntimes=20, maxtime 2e5): popsize 200 still runs the fast forward kernel with
+    linear-domain vectors ~1e150; for 100 and 40 the host bound routes the batch
+    to the generic kernel and the traceback to the closed-form transitions (the
+    reference only ever forms exp(lnE2[b] + lnB[a]), which stays finite)"""
+    d = sim.simulate_problem(8, 1500, ntimes=20, seed=131, popsize=popsize,
+                             internal=internal)
+    compare_with_oracle(d, libc_rand(31, 1500))
+
+
+def test_checkpointed_table_second_traceback(libc_rand, monkeypatch):
+    """several tracebacks of one forward pass (upload_rand + traceback, twice):
+    after the first one the rebuilt segments have overwritten the first
+    resident table, so the second one must rebuild every segment"""
+    monkeypatch.setenv("AWB_SEG_DOUBLES", "30000")
+    for resident in ("1", "2", "3"):
+        monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
+        d = sim.simulate_problem(10, 3000, ntimes=20, seed=141)
+        b = api.Batch([d], checkpoint=True)
+        b.upload().setup().forward()
+        assert b.segments()[0] > 3
+        for seed in (7, 8, 9):
+            r = libc_rand(seed, 3000)
+            o = ol.run_oracle(d, r)
+            b.traceback([r]).sync()
+            div = first_divergence(b.path(), o["path"])
+            assert div is None, ("traceback with draws %d diverges at site %d"
+                                 % (seed, div))
+        b.close()

@@ -127,3 +127,58 @@ def test_layout_rejects_bad_input():
         bad["mappings"][1, 0] = -1 if bad["mappings"][1, 0] != -1 else 0
         with pytest.raises(ValueError):
             el.Emul(bad)
+
+
+def test_layout_rejects_malformed_trees():
+    """one-child nodes, leaves not listed first, equal-age parent cycles and
+    SPR times beyond the time grid are refused on the host (they would corrupt
+    the host walk or index device tables out of bounds)"""
+    for internal in (False, True):
+        d = sim.simulate_problem(6, 100, seed=23, internal=internal)
+        V = d["ptrees"].shape[1]
+        nl = (V + 1) // 2
+        # a node with exactly one child: move one child of some internal node
+        # under a leaf
+        bad = dict(d)
+        bad["ptrees"] = d["ptrees"].copy()
+        kid = int(np.nonzero(d["ptrees"][0] >= nl)[0][0])
+        bad["ptrees"][0, kid] = 0 if kid != 0 else 1
+        with pytest.raises(ValueError):
+            el.Emul(bad)
+        # an equal-age cycle between two internal nodes (each keeps two children
+        # by swapping a child for the other node)
+        bad = dict(d)
+        bad["ptrees"] = d["ptrees"].copy()
+        bad["ages"] = d["ages"].copy()
+        a, b = nl, nl + 1
+        bad["ptrees"][0, a] = b
+        bad["ptrees"][0, b] = a
+        bad["ages"][0, a] = bad["ages"][0, b] = 3
+        with pytest.raises(ValueError):
+            el.Emul(bad)
+        # SPR coalescence time beyond the grid
+        if d["sprs"].shape[0] > 1:
+            bad = dict(d)
+            bad["sprs"] = d["sprs"].copy()
+            bad["sprs"][1, 3] = int(np.ravel(d["ntimes"])[0]) + 5
+            with pytest.raises(ValueError):
+                el.Emul(bad)
+
+
+@pytest.mark.parametrize("popsize,expect", [(1e4, False), (200., False), (40., True)])
+def test_layout_flags_linear_domain_overflow(popsize, expect):
+    """exp(lnB) overflows once the cumulative coalescent rate passes ~709
+    (ntimes=20, maxtime 2e5, popsize <= 60): the host bound must flag every
+    problem whose linear-domain vectors are not finite (the batch then avoids
+    the kernels that read them), and must not flag ordinary ones"""
+    d = sim.simulate_problem(8, 300, ntimes=20, seed=31, popsize=popsize)
+    e = el.Emul(d)
+    assert e.lin_unsafe() == expect
+    e.setup()
+    m = e.lin_max()
+    if not e.lin_unsafe():
+        assert np.isfinite(m)
+    if not np.isfinite(m):
+        assert e.lin_unsafe()
+    # the tables the generic path uses stay finite and match the oracle
+    check_problem(d)
