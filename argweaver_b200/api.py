@@ -60,6 +60,7 @@ def lib():
         L.awb_batch_kernel_launches.argtypes = [C.c_void_p]
         L.awb_batch_segments.argtypes = [C.c_void_p]
         L.awb_batch_resident_segments.argtypes = [C.c_void_p]
+        L.awb_batch_forward_kernel.argtypes = [C.c_void_p]
         L.awb_batch_get_path.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.awb_batch_get_logz.argtypes = [C.c_void_p, C.c_int,
                                          C.POINTER(C.c_double)]
@@ -259,6 +260,10 @@ class Batch(object):
         kept per window)."""
         return (lib().awb_batch_segments(self.h),
                 lib().awb_batch_resident_segments(self.h))
+
+    def fast_path(self):
+        """'fast' or 'generic': the forward kernel this batch's shape selects."""
+        return "fast" if lib().awb_batch_forward_kernel(self.h) else "generic"
 
     def timings(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()

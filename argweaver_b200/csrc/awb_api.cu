@@ -1024,6 +1024,10 @@ extern "C" int awb_batch_nsites(const awb_batch *b, int i) { return b->L[i].n; }
 
 extern "C" int awb_batch_kernel_launches(const awb_batch *b) { return b->launches; }
 extern "C" int awb_batch_segments(const awb_batch *b) { return b->maxseg; }
+extern "C" int awb_batch_forward_kernel(const awb_batch *b)
+{
+    return batch_fast_path(b) ? 1 : 0;
+}
 extern "C" int awb_batch_resident_segments(const awb_batch *b)
 {
     return b->bound ? b->nslots : 1;

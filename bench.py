@@ -2,16 +2,19 @@
 """bench.py -- the driver's benchmark contract for the threading-HMM path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--config 1|2|3|4|5]
 
 A *step* is one pass of the hot path (per-block setup, variant-site emissions,
 forward recursion, stochastic traceback) over a batch of independent genome
-windows resident on the GPU.  The workload is BASELINE.json configs[2]
-("k=50, L=10 Mb, ntimes=20: leaf plus internal-branch (subtree) threading"),
-at site compression c=10 (10^6 compressed sites per window), with
-`--windows` windows per GPU (half threaded as a new leaf = external mode, half
-as a re-threaded subtree = internal mode).  Multi-GPU runs give every rank its
-own windows (weak scaling; windows are independent, there is no collective in
-the data path -- only a small all_gather of per-window logZ at the end).
+windows resident on the GPU.  The default workload is BASELINE.json configs[2]
+("k=50, L=10 Mb, ntimes=20: leaf plus internal-branch (subtree) threading") at
+site compression c=10 (10^6 compressed sites per window), half of the windows
+threaded as a new leaf (external mode), half as a re-threaded subtree (internal
+mode).  `--config` selects the other named shapes (CONFIGS below).  Multi-GPU
+runs give every rank its own windows (weak scaling; windows are independent,
+there is no collective in the data path -- only a small all_gather of
+per-window logZ at the end); config 5 is the one strong-scaling case (8 windows
+in total, shared out over the ranks).
 
 metric `value`  = sum over windows of (sum_blocks blocklen*nstates) / device time
 `e2e`           = same, through the public API with host (pinned) inputs: batch
@@ -25,11 +28,15 @@ metric `value`  = sum over windows of (sum_blocks blocklen*nstates) / device tim
                   the measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline`  = the UNMODIFIED reference's own forward+traceback
                   (oracle/_ref/ref_bench, 1 core) on a bounded sample of the
-                  same workload.
+                  same workload, one external-mode and one internal-mode window.
+`parity`        = the same sample problems run on the GPU in the same process
+                  and compared with what the reference just produced: sampled
+                  paths (identical draws) and forward rows.
 
 --impl reference times the reference's CPU implementation (oracle/_ref/ref_bench)
 with one single-threaded worker per host core on bounded samples of the same
-workload.
+workload (half of the workers on the external-mode, half on the internal-mode
+sample).
 """
 
 import argparse
@@ -51,6 +58,24 @@ METRIC = "hmm_sites_x_states_per_sec"
 UNIT = "sites*states/s"
 REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
 
+# BASELINE.json configs[i-1].  `windows`: independent windows per GPU (0: one per
+# SM with the checkpointed table); `total_windows`: fixed number shared out over
+# the ranks (strong scaling).
+CONFIGS = {
+    1: dict(k=8, sites=10000, ntimes=20, windows=148, checkpoint=0,
+            name="config1: arg-sim -k 8 -L 100000 -N 10000 -r 1.6e-8 -m 1.8e-8, "
+                 "--ntimes 20 --maxtime 200e3 -c 10 (README quick start)"),
+    2: dict(k=20, sites=100000, ntimes=20, windows=148, checkpoint=0,
+            name="config2: k=20, L=1 Mb, ntimes=20, c=10: full-thread resampling"),
+    3: dict(k=50, sites=1000000, ntimes=20, windows=148, checkpoint=1,
+            name="config3: arg-sim k=50, L=10 Mb, ntimes=20, maxtime=200e3, c=10"),
+    4: dict(k=100, sites=1000000, ntimes=40, windows=12, checkpoint=0,
+            name="config4: k=100, L=10 Mb, ntimes=40, c=10: large state space"),
+    5: dict(k=50, sites=1000000, ntimes=20, total_windows=8, checkpoint=0,
+            name="config5: arg-sample-genome, k=50, 8 independent 10 Mb windows "
+                 "sharded across the GPUs"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -58,29 +83,49 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--k", type=int, default=50)
-    ap.add_argument("--sites", type=int, default=1000000,
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--sites", type=int, default=0,
                     help="compressed sites per window (L/c)")
-    ap.add_argument("--ntimes", type=int, default=20)
+    ap.add_argument("--ntimes", type=int, default=0)
     ap.add_argument("--windows", type=int, default=0,
-                    help="independent windows per GPU (default: 148 with the "
-                         "checkpointed table, 38 with the whole table)")
-    ap.add_argument("--checkpoint", type=int, default=1,
+                    help="independent windows per GPU (default: per config)")
+    ap.add_argument("--checkpoint", type=int, default=-1,
                     help="1: AWB_CHECKPOINT (forward table kept one segment at a "
                          "time, forward recursion run twice); 0: whole table")
     ap.add_argument("--cpu-sample-sites", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.k = a.k or c["k"]
+    a.sites = a.sites or c["sites"]
+    a.ntimes = a.ntimes or c["ntimes"]
+    if a.checkpoint < 0:
+        a.checkpoint = c["checkpoint"]
+    a.strong = "total_windows" in c and a.windows <= 0
+    a.total_windows = c.get("total_windows", 0)
     if a.windows <= 0:
+        a.windows = c.get("windows", 0)
+    if a.windows <= 0 and not a.strong:
         a.windows = 148 if a.checkpoint else 38
     return a
 
 
+def config_dict(a):
+    """The workload, identical for both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "k": a.k, "ntimes": a.ntimes,
+            "sites_per_window": a.sites, "compress": 10,
+            "modes": "even windows external (new leaf), odd windows internal "
+                     "(subtree)",
+            "l2": "inputs larger than L2: every step streams its windows' forward "
+                  "tables (8 B per site*state, GBs per GPU; `run.table_gb_per_gpu` "
+                  "in the b200 arm) and per-block tables through HBM"}
+
+
 def workload_name(a):
-    return ("config3: arg-sim k=%d, L=%.0f Mb, ntimes=%d, maxtime=200e3, c=10 "
-            "(%d compressed sites/window); leaf + subtree threading"
-            % (a.k, a.sites * 10 / 1e6, a.ntimes, a.sites))
+    return ("%s (%d compressed sites/window); leaf + subtree threading"
+            % (CONFIGS[a.config]["name"], a.sites))
 
 
 # --------------------------------------------------------------------- clocks
@@ -147,26 +192,29 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------ reference
 
-def truncated_problem(a, nsites, seed=1, internal=False):
+def sample_problems(a):
+    """The bounded CPU sample of the workload: the first `cpu_sample_sites`
+    sites of one external-mode and one internal-mode window."""
     from argweaver_b200 import sim
-    return sim.simulate_problem(a.k, nsites, ntimes=a.ntimes, seed=seed,
-                                internal=internal)
+    n = min(a.cpu_sample_sites, a.sites)
+    return [sim.simulate_problem(a.k, n, ntimes=a.ntimes, seed=1 + i,
+                                 internal=bool(i)) for i in range(2)], n
 
 
-def run_ref_bench(problem, threads=1, reps=1):
-    """Time the unmodified reference on a problem; returns dict or None."""
-    from argweaver_b200.flatfile import write_awf
-    if not os.path.exists(REF_BENCH):
-        return None
-    with tempfile.TemporaryDirectory() as tmp:
-        fn = os.path.join(tmp, "p.awf")
-        write_awf(fn, problem)
-        out = subprocess.run([REF_BENCH, "--in", fn, "--reps", str(reps),
-                              "--threads", str(threads)], capture_output=True,
-                             text=True)
-    if out.returncode != 0:
-        return None
-    kv = dict(re.findall(r"(\w+)=([-0-9.e+]+)", out.stdout))
+def ref_bench_start(fn, threads=1, reps=1, out=None, seed=1, stride=1):
+    cmd = [REF_BENCH, "--in", fn, "--reps", str(reps), "--threads", str(threads),
+           "--rand-seed", str(seed)]
+    if out:
+        cmd += ["--out", out, "--fw-stride", str(stride)]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                            text=True)
+
+
+def ref_bench_result(proc):
+    so, se = proc.communicate()
+    if proc.returncode != 0:
+        raise RuntimeError("ref_bench failed: " + se[-1000:])
+    kv = dict(re.findall(r"(\w+)=([-0-9.e+]+)", so))
     return {k: float(v) for k, v in kv.items()}
 
 
@@ -184,62 +232,142 @@ def run_oracle_port(problem):
     o = run.outputs()
     ss = float(np.sum(o["nstates"].astype(np.float64) * problem["blocklens"]))
     return {"forward_s": t1 - t0, "trace_s": t2 - t1, "wall_s": t2 - t0,
-            "states_sites": ss, "threads": 1}
+            "states_sites": ss, "threads": 1, "path": o["path"]}
 
 
-def cpu_baseline(a):
-    prob = truncated_problem(a, a.cpu_sample_sites, seed=1)
-    res = run_ref_bench(prob, threads=1, reps=1)
-    kind = "reference"
-    if res is None:
-        res = run_oracle_port(prob)
+def gpu_parity(problems, seeds, refs, ctx):
+    """Run the sample problems on the GPU (whole table) and compare with what
+    the reference produced for them: paths (same libc rand() draws) and the
+    forward rows the reference dumped."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_lib
+    from argweaver_b200 import api
+    libc = ctypes.CDLL("libc.so.6")
+    out = {"path_identical": True, "first_divergence": None, "fw_max_rel": 0.0,
+           "sites_compared": 0, "fw_rows_compared": 0,
+           "against": "oracle/_ref/ref_bench (unmodified reference), same "
+                      "problems, same srand() seeds"}
+    for d, seed, ref in zip(problems, seeds, refs):
+        n = int(np.sum(d["blocklens"]))
+        libc.srand(seed)
+        r = np.array([libc.rand() for _ in range(n)], np.int32)
+        b = api.Batch([d], ctx)
+        b.upload().setup().forward().traceback([r]).sync()
+        path = b.path(0)
+        bad = np.nonzero(path != ref["path"])[0]
+        if bad.size:
+            out["path_identical"] = False
+            if out["first_divergence"] is None:
+                out["first_divergence"] = int(bad.max())   # the walk runs backwards
+        lay = b.layout(0)
+        mine = ref_lib.rows_of(b.fw(0), lay["fw_off"], ref["nstates"],
+                               d["blocklens"], ref["fw_sites"])
+        with np.errstate(all="ignore"):
+            rel = np.abs(mine - ref["fw"]) / np.maximum(
+                np.maximum(np.abs(mine), np.abs(ref["fw"])), 1e-300)
+        rel[mine == ref["fw"]] = 0.0
+        out["fw_max_rel"] = max(out["fw_max_rel"], float(np.max(rel)))
+        out["sites_compared"] += n
+        out["fw_rows_compared"] += int(len(ref["fw_sites"]))
+        b.close()
+    return out
+
+
+def cpu_baseline(a, ctx=None):
+    """1 core of the unmodified reference on the bounded sample; with `ctx`,
+    the GPU runs the same problems and the results are compared (parity)."""
+    from argweaver_b200.flatfile import read_awf, write_awf
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    problems, n = sample_problems(a)
+    parity = None
+    if not os.path.exists(REF_BENCH):
+        res = [run_oracle_port(p) for p in problems]
         kind = "port"
-    t = res["forward_s"] + res["trace_s"]
-    return {"value": res["states_sites"] / t, "unit": UNIT, "cores": 1,
-            "kind": kind,
-            "forward_s": res["forward_s"], "trace_s": res["trace_s"],
-            "sample": "forward+traceback of one external-mode window, first "
-                      "%d of %d compressed sites (k=%d, ntimes=%d), 1 core"
-                      % (a.cpu_sample_sites, a.sites, a.k, a.ntimes)}
+    else:
+        import ref_lib
+        kind = "reference"
+        res, refs = [], []
+        with tempfile.TemporaryDirectory() as tmp:
+            for i, p in enumerate(problems):
+                fn = os.path.join(tmp, "p%d.awf" % i)
+                fo = os.path.join(tmp, "r%d.awf" % i)
+                write_awf(fn, ref_lib.problem_for_file(p))
+                # enough repetitions for ~5 s of CPU work per mode
+                est = a.k * 6.0 * n / 3.0e7
+                reps = int(max(1, min(200, round(5.0 / max(est, 1e-3)))))
+                res.append(ref_bench_result(ref_bench_start(
+                    fn, 1, reps, out=fo, seed=11 + i, stride=max(1, n // 400))))
+                refs.append(read_awf(fo))
+        if ctx is not None:
+            parity = gpu_parity(problems, [11, 12], refs, ctx)
+    t = sum(r["forward_s"] + r["trace_s"] for r in res)
+    ss = sum(r["states_sites"] for r in res)
+    out = {"value": ss / t, "unit": UNIT, "cores": 1, "kind": kind,
+           "forward_s": sum(r["forward_s"] for r in res),
+           "trace_s": sum(r["trace_s"] for r in res),
+           "sample": "forward+traceback of one external-mode and one "
+                     "internal-mode window, first %d of %d compressed sites "
+                     "(k=%d, ntimes=%d), 1 core" % (n, a.sites, a.k, a.ntimes)}
+    return out, parity
 
 
 def bench_reference(a, rank, world):
     if rank != 0:
         return
+    from argweaver_b200.flatfile import write_awf
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     cores = os.cpu_count() or 1
-    nsites = min(a.cpu_sample_sites, a.sites)
-    prob = truncated_problem(a, nsites, seed=1)
+    problems, nsites = sample_problems(a)
     kind = "reference" if os.path.exists(REF_BENCH) else "port"
     times, ss = [], 0.0
-    for step in range(a.warmup + a.steps):
-        t0 = time.time()
+    with tempfile.TemporaryDirectory() as tmp:
+        fns = []
         if kind == "reference":
-            res = run_ref_bench(prob, threads=cores, reps=1)
-            wall = res["wall_s"]
-            ss = res["states_sites"] * cores
-        else:
-            res = run_oracle_port(prob)
-            wall = res["wall_s"]
-            ss = res["states_sites"]
-            cores = 1
-        if step >= a.warmup:
-            times.append(wall)
-        del t0
+            import ref_lib
+            for i, p in enumerate(problems):
+                fns.append(os.path.join(tmp, "p%d.awf" % i))
+                write_awf(fns[-1], ref_lib.problem_for_file(p))
+        # small configurations: repeat inside the workers so that a step is
+        # seconds of work, not process start-up
+        est = a.k * 6.0 * nsites / 3.0e7
+        reps = int(max(1, min(500, round(1.0 / max(est, 1e-3)))))
+        for step in range(a.warmup + a.steps):
+            if kind == "reference":
+                # half of the cores on the external-mode sample, half on the
+                # internal-mode one, all at once
+                th = [cores - cores // 2, cores // 2]
+                t0 = time.time()
+                procs = [ref_bench_start(fns[i], th[i], reps) for i in range(2)
+                         if th[i] > 0]
+                res = [ref_bench_result(p) for p in procs]
+                wall = time.time() - t0
+                ss = sum(r["states_sites"] * r["threads"] * r["reps"] for r in res)
+            else:
+                res = [run_oracle_port(p) for p in problems]
+                wall = sum(r["wall_s"] for r in res)
+                ss = sum(r["states_sites"] for r in res)
+                cores = 1
+            if step >= a.warmup:
+                times.append(wall)
     t = float(np.mean(times))
     value = ss / t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong" if a.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "k": a.k, "ntimes": a.ntimes,
-                   "sites_per_window": a.sites, "compress": 10},
+        "config": config_dict(a),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
                          "kind": kind,
                          "sample": "each step: %d concurrent single-threaded "
-                                   "workers (one per host core), each running "
-                                   "forward+traceback on the first %d sites of "
-                                   "an external-mode window" % (cores, nsites)},
+                                   "workers (one per host core; half on an "
+                                   "external-mode, half on an internal-mode "
+                                   "window), each running forward+traceback %d "
+                                   "time(s) on the first %d sites of its window; "
+                                   "wall time includes process start and reading "
+                                   "the problem file" % (cores, reps, nsites)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -265,10 +393,16 @@ def bench_b200(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic windows for this rank (pinned host memory)
-    W = a.windows
+    if a.strong:
+        mine = list(shard.my_windows(a.total_windows, rank, world))
+        total_windows = a.total_windows
+    else:
+        mine = list(shard.my_windows(a.windows * world, rank, world))
+        total_windows = a.windows * world
+    W = len(mine)
     problems, rands, keep = [], [], []
-    for w in range(W):
-        seed = 1000 + shard.my_windows(W * world, rank, world)[w]
+    for w in mine:
+        seed = 1000 + w
         d = sim.simulate_problem(a.k, a.sites, ntimes=a.ntimes, seed=seed,
                                  internal=(w % 2 == 1))
         # the simulator's SPRs keep node indices stable, i.e. the default node
@@ -291,48 +425,61 @@ def bench_b200(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident measurement (`value`)
-    batch = api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
-    batch.upload().upload_rand(rands).sync()
-    ss_local = batch.total_states_sites()
-    fw_bytes = sum(8.0 * batch.states_sites(i) for i in range(W))
+    ms_local = 0.0
+    ss_local = 0.0
+    fw_bytes = 0.0
+    stage = {"setup_ms": 0.0, "forward_ms": 0.0, "traceback_ms": 0.0}
+    launches = 0
+    logz_local = []
+    nseg, nres = 1, 1
+    h2d = d2h = 0
+    clocks = None
+    fast_path = None
+    e2e_ms_local = None
+    e2e_latency_ms = None
+    if W > 0:
+        # ---- device-resident measurement (`value`)
+        batch = api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
+        batch.upload().upload_rand(rands).sync()
+        ss_local = batch.total_states_sites()
+        fw_bytes = sum(8.0 * batch.states_sites(i) for i in range(W))
 
-    def step():
-        batch.setup().forward().traceback()
+        def step():
+            batch.setup().forward().traceback()
 
-    for _ in range(a.warmup):
-        step()
-    batch.sync()
-    launches0 = batch.kernel_launches()
+        for _ in range(a.warmup):
+            step()
+        batch.sync()
+        launches0 = batch.kernel_launches()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.record(0)
-    stage = {"setup_ms": 0.0, "forward_ms": 0.0, "traceback_ms": 0.0}
-    for _ in range(a.steps):
-        step()
-        if a.steps <= 8:
-            tm = batch.timings()       # syncs the stream; per-stage CUDA events
-            for k2 in stage:
-                stage[k2] += tm[k2] / a.steps
-    ctx.record(1)
+    if W > 0:
+        ctx.record(0)
+        for _ in range(a.steps):
+            step()
+            if a.steps <= 8:
+                tm = batch.timings()       # syncs the stream; per-stage CUDA events
+                for k2 in stage:
+                    stage[k2] += tm[k2] / a.steps
+        ctx.record(1)
     barrier()
     clocks = sampler.stop()
-    ms_local = ctx.elapsed_ms(0, 1) / a.steps
-    launches = (batch.kernel_launches() - launches0) // max(a.steps, 1)
-    if a.steps > 8:
-        stage = batch.timings()
-    logz_local = [batch.logz(i) for i in range(W)]
-    status = [batch.status(i) for i in range(W)]
-    assert all(s == -1 for s in status), "forward hit a non-positive column"
-    nseg, nres = batch.segments()
-    h2d = batch.h2d_bytes() + sum(r.nbytes for r in rands)
-    d2h = sum(4 * batch.nsites(i) for i in range(W))
-    batch.close()
+    if W > 0:
+        ms_local = ctx.elapsed_ms(0, 1) / a.steps
+        launches = (batch.kernel_launches() - launches0) // max(a.steps, 1)
+        if a.steps > 8:
+            stage = batch.timings()
+        logz_local = [batch.logz(i) for i in range(W)]
+        status = [batch.status(i) for i in range(W)]
+        assert all(s == -1 for s in status), "forward hit a non-positive column"
+        nseg, nres = batch.segments()
+        fast_path = batch.fast_path()
+        h2d = batch.h2d_bytes() + sum(r.nbytes for r in rands)
+        d2h = sum(4 * batch.nsites(i) for i in range(W))
+        batch.close()
 
     # ---- end to end through the public API, host buffers in pinned memory
-    e2e_ms_local = None
-    e2e_latency_ms = None
     if not a.no_e2e:
         path_bufs = []
         for w in range(W):
@@ -349,35 +496,42 @@ def bench_b200(a, rank, world, local_rank):
         def create():
             return api.Batch(problems, ctx, checkpoint=bool(a.checkpoint))
 
-        nsteps = max(1, min(a.steps, 3))
-        stream = api.sample_thread_stream(
-            ((problems, rands) for _ in range(nsteps + 2)), ctx,
-            checkpoint=bool(a.checkpoint), out=lambda i: path_bufs[i])
-        next(stream)                       # warm-up batch (and batch 1 is created)
+        nsteps = max(1, a.steps)
+        if W > 0:
+            stream = api.sample_thread_stream(
+                ((problems, rands) for _ in range(nsteps + 2)), ctx,
+                checkpoint=bool(a.checkpoint), out=lambda i: path_bufs[i])
+            next(stream)                   # warm-up batch (and batch 1 is created)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(nsteps):            # (each of them also creates its successor)
-            next(stream)
+        if W > 0:
+            for _ in range(nsteps):        # (each of them also creates its successor)
+                next(stream)
         torch.cuda.synchronize()
         e2e_ms_local = (time.perf_counter() - t0) * 1e3 / nsteps
-        stream.close()
+        if W > 0:
+            stream.close()
         # latency of ONE isolated batch (nothing overlapped): create -> paths
         barrier()
-        t0 = time.perf_counter()
-        b1 = create()
-        b1.upload().setup().forward().traceback(rands).sync()
-        _ = [b1.path(i, out=path_bufs[i]) for i in range(W)]
-        b1.close()
-        e2e_latency_ms = (time.perf_counter() - t0) * 1e3
+        if W > 0:
+            t0 = time.perf_counter()
+            b1 = create()
+            b1.upload().setup().forward().traceback(rands).sync()
+            _ = [b1.path(i, out=path_bufs[i]) for i in range(W)]
+            b1.close()
+            e2e_latency_ms = (time.perf_counter() - t0) * 1e3
 
     # ---- reduce over ranks: max time, sum work (argweaver_b200/shard.py)
     d_ = dist if world > 1 else None
     ms = shard.all_max(ms_local, d_)
     ss = shard.all_sum(ss_local, d_)
     fwd_ms = shard.all_max(stage["forward_ms"], d_)
+    fw_bytes_all = shard.all_sum(fw_bytes, d_)
     e2e_ms = shard.all_max(e2e_ms_local, d_) if e2e_ms_local is not None else None
+    h2d_all = shard.all_sum(float(h2d), d_)
+    d2h_all = shard.all_sum(float(d2h), d_)
     # the only exchange of the workload: per-window log-likelihoods to rank 0
-    logz_all = shard.gather_window_values(logz_local, W * world, d_)
+    logz_all = shard.gather_window_values(logz_local, total_windows, d_)
 
     if rank == 0:
         peaks = {}
@@ -388,33 +542,37 @@ def bench_b200(a, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else \
             "fallback 6650 GB/s (B200_PROFILING.md)"
-        achieved = fw_bytes / (fwd_ms * 1e-3) / 1e9
-        # DRAM traffic of the same kernel from the committed ncu capture
-        # (profiles/), valid only for the configuration it was taken on
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles",
-                                             "r1_forward_traffic.json")))
-            c = tj["config"]
-            if (c["k"], c["ntimes"], c["sites_per_window"], c["windows_per_gpu"],
-                    c.get("checkpoint", 0)) == (a.k, a.ntimes, a.sites, W,
-                                                a.checkpoint):
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        except Exception:
-            pass
+        # per GPU: the slowest rank's forward stage over its share of the bytes
+        achieved = (fw_bytes_all / world) / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+        # DRAM traffic of the same kernel: NOT measured in this run -- taken
+        # from the committed ncu capture of the same configuration, if any
+        traffic, traffic_src = None, None
+        for fn in ("r2_forward_traffic.json", "r1_forward_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                c = tj["config"]
+                if (c["k"], c["ntimes"], c["sites_per_window"], c["windows_per_gpu"],
+                        c.get("checkpoint", 0)) == (a.k, a.ntimes, a.sites, W,
+                                                    a.checkpoint):
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    traffic_src = ("profiles/%s (ncu --set full capture of this "
+                                   "configuration, not measured in this run)" % fn)
+                    break
+            except Exception:
+                pass
         line = {
             "metric": METRIC, "value": ss / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if a.strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(a), "k": a.k, "ntimes": a.ntimes,
-                "sites_per_window": a.sites, "compress": 10,
-                "windows_per_gpu": W, "modes": "even windows external (new "
-                "leaf), odd windows internal (subtree)",
-                "l2": "inputs larger than L2: %.1f GB of forward table per GPU "
-                      "streamed per step" % (fw_bytes / 1e9),
+            "config": config_dict(a),
+            "run": {
+                "windows_per_gpu": W if not a.strong else
+                "%d windows in total over %d GPU(s)" % (total_windows, world),
+                "table_gb_per_gpu": fw_bytes / 1e9,
                 "parallelism": "windows sharded across GPUs, one CTA per window",
+                "forward_kernel": fast_path,
                 "table": ("checkpointed: %d segments of <= 128 MiB per window, "
                           "%d segment tables kept per window (all the device "
                           "memory allows); the traceback rebuilds the other "
@@ -426,8 +584,8 @@ def bench_b200(a, rank, world, local_rank):
             "clocks": clocks,
             "e2e": None if e2e_ms is None else {
                 "value": ss / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                "ms_per_step": e2e_ms, "steps": max(1, a.steps),
                 "single_batch_latency_ms": e2e_latency_ms,
                 "note": "stream of batches through the public API, host (pinned) "
                         "buffers: the host-only layout of batch n+1 "
@@ -440,9 +598,11 @@ def bench_b200(a, rank, world, local_rank):
             "forward_only": {"value": ss / (fwd_ms * 1e-3) if fwd_ms > 0 else None,
                              "unit": UNIT},
             "roofline": {
-                "kernel": "awb_forward_fast_kernel", "bound": "hbm",
+                "kernel": "awb_forward_fast_kernel" if fast_path == "fast"
+                else "awb_forward_kernel", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fw_bytes,
                 "note": "8 B per site*state (FP64 forward-table store) over the "
                         "forward stage of the step (per-segment emission + forward "
@@ -451,7 +611,7 @@ def bench_b200(a, rank, world, local_rank):
             "logz_mean": float(np.mean(logz_all)),
         }
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(a)
+            line["cpu_baseline"], line["parity"] = cpu_baseline(a, ctx)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

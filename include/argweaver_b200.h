@@ -146,6 +146,9 @@ int awb_batch_kernel_launches(const awb_batch *b);
  * that many segments of the forward pass are not rebuilt for the traceback).
  * Both 1 without AWB_CHECKPOINT. */
 int awb_batch_segments(const awb_batch *b);
+/* which forward kernel the batch's shape selects: 1 = the register-resident
+ * fast kernel (awb_forward_fast.cuh), 0 = the generic one (awb_forward.cuh) */
+int awb_batch_forward_kernel(const awb_batch *b);
 int awb_batch_resident_segments(const awb_batch *b);
 
 /* results (device -> host) */

@@ -7,7 +7,10 @@
 // (b) validating generated problems against the reference on the CPU.
 //
 // usage: ref_bench --in problem.awf [--out result.awf] [--reps R] [--threads N]
-//                  [--rand-seed S]
+//                  [--rand-seed S] [--fw-stride K]
+//   --fw-stride K : with --out, keep only the forward rows of sites 0, K, 2K, ...
+//                 (and the last site) -- at-size parity tests compare those rows
+//                 and the whole sampled path
 //   --threads N : N independent processes-worth of work run by N forked
 //                 children on the same problem (the reference is single
 //                 threaded; this is how arg-sample-genome uses N cores).
@@ -121,6 +124,8 @@ static void load(const char *fn, Loaded &L)
     }
 }
 
+static int g_fw_stride = 1;
+
 static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
                      const char *out_file)
 {
@@ -151,7 +156,7 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
     if (out_file) {
         FILE *out = awf_create(out_file);
         vector<double> fwflat;
-        vector<int> nstates;
+        vector<int> nstates, fwsites;
         States states;
         int pos = trees->start_coord;
         for (LocalTrees::const_iterator it = trees->begin();
@@ -159,13 +164,19 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
             get_coal_states(it->tree, model->ntimes, states, L.internal);
             nstates.push_back(states.size());
             const int S1 = max((int) states.size(), 1);
-            for (int i = pos; i < pos + it->blocklen; i++)
+            for (int i = pos; i < pos + it->blocklen; i++) {
+                const int rel = i - trees->start_coord;
+                if (rel % g_fw_stride != 0 && rel != n - 1)
+                    continue;
+                fwsites.push_back(rel);
                 for (int j = 0; j < S1; j++)
                     fwflat.push_back(fw[i][j]);
+            }
             pos += it->blocklen;
         }
         awf_write1(out, "nstates", AWF_I32, nstates.size(), &nstates[0]);
         awf_write1(out, "fw", AWF_F64, fwflat.size(), &fwflat[0]);
+        awf_write1(out, "fw_sites", AWF_I32, fwsites.size(), &fwsites[0]);
         awf_write1(out, "path", AWF_I32, n, &path_alloc[0]);
         fclose(out);
     }
@@ -183,6 +194,7 @@ int main(int argc, char **argv)
         else if (a == "--reps") reps = atoi(argv[i + 1]);
         else if (a == "--threads") threads = atoi(argv[i + 1]);
         else if (a == "--rand-seed") rand_seed = (unsigned) atol(argv[i + 1]);
+        else if (a == "--fw-stride") g_fw_stride = max(1, atoi(argv[i + 1]));
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     if (!in_file) { fprintf(stderr, "need --in\n"); return 1; }
