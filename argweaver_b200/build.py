@@ -23,6 +23,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # internal references bind inside the library: a host program that defines
+    # the reference's own symbols of the same names (arg-sample) cannot interpose
+    "-Xlinker", "-Bsymbolic",
     "--fmad=true",
 ]
 

@@ -1134,20 +1134,35 @@ static int default_ctx(awb_ctx **ctx)
     return 0;
 }
 
-extern "C" int awb_thread_sample(const awb_problem *p, const int *rand_ints,
-                                 int rand_max, int *path, double *logz)
+extern "C" int awb_thread_sample_cond(const awb_problem *p, const double *prior,
+                                      int last_state, const int *rand_ints,
+                                      int rand_max, int *path, double *logz)
 {
     awb_ctx *ctx;
     if (default_ctx(&ctx)) return 1;
     awb_batch *b = NULL;
     if (awb_batch_create(ctx, 1, p, 0, &b)) return 1;
+    const double *priors[1] = { prior };
     int rc = awb_batch_upload(b) || awb_batch_setup(b) ||
-        awb_batch_forward(b, NULL) ||
-        awb_batch_traceback(b, &rand_ints, rand_max, NULL) || awb_batch_sync(b);
+        awb_batch_forward(b, prior ? priors : NULL) ||
+        awb_batch_traceback(b, &rand_ints, rand_max,
+                            last_state >= 0 ? &last_state : NULL) ||
+        awb_batch_sync(b);
+    int bad = -1;
+    if (!rc) rc = awb_batch_get_status(b, 0, &bad);
+    if (!rc && bad >= 0)
+        rc = fail("forward column " + std::to_string(bad) +
+                  " has no positive entry (sample_thread.cpp:443-444)");
     if (!rc && path) rc = awb_batch_get_path(b, 0, path);
     if (!rc && logz) rc = awb_batch_get_logz(b, 0, logz);
     awb_batch_destroy(b);
     return rc;
+}
+
+extern "C" int awb_thread_sample(const awb_problem *p, const int *rand_ints,
+                                 int rand_max, int *path, double *logz)
+{
+    return awb_thread_sample_cond(p, NULL, -1, rand_ints, rand_max, path, logz);
 }
 
 extern "C" int awb_forward_table(const awb_problem *p, const double *prior,

@@ -560,7 +560,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         // branch scans in registers while the F-scribes sum the rows
         const double x0 = Da * c;
         const double y0 = x0 * hb;
-        double py = y0, q = x0;
+        // exclusive sums PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a: the
+        // neighbour's term first, then an inclusive scan of those (an inclusive
+        // scan minus the own term cancels: h grows like exp(cumulative
+        // coalescent rate), so y0 can exceed the sum below it by many orders)
+        double py = __shfl_up_sync(0xffffffffu, y0, 1) * upm[0];
+        double q = __shfl_down_sync(0xffffffffu, x0, 1) * dnm[0];
 #pragma unroll
         for (int l = 0; l < NL; l++) {
             const double ty = __shfl_up_sync(0xffffffffu, py, 1 << l);
@@ -568,8 +573,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             py = fma(ty, upm[l], py);
             q = fma(tq, dnm[l], q);
         }
-        // exclusive sums: PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a
-        const double PY = py - y0, Q = q - x0;
+        const double PY = py, Q = q;
         const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
         // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
         __stcs(w2, c2 * awb_lds(inv_s + iofs));      // streaming: L1 is for the block tables

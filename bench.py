@@ -96,6 +96,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mcmc-iters", type=int, default=-1,
+                    help="iterations of the arg-sample pair (metric ii); default: "
+                         "100 for config 1, 3 for config 2, none otherwise; 0: skip")
     a = ap.parse_args()
     c = CONFIGS[a.config]
     a.k = a.k or c["k"]
@@ -310,6 +313,64 @@ def cpu_baseline(a, ctx=None):
                      "internal-mode window, first %d of %d compressed sites "
                      "(k=%d, ntimes=%d), 1 core" % (n, a.sites, a.k, a.ntimes)}
     return out, parity
+
+
+ARG_SAMPLE = os.path.join(ROOT, "oracle", "_ref", "arg-sample")
+ARG_SAMPLE_B200 = os.path.join(ROOT, "oracle", "_ref", "arg-sample-b200")
+
+
+def mcmc_pair(a, iters):
+    """BASELINE metric (ii), arg-sample MCMC iterations per second: the
+    UNMODIFIED reference binary (oracle/_ref/arg-sample, 1 core -- it is
+    single-threaded) and the same binary with its threading path on the device
+    (oracle/_ref/arg-sample-b200 = the reference's objects + the adapter
+    oracle/sample_thread_b200.cpp over libargweaver_b200.so), same generated
+    .sites file, same seed.  One chain issues its thread samples one after
+    another, so this is the single-window latency of the path, not its batched
+    throughput.  iters/s = iterations / sum of the per-iteration `sample time`
+    lines of the run's log (arg-sample.cpp:676)."""
+    from argweaver_b200 import sim
+    if not (os.path.exists(ARG_SAMPLE) and os.path.exists(ARG_SAMPLE_B200)):
+        return {"unavailable": "oracle/_ref/arg-sample[-b200] not built"}
+    out = {"metric": "arg_sample_mcmc_iters_per_sec", "iters": iters,
+           "config": "k=%d, %d compressed sites (-c 10), ntimes=%d, -x 1"
+                     % (a.k, a.sites, a.ntimes)}
+    with tempfile.TemporaryDirectory() as tmp:
+        seqs = sim.simulate_arg(a.k - 1, a.sites, a.ntimes, seed=77)[8]
+        sites = os.path.join(tmp, "gen.sites")
+        sim.write_sites(sites, seqs, compress=10)
+        stats = {}
+        for name, binary in (("reference", ARG_SAMPLE), ("b200", ARG_SAMPLE_B200)):
+            o = os.path.join(tmp, name)
+            cmd = [binary, "-s", sites, "-N", "10000", "-r", "1.6e-8", "-m",
+                   "1.8e-8", "--ntimes", str(a.ntimes), "--maxtime", "200e3",
+                   "-c", "10", "-n", str(iters), "-x", "1", "-q", "-o", o]
+            env = dict(os.environ)
+            env["AWB_ADAPTER_REPORT"] = "1"
+            t0 = time.time()
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            wall = time.time() - t0
+            if r.returncode != 0:
+                return {"unavailable": "%s failed: %s" % (name, r.stderr[-300:])}
+            tms = []
+            for m in re.finditer(r"^sample time:\s*([0-9.]+)\s*(us|ms|s|m|h)\b",
+                                 open(o + ".log").read(), re.M):
+                tms.append(float(m.group(1)) * {"us": 1e-6, "ms": 1e-3, "s": 1.0,
+                                                "m": 60.0, "h": 3600.0}[m.group(2)])
+            stats[name] = open(o + ".stats").read()
+            out[name] = {"iters_per_s": len(tms) / sum(tms) if tms else None,
+                         "wall_s": wall, "cores": 1}
+            if name == "b200":
+                m = re.search(r"device thread samples: (\d+) reference fallbacks: "
+                              r"(\d+) device seconds: ([0-9.]+)", r.stderr)
+                if m:
+                    out[name].update(device_thread_samples=int(m.group(1)),
+                                     reference_fallbacks=int(m.group(2)),
+                                     device_seconds=float(m.group(3)))
+        out["stats_identical"] = stats["reference"] == stats["b200"]
+        if out["reference"]["iters_per_s"] and out["b200"]["iters_per_s"]:
+            out["speedup"] = out["b200"]["iters_per_s"] / out["reference"]["iters_per_s"]
+    return out
 
 
 def bench_reference(a, rank, world):
@@ -612,8 +673,16 @@ def bench_b200(a, rank, world, local_rank):
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"], line["parity"] = cpu_baseline(a, ctx)
+            iters = a.mcmc_iters
+            if iters < 0:
+                iters = {1: 100, 2: 3}.get(a.config, 0)
+            if iters > 0:
+                ctx.close()            # the sampler process takes the device
+                ctx = None
+                line["mcmc"] = mcmc_pair(a, iters)
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

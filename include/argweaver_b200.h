@@ -168,6 +168,14 @@ int64_t awb_batch_debug_bytes(awb_batch *b, int i, const char *name);
  * traceback + download, for a single problem. */
 int awb_thread_sample(const awb_problem *p, const int *rand_ints, int rand_max,
                       int *path, double *logz);
+/* the same with a caller-supplied first column (prior_given; prior == NULL:
+ * the model's prior) and a given last state (last_state_given; -1: sample it;
+ * the draws then start with the second-to-last site, n-1 of them) -- what
+ * cond_sample_arg_thread[_internal] pass (sample_thread.cpp:700-865).  Fails
+ * when a forward column has no positive entry (the reference asserts). */
+int awb_thread_sample_cond(const awb_problem *p, const double *prior,
+                           int last_state, const int *rand_ints, int rand_max,
+                           int *path, double *logz);
 int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
                       double *logz);
 
