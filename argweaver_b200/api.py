@@ -74,6 +74,31 @@ def lib():
                                           C.c_void_p, C.c_int64]
         L.awb_batch_debug_bytes.restype = C.c_int64
         L.awb_batch_debug_bytes.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        if not hasattr(L, "awb_sites_read"):
+            _lib = L            # an older build loaded through AWB_LIB (A/B probes)
+            return _lib
+        L.awb_sites_read.argtypes = [C.c_char_p, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]
+        L.awb_sites_from_columns.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_void_p)]
+        L.awb_sites_free.argtypes = [C.c_void_p]
+        for nm in ("nseqs", "ncols", "start", "end", "mapping_size"):
+            getattr(L, "awb_sites_" + nm).argtypes = [C.c_void_p]
+        L.awb_sites_name.restype = C.c_char_p
+        L.awb_sites_name.argtypes = [C.c_void_p, C.c_int]
+        L.awb_sites_positions.restype = C.POINTER(C.c_int)
+        L.awb_sites_positions.argtypes = [C.c_void_p]
+        L.awb_sites_columns.restype = C.POINTER(C.c_ubyte)
+        L.awb_sites_columns.argtypes = [C.c_void_p]
+        L.awb_sites_mapping.restype = C.POINTER(C.c_int)
+        L.awb_sites_mapping.argtypes = [C.c_void_p]
+        L.awb_sites_compress.argtypes = [C.c_void_p, C.c_int]
+        L.awb_sites_to_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.awb_arg_likelihood.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.awb_arg_prior.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.awb_arg_joint.argtypes = [C.c_void_p, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -331,6 +356,124 @@ def forward_algorithm(problem, prior=None, ctx=None):
         return b.fw(0), b.layout(0), b.logz(0)
     finally:
         b.close()
+
+
+class Sites(object):
+    """A .sites alignment (``awb_sites``; reference ``Sites``,
+    sequences.h:211-268): variant columns only.  ``read`` ~ read_sites,
+    ``compress`` ~ find_compress_cols + compress_sites, ``sequences`` ~
+    make_sequences_from_sites; ``packed()`` gives the arrays a problem dict takes
+    instead of dense ``seqs``."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def read(cls, filename, region=None):
+        h = C.c_void_p()
+        a, b = region if region else (-1, -1)
+        _check(lib().awb_sites_read(filename.encode(), int(a), int(b), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_columns(cls, positions, cols, start, end):
+        positions = np.ascontiguousarray(positions, np.int32)
+        cols = np.ascontiguousarray(cols, np.uint8)
+        h = C.c_void_p()
+        _check(lib().awb_sites_from_columns(
+            cols.shape[1] if cols.ndim == 2 else 0, int(start), int(end),
+            len(positions), positions.ctypes.data, cols.ctypes.data, C.byref(h)))
+        return cls(h)
+
+    nseqs = property(lambda self: lib().awb_sites_nseqs(self.h))
+    ncols = property(lambda self: lib().awb_sites_ncols(self.h))
+    start = property(lambda self: lib().awb_sites_start(self.h))
+    end = property(lambda self: lib().awb_sites_end(self.h))
+
+    def names(self):
+        return [lib().awb_sites_name(self.h, i).decode() for i in range(self.nseqs)]
+
+    def positions(self):
+        n = self.ncols
+        return (np.ctypeslib.as_array(lib().awb_sites_positions(self.h), (n,)).copy()
+                if n else np.zeros(0, np.int32))
+
+    def columns(self):
+        n, k = self.ncols, self.nseqs
+        return (np.ctypeslib.as_array(lib().awb_sites_columns(self.h), (n * k,))
+                .reshape(n, k).copy() if n else np.zeros((0, k), np.uint8))
+
+    def compress(self, compress):
+        """False when the alignment cannot be compressed at this level."""
+        rc = lib().awb_sites_compress(self.h, int(compress))
+        if rc == 1:
+            _check(rc)
+        return rc == 0
+
+    def mapping(self):
+        n = lib().awb_sites_mapping_size(self.h)
+        return (np.ctypeslib.as_array(lib().awb_sites_mapping(self.h), (n,)).copy()
+                if n > 0 else np.zeros(0, np.int32))
+
+    def sequences(self, default_char="A"):
+        out = np.empty((self.nseqs, self.end - self.start), np.uint8)
+        _check(lib().awb_sites_to_sequences(self.h, out.ctypes.data,
+                                            ord(default_char)))
+        return out
+
+    def packed(self):
+        """dict(var_pos, var_cols, nseqs, seqlen) relative to the region start"""
+        return dict(var_pos=self.positions() - self.start, var_cols=self.columns(),
+                    nseqs=self.nseqs, seqlen=self.end - self.start)
+
+    def close(self):
+        if self.h:
+            lib().awb_sites_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_columns(seqs):
+    """The variant-columns form of dense rows, as a .sites file holds them
+    (sequences.cpp:136-158): the columns whose rows differ -- plus the all-'N'
+    ones, which are masked sites.  Columns with one base in every row become the
+    default character; the threading HMM does not tell such columns apart
+    (emit.cpp:30-58, :807-828).  dict(var_pos, var_cols, nseqs, seqlen)."""
+    seqs = np.asarray(seqs, np.uint8)
+    var = np.nonzero((seqs != seqs[0]).any(axis=0) |
+                     (seqs[0] == ord("N")))[0].astype(np.int32)
+    return dict(var_pos=var, var_cols=np.ascontiguousarray(seqs[:, var].T),
+                nseqs=seqs.shape[0], seqlen=seqs.shape[1])
+
+
+def arg_likelihood(arg):
+    """calc_arg_likelihood (total_prob.cpp:19-42) of a complete ARG (dict with
+    the tree, model and sequence keys of a problem)."""
+    d = dict(arg)
+    d.setdefault("new_chrom", 0)
+    d.setdefault("internal", 0)
+    d.setdefault("seqids", np.arange((np.asarray(d["ptrees"]).shape[1] + 1) // 2))
+    p, keep = make_problem(d)
+    out = C.c_double()
+    _check(lib().awb_arg_likelihood(C.byref(p), C.byref(out)))
+    return out.value
+
+
+def arg_prior(arg):
+    """calc_arg_prior (total_prob.cpp:262-299)."""
+    d = dict(arg)
+    d.setdefault("new_chrom", 0)
+    d.setdefault("internal", 0)
+    d.setdefault("seqids", np.arange((np.asarray(d["ptrees"]).shape[1] + 1) // 2))
+    p, keep = make_problem(d)
+    out = C.c_double()
+    _check(lib().awb_arg_prior(C.byref(p), C.byref(out)))
+    return out.value
 
 
 def sample_thread(problem, rand_ints, rand_max=RAND_MAX, ctx=None):

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "--fmad=true",
 ]
 
-CUDA_SOURCES = ["awb_api.cu", "awb_compat.cu"]
+CUDA_SOURCES = ["awb_api.cu", "awb_compat.cu", "awb_totalprob.cu", "awb_sites.cpp"]
 CUDA_DEPS = ["awb_setup.cuh", "awb_forward.cuh", "awb_forward_fast.cuh", "awb_traceback.cuh",
              "awb_emit.cuh", "awb_common.cuh", "awb_layout.h"]
 

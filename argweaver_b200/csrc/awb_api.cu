@@ -45,6 +45,9 @@ static int fail(const std::string &msg)
     return 1;
 }
 
+// (for the other translation units of the library)
+int awb_fail_msg(const std::string &msg) { return fail(msg); }
+
 #define CUDA_OK(call)                                                        \
     do {                                                                     \
         cudaError_t e_ = (call);                                             \
@@ -67,9 +70,31 @@ extern "C" int awb_device_count(void)
 __global__ void awb_kind_kernel(const AwbChain *chains)
 {
     const AwbChain &ch = chains[blockIdx.y];
+    if (ch.seqs) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ch.nsites;
+             i += gridDim.x * blockDim.x)
+            awb_site_kind(ch, i);
+        return;
+    }
+    // the alignment as variant columns: every other site is the default
+    // character in every row; then one thread per variant column
+    const unsigned char dflt = ch.default_char == 'N' ? AWB_SITE_MASKED : AWB_SITE_INVARIANT;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ch.nsites;
          i += gridDim.x * blockDim.x)
-        awb_site_kind(ch, i);
+        ch.kind[i] = dflt;
+}
+
+__global__ void awb_kind_packed_kernel(const AwbChain *chains)
+{
+    const AwbChain &ch = chains[blockIdx.y];
+    if (ch.seqs)
+        return;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ch.nvar;
+         v += gridDim.x * blockDim.x) {
+        const long long i = (long long) ch.var_pos[v] - ch.start_coord;
+        if (i >= 0 && i < ch.nsites)
+            awb_site_kind(ch, (int) i, v);
+    }
 }
 
 __global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
@@ -232,6 +257,8 @@ struct awb_batch {
     int64_t h2d_bytes;
     bool uploaded, setup_done, forward_done, rand_uploaded, rand_in_use;
     bool ckpt;                 // checkpointed forward table (AWB_CHECKPOINT)
+    bool any_packed;           // some problem gives its alignment as variant columns
+    int maxnvar;
     bool lin_unsafe;           // some problem's linear-domain vectors may overflow
                                //   (awb_layout.h): generic forward kernel, closed-form
                                //   transitions in the traceback
@@ -349,17 +376,36 @@ extern "C" void awb_batch_destroy(awb_batch *b)
     delete b;
 }
 
-// shapes the register-resident forward kernel covers (awb_forward_fast.cuh)
+// Shape of the register-resident forward kernel (awb_forward_fast.cuh) for a
+// batch: TMAX (time rows), U (states per compute thread), compute threads NT.
+// U = 1 needs every branch inside one warp (<= 32 states: always so with up to
+// 33 time points); U = 2 / 4 also take branches of 33..64 states.
+struct FastShape {
+    int tmax, U, NT, threads;
+    bool ok;
+};
+
+static FastShape batch_fast_shape(const awb_batch *b)
+{
+    FastShape f;
+    const int Tm1 = b->maxT - 1;
+    f.tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
+    f.U = 1;
+    if (f.tmax > 20 || b->maxcnt > 32 || b->maxNS + AWB_FWD_HELPERS > 1024)
+        f.U = 2;
+    if (f.U == 2 && (b->maxNS + 63) / 64 * 32 > 512)
+        f.U = 4;
+    f.NT = (b->maxNS + 32 * f.U - 1) / (32 * f.U) * 32;
+    f.threads = f.NT + AWB_FWD_HELPERS;
+    f.ok = !getenv("AWB_FORCE_GENERIC") && !b->lin_unsafe && b->maxcnt <= 64 &&
+        f.threads <= (f.U == 1 ? 1024 : 608) &&
+        awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap) <= 200 * 1024;
+    return f;
+}
+
 static bool batch_fast_path(const awb_batch *b)
 {
-    const int Tm1 = b->maxT - 1;
-    const int threads = b->maxNS + AWB_FWD_HELPERS;
-    const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
-    // (a branch longer than a warp would need a cross-warp carry in the scans)
-    return !getenv("AWB_FORCE_GENERIC") && !b->lin_unsafe && threads <= 1024 &&
-        b->maxcnt <= 32 &&
-        !(tmax == 64 && threads > 384) &&
-        awb_fwd_fast_smem_bytes(b->maxNS, tmax, b->zcap) <= 200 * 1024;
+    return batch_fast_shape(b).ok;
 }
 
 extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
@@ -390,6 +436,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->rand_uploaded = false;
     b->rand_in_use = false;
     b->lin_unsafe = false;
+    b->any_packed = false;
+    b->maxnvar = 0;
     b->tables_stale = false;
     b->ckpt = false;
 
@@ -437,6 +485,10 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         if (L.zcap > b->zcap) b->zcap = L.zcap;
         if (L.maxcnt > b->maxcnt) b->maxcnt = L.maxcnt;
         if (L.lin_unsafe) b->lin_unsafe = true;
+        if (L.packed) {
+            b->any_packed = true;
+            if (problems[c].nvar > b->maxnvar) b->maxnvar = problems[c].nvar;
+        }
         for (size_t i = 0; i < L.copies.size(); i++)
             b->h2d_bytes += (int64_t) L.copies[i].bytes;
     }
@@ -721,36 +773,47 @@ static int launch_emit(awb_batch *b, int seg, int pass)
     return 0;
 }
 
-static int launch_forward_fast(awb_batch *b, int seg, int pass)
+// nsub: segments per chain worked on at once (seg, seg-1, ...): only the second
+// pass of a checkpointed table has independent segments
+static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
 {
     cudaStream_t st = b->ctx->stream;
-    const int Tm1 = b->maxT - 1;
-    const int FNS = b->maxNS;
-    const int threads = FNS + AWB_FWD_HELPERS;
+    const FastShape f = batch_fast_shape(b);
+    const int threads = f.threads;
     int maxd = 1;
     while (maxd < b->maxcnt) maxd <<= 1;
-    const int tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
-    const size_t fsmem = awb_fwd_fast_smem_bytes(FNS, tmax, b->zcap);
-#define AWB_LAUNCH_FAST(TM, NL, MT)                                              \
+    const size_t fsmem = awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap);
+    const dim3 grid(b->C, nsub);
+#define AWB_LAUNCH_FAST(TM, NL, MT, UU, MB)                                      \
     do {                                                                         \
         if (fsmem > 48 * 1024)                                                   \
-            CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT>,    \
+            CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT, UU, MB>, \
                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));      \
-        awb_forward_fast_kernel<TM, NL, MT><<<b->C, threads, fsmem, st>>>(       \
+        awb_forward_fast_kernel<TM, NL, MT, UU, MB><<<grid, threads, fsmem, st>>>( \
             b->d_chains, seg, pass, b->zcap);                                    \
     } while (0)
     const bool lev4 = maxd <= 16;
-    if (tmax == 20) {
-        if (threads <= 384) { if (lev4) AWB_LAUNCH_FAST(20, 4, 384); else AWB_LAUNCH_FAST(20, 5, 384); }
-        else if (threads <= 512) { if (lev4) AWB_LAUNCH_FAST(20, 4, 512); else AWB_LAUNCH_FAST(20, 5, 512); }
-        else if (threads <= 640) { if (lev4) AWB_LAUNCH_FAST(20, 4, 640); else AWB_LAUNCH_FAST(20, 5, 640); }
-        else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768);
-        else AWB_LAUNCH_FAST(20, 5, 1024);
-    } else if (tmax == 40) {
-        if (threads <= 512) AWB_LAUNCH_FAST(40, 5, 512);
-        else AWB_LAUNCH_FAST(40, 5, 1024);
+    const bool two = (long long) b->C * nsub > b->ctx->sm_count && !getenv("AWB_K4_ONE_PER_SM");
+    if (f.tmax == 20 && f.U == 1) {
+        if (threads <= 320) { if (lev4) AWB_LAUNCH_FAST(20, 4, 320, 1, 3); else AWB_LAUNCH_FAST(20, 5, 320, 1, 3); }
+        else if (threads <= 576) {
+            // two CTAs per SM only pay when there are that many (56 registers a
+            // thread instead of 112 cost 14 % on a lone CTA)
+            if (two) { if (lev4) AWB_LAUNCH_FAST(20, 4, 576, 1, 2); else AWB_LAUNCH_FAST(20, 5, 576, 1, 2); }
+            else { if (lev4) AWB_LAUNCH_FAST(20, 4, 576, 1, 1); else AWB_LAUNCH_FAST(20, 5, 576, 1, 1); }
+        }
+        else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768, 1, 1);
+        else AWB_LAUNCH_FAST(20, 5, 1024, 1, 1);
+    } else if (f.tmax == 20) {
+        if (f.U == 2) AWB_LAUNCH_FAST(20, 5, 608, 2, 1);
+        else AWB_LAUNCH_FAST(20, 5, 608, 4, 1);
+    } else if (f.tmax == 40) {
+        if (f.U == 2 && threads <= 352) AWB_LAUNCH_FAST(40, 5, 352, 2, 2);
+        else if (f.U == 2) AWB_LAUNCH_FAST(40, 5, 608, 2, 1);
+        else AWB_LAUNCH_FAST(40, 5, 608, 4, 1);
     } else {
-        AWB_LAUNCH_FAST(64, 5, 384);
+        if (f.U == 2) AWB_LAUNCH_FAST(64, 5, 608, 2, 1);
+        else AWB_LAUNCH_FAST(64, 5, 608, 4, 1);
     }
 #undef AWB_LAUNCH_FAST
     b->launches++;
@@ -819,6 +882,13 @@ extern "C" int awb_batch_setup(awb_batch *b)
         dim3 grid((b->maxn + 255) / 256, b->C);
         if (grid.x > 4096) grid.x = 4096;
         awb_kind_kernel<<<grid, 256, 0, st>>>(b->d_chains);
+        if (b->any_packed) {
+            dim3 grid2((b->maxnvar + 255) / 256, b->C);
+            if (grid2.x > 1024) grid2.x = 1024;
+            if (grid2.x < 1) grid2.x = 1;
+            awb_kind_packed_kernel<<<grid2, 256, 0, st>>>(b->d_chains);
+            b->launches++;
+        }
     }
     b->launches += b->maxB > 1 ? 4 : 3;
     // variant-site emissions go into the forward table; with a checkpointed
@@ -949,10 +1019,24 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         // same forward pass: the rebuilt segments have taken turns in table 0,
         // which is also the first resident one, so every table is rebuilt)
         const int pass = b->tables_stale ? 2 : 1;
-        for (int s = b->maxseg - 1; s >= 0; s--) {
-            if (launch_emit(b, s, pass) || launch_forward_fast(b, s, pass) ||
-                launch_traceback(b, rand_max, s))
+        // With three or more tables per window two consecutive segments are
+        // rebuilt side by side (independent chains: each starts from its own
+        // stored column), which puts two CTAs on every SM; the traceback then
+        // walks through them in order.  Never across the boundary of the
+        // resident segments of the longest window, whose tables are still in use.
+        const bool pairs = b->nslots >= 3 && !getenv("AWB_NO_PAIRS");
+        for (int s = b->maxseg - 1; s >= 0;) {
+            const bool res_s = s >= b->maxseg - b->nslots;
+            const int nsub = (pairs && !res_s && s >= 1) ? 2 : 1;
+            for (int y = 0; y < nsub; y++)
+                if (launch_emit(b, s - y, pass))
+                    return 1;
+            if (launch_forward_fast(b, s, pass, nsub))
                 return 1;
+            for (int y = 0; y < nsub; y++)
+                if (launch_traceback(b, rand_max, s - y))
+                    return 1;
+            s -= nsub;
         }
         if (b->maxseg > b->nslots)
             b->tables_stale = true;
@@ -1069,10 +1153,30 @@ extern "C" int awb_batch_get_fw(awb_batch *b, int i, double *fw)
         return fail("awb_batch_get_fw: the forward table is not kept with AWB_CHECKPOINT");
     CUDA_OK(cudaSetDevice(b->ctx->device));
     if (!b->bound) return fail("awb_batch_get_fw: nothing has been uploaded or computed");
-    CUDA_OK(cudaMemcpyAsync(fw, b->h_chains[i].fw,
-                            sizeof(double) * b->L[i].fw_off[b->L[i].B],
+    const AwbLayout &L = b->L[i];
+    CUDA_OK(cudaMemcpyAsync(fw, b->h_chains[i].fw, sizeof(double) * L.fw_off[L.B],
                             cudaMemcpyDeviceToHost, b->ctx->stream));
     CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    if (batch_fast_path(b)) {
+        // the fast kernel stores the columns as the recursion carries them (a
+        // positive scale per row; awb_forward_fast.cuh): hand them out the way
+        // the reference stores them, every column after the first summing to 1
+        // (sample_thread.cpp:292-294, :386-388)
+        for (int blk = 0; blk < L.B; blk++) {
+            const int S1 = L.nstates[blk] > 0 ? L.nstates[blk] : 1;
+            double *row = fw + L.fw_off[blk];
+            for (int r = 0; r < L.block_start[blk + 1] - L.block_start[blk]; r++, row += S1) {
+                if (blk == 0 && r == 0)
+                    continue;               // the prior, kept as given
+                double sum = 0.0;
+                for (int j = 0; j < S1; j++)
+                    sum += row[j];
+                const double inv = 1.0 / sum;
+                for (int j = 0; j < S1; j++)
+                    row[j] *= inv;
+            }
+        }
+    }
     return 0;
 }
 

@@ -86,7 +86,13 @@ struct AwbChain {
     const int *subtree_roots; // [B] (internal) or NULL
     const int *rowidx;        // [nrows] rows of seqs compared for invariance:
                               //   leaves' seqids, then new_chrom (external)
-    const unsigned char *seqs; // [nseqs][seqlen]
+    const unsigned char *seqs; // [nseqs][seqlen], or NULL when the alignment is given
+                              //   as its variant columns only:
+    int nvar;                 // variant columns
+    const int *var_pos;       // [nvar] ascending column indices of the dense rows
+    const unsigned char *var_cols; // [nvar][nseqs]
+    int default_char;         // every other column of every row
+    double infsites_penalty;  // < 1: infinite-sites penalty on (0 / 1: off)
 
     // ---- layout (host computed)
     const int *block_start;   // [B+1] site offset of each block (0-based in chain)
@@ -161,6 +167,31 @@ struct AwbChain {
     int last_state;           // traceback: -1 = sample last column
 };
 
+// ------------------------------------------------------------------ sequences
+
+// index of dense column `col` among the variant columns, or -1
+AWB_HD inline int awb_var_find(const AwbChain &ch, long long col)
+{
+    int lo = 0, hi = ch.nvar - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = ch.var_pos[mid];
+        if (v == col) return mid;
+        if (v < col) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// character of sequence `row` at dense column `col`; vc = awb_var_find(col) when
+// the alignment is packed (ch.seqs == NULL)
+AWB_HD inline unsigned char awb_seq_at(const AwbChain &ch, int row, size_t col, int vc)
+{
+    if (ch.seqs)
+        return ch.seqs[(size_t) row * ch.seqlen + col];
+    return vc >= 0 ? ch.var_cols[(size_t) vc * ch.nseqs + row] :
+        (unsigned char) ch.default_char;
+}
+
 // ------------------------------------------------------------------ math
 
 // common.h:157-163
@@ -205,10 +236,14 @@ AWB_HD inline AwbSeg awb_seg(const AwbChain &ch, int s)
     g.site0 = ch.block_start[g.b0];
     g.nsites = ch.block_start[g.b1] - g.site0 + g.extra;
     // the last nslots segments have a table of their own (and stay resident
-    // after the forward pass); all earlier ones take turns in table 0
+    // after the forward pass); all earlier ones take turns in the top two tables
+    // by parity (table 0 when there are fewer than three): those are the
+    // tables of the last two segments, which the traceback has left behind by
+    // the time it rebuilds an earlier segment -- so two consecutive segments can
+    // be rebuilt side by side
     const int R = ch.nslots < ch.nseg ? ch.nslots : ch.nseg;
     g.resident = s >= ch.nseg - R;
-    const int slot = g.resident ? s - (ch.nseg - R) : 0;
+    const int slot = g.resident ? s - (ch.nseg - R) : (R >= 3 ? R - 1 - (s & 1) : 0);
     g.fwbias = ch.fw_off[g.b0] - (long long) slot * ch.seg_doubles;
     g.fsoff = (long long) slot * ch.seg_sites * (ch.model.ntimes - 1);
     return g;
@@ -274,8 +309,9 @@ AWB_HD inline int awb_imin(int a, int b) { return a < b ? a : b; }
 // decreasing branch length, so the number of warps is close to S/32.  Used by
 // the host layout (to size the thread map) and by K1 (to fill it): both must
 // run the same code.  tmap/nfirst may be NULL (count only).  Returns the number
-// of thread slots (a multiple of 32).  Branches longer than 32 states take
-// whole warps (such a block runs on the generic kernel anyway).
+// of thread slots (a multiple of 32).  A branch of 33..64 states takes the slots
+// of two whole warps, starting at an even one: the forward kernel then keeps
+// it in two register sets of one warp (awb_forward_fast.cuh).
 AWB_HD inline int awb_pack_branches(const short *cnt, int V,
                                     unsigned short *tmap, const short *nfirst,
                                     int cap)
@@ -300,9 +336,12 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
             const int c = len == 63 ? cnt[i] : len + 1;
             int slot;
             if (c > 32) {
+                // 33..64 states: two whole warps' worth of slots starting at an
+                // even one (the long branches come first, two each)
+                nw = (nw + 1) & ~1;
                 slot = 32 * nw;
-                for (int x = 0; x < (c + 31) / 32; x++)
-                    fill[nw++] = 32;
+                fill[nw++] = 32;
+                fill[nw++] = 32;
             } else {
                 int w = 0;
                 while (w < nw && fill[w] + c > 32)

@@ -810,3 +810,39 @@ extern "C" void sample_hmm_posterior(int n, int nstates, double **trans, double 
     }
     cuda_check("sample_hmm_posterior");
 }
+
+// ------------------------------------------------------------------ total_prob.cpp
+
+// total_prob.cpp:316-326
+extern "C" double arghmm_likelihood(LocalTrees *trees, double *times, int ntimes,
+                                    double mu, char **seqs, int nseqs, int seqlen)
+{
+    CompatProblem cp;
+    fill_problem(cp, trees, times, ntimes, NULL, 0.0, mu, seqs, nseqs, seqlen, false);
+    double lnl = 0.0;
+    COMPAT_OK(awb_arg_likelihood(&cp.p, &lnl), "awb_arg_likelihood");
+    return lnl;
+}
+
+// total_prob.cpp:345-352
+extern "C" double arghmm_prior_prob(LocalTrees *trees, double *times, int ntimes,
+                                    double *popsizes, double rho)
+{
+    CompatProblem cp;
+    fill_problem(cp, trees, times, ntimes, popsizes, rho, 0.0, NULL, 0, 0, false);
+    double lnl = 0.0;
+    COMPAT_OK(awb_arg_prior(&cp.p, &lnl), "awb_arg_prior");
+    return lnl;
+}
+
+// total_prob.cpp:369-377
+extern "C" double arghmm_joint_prob(LocalTrees *trees, double *times, int ntimes,
+                                    double *popsizes, double mu, double rho,
+                                    char **seqs, int nseqs, int seqlen)
+{
+    CompatProblem cp;
+    fill_problem(cp, trees, times, ntimes, popsizes, rho, mu, seqs, nseqs, seqlen, false);
+    double lik = 0.0, prior = 0.0;
+    COMPAT_OK(awb_arg_joint(&cp.p, &lik, &prior), "awb_arg_joint");
+    return lik + prior;
+}

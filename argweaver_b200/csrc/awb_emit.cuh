@@ -24,13 +24,13 @@
 #endif
 
 // emit.cpp:30-58 (find_invariant_sites, find_masked_sites) for one site
-AWB_HD inline void awb_site_kind(const AwbChain &ch, int i)
+AWB_HD inline void awb_site_kind(const AwbChain &ch, int i, int vc = -1)
 {
     const size_t col = (size_t) ch.start_coord + i;
-    const unsigned char c = ch.seqs[(size_t) ch.rowidx[0] * ch.seqlen + col];
+    const unsigned char c = awb_seq_at(ch, ch.rowidx[0], col, vc);
     bool mut = false;
     for (int r = 1; r < ch.nrows; r++) {
-        if (ch.seqs[(size_t) ch.rowidx[r] * ch.seqlen + col] != c) {
+        if (awb_seq_at(ch, ch.rowidx[r], col, vc) != c) {
             mut = true;
             break;
         }
@@ -70,9 +70,30 @@ AWB_HD inline int awb_find_block(const AwbChain &ch, int i)
 
 // scratch per worker group: inner[4V], outer[4V], mut[V], nomut[V] doubles and
 // inmain[V] bytes
+// ... and, for the infinite-sites rule, the parsimony sets sets[V], anc[V] bytes
 AWB_HD inline size_t awb_emit_scratch_bytes(int V)
 {
-    return (size_t) V * (10 * sizeof(double)) + (((size_t) V + 7) & ~(size_t) 7);
+    return (size_t) V * (10 * sizeof(double)) + ((3 * (size_t) V + 7) & ~(size_t) 7);
+}
+
+AWB_HD inline int awb_base_bit(unsigned char c)
+{
+    switch (c) {                      // 1 << dna2int[c]; 0 for 'N' (emit.cpp:916-920)
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 4;
+    case 'T': case 't': return 8;
+    }
+    return 0;
+}
+
+AWB_HD inline int awb_lanes_or(int x)
+{
+#if defined(__CUDA_ARCH__)
+    return (int) __reduce_or_sync(0xffffffffu, (unsigned) x);
+#else
+    return x;
+#endif
 }
 
 // tree arrays of block b: parent/age (int), child0/child1/order (short).  The
@@ -96,6 +117,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
     const int maintree_root = internal ? c1[root] : root;
     const int subtree_root = internal ? c0[root] : root;
     const size_t col = (size_t) ch.start_coord + i;
+    const int vc = ch.seqs ? -1 : awb_var_find(ch, (long long) col);
 
     double *inner = (double *) scratch;
     double *outer = inner + 4 * (size_t) V;
@@ -119,8 +141,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         nomut[j] = nomu_j;
         inmain[j] = 0;
         if (c0[j] == -1)
-            awb_leaf_row(ch.seqs[(size_t) ch.rowidx[j] * ch.seqlen + col],
-                         inner + 4 * j);
+            awb_leaf_row(awb_seq_at(ch, ch.rowidx[j], col, vc), inner + 4 * j);
     }
     AWB_LANESYNC();
 
@@ -187,14 +208,75 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         AWB_LANESYNC();
     }
 
+    // ---- infinite-sites rule (get_infinite_sites_states, emit.cpp:457-589):
+    // unweighted parsimony sets of the site (parsimony_ancestral_set,
+    // emit.cpp:898-945), level by level like the partials; a state is valid when
+    // the threaded lineage's base set meets the set of its node or of the
+    // node's parent.  Invalid states have their emission multiplied by the
+    // penalty (emit.cpp:848-862).
+    const bool infsites = ch.infsites_penalty < 1.0;
+    unsigned char *sets = inmain + V;
+    unsigned char *anc = sets + V;
+    int cset = 0;
+    bool allvalid = true;
+    if (infsites) {
+        for (int L = 0; L < nlev; L++) {
+            const int q0 = lstart[L], cntL = lstart[L + 1] - q0;
+            for (int idx = lane; idx < cntL; idx += nlanes) {
+                const int j = order[q0 + idx];
+                if (c0[j] == -1) {
+                    sets[j] = (unsigned char)
+                        awb_base_bit(awb_seq_at(ch, ch.rowidx[j], col, vc));
+                } else {
+                    const int l = sets[c0[j]], r = sets[c1[j]];
+                    sets[j] = (unsigned char) ((l & r) ? (l & r) : (l | r));
+                }
+            }
+            AWB_LANESYNC();
+        }
+        // bases of the leaves on either side
+        int mainset = 0, subset = 0;
+        for (int j = lane; j < V; j += nlanes) {
+            if (c0[j] == -1) {
+                if (inmain[j]) mainset |= sets[j]; else subset |= sets[j];
+            }
+        }
+        mainset = awb_lanes_or(mainset);
+        subset = awb_lanes_or(subset);
+        if (internal) {
+            cset = sets[subtree_root];
+        } else {
+            cset = awb_base_bit(awb_seq_at(ch, ch.rowidx[ch.nrows - 1], col, vc));
+            subset = cset;
+        }
+        // distinct bases on the two sides: the lineage can go anywhere
+        allvalid = !(subset & mainset);
+        if (!allvalid) {
+            for (int L = nlev - 1; L >= 0; L--) {
+                const int q0 = lstart[L], cntL = lstart[L + 1] - q0;
+                for (int idx = lane; idx < cntL; idx += nlanes) {
+                    const int j = order[q0 + idx];
+                    if (!inmain[j])
+                        continue;
+                    if (j == maintree_root) {
+                        anc[j] = sets[j];
+                    } else {
+                        const int ps = anc[parent[j]] & sets[j];
+                        anc[j] = (unsigned char) (ps ? ps : sets[j]);
+                    }
+                }
+                AWB_LANESYNC();
+            }
+        }
+    }
+
     // the branch being threaded: new leaf (external) or the subtree root
     double in2[4];
     if (internal) {
         for (int x = 0; x < 4; x++)
             in2[x] = inner[4 * subtree_root + x];
     } else {
-        awb_leaf_row(ch.seqs[(size_t) ch.rowidx[ch.nrows - 1] * ch.seqlen + col],
-                     in2);
+        awb_leaf_row(awb_seq_at(ch, ch.rowidx[ch.nrows - 1], col, vc), in2);
     }
     // branch of the threaded lineage below the coalescence point: from the
     // subtree root's time (internal) or from time 0.0 (external) up to the
@@ -239,6 +321,12 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                 emit += p1 * p2 * p3 * .25;
             else
                 emit += p1 * p2 * .25;
+        }
+        if (infsites && !allvalid) {
+            const bool valid = (cset & anc[node2]) ||
+                (node2 != maintree_root && (cset & anc[p]));
+            if (!valid)
+                emit *= ch.infsites_penalty;
         }
         out[k] = emit;
     }

@@ -12,14 +12,14 @@
 //   W_k   = sum_{a on branch(k)} tmatrix2[a][k] * col[(node_k, a)]
 //
 // and tmatrix2 (reference sample_thread.cpp:218-225) separates in (a, b), so
-// with x_a = D[a]*col[(n,a)] along the branch n of state k = (n, b):
+// along the branch n of state k = (n, b), with x_a = D[a]*col[(n,a)]:
 //
-//   W_k = E e2[b] * PY + x_b * A2 + A3 * Q + norecombs[b]*col[k]
+//   W_k = A1 * PY + A2' * col[k] + A3 * Q
 //   PY = sum_{a<b} x_a (h[a] - Bc)   Q = sum_{a>b} x_a
 //
-// (Bc, A2, A3 per-state constants, see load_compute).  PY and Q are exclusive
-// prefix / suffix sums along one branch; the separable form agrees with the
-// literal band to ~4e-15 relative (checked on random columns).
+// (Bc, A1, A2' = D[b]*A2 + norecombs[b], A3 per-state constants, see
+// load_compute).  PY and Q are exclusive prefix / suffix sums along one branch;
+// the separable form agrees with the literal band to ~4e-15 relative.
 //
 // Mapping to the SM (numbers measured on B200, scripts/microbench.cu:
 // dependent DFMA 8.4 cycles, 64-bit SHFL+DADD 35, LDS 33, bar.sync 33,
@@ -27,36 +27,43 @@
 // FP64 operations, not a bandwidth problem, so the kernel is organised around
 // that chain:
 //
-//   compute warps   one thread per state in NODE-MAJOR order, packed
-//                   (first-fit decreasing, K1) so that the states of a branch
-//                   never straddle a warp: PY and Q are segmented warp-shuffle
-//                   scans in registers, branch-free (0/1 multipliers, one DFMA
-//                   per level and quantity); a warp runs only the levels its
-//                   longest branch needs.
+//   compute warps   U states per thread (U = 1, 2 or 4 register sets) in
+//                   NODE-MAJOR order, packed (first-fit decreasing, K1) so that
+//                   the states of a branch are consecutive lanes of ONE set of
+//                   one warp (a branch of 33..64 states -- possible with more
+//                   than 33 time points -- takes set u and the first lanes of
+//                   set u+1 of the same warp): PY and Q are segmented
+//                   warp-shuffle scans in registers.  The segment bounds ride
+//                   in the shuffle's own clamp operand (shfl.sync.up/down with
+//                   c = first / last lane of the branch) and its predicate
+//                   output gates the add: no masks, no multipliers.
 //   F-scribes       two warps owning no state: between barrier 1 and barrier 2
 //                   their 64 lanes turn the column (staged in shared memory in
 //                   TIME-MAJOR order) into the per-time sums F[a] and then,
-//                   one lane per b with the matrix column in registers, into
-//                   R[b]; a compute thread reads a single value.
-//   norm warp       one warp that only waits on barrier 2: column norm, 1/norm,
-//                   logZ, rescale factor, and the per-time sums of the stored
-//                   column (fsum) for the traceback.  Its division and log()
-//                   are off the critical cycle; consumers pick the results up
-//                   two steps later.
+//                   one lane per b, into R[b]; a compute thread reads a single
+//                   value.
+//   norm warp       one warp that only waits on barrier 2: column norm, logZ,
+//                   the lagged rescale factor, and the per-time sums of the
+//                   stored column (fsum) for the traceback.  Its division and
+//                   log() are off the critical cycle.
 //
 //   step(site):  STS value (time-major slot)
 //                B1 (compute + F-scribes)
-//                    compute:  store column site-2 to HBM scaled by its 1/norm ;
-//                              fetch next emission ; branch scans -> W
+//                    compute:  fetch next emission ; branch scans -> W
 //                    F-scribes: F[a] ; B3 (scribes) ; R[b]
 //                B2 (everybody)
-//                    compute:  col(site+1) = (R[b] + W) * emission
+//                    compute:  col(site+1) = (R[b] + W) * emission -> table
 //                    norm warp: norm(site) ...
 //
 // The forward table is written once, 8 B per site*state, in the reference's
-// state order.  Columns are carried unnormalised; a factor published for
-// column s is applied when column s+3 is formed (every AWB_FWD_RS = 4 sites),
-// which bounds the magnitude by the product of at most RS+2 one-step norms.
+// state order, AS CARRIED: a column is stored with the scale it has in the
+// recursion (a factor published for column s is applied when column s+3 is
+// formed, every AWB_FWD_RS = 4 sites, which bounds the magnitude by the product
+// of at most RS+2 one-step norms), not renormalised to sum 1.  Everything
+// downstream is scale-free per row: the traceback compares partial sums of
+// fw[i][j]*T[j->k] with a fraction of their total, and fsum holds the per-time
+// sums of the row as stored.  awb_batch_get_fw normalises the copy it returns
+// (rows sum to 1, as the reference stores them).
 //
 // A launch works on one AwbSeg: the whole window, or one segment of a
 // checkpointed table (awb_common.cuh, awb_api.cu).
@@ -69,14 +76,13 @@
 #define AWB_FWD_FSCRIBES AWB_NSCRIBE          // F-scribe lanes
 #define AWB_FWD_HELPERS (AWB_NSCRIBE + 32)    // F-scribes + norm warp
 
-// shared memory (doubles): Fs[2][TMAX+2] | Rs[2][TMAX+2] | scaleS[2] | invS[4] |
-// dummy[2] | colS[2][NS] | zT[zcap]
+// shared memory (doubles): Fs[2][TMAX+2] | Rs[2][TMAX+2] | scaleS[2] | invL[2] |
+// dummy[2] | tmS[TMAX/2][NSCRIBE][2] | colS[2][NS] | zT[zcap]     (NS = state slots)
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX, int zcap)
 {
-    return (2 * (size_t) NS + (size_t) zcap + 4 * (size_t) (TMAX + 2) + 6 + 2) * sizeof(double);
+    return (2 * (size_t) NS + (size_t) zcap + 4 * (size_t) (TMAX + 2) + 6 +
+            (size_t) (TMAX + 1) / 2 * AWB_NSCRIBE * 2) * sizeof(double);
 }
-
-template <int N> struct AwbInt { static constexpr int value = N; };
 
 __device__ __forceinline__ void awb_sts(unsigned addr, double v)
 {
@@ -114,6 +120,65 @@ __device__ __forceinline__ void awb_lane_run(int key, int lane, int &first, int 
     last = above ? (__ffs(above) - 2) : 31;
 }
 
+// Segmented scan steps.  shfl.sync.up with clamp operand c = first lane of my
+// segment gives p = (lane - delta >= c); shfl.sync.down with c = last lane
+// gives p = (lane + delta <= c) (PTX ISA, shfl.sync: segmask bits 0).  The
+// predicate gates the add, so a step is two SHFL.32 and one predicated DADD.
+__device__ __forceinline__ double awb_scan_up(double v, int delta, int cfirst)
+{
+    double r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t.reg .f64 t;\n\t"
+                 "mov.b64 {lo, hi}, %1;\n\t"
+                 "shfl.sync.up.b32 lo|p, lo, %2, %3, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 hi, hi, %2, %3, 0xffffffff;\n\t"
+                 "mov.b64 t, {lo, hi};\n\t"
+                 "mov.f64 %0, %1;\n\t"
+                 "@p add.f64 %0, %1, t;\n\t}"
+                 : "=d"(r) : "d"(v), "r"(delta), "r"(cfirst));
+    return r;
+}
+
+__device__ __forceinline__ double awb_scan_down(double v, int delta, int clast)
+{
+    double r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t.reg .f64 t;\n\t"
+                 "mov.b64 {lo, hi}, %1;\n\t"
+                 "shfl.sync.down.b32 lo|p, lo, %2, %3, 0xffffffff;\n\t"
+                 "shfl.sync.down.b32 hi, hi, %2, %3, 0xffffffff;\n\t"
+                 "mov.b64 t, {lo, hi};\n\t"
+                 "mov.f64 %0, %1;\n\t"
+                 "@p add.f64 %0, %1, t;\n\t}"
+                 : "=d"(r) : "d"(v), "r"(delta), "r"(clast));
+    return r;
+}
+
+// the neighbour's value inside the segment, 0 at its edge
+__device__ __forceinline__ double awb_prev_in_seg(double v, int cfirst)
+{
+    double r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+                 "mov.b64 {lo, hi}, %1;\n\t"
+                 "shfl.sync.up.b32 lo|p, lo, 1, %2, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 hi, hi, 1, %2, 0xffffffff;\n\t"
+                 "mov.b64 %0, {lo, hi};\n\t"
+                 "@!p mov.f64 %0, 0d0000000000000000;\n\t}"
+                 : "=d"(r) : "d"(v), "r"(cfirst));
+    return r;
+}
+
+__device__ __forceinline__ double awb_next_in_seg(double v, int clast)
+{
+    double r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+                 "mov.b64 {lo, hi}, %1;\n\t"
+                 "shfl.sync.down.b32 lo|p, lo, 1, %2, 0xffffffff;\n\t"
+                 "shfl.sync.down.b32 hi, hi, 1, %2, 0xffffffff;\n\t"
+                 "mov.b64 %0, {lo, hi};\n\t"
+                 "@!p mov.f64 %0, 0d0000000000000000;\n\t}"
+                 : "=d"(r) : "d"(v), "r"(clast));
+    return r;
+}
+
 __device__ __forceinline__ double2 awb_lds2(unsigned addr)
 {
     double2 v;
@@ -122,21 +187,34 @@ __device__ __forceinline__ double2 awb_lds2(unsigned addr)
     return v;
 }
 
+__device__ __forceinline__ void awb_sts2(unsigned addr, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(x), "d"(y) : "memory");
+}
+
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
-template <int TMAX, int NLEV, int MAXTHREADS>
-__global__ void __launch_bounds__(MAXTHREADS, 1)
+// U: states per compute thread (register sets); MINB: CTAs per SM the register
+// budget is cut for
+template <int TMAX, int NLEV, int MAXTHREADS, int U, int MINB>
+__global__ void __launch_bounds__(MAXTHREADS, MINB)
 awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
 {
+    static_assert(TMAX % 4 == 0, "the scribes' R loop takes four rows at a time");
+    static_assert(U == 1 || U == 2 || U == 4, "register sets come singly or in pairs");
+    // grid: x = chain, y = one of the segments worked on at once (the second
+    // pass of a checkpointed table rebuilds independent segments: seg, seg-1, ..)
     const AwbChain &chg = chains[blockIdx.x];
+    seg -= (int) blockIdx.y;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int NS = blockDim.x - AWB_FWD_HELPERS;     // compute threads
-    const int NB1 = NS + AWB_FWD_FSCRIBES;           // barrier 1 participants
-    const int NB2 = NS + AWB_FWD_HELPERS;            // barrier 2 participants
+    const int NT = blockDim.x - AWB_FWD_HELPERS;     // compute threads
+    const int NS = NT * U;                           // state slots
+    const int NB1 = NT + AWB_FWD_FSCRIBES;           // barrier 1 participants
+    const int NB2 = NT + AWB_FWD_HELPERS;            // barrier 2 participants
     const int T = chg.model.ntimes;
     // the blocks / sites of this launch (checkpointed table: one segment)
     const AwbSeg g = awb_seg(chg, seg);
@@ -153,22 +231,24 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const int *__restrict__ blocklensg = chg.blocklens;
 
     // the small arrays come first, at compile-time offsets from the start of
-    // shared memory (the site loops address them every site; offsets that
-    // depend on the CTA size were being recomputed from blockDim there)
+    // shared memory (the site loops address them every site)
     extern __shared__ double smem_f[];
+    constexpr int TMS = (TMAX + 1) / 2 * AWB_NSCRIBE * 2;   // doubles of tmS
     double *FsS = smem_f;                      // [2][TMAX+2] per-time sums
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
-    double *invS = scaleS + 2;                 // [4] 1/norm of recent columns
-    double *dummyS = invS + 4;                 // [2] [0]: idle lanes store here; [1] = 1.0
-    double *colS = dummyS + 2;                 // [2][NS] last column of a block in
+    double *invL = scaleS + 2;                 // [2] [0]: 1/norm of the last column
+    double *dummyS = invL + 2;                 // [2] [0]: idle lanes store here; [1] = 1.0
+    double *tmS = dummyS + 2;                  // scribe lane sl keeps column sl of the
+                                               //   block's time matrix: [(a/2)][sl][a&1]
+    double *colS = tmS + TMS;                  // [2][NS] last column of a block in
                                                //   state order, by block parity
     double *zT = colS + 2 * NS;                // [zcap] column, time-major rows,
                                                //   zero-padded for the scribes (K1)
 
-    for (int x = tid; x < 2 * NS + zcap + 4 * (TMAX + 2) + 8; x += blockDim.x) {
+    for (int x = tid; x < 2 * NS + zcap + 4 * (TMAX + 2) + 6 + TMS; x += blockDim.x) {
         const int y = x - 4 * (TMAX + 2);
-        smem_f[x] = ((y >= 0 && y < 6) || y == 7) ? 1.0 : 0.0;   // scaleS, invS, one
+        smem_f[x] = ((y >= 0 && y < 4) || y == 5) ? 1.0 : 0.0;   // scaleS, invL, one
     }
     __syncthreads();
 
@@ -180,8 +260,9 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const unsigned Fs_s = (unsigned) __cvta_generic_to_shared(FsS);
     const unsigned Rs_s = (unsigned) __cvta_generic_to_shared(RsS);
     const unsigned scale_s = (unsigned) __cvta_generic_to_shared(scaleS);
-    const unsigned inv_s = (unsigned) __cvta_generic_to_shared(invS);
+    const unsigned invl_s = (unsigned) __cvta_generic_to_shared(invL);
     const unsigned dummy_s = (unsigned) __cvta_generic_to_shared(dummyS);
+    const unsigned tm_s = (unsigned) __cvta_generic_to_shared(tmS);
     constexpr unsigned RSTR = (TMAX + 2) * 8;
 
     if (tid >= NB1) {
@@ -283,24 +364,18 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             for (int d = 16; d >= 1; d >>= 1)
                 x += __shfl_xor_sync(0xffffffffu, x, d);
             const double nrm = x;
-            const double inv = 1.0 / nrm;
-            if (lane == 0)
-                awb_sts(inv_s + 8u * (site & 3), inv);
             // per-time sums of the column as it is stored (the traceback forms
-            // its row totals from these); the prior column is stored unscaled
-            {
-                const double sc = (site == 0 && !(chg.ckpt && seg > 0)) ? 1.0 : inv;
-                if (lane < T - 1)
-                    __stcs(fsumg + (size_t) site * (T - 1) + lane, f0 * sc);
-                if (lane + 32 < T - 1)
-                    __stcs(fsumg + (size_t) site * (T - 1) + lane + 32, f1 * sc);
-            }
+            // its row totals from these)
+            if (lane < T - 1)
+                __stcs(fsumg + (size_t) site * (T - 1) + lane, f0);
+            if (lane + 32 < T - 1)
+                __stcs(fsumg + (size_t) site * (T - 1) + lane + 32, f1);
             if (!(nrm > 0.0) && bad_site < 0)
                 bad_site = site;
             if ((site & (AWB_FWD_RS - 1)) == 0) {
                 // this factor is applied when column site+3 is formed
                 if (lane == 0)
-                    awb_sts(scale_s + 8u * ((site / AWB_FWD_RS) & 1), inv);
+                    awb_sts(scale_s + 8u * ((site / AWB_FWD_RS) & 1), 1.0 / nrm);
                 if (site + 3 <= n - 1) {
                     lprod *= nrm;
                     if (++nprod == 8) {
@@ -311,6 +386,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 }
             }
             if (site == n - 1 && lane == 0) {
+                awb_sts(invl_s, 1.0 / nrm);
                 // (a segment that starts from a stored, normalised column adds
                 // the log-likelihood of its own sites; the recompute pass adds
                 // nothing)
@@ -331,16 +407,17 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         return;
     }
 
-    if (tid >= NS) {
+    if (tid >= NT) {
         // =================================================================
         // F-scribes: per-time sums between barrier 1 and barrier 2
         // =================================================================
-        const int sl = tid - NS;                         // scribe lane 0..63
+        const int sl = tid - NT;                         // scribe lane 0..63
         const double *__restrict__ tmatrixg = chg.tmatrix;
         const unsigned short *__restrict__ sc_startg = chg.sc_start;
         const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
         const unsigned char *__restrict__ sc_rowg = chg.sc_row;
         const unsigned char *__restrict__ sc_strideg = chg.sc_stride;
+        const unsigned tml_s = tm_s + 16u * (unsigned) sl;      // my column, pair 0
         int site = 0;
         for (int b = bbeg; b < bend; b++) {
             const int blen = (b == bextra) ? 1 : blocklensg[b];
@@ -356,18 +433,22 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             awb_lane_run(key, lane, seglane, segend);
             const bool sc_last = (lane == segend) && (sc_row != 255);
             const int span = __reduce_max_sync(0xffffffffu, segend - seglane);
+#ifdef AWB_K4_SCRIBE_FMA
             double um[5];
 #pragma unroll
             for (int l = 0; l < 5; l++)
                 um[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
+#endif
             const unsigned z_s = zT_s + 8u * (unsigned) sc_start;
             // the slots of this lane beyond its real ones are padding: zero them
             // for this block (the compute warps only write real slots; the
             // previous block is past its last barrier 2)
             for (int q = sc_cnt; q < CH; q++)
                 awb_sts(z_s + zstep * (unsigned) q, 0.0);
-            // column `sl` of the block's time-by-time matrix: this lane turns
-            // the per-time sums F into R[sl] for the compute warps
+            // column `sl` of the block's time-by-time matrix, parked in this
+            // lane's own shared-memory slots (nobody else reads them): this
+            // lane turns the per-time sums F into R[sl] for the compute warps
+#ifdef AWB_K4_TMREG
             double tmc[TMAX];
             {
                 const bool rl = (sl < T - 1) && nstatesg[b] > 0;
@@ -376,6 +457,18 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 for (int a = 0; a < TMAX; a++)
                     tmc[a] = (rl && a < T - 1) ? tmg[a * T] : 0.0;
             }
+#else
+            {
+                const bool rl = (sl < T - 1) && nstatesg[b] > 0;
+                const double *tmg = tmatrixg + (size_t) b * T * T + (rl ? sl : 0);
+#pragma unroll 4
+                for (int a = 0; a < TMAX; a += 2) {
+                    const double t0 = (rl && a < T - 1) ? tmg[a * T] : 0.0;
+                    const double t1 = (rl && a + 1 < T - 1) ? tmg[(a + 1) * T] : 0.0;
+                    awb_sts2(tml_s + (unsigned) (a / 2) * (16u * AWB_NSCRIBE), t0, t1);
+                }
+            }
+#endif
 
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
@@ -395,30 +488,39 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 double v = v0 + v1;
 #pragma unroll
                 for (int l = 0; l < 5; l++) {
+#ifdef AWB_K4_SCRIBE_FMA
                     if ((1 << l) <= span) {
                         const double t = __shfl_up_sync(0xffffffffu, v, 1 << l);
                         v = fma(t, um[l], v);
                     }
+#else
+                    if ((1 << l) <= span)
+                        v = awb_scan_up(v, 1 << l, seglane);
+#endif
                 }
                 if (sc_last)
                     awb_sts(Fp_s + 8u * (unsigned) sc_row, v);
                 awb_bar_sync(3, AWB_FWD_FSCRIBES);
                 if (i + 1 < blen && sl < T - 1) {
-                    double2 f[(TMAX + 1) / 2];
-#pragma unroll
-                    for (int a = 0; a < (TMAX + 1) / 2; a++)
-                        f[a] = awb_lds2(Fp_s + 16u * a);
                     double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
 #pragma unroll
                     for (int a = 0; a + 3 < TMAX; a += 4) {
-                        ra = fma(tmc[a], f[a / 2].x, ra);
-                        rb = fma(tmc[a + 1], f[a / 2].y, rb);
-                        rc = fma(tmc[a + 2], f[a / 2 + 1].x, rc);
-                        rd = fma(tmc[a + 3], f[a / 2 + 1].y, rd);
+                        const double2 f0 = awb_lds2(Fp_s + 8u * a);
+                        const double2 f1 = awb_lds2(Fp_s + 8u * a + 16u);
+#ifdef AWB_K4_TMREG
+                        const double2 t0 = make_double2(tmc[a], tmc[a + 1]);
+                        const double2 t1 = make_double2(tmc[a + 2], tmc[a + 3]);
+#else
+                        const double2 t0 =
+                            awb_lds2(tml_s + (unsigned) (a / 2) * (16u * AWB_NSCRIBE));
+                        const double2 t1 =
+                            awb_lds2(tml_s + (unsigned) (a / 2 + 1) * (16u * AWB_NSCRIBE));
+#endif
+                        ra = fma(t0.x, f0.x, ra);
+                        rb = fma(t0.y, f0.y, rb);
+                        rc = fma(t1.x, f1.x, rc);
+                        rd = fma(t1.y, f1.y, rd);
                     }
-#pragma unroll
-                    for (int a = TMAX - (TMAX % 4); a < TMAX; a++)
-                        ra = fma(tmc[a], (a & 1) ? f[a / 2].y : f[a / 2].x, ra);
                     awb_sts(Rs_s + (site & 1) * RSTR + 8u * (unsigned) sl,
                             (ra + rb) + (rc + rd));
                 }
@@ -432,190 +534,237 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     // =====================================================================
     // compute warps
     // =====================================================================
-    // Every instruction of this loop is issued by ~15 warps per site on 4
-    // schedulers, so the loop is written for instruction count: 32-bit shared
-    // addresses with ring offsets kept incrementally, a pointer ring for the
-    // lagged table stores (idle lanes and not-to-be-stored columns point at a
-    // per-thread sink).
+    // Every instruction of this loop is issued by all compute warps per site on
+    // 4 schedulers, so the loop is written for instruction count: 32-bit shared
+    // addresses with ring offsets kept incrementally, idle lanes pointing at a
+    // per-thread sink (no null checks or selects).
     const unsigned char *__restrict__ kindg = chg.kind + g.site0;
     double *__restrict__ fwg = chg.fw - g.fwbias;
-    const long long *__restrict__ row_offg = chg.row_off;
-    const long long *__restrict__ fw_offg = chg.fw_off;
-    const long long *__restrict__ trow_offg = chg.trow_off;
-    const long long *__restrict__ ent_offg = chg.ent_off;
-    const unsigned short *__restrict__ tmapg = chg.tmap;
-    const unsigned short *__restrict__ ipermg = chg.iperm;
-    const short *__restrict__ st_nodeg = chg.st_node;
-    const signed char *__restrict__ st_timeg = chg.st_time;
-    const signed char *__restrict__ st_ageg = chg.st_age;
-    const double *__restrict__ inv_emitg = chg.inv_emit;
-    const double *__restrict__ ling = chg.lin;
-    const unsigned short *__restrict__ sw_startg = chg.sw_start;
-    const unsigned short *__restrict__ sw_cntg = chg.sw_cnt;
-    const unsigned short *__restrict__ sw_srcg = chg.sw_src;
-    const double *__restrict__ sw_probg = chg.sw_prob;
+    const int warp = tid >> 5;
     double *const sink = chg.sink + tid;
 
-    // ---- my state in the current block
-    int jj = 0, S = 0, S1 = 1;
+    // ---- my states in the current block (register set u = slot (warp*U+u)*32+lane)
+    int jj[U];
+    bool active[U], live[U];               // live: active and S > 0
+    unsigned zaddr[U], raddr[U];
+    int cfirst[U], clast[U];               // first / last lane of my branch
+    double inv_e[U], Da[U], H[U], A1[U], A2[U], A3[U];
+    double c[U];
+    double *nxt[U];
+    int S = 0, S1 = 1;
     long long r0 = 0;
-    bool active = false, live = false;     // live: active and S > 0
-    unsigned zaddr = dummy_s, raddr = Rs_s;
-    long long step = 0;                    // bytes from my entry of one row to the next
-    double inv_e = 0.0, em = 0.0, Da = 0.0, hb = 0.0, A1 = 0.0, A2 = 0.0,
-        A3 = 0.0, nrb = 1.0;
-    double upm[NLEV], dnm[NLEV];
+    unsigned rowstep = 0;                  // bytes between consecutive rows of the block
+    bool wlong = false;                    // this warp holds a branch of > 32 states
+    bool headl[(U + 1) / 2], contl[(U + 1) / 2];
 
     auto load_compute = [&](int bb) {
         S = nstatesg[bb];
         S1 = S > 0 ? S : 1;
-        r0 = row_offg[bb];
-        const long long tr0 = trow_offg[bb];
-        const int NSb = (int) (trow_offg[bb + 1] - tr0);
-        unsigned short tj = 0xFFFF;
-        if (tid < NSb)
-            tj = tmapg[tr0 + tid];
-        active = (tj != 0xFFFF);
-        live = active && S > 0;
-        jj = active ? (int) tj : 0;
-        int atime = 0, cage = 0, node = -1, tpos = 0;
-        inv_e = active ? 1.0 : 0.0;
-        em = inv_e;
-        if (live) {
-            atime = st_timeg[r0 + jj];
-            cage = st_ageg[r0 + jj];
-            node = st_nodeg[r0 + jj];
-            tpos = ipermg[r0 + jj];
-            inv_e = inv_emitg[r0 + jj];
-        }
-        zaddr = active ? zT_s + 8u * (unsigned) tpos : dummy_s;
-        raddr = Rs_s + 8u * (unsigned) atime;
-        step = active ? 8ll * S1 : 0ll;
-        const int key = live ? node : (0x10000 + lane);
-        int seglane, segend;
-        awb_lane_run(key, lane, seglane, segend);
+        r0 = chg.row_off[bb];
+        rowstep = 8u * (unsigned) S1;
+        const long long tr0 = chg.trow_off[bb];
+        const int NSb = (int) (chg.trow_off[bb + 1] - tr0);
+        int node[U];
+        wlong = false;
 #pragma unroll
-        for (int l = 0; l < NLEV; l++) {
-            upm[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
-            dnm[l] = (lane + (1 << l) <= segend) ? 1.0 : 0.0;
+        for (int u = 0; u < U; u++) {
+            const int slot = (warp * U + u) * 32 + lane;
+            unsigned short tj = 0xFFFF;
+            if (slot < NSb)
+                tj = chg.tmap[tr0 + slot];
+            active[u] = (tj != 0xFFFF);
+            live[u] = active[u] && S > 0;
+            jj[u] = active[u] ? (int) tj : 0;
+            int atime = 0, cage = 0, tpos = 0;
+            node[u] = -1;
+            inv_e[u] = active[u] ? 1.0 : 0.0;
+            if (live[u]) {
+                atime = chg.st_time[r0 + jj[u]];
+                cage = chg.st_age[r0 + jj[u]];
+                node[u] = chg.st_node[r0 + jj[u]];
+                tpos = chg.iperm[r0 + jj[u]];
+                inv_e[u] = chg.inv_emit[r0 + jj[u]];
+            }
+            zaddr[u] = active[u] ? zT_s + 8u * (unsigned) tpos : dummy_s;
+            raddr[u] = Rs_s + 8u * (unsigned) atime;
+            const int key = live[u] ? node[u] : (0x10000 + lane);
+            awb_lane_run(key, lane, cfirst[u], clast[u]);
+            if (live[u]) {
+                const double *lin = chg.lin + (size_t) bb * 7 * T;
+                const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
+                const double a1 = lin[3 * T + atime];
+                Da[u] = lin[0 * T + atime];
+                H[u] = Da[u] * (lin[1 * T + atime] - Bc);
+                A1[u] = a1;
+                A2[u] = fma(Da[u], lin[4 * T + atime] - a1 * Bc, lin[6 * T + atime]);
+                A3[u] = lin[5 * T + atime] - a1 * Bc;
+            } else {
+                // idle lane (everything 0), or the size-1 state space (identity)
+                Da[u] = 0.0; H[u] = 0.0; A1[u] = 0.0; A3[u] = 0.0;
+                A2[u] = active[u] ? 1.0 : 0.0;
+            }
         }
-        if (live) {
-            const double *lin = ling + (size_t) bb * 7 * T;
-            const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
-            Da = lin[0 * T + atime];
-            hb = lin[1 * T + atime] - Bc;
-            A1 = lin[3 * T + atime];
-            A2 = lin[4 * T + atime] - A1 * Bc;
-            A3 = lin[5 * T + atime] - A1 * Bc;
-            nrb = lin[6 * T + atime];
-        } else {
-            // idle lane (everything 0), or the size-1 state space (identity)
-            Da = 0.0; hb = 0.0; A1 = 0.0; A2 = 0.0; A3 = 0.0;
-            nrb = active ? 1.0 : 0.0;
+        if (U > 1) {
+            // a branch of 33..64 states fills set u (even) and continues in the
+            // first lanes of set u+1 (K1 packs it that way)
+#pragma unroll
+            for (int u = 0; u + 1 < U; u += 2) {
+                const int n31 = __shfl_sync(0xffffffffu, node[u], 31);
+                const int n0 = __shfl_sync(0xffffffffu, node[u + 1], 0);
+                const bool lng = (n31 >= 0) && (n31 == n0);
+                headl[u / 2] = lng && node[u] == n31;
+                contl[u / 2] = lng && node[u + 1] == n31;
+                wlong = wlong || lng;
+            }
         }
     };
 
     load_compute(bbeg);
-    // columns site, site-1, site-2 of my state; w0/w1/w2 = where they go in the
-    // table (the sink for the prior column, which is kept as the caller gave it);
-    // nxt = my entry of the row of the next site (emission in, column out)
-    double c = 0.0, c1 = 0.0, c2 = 0.0;
-    double *w0 = sink, *w1 = sink, *w2 = sink;
-    double *nxt = sink;
-    if (active) {
-        // first column: the prior (K1 or caller), kept as given.  With a
-        // checkpointed table the prior is saved aside on the first pass (the
-        // table memory is reused by the other segments) and put back for the
-        // second; a later segment starts from its stored first column, which
-        // goes into the table like any other column.
-        double *row0 = fwg + fw_offg[bbeg] + jj;
-        if (!chg.ckpt) {
-            c = *row0;
-        } else if (seg == 0) {
-            if (pass == 0) {
-                c = *row0;
-                chg.ckptcol[jj] = c;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        c[u] = 0.0;
+        nxt[u] = sink;
+        if (active[u]) {
+            // first column: the prior (K1 or caller), kept as given.  With a
+            // checkpointed table the prior is saved aside on the first pass (the
+            // table memory is reused by the other segments) and put back for the
+            // second; a later segment starts from its stored first column, which
+            // goes into the table like any other column.
+            double *row0 = fwg + chg.fw_off[bbeg] + jj[u];
+            if (!chg.ckpt) {
+                c[u] = *row0;
+            } else if (seg == 0) {
+                // (K1 / the caller put the prior at the start of table 0; the
+                // segment's own table may be another one)
+                if (pass == 0) {
+                    c[u] = chg.fw[chg.fw_off[bbeg] + jj[u]];
+                    chg.ckptcol[jj[u]] = c[u];
+                } else {
+                    c[u] = chg.ckptcol[jj[u]];
+                }
+                *row0 = c[u];
             } else {
-                c = chg.ckptcol[jj];
-                *row0 = c;
+                c[u] = chg.ckptcol[(size_t) seg * chg.maxS + jj[u]];
+                *row0 = c[u];
             }
-        } else {
-            c = chg.ckptcol[(size_t) seg * chg.maxS + jj];
-            w0 = row0;
+            nxt[u] = row0 + S1;
         }
-        nxt = fwg + fw_offg[bbeg] + S1 + jj;
     }
     const unsigned char *kp = kindg + 2;
     unsigned kind_next = (n > 1) ? kindg[1] : 0;
-    // ring offsets (bytes): iofs = ((site-2)&3)*8 into invS, rofs = (site&1)*RSTR
-    // into Rs, sofs = (((site-2)/RS)&1)*8 into scaleS
-    unsigned iofs = 16, rofs = 0, sofs = 0;
+    // ring offsets (bytes): rofs = (site&1)*RSTR into Rs, sofs = (((site-2)/RS)&1)*8
+    // into scaleS; rcnt = (site - 2) & (RS - 1)
+    unsigned rofs = 0, sofs = 0;
+    int rcnt = AWB_FWD_RS - 2;
 
     // one site that is followed by a site of the same block
-    auto site_step = [&](auto nlc) {
-        constexpr int NL = decltype(nlc)::value;
-        awb_sts(zaddr, c);
+    auto site_step = [&]() {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            awb_sts(zaddr[u], c[u]);
         awb_bar_sync(1, NB1);
 
-        // branch scans in registers while the F-scribes sum the rows
-        const double x0 = Da * c;
-        const double y0 = x0 * hb;
-        // exclusive sums PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a: the
+        // branch scans in registers while the F-scribes sum the rows.
+        // Exclusive sums PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a: the
         // neighbour's term first, then an inclusive scan of those (an inclusive
         // scan minus the own term cancels: h grows like exp(cumulative
         // coalescent rate), so y0 can exceed the sum below it by many orders)
-        double py = __shfl_up_sync(0xffffffffu, y0, 1) * upm[0];
-        double q = __shfl_down_sync(0xffffffffu, x0, 1) * dnm[0];
+        double W[U];
+        double py[U], q[U], x0[U], y0[U];
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-            const double ty = __shfl_up_sync(0xffffffffu, py, 1 << l);
-            const double tq = __shfl_down_sync(0xffffffffu, q, 1 << l);
-            py = fma(ty, upm[l], py);
-            q = fma(tq, dnm[l], q);
+        for (int u = 0; u < U; u++) {
+            x0[u] = Da[u] * c[u];
+            y0[u] = H[u] * c[u];
+#ifdef AWB_K4_INCL
+            py[u] = y0[u];
+            q[u] = x0[u];
+#else
+            py[u] = awb_prev_in_seg(y0[u], cfirst[u]);
+            q[u] = awb_next_in_seg(x0[u], clast[u]);
+#endif
         }
-        const double PY = py, Q = q;
-        const double W = fma(A1, PY, fma(x0, A2, fma(A3, Q, nrb * c)));
-        // store column site-2 scaled by its 1/norm (norm warp, 2 steps ago)
-        __stcs(w2, c2 * awb_lds(inv_s + iofs));      // streaming: L1 is for the block tables
+#pragma unroll
+        for (int l = 0; l < NLEV; l++) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                py[u] = awb_scan_up(py[u], 1 << l, cfirst[u]);
+                q[u] = awb_scan_down(q[u], 1 << l, clast[u]);
+            }
+        }
+        if (U > 1 && wlong) {
+            // carries of a branch that runs from set u into set u+1
+#pragma unroll
+            for (int u = 0; u + 1 < U; u += 2) {
+                const double up = __shfl_sync(0xffffffffu, py[u] + y0[u], 31);
+                const double dn = __shfl_sync(0xffffffffu, q[u + 1] + x0[u + 1], 0);
+                if (contl[u / 2]) py[u + 1] += up;
+                if (headl[u / 2]) q[u] += dn;
+            }
+        }
+#ifdef AWB_K4_INCL
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            py[u] -= y0[u];
+            q[u] -= x0[u];
+        }
+#endif
         const unsigned kd = kind_next;
         kind_next = *kp++;
-        double e = inv_e;
-        if (kd != AWB_SITE_INVARIANT)               // uniform, ~3 % of the sites
-            e = (kd == AWB_SITE_VARIANT) ? (live ? *nxt : inv_e) : em;
+        double e[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            W[u] = fma(A1[u], py[u], fma(c[u], A2[u], A3[u] * q[u]));
+            e[u] = inv_e[u];
+        }
+        if (kd != AWB_SITE_INVARIANT) {             // uniform, ~3 % of the sites
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (kd == AWB_SITE_VARIANT)
+                    e[u] = live[u] ? *nxt[u] : inv_e[u];
+                else
+                    e[u] = active[u] ? 1.0 : 0.0;
+            }
+        }
         awb_bar_sync(2, NB2);
 
-        // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
-        // the lagged rescale factor every fourth site ((site & 3) == 2), the
+        // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes.
+        // The lagged rescale factor every fourth site ((site & 3) == 2), the
         // constant 1.0 otherwise: branch-free (a branch around a volatile load
         // costs a branch resolution per warp and site)
-        const bool resc = iofs == 0;
+        const bool resc = rcnt == 0;
         const double sc = awb_lds(resc ? scale_s + sofs : dummy_s + 8u);
-        double cn = (awb_lds(raddr + rofs) + W) * (e * sc);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double cn = (awb_lds(raddr[u] + rofs) + W[u]) * (e[u] * sc);
+            __stcs(nxt[u], cn);                 // streaming: L1 is for the block tables
+            c[u] = cn;
+            if (active[u])
+                nxt[u] = (double *) ((char *) nxt[u] + rowstep);
+        }
         sofs ^= resc ? 8u : 0u;
-        iofs = (iofs + 8u) & 24u;
+        rcnt = (rcnt + 1) & (AWB_FWD_RS - 1);
         rofs ^= RSTR;
-        c2 = c1; c1 = c; c = cn;
-        w2 = w1; w1 = w0; w0 = nxt;
-        nxt = (double *) ((char *) nxt + step);
     };
 
     for (int b = bbeg; b < bend; b++) {
         const int blen = (b == bextra) ? 1 : blocklensg[b];
 
         // ---------------- sites that are followed by a site of the same block
-        // (ONE scan variant for all warps.  A variant per warp with just the
-        // levels its longest branch needs was no faster per site and cost 0.6 us
-        // per block: a warp changing variant at a block boundary runs cold
-        // instructions, and the variants compete for the instruction cache.)
+#ifdef AWB_K4_UNROLL1
+#pragma unroll 1
+#endif
         for (int i = blen - 1; i > 0; i--)
-            site_step(AwbInt<NLEV>());
+            site_step();
 
         // ---------------- last site of the block
         {
-            awb_sts(zaddr, c);
-            awb_sts(active ? col_s + 8u * (unsigned) ((b & 1) * NS + jj) : dummy_s, c);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                awb_sts(zaddr[u], c[u]);
+                awb_sts(active[u] ? col_s + 8u * (unsigned) ((b & 1) * NS + jj[u]) : dummy_s,
+                        c[u]);
+            }
             awb_bar_sync(1, NB1);
-            __stcs(w2, c2 * awb_lds(inv_s + iofs));      // streaming: L1 is for the block tables
             const unsigned kd = kind_next;
             kind_next = *kp++;
             awb_bar_sync(2, NB2);
@@ -624,51 +773,58 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
 
             // breakpoint: gather through the switch CSR (sample_thread.cpp:345-389)
             double scale = 1.0;
-            if (iofs == 0) {
+            if (rcnt == 0) {
                 scale = awb_lds(scale_s + sofs);
                 sofs ^= 8u;
             }
-            iofs = (iofs + 8u) & 24u;
+            rcnt = (rcnt + 1) & (AWB_FWD_RS - 1);
             rofs ^= RSTR;
-            c2 = c1; c1 = c;
-            w2 = w1; w1 = w0;
             load_compute(b + 1);
-            double sum = 0.0;
-            double e = em;
-            if (active) {
-                const int st = sw_startg[r0 + jj];
-                const int cnt = sw_cntg[r0 + jj];
-                const unsigned short *es = sw_srcg + ent_offg[b + 1] + st;
-                const double *ep = sw_probg + ent_offg[b + 1] + st;
-                // the old block's last column; the buffer alternates with the
-                // block so a one-site block cannot overwrite it early
-                const double *cold = colS + (b & 1) * NS;
-                for (int x = 0; x < cnt; x++)
-                    sum += cold[es[x]] * ep[x];
-                w0 = fwg + fw_offg[b + 1] + jj;
-                if (S > 0) {
-                    e = inv_e;
-                    if (kd == AWB_SITE_VARIANT)
-                        e = *w0;
-                    else if (kd == AWB_SITE_MASKED)
-                        e = 1.0;
+            // the old block's last column; the buffer alternates with the
+            // block so a one-site block cannot overwrite it early
+            const double *cold = colS + (b & 1) * NS;
+            const long long e0 = chg.ent_off[b + 1];
+            double *rowb = fwg + chg.fw_off[b + 1];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (active[u]) {
+                    const int st = chg.sw_start[r0 + jj[u]];
+                    const int cnt = chg.sw_cnt[r0 + jj[u]];
+                    const unsigned short *es = chg.sw_src + e0 + st;
+                    const double *ep = chg.sw_prob + e0 + st;
+                    double sum = 0.0;
+                    for (int x = 0; x < cnt; x++)
+                        sum += cold[es[x]] * ep[x];
+                    double *w0 = rowb + jj[u];
+                    double e = 1.0;
+                    if (S > 0) {
+                        e = inv_e[u];
+                        if (kd == AWB_SITE_VARIANT)
+                            e = *w0;
+                        else if (kd == AWB_SITE_MASKED)
+                            e = 1.0;
+                    }
+                    c[u] = sum * e * scale;
+                    __stcs(w0, c[u]);
+                    nxt[u] = w0 + S1;
+                } else {
+                    c[u] = 0.0;
+                    nxt[u] = sink;
                 }
-                nxt = w0 + S1;
-            } else {
-                w0 = sink;
-                nxt = sink;
             }
-            c = sum * e * scale;
         }
     }
 
-    // ---- the last two columns: their 1/norm is complete after the final barrier
+    // ---- the column of the extra site is the first column of the next segment
+    // (normalised: its 1/norm is complete after the final barrier)
     __syncthreads();
-    *w1 = c1 * invS[(n - 2) & 3];
-    *w0 = c * invS[(n - 1) & 3];
-    // the column of the extra site is the first column of the next segment
-    if (g.extra && pass == 0 && active)
-        chg.ckptcol[(size_t) (seg + 1) * chg.maxS + jj] = c * invS[(n - 1) & 3];
+    if (g.extra && pass == 0) {
+        const double il = invL[0];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (active[u])
+                chg.ckptcol[(size_t) (seg + 1) * chg.maxS + jj[u]] = c[u] * il;
+    }
 }
 
 #endif // AWB_FORWARD_FAST_CUH

@@ -41,6 +41,8 @@ struct AwbLayout {
     // range, e.g. tiny population sizes): the batch then runs the generic
     // forward kernel and the traceback uses the closed-form transitions
     int lin_unsafe;
+    bool packed;                    // the alignment comes as variant columns (var_cols)
+    size_t o_varpos;
     // Jukes-Cantor branch probabilities by time-index pair (emission kernel):
     // ptab[(y*T + x)*2 + {0: mutation, 1: none}] for a branch from time y up to
     // time x, and p0tab[x*2 + ..] for a branch from time 0.0 up to time x
@@ -261,7 +263,10 @@ inline bool awb_count_states_checked(const awb_problem &p, int b, std::vector<in
             }
             if (cnt > maxcnt) maxcnt = cnt;
             if (cnt > 32) {
-                tpos = ((tpos + 31) & ~31) + ((cnt + 31) & ~31);
+                // (two whole warps' worth of slots, starting at an even one: the
+                // forward kernel keeps such a branch in two register sets of
+                // one warp)
+                tpos = ((tpos + 63) & ~63) + 64;
             } else {
                 if ((tpos & 31) + cnt > 32)
                     tpos = (tpos + 31) & ~31;
@@ -388,10 +393,20 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     if (T < 3 || T > AWB_MAXT) { err = "ntimes must be in [3, 64]"; return false; }
     if (V < 1 || V > AWB_MAXV) { err = "nnodes must be in [1, 1024]"; return false; }
     if (B < 1) { err = "ntrees must be >= 1"; return false; }
-    if (!p.times || !p.popsizes || !p.seqs || !p.seqids || !p.ptrees ||
+    if (!p.times || !p.popsizes || (!p.seqs && !p.var_cols) || !p.seqids || !p.ptrees ||
         !p.ages || !p.sprs || !p.blocklens) {
         err = "null input array";
         return false;
+    }
+    L.packed = p.var_cols != 0;
+    if (L.packed) {
+        if (p.nvar < 0 || (p.nvar > 0 && !p.var_pos)) { err = "bad variant columns"; return false; }
+        for (int i = 0; i < p.nvar; i++)
+            if (p.var_pos[i] < 0 || p.var_pos[i] >= p.seqlen ||
+                (i > 0 && p.var_pos[i] <= p.var_pos[i - 1])) {
+                err = "variant positions must be ascending, unique and inside the sequence";
+                return false;
+            }
     }
     if (p.nleaves != (V + 1) / 2) { err = "nleaves != (nnodes+1)/2"; return false; }
     for (int i = 0; i + 1 < T; i++)
@@ -588,7 +603,8 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     AWB_PLACE(o_ptrees, BV * sizeof(int));
     AWB_PLACE(o_ages, BV * sizeof(int));
     AWB_PLACE(o_mappings, BV * sizeof(int));
-    AWB_PLACE(o_seqs, (size_t) p.nseqs * p.seqlen);
+    AWB_PLACE(o_seqs, L.packed ? (size_t) p.nvar * p.nseqs : (size_t) p.nseqs * p.seqlen);
+    AWB_PLACE(o_varpos, L.packed ? (size_t) p.nvar * sizeof(int) : 0);
     // the small inputs and the arrays made above, next to each other and in the
     // order of L.copies: they go up as ONE copy from a pinned staging buffer
     // (awb_api.cu)
@@ -708,7 +724,14 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
     L.copies.push_back({ L.o_ages, p.ages, BV * sizeof(int), 0 });
     if (p.mappings)
         L.copies.push_back({ L.o_mappings, p.mappings, BV * sizeof(int), 0 });
-    L.copies.push_back({ L.o_seqs, p.seqs, (size_t) p.nseqs * p.seqlen, 0 });
+    if (L.packed) {
+        if (p.nvar > 0) {
+            L.copies.push_back({ L.o_seqs, p.var_cols, (size_t) p.nvar * p.nseqs, 0 });
+            L.copies.push_back({ L.o_varpos, p.var_pos, (size_t) p.nvar * sizeof(int), 0 });
+        }
+    } else {
+        L.copies.push_back({ L.o_seqs, p.seqs, (size_t) p.nseqs * p.seqlen, 0 });
+    }
     L.copies.push_back({ L.o_sprs, p.sprs, (size_t) B * 4 * sizeof(int), 1 });
     L.copies.push_back({ L.o_blocklens, p.blocklens, (size_t) B * sizeof(int), 1 });
     if (L.has_subtree_roots)
@@ -770,7 +793,17 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.subtree_roots = L.has_subtree_roots ?
         (const int *) (base + L.o_subtree_roots) : 0;
     AWB_P(const int *, rowidx, o_rowidx);
-    AWB_P(const unsigned char *, seqs, o_seqs);
+    if (L.packed) {
+        ch.seqs = 0;
+        ch.nvar = p.nvar;
+        AWB_P(const unsigned char *, var_cols, o_seqs);
+        AWB_P(const int *, var_pos, o_varpos);
+    } else {
+        AWB_P(const unsigned char *, seqs, o_seqs);
+    }
+    ch.default_char = p.default_char ? p.default_char : 'A';
+    ch.infsites_penalty = (p.infsites_penalty > 0.0 && p.infsites_penalty < 1.0) ?
+        p.infsites_penalty : 1.0;
     AWB_P(const int *, block_start, o_block_start);
     AWB_P(const int *, nstates, o_nstates);
     AWB_P(const long long *, row_off, o_row_off);

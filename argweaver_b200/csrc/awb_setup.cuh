@@ -532,7 +532,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                     const int cnt = ncnt[i];
                     if (cnt <= 0) continue;
                     if (cnt > 32)
-                        tpos = (tpos + 31) & ~31;
+                        tpos = (tpos + 63) & ~63;
                     else if ((tpos & 31) + cnt > 32)
                         tpos = (tpos + 31) & ~31;
                     for (int t = 0; t < cnt; t++)
@@ -540,7 +540,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                             ch.tmap[tr0 + tpos + t] = (unsigned short) (nfirst[i] + t);
                     tpos += cnt;
                     if (cnt > 32)
-                        tpos = (tpos + 31) & ~31;
+                        tpos = (tpos + 63) & ~63;
                 }
                 if (tpos > NSb)
                     return 6;

@@ -21,6 +21,8 @@ class AwbProblem(C.Structure):
         ("ptrees", _c_int_p), ("ages", _c_int_p), ("sprs", _c_int_p),
         ("mappings", _c_int_p), ("blocklens", _c_int_p),
         ("subtree_roots", _c_int_p),
+        ("nvar", C.c_int), ("var_pos", _c_int_p), ("var_cols", _c_u8_p),
+        ("default_char", C.c_ubyte), ("infsites_penalty", C.c_double),
     ]
 
 
@@ -40,7 +42,20 @@ def normalize(d):
     q["popsizes"] = np.ascontiguousarray(d["popsizes"], np.float64)
     q["rho"] = float(_scalar(d, "rho"))
     q["mu"] = float(_scalar(d, "mu"))
-    q["seqs"] = np.ascontiguousarray(d["seqs"], np.uint8)
+    # dense rows, or ("var_pos", "var_cols", "nseqs", "seqlen"): the variant
+    # columns only (awb_problem.var_cols)
+    q["var_pos"] = q["var_cols"] = None
+    if d.get("var_cols") is not None:
+        q["var_pos"] = np.ascontiguousarray(d["var_pos"], np.int32)
+        q["var_cols"] = np.ascontiguousarray(d["var_cols"], np.uint8)
+        q["nseqs"] = int(_scalar(d, "nseqs"))
+        q["seqlen"] = int(_scalar(d, "seqlen"))
+        if q["var_cols"].shape != (len(q["var_pos"]), q["nseqs"]):
+            raise ValueError("var_cols must be [nvar][nseqs]")
+        q["seqs"] = None
+    else:
+        q["seqs"] = np.ascontiguousarray(d["seqs"], np.uint8)
+    q["infsites_penalty"] = float(_scalar(d, "infsites_penalty", 0.0))
     q["seqids"] = np.ascontiguousarray(d["seqids"], np.int32)
     q["new_chrom"] = int(_scalar(d, "new_chrom"))
     q["internal"] = int(_scalar(d, "internal"))
@@ -63,7 +78,7 @@ def normalize(d):
         if q[key] is not None and q[key].shape != shape:
             raise ValueError("%s has shape %s, expected %s"
                              % (key, q[key].shape, shape))
-    if q["seqs"].ndim != 2:
+    if q["seqs"] is not None and q["seqs"].ndim != 2:
         raise ValueError("seqs must be [nseqs][seqlen]")
     if q["seqids"].ndim != 1:
         raise ValueError("seqids must be one-dimensional")
@@ -90,8 +105,16 @@ def make_problem(d):
     p.popsizes = q["popsizes"].ctypes.data_as(_c_dbl_p)
     p.rho = q["rho"]
     p.mu = q["mu"]
-    p.nseqs, p.seqlen = q["seqs"].shape
-    p.seqs = q["seqs"].ctypes.data_as(_c_u8_p)
+    if q["seqs"] is not None:
+        p.nseqs, p.seqlen = q["seqs"].shape
+        p.seqs = q["seqs"].ctypes.data_as(_c_u8_p)
+    else:
+        p.nseqs, p.seqlen = q["nseqs"], q["seqlen"]
+        p.seqs = None
+        p.nvar = len(q["var_pos"])
+        p.var_pos = q["var_pos"].ctypes.data_as(_c_int_p)
+        p.var_cols = q["var_cols"].ctypes.data_as(_c_u8_p)
+    p.infsites_penalty = q["infsites_penalty"]
     p.nleaves = len(q["seqids"])
     p.seqids = q["seqids"].ctypes.data_as(_c_int_p)
     p.new_chrom = q["new_chrom"]

@@ -70,6 +70,22 @@ typedef struct awb_problem {
     const int *mappings;        /* [ntrees][nnodes] or NULL (= identity except broken node) */
     const int *blocklens;       /* [ntrees] */
     const int *subtree_roots;   /* [ntrees] child[0] of the root (internal) or NULL */
+
+    /* Optional: the alignment as its variant columns only, the form a .sites
+     * file holds (Sites, sequences.h:211-268) -- every other column of every row
+     * is `default_char`, as make_sequences_from_sites fills it
+     * (sequences.cpp:323-352).  When var_cols != NULL it REPLACES seqs (which
+     * may be NULL): ~3 % of the bytes go to the device.  Positions are column
+     * indices of the (imaginary) dense rows, ascending and unique. */
+    int nvar;
+    const int *var_pos;            /* [nvar] */
+    const unsigned char *var_cols; /* [nvar][nseqs] */
+    unsigned char default_char;    /* 0: 'A' */
+
+    /* Optional emission mode (ArgModel::infsites_penalty, model.h:348): states
+     * that would need a second mutation at a site have their emission multiplied
+     * by this penalty (emit.cpp:457-589, :848-862).  0 or >= 1: off. */
+    double infsites_penalty;
 } awb_problem;
 
 typedef struct awb_ctx awb_ctx;       /* one CUDA device + stream             */
@@ -179,6 +195,45 @@ int awb_thread_sample_cond(const awb_problem *p, const double *prior,
 int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
                       double *logz);
 
+/* .sites ingest and site compression, the step in front of the path
+ * (arg-sample.cpp:965-1007): read_sites (sequences.cpp:173-303),
+ * find_compress_cols + compress_sites (:523-609), make_sequences_from_sites
+ * (:323-352).  Host-only.  Positions are 0-based; columns are [ncols][nseqs]
+ * upper-case characters.  awb_sites_positions / awb_sites_columns can be passed
+ * on as awb_problem.var_pos / var_cols (with nseqs, seqlen = end - start). */
+typedef struct awb_sites awb_sites;
+int awb_sites_read(const char *filename, int subregion_start /* -1: none */,
+                   int subregion_end, awb_sites **out);
+int awb_sites_from_columns(int nseqs, int start_coord, int end_coord, int ncols,
+                           const int *positions, const unsigned char *cols,
+                           awb_sites **out);
+void awb_sites_free(awb_sites *s);
+int awb_sites_nseqs(const awb_sites *s);
+int awb_sites_ncols(const awb_sites *s);
+int awb_sites_start(const awb_sites *s);
+int awb_sites_end(const awb_sites *s);
+const char *awb_sites_name(const awb_sites *s, int i);
+const int *awb_sites_positions(const awb_sites *s);
+const unsigned char *awb_sites_columns(const awb_sites *s);
+/* -c / --compress-seq: 0 = done, 2 = cannot be compressed at this level (the
+ * sites are left as they were), 1 = error */
+int awb_sites_compress(awb_sites *s, int compress);
+/* SitesMapping::all_sites after awb_sites_compress (compressed -> old coordinate) */
+int awb_sites_mapping_size(const awb_sites *s);
+const int *awb_sites_mapping(const awb_sites *s);
+int awb_sites_to_sequences(const awb_sites *s, unsigned char *seqs /*[nseqs][end-start]*/,
+                           unsigned char default_char /* 0: 'A' */);
+
+/* Log-likelihood and log-prior of a COMPLETE ARG (the `likelihood` and `prior`
+ * columns of arg-sample's .stats file, arg-sample.cpp:444-488):
+ * calc_arg_likelihood (total_prob.cpp:19-42) and calc_arg_prior (:262-299).
+ * `arg` uses the tree, model and sequence fields of awb_problem (ntrees trees over
+ * nleaves = (nnodes+1)/2 sequences, leaf j reading row seqids[j]); the threading
+ * fields (new_chrom, internal, minage, mappings, subtree_roots) are ignored. */
+int awb_arg_likelihood(const awb_problem *arg, double *lnl);
+int awb_arg_prior(const awb_problem *arg, double *lnl);
+int awb_arg_joint(const awb_problem *arg, double *likelihood, double *prior);
+
 /* ------------------------------------------------------------------------
  * Reference-compatible symbols (same names / signatures as libargweaver.so).
  * `LocalTrees` is an opaque handle owned by this library.
@@ -239,6 +294,15 @@ double **new_transition_probs_switch(
     double *time_steps, int *nbranches, int *nrecombs, int *ncoals,
     double *popsizes, double rho);
 void delete_transition_probs(double **transmat, int nstates);
+
+/* total_prob.cpp:316-377 */
+double arghmm_likelihood(LocalTrees *trees, double *times, int ntimes, double mu,
+                         char **seqs, int nseqs, int seqlen);
+double arghmm_prior_prob(LocalTrees *trees, double *times, int ntimes,
+                         double *popsizes, double rho);
+double arghmm_joint_prob(LocalTrees *trees, double *times, int ntimes,
+                         double *popsizes, double mu, double rho, char **seqs,
+                         int nseqs, int seqlen);
 
 /* hmm.cpp:13-98 generic dense log-space HMM */
 void forward_step(double *col1, double *col2, int nstates1, int nstates2,

@@ -67,6 +67,9 @@ static void load(const char *fn, Loaded &L)
     double *popsizes = (double *) awf_need(af, "popsizes")->data;
     L.model = new ArgModel(T, times, popsizes, awf_double(af, "rho"),
                            awf_double(af, "mu"));
+    // optional emission mode (ArgModel::infsites_penalty, model.h:348)
+    if (awf_find(af, "infsites_penalty"))
+        L.model->infsites_penalty = awf_double(af, "infsites_penalty");
     awf_array *seqs = awf_need(af, "seqs");
     const int nseqs = seqs->dims[0], seqlen = seqs->dims[1];
     for (int i = 0; i < nseqs; i++)

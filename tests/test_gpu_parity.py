@@ -386,3 +386,69 @@ def test_checkpointed_table_second_traceback(libc_rand, monkeypatch):
             assert div is None, ("traceback with draws %d diverges at site %d"
                                  % (seed, div))
         b.close()
+
+
+@pytest.mark.parametrize("k,n,T,internal,seed", [
+    (100, 1500, 40, False, 11),     # BASELINE config 4 shape: four states per thread
+    (100, 1200, 40, True, 12),
+    (4, 800, 40, False, 13),        # branches of up to 39 states: two register sets
+    (12, 800, 64, False, 16),
+    (150, 1000, 20, False, 17),     # > 928 states at 20 time points
+    (40, 3000, 40, True, 18)])
+def test_fast_kernel_covers_large_and_long_shapes(k, n, T, internal, seed, libc_rand):
+    """state spaces beyond one state per thread and branches longer than a warp
+    run on the register-resident forward kernel (several register sets per
+    thread, awb_forward_fast.cuh), whole table and checkpointed"""
+    d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
+    r = libc_rand(100 + seed, n)
+    o = ol.run_oracle(d, r)
+    b = run_gpu(d, r, keep_debug=False)
+    assert b.fast_path() == "fast"
+    assert_close(b.fw(), o["fw"], "fw", RTOL)
+    assert abs(b.logz() - o["logZ"]) <= RTOL * abs(o["logZ"])
+    assert first_divergence(b.path(), o["path"]) is None
+    b.close()
+
+
+@pytest.mark.parametrize("resident", ["1", "2", "5"])
+def test_checkpointed_config4_shape(resident, libc_rand, monkeypatch):
+    """k=100, ntimes=40 with a checkpointed table (refused before the fast
+    kernel covered the shape)"""
+    monkeypatch.setenv("AWB_SEG_DOUBLES", "400000")
+    monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
+    d = sim.simulate_problem(100, 4000, ntimes=40, seed=41, internal=True)
+    r = libc_rand(141, 4000)
+    o = ol.run_oracle(d, r)
+    b = api.Batch([d], checkpoint=True)
+    b.upload().setup().forward().traceback([r]).sync()
+    assert b.segments()[0] >= 6
+    assert abs(b.logz() - o["logZ"]) <= RTOL * abs(o["logZ"])
+    div = first_divergence(b.path(), o["path"])
+    assert div is None, "path diverges at site %d" % div
+    b.close()
+
+
+@pytest.mark.parametrize("resident", ["3", "4", "6"])
+def test_checkpointed_pairs_windows_of_different_length(resident, libc_rand, monkeypatch):
+    """with three or more tables per window the traceback rebuilds two
+    consecutive segments side by side; windows with different segment counts
+    in one batch (a segment pair of the longest window straddles the resident
+    boundary of a shorter one), repeated tracebacks included"""
+    monkeypatch.setenv("AWB_SEG_DOUBLES", "25000")
+    monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
+    specs = [(10, 3000, 20, False, 61), (12, 1700, 20, True, 62), (6, 2300, 20, False, 63),
+             (10, 2900, 20, True, 64), (8, 400, 20, False, 65)]
+    ds = [sim.simulate_problem(k, n, ntimes=T, seed=s, internal=i)
+          for (k, n, T, i, s) in specs]
+    ck = api.Batch(ds, checkpoint=True)
+    ck.upload().setup().forward()
+    assert ck.segments()[0] > 8
+    for rep in range(2):
+        rs = [libc_rand(10 * rep + s, n) for (k, n, T, i, s) in specs]
+        ck.traceback(rs).sync()
+        for c, d in enumerate(ds):
+            o = ol.run_oracle(d, rs[c])
+            div = first_divergence(ck.path(c), o["path"])
+            assert div is None, "window %d diverges at site %d" % (c, div)
+            assert abs(ck.logz(c) - o["logZ"]) <= RTOL * abs(o["logZ"])
+    ck.close()
