@@ -18,6 +18,7 @@ from .problem import AwbProblem, make_problem
 KEEP_DEBUG = 1
 CHECKPOINT = 2      # AWB_CHECKPOINT: segment-wise forward table (see the header)
 RAND_MAX = 2147483647
+RNG_WORDS = 34      # AWB_RNG_WORDS
 
 _lib = None
 
@@ -95,12 +96,36 @@ def lib():
         L.awb_sites_mapping.argtypes = [C.c_void_p]
         L.awb_sites_compress.argtypes = [C.c_void_p, C.c_int]
         L.awb_sites_to_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.awb_libc_rand_snapshot.argtypes = [C.c_void_p]
+        L.awb_libc_rand_advance.argtypes = [C.c_longlong]
+        L.awb_libc_rand_advance.restype = None
+        L.awb_rng_draw.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.awb_batch_sample_recombs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.awb_batch_get_recomb_count.argtypes = [C.c_void_p, C.c_int,
+                                                 C.POINTER(C.c_int),
+                                                 C.POINTER(C.c_int)]
+        L.awb_batch_get_recombs.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.awb_arg_likelihood.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.awb_arg_prior.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.awb_arg_joint.argtypes = [C.c_void_p, C.POINTER(C.c_double),
                                     C.POINTER(C.c_double)]
         _lib = L
     return _lib
+
+
+def libc_rand_snapshot():
+    """State of this process's libc rand() stream (awb_libc_rand_snapshot)."""
+    st = np.empty(RNG_WORDS, np.int32)
+    _check(lib().awb_libc_rand_snapshot(st.ctypes.data))
+    return st
+
+
+def rng_draw(state, n):
+    """n values of glibc's rand() generator from `state` (advanced in place)."""
+    out = np.empty(n, np.int32)
+    _check(lib().awb_rng_draw(state.ctypes.data, int(n), out.ctypes.data))
+    return out
 
 
 def _check(rc):
@@ -249,6 +274,26 @@ class Batch(object):
             ls = self._ls.ctypes.data
         _check(lib().awb_batch_traceback(self.h, ra, int(rand_max), ls))
         return self
+
+    def sample_recombs(self, rng_states, rand_max=RAND_MAX):
+        """Recombination points of the sampled paths (sample_recombinations,
+        recomb.cpp:151-235).  rng_states: [n][RNG_WORDS] int32, one libc rand()
+        state per problem (libc_rand_snapshot)."""
+        st = np.ascontiguousarray(rng_states, np.int32).reshape(self.n, RNG_WORDS)
+        _check(lib().awb_batch_sample_recombs(self.h, st.ctypes.data, int(rand_max)))
+        return self
+
+    def recombs(self, i=0):
+        """(pos, node, time, draws): the recombination points of problem i and the
+        number of rand() values the sampler consumed."""
+        n, d = C.c_int(), C.c_int()
+        _check(lib().awb_batch_get_recomb_count(self.h, i, C.byref(n), C.byref(d)))
+        pos = np.empty(n.value, np.int32)
+        node = np.empty(n.value, np.int32)
+        time = np.empty(n.value, np.int32)
+        _check(lib().awb_batch_get_recombs(self.h, i, n.value, pos.ctypes.data,
+                                           node.ctypes.data, time.ctypes.data))
+        return pos, node, time, d.value
 
     def sync(self):
         _check(lib().awb_batch_sync(self.h))

@@ -31,7 +31,7 @@ NVCC_FLAGS = [
 
 CUDA_SOURCES = ["awb_api.cu", "awb_compat.cu", "awb_totalprob.cu", "awb_sites.cpp"]
 CUDA_DEPS = ["awb_setup.cuh", "awb_forward.cuh", "awb_forward_fast.cuh", "awb_traceback.cuh",
-             "awb_emit.cuh", "awb_common.cuh", "awb_layout.h"]
+             "awb_emit.cuh", "awb_common.cuh", "awb_layout.h", "awb_recomb.cuh"]
 
 
 def _stale(target, sources):

@@ -32,6 +32,7 @@
 #include "awb_forward.cuh"
 #include "awb_forward_fast.cuh"
 #include "awb_layout.h"
+#include "awb_recomb.cuh"
 #include "awb_setup.cuh"
 #include "awb_traceback.cuh"
 
@@ -209,6 +210,24 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     }
 }
 
+// one warp per window (awb_recomb.cuh)
+__global__ void awb_recomb_kernel(const AwbChain *chains, const int *rng_states,
+                                  int rand_max, int *out, const long long *out_off,
+                                  int *info)
+{
+    const AwbChain &ch = chains[blockIdx.x];
+    const int *st = rng_states + (size_t) blockIdx.x * AWB_RNG_WORDS;
+    AwbRng rng;
+    for (int i = 0; i < 31; i++)
+        rng.r[i] = st[i];
+    rng.f = st[31];
+    rng.b = st[32];
+    const int cap = ch.nsites;
+    int *o = out + out_off[blockIdx.x];
+    awb_sample_recombs(ch, rng, rand_max, o, o + cap, o + 2 * (size_t) cap, cap,
+                       info + 2 * blockIdx.x, (int) threadIdx.x);
+}
+
 // ---------------------------------------------------------------- host side
 
 #define AWB_UPLOAD_GROUPS 4
@@ -266,6 +285,13 @@ struct awb_batch {
                                //   over the tables the forward pass left resident
     int maxseg;                // most segments of any problem
     int maxsegsites;           // most sites of any segment
+    // recombination points (awb_batch_sample_recombs): [pos | node | time] per
+    // window, the (count, draws) pairs and the generator states
+    int *d_rec;
+    long long *d_rec_off;
+    int *d_rec_info, *d_rng;
+    std::vector<long long> rec_off;
+    bool recombs_done;
 };
 
 extern "C" int awb_ctx_create(int device, awb_ctx **out)
@@ -373,6 +399,10 @@ extern "C" void awb_batch_destroy(awb_batch *b)
         else
             cudaFree(b->arena);
     }
+    if (b->d_rec) cudaFree(b->d_rec);
+    if (b->d_rec_off) cudaFree(b->d_rec_off);
+    if (b->d_rec_info) cudaFree(b->d_rec_info);
+    if (b->d_rng) cudaFree(b->d_rng);
     delete b;
 }
 
@@ -440,6 +470,10 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->maxnvar = 0;
     b->tables_stale = false;
     b->ckpt = false;
+    b->d_rec = NULL;
+    b->d_rec_off = NULL;
+    b->d_rec_info = b->d_rng = NULL;
+    b->recombs_done = false;
 
     const auto t_create0 = std::chrono::steady_clock::now();
     // host layout of every problem (integer work), one host thread per problem
@@ -1221,6 +1255,120 @@ extern "C" int64_t awb_batch_debug_bytes(awb_batch *b, int i, const char *name)
     return (int64_t) bytes;
 }
 
+// ---------------------------------------------------------------- recombination points
+
+// glibc's rand() is random_r on a hidden TYPE_3 state (31 words, r[i] += r[i-3]);
+// initstate() hands out the old state array with the rear index stored in front
+// of it (glibc stdlib/random_r.c: __initstate_r / __setstate_r).
+extern "C" int awb_libc_rand_snapshot(int *state)
+{
+    static char tmp[128];
+    char *old = initstate(1u, tmp, sizeof(tmp));
+    if (!old)
+        return fail("initstate failed");
+    const int *w = (const int *) old;
+    const int type = w[0] % 5, rear = w[0] / 5;
+    int rc = 0;
+    if (type != 3 || rear < 0 || rear >= 31) {
+        rc = fail("libc rand() is not in its default (TYPE_3) state");
+    } else {
+        for (int i = 0; i < 31; i++)
+            state[i] = w[1 + i];
+        state[31] = (rear + 3) % 31;     // front index
+        state[32] = rear;
+        state[33] = type;
+    }
+    setstate(old);
+    return rc;
+}
+
+extern "C" void awb_libc_rand_advance(long long ndraws)
+{
+    for (long long i = 0; i < ndraws; i++)
+        rand();
+}
+
+extern "C" int awb_rng_draw(int *state, int n, int *out)
+{
+    AwbRng g;
+    for (int i = 0; i < 31; i++)
+        g.r[i] = state[i];
+    g.f = state[31];
+    g.b = state[32];
+    for (int i = 0; i < n; i++) {
+        const int v = (int) awb_rng_next(g);
+        if (out) out[i] = v;
+    }
+    for (int i = 0; i < 31; i++)
+        state[i] = g.r[i];
+    state[31] = g.f;
+    state[32] = g.b;
+    return 0;
+}
+
+extern "C" int awb_batch_sample_recombs(awb_batch *b, const int *rng_states,
+                                        int rand_max)
+{
+    if (!b->forward_done || !b->rand_in_use)
+        return fail("awb_batch_sample_recombs: the traceback has not run");
+    if (!rng_states)
+        return fail("awb_batch_sample_recombs: rng_states is required");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (!b->d_rec) {
+        b->rec_off.assign(b->C + 1, 0);
+        for (int c = 0; c < b->C; c++)
+            b->rec_off[c + 1] = b->rec_off[c] + 3ll * b->L[c].n;
+        CUDA_OK(cudaMalloc((void **) &b->d_rec, sizeof(int) * (size_t) b->rec_off[b->C]));
+        CUDA_OK(cudaMalloc((void **) &b->d_rec_off, sizeof(long long) * (b->C + 1)));
+        CUDA_OK(cudaMalloc((void **) &b->d_rec_info, sizeof(int) * 2 * b->C));
+        CUDA_OK(cudaMalloc((void **) &b->d_rng, sizeof(int) * AWB_RNG_WORDS * b->C));
+        CUDA_OK(cudaMemcpyAsync(b->d_rec_off, b->rec_off.data(),
+                                sizeof(long long) * (b->C + 1), cudaMemcpyHostToDevice, st));
+    }
+    CUDA_OK(cudaMemcpyAsync(b->d_rng, rng_states, sizeof(int) * AWB_RNG_WORDS * b->C,
+                            cudaMemcpyHostToDevice, st));
+    awb_recomb_kernel<<<b->C, 32, 0, st>>>(b->d_chains, b->d_rng, rand_max, b->d_rec,
+                                           b->d_rec_off, b->d_rec_info);
+    CUDA_OK(cudaGetLastError());
+    // (rng_states and rec_off may be pageable: the copies above must not outlive them)
+    CUDA_OK(cudaStreamSynchronize(st));
+    b->launches++;
+    b->recombs_done = true;
+    return 0;
+}
+
+extern "C" int awb_batch_get_recomb_count(awb_batch *b, int i, int *nrecombs, int *draws)
+{
+    if (!b->recombs_done) return fail("awb_batch_get_recomb_count: nothing sampled");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    int info[2];
+    CUDA_OK(cudaMemcpyAsync(info, b->d_rec_info + 2 * i, sizeof(info),
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    if (nrecombs) *nrecombs = info[0];
+    if (draws) *draws = info[1];
+    return 0;
+}
+
+extern "C" int awb_batch_get_recombs(awb_batch *b, int i, int count, int *pos,
+                                     int *node, int *time)
+{
+    if (!b->recombs_done) return fail("awb_batch_get_recombs: nothing sampled");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    const int cap = b->L[i].n;
+    if (count > cap) count = cap;
+    if (count <= 0) return 0;
+    int *dst[3] = { pos, node, time };
+    for (int k = 0; k < 3; k++)
+        if (dst[k])
+            CUDA_OK(cudaMemcpyAsync(dst[k], b->d_rec + b->rec_off[i] + (size_t) k * cap,
+                                    sizeof(int) * count, cudaMemcpyDeviceToHost,
+                                    b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
 // ---------------------------------------------------------------- one-shot
 
 static awb_ctx *g_default_ctx = NULL;
@@ -1259,6 +1407,49 @@ extern "C" int awb_thread_sample_cond(const awb_problem *p, const double *prior,
                   " has no positive entry (sample_thread.cpp:443-444)");
     if (!rc && path) rc = awb_batch_get_path(b, 0, path);
     if (!rc && logz) rc = awb_batch_get_logz(b, 0, logz);
+    awb_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int awb_thread_sample_recombs(const awb_problem *p, const double *prior,
+                                         int last_state, const int *rand_ints,
+                                         int rand_max, const int *rng_state,
+                                         int *path, double *logz, int cap,
+                                         int *nrecombs, int *pos, int *node,
+                                         int *time, int *draws)
+{
+    awb_ctx *ctx;
+    if (default_ctx(&ctx)) return 1;
+    awb_batch *b = NULL;
+    if (awb_batch_create(ctx, 1, p, 0, &b)) return 1;
+    const double *priors[1] = { prior };
+    int snap[AWB_RNG_WORDS];
+    int rc = 0;
+    if (!rng_state) {
+        // the caller's libc stream, as it stands after the traceback's draws
+        rc = awb_libc_rand_snapshot(snap);
+        rng_state = snap;
+    }
+    rc = rc || awb_batch_upload(b) || awb_batch_setup(b) ||
+        awb_batch_forward(b, prior ? priors : NULL) ||
+        awb_batch_traceback(b, &rand_ints, rand_max,
+                            last_state >= 0 ? &last_state : NULL) ||
+        awb_batch_sample_recombs(b, rng_state, rand_max) ||
+        awb_batch_sync(b);
+    int bad = -1;
+    if (!rc) rc = awb_batch_get_status(b, 0, &bad);
+    if (!rc && bad >= 0)
+        rc = fail("forward column " + std::to_string(bad) +
+                  " has no positive entry (sample_thread.cpp:443-444)");
+    if (!rc && path) rc = awb_batch_get_path(b, 0, path);
+    if (!rc && logz) rc = awb_batch_get_logz(b, 0, logz);
+    int n = 0, d = 0;
+    if (!rc) rc = awb_batch_get_recomb_count(b, 0, &n, &d);
+    if (!rc) rc = awb_batch_get_recombs(b, 0, n < cap ? n : cap, pos, node, time);
+    if (!rc && rng_state == snap)
+        awb_libc_rand_advance(d);        // leave libc where the reference would
+    if (nrecombs) *nrecombs = n;
+    if (draws) *draws = d;
     awb_batch_destroy(b);
     return rc;
 }

@@ -17,9 +17,11 @@
 // its libc stream by that many (awb_libc_rand_snapshot / awb_libc_rand_advance in
 // awb_api.cu), which leaves the stream exactly where the reference would.
 //
-// One thread per window: the walk is sequential in the random stream, and its
-// cost (a pass over the path, a few dozen flops per block) is ~1 % of the
-// forward pass.
+// One warp per window: the walk is sequential in the random stream, so every
+// lane runs the same scalar code (lane 0 writes the output); the only part with
+// any volume -- skipping over the sites at which the path stays put and no
+// recombination is due, ~99.9 % of them -- is done 32 sites at a time with a
+// coalesced load and a ballot.
 #ifndef AWB_RECOMB_CUH
 #define AWB_RECOMB_CUH
 
@@ -104,9 +106,10 @@ AWB_HD inline double awb_recomb_prob(const AwbModel &m, const int *parent,
 
 // The walk over one window.  out_pos/out_node/out_time[cap]; info[0] = number of
 // recombinations (the true count, also when it exceeds cap), info[1] = draws.
+// lane: 0..31 on the device (whole warp calls), -1 for a single host thread
 AWB_HD inline void awb_sample_recombs(const AwbChain &ch, AwbRng &rng, int rand_max,
                                       int *out_pos, int *out_node, int *out_time,
-                                      int cap, int *info)
+                                      int cap, int *info, int lane)
 {
     const AwbModel &m = ch.model;
     const int T = m.ntimes, V = ch.nnodes;
@@ -155,8 +158,22 @@ AWB_HD inline void awb_sample_recombs(const AwbChain &ch, AwbRng &rng, int rand_
                     // nothing is drawn until the next change of state or
                     // next_recomb, whichever comes first
                     int x = i + 1;
+#ifdef __CUDA_ARCH__
+                    const int lim = awb_imin(end, next_recomb);
+                    for (;;) {
+                        const int xx = x + lane;
+                        const bool stop = xx < lim ? (path[xx] != last) : true;
+                        const unsigned sm = __ballot_sync(0xffffffffu, stop);
+                        if (sm) {
+                            x += __ffs(sm) - 1;
+                            break;
+                        }
+                        x += 32;
+                    }
+#else
                     while (x < end && x < next_recomb && path[x] == last)
                         x++;
+#endif
                     i = x - 1;
                     continue;
                 }
@@ -199,7 +216,7 @@ AWB_HD inline void awb_sample_recombs(const AwbChain &ch, AwbRng &rng, int rand_
                 acc += probs[x];
                 if (acc >= pick) { sel = x; break; }
             }
-            if (nrec < cap) {
+            if (nrec < cap && lane <= 0) {
                 out_pos[nrec] = i;
                 out_node[nrec] = cnode[sel];
                 out_time[nrec] = ctime[sel];
@@ -207,8 +224,10 @@ AWB_HD inline void awb_sample_recombs(const AwbChain &ch, AwbRng &rng, int rand_
             nrec++;
         }
     }
-    info[0] = nrec;
-    info[1] = draws;
+    if (lane <= 0) {
+        info[0] = nrec;
+        info[1] = draws;
+    }
 }
 
 #endif // AWB_RECOMB_CUH

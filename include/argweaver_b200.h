@@ -195,6 +195,38 @@ int awb_thread_sample_cond(const awb_problem *p, const double *prior,
 int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
                       double *logz);
 
+/* Recombination points of the sampled thread, the step right after the
+ * traceback (sample_recombinations, recomb.cpp:151-235, with
+ * recomb_prob_unnormalized :14-117 and get_possible_recomb :122-141), on the
+ * device: path and per-block tables never leave it.  The reference draws a
+ * data-dependent number of values from libc rand() here, so the kernel runs
+ * glibc's own generator (TYPE_3 additive feedback, random_r.c) from a snapshot
+ * of the caller's state -- AWB_RNG_WORDS ints per window: r[0..30], front index,
+ * rear index, type -- and reports how many draws it took.
+ *   awb_libc_rand_snapshot   the calling process's rand() state (glibc only)
+ *   awb_libc_rand_advance    consume that many rand() values
+ *   awb_rng_draw             the same generator on the host (advances `state`)
+ * Positions are site indices of the window (0-based); node -1 is the new leaf
+ * (external mode, recomb.cpp:146). */
+#define AWB_RNG_WORDS 34
+int awb_libc_rand_snapshot(int *state /* [AWB_RNG_WORDS] */);
+void awb_libc_rand_advance(long long ndraws);
+int awb_rng_draw(int *state, int n, int *out /* [n] or NULL */);
+int awb_batch_sample_recombs(awb_batch *b, const int *rng_states /* [n][AWB_RNG_WORDS] */,
+                             int rand_max);
+int awb_batch_get_recomb_count(awb_batch *b, int i, int *nrecombs, int *draws);
+int awb_batch_get_recombs(awb_batch *b, int i, int count, int *pos, int *node,
+                          int *time);
+/* one problem: traceback + recombination points.  rng_state NULL: snapshot the
+ * process's libc stream (taken after the caller has drawn rand_ints from it)
+ * and advance it by the draws used, which leaves it where the reference's
+ * sample_arg_thread would (sample_thread.cpp:578-632). */
+int awb_thread_sample_recombs(const awb_problem *p, const double *prior,
+                              int last_state, const int *rand_ints, int rand_max,
+                              const int *rng_state, int *path, double *logz,
+                              int cap, int *nrecombs, int *pos, int *node,
+                              int *time, int *draws);
+
 /* .sites ingest and site compression, the step in front of the path
  * (arg-sample.cpp:965-1007): read_sites (sequences.cpp:173-303),
  * find_compress_cols + compress_sites (:523-609), make_sequences_from_sites

@@ -31,6 +31,7 @@
 #include "argweaver/logging.h"
 #include "argweaver/matrices.h"
 #include "argweaver/model.h"
+#include "argweaver/recomb.h"
 #include "argweaver/sample_thread.h"
 #include "argweaver/sequences.h"
 #include "argweaver/states.h"
@@ -157,6 +158,20 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
     *tt = t2 - t1;
 
     if (out_file) {
+        // the step after the traceback (sample_thread.cpp:617-622): the libc
+        // stream continues where the traceback left it
+        vector<int> recomb_pos;
+        vector<NodePoint> recombs;
+        sample_recombinations(trees, model, &matrix_iter2, thread_path,
+                              recomb_pos, recombs, L.internal);
+        vector<int> rnode, rtime;
+        for (size_t i = 0; i < recombs.size(); i++) {
+            recomb_pos[i] -= trees->start_coord;
+            rnode.push_back(recombs[i].node);
+            rtime.push_back(recombs[i].time);
+        }
+        const int next_rand = rand();   // where the stream stands afterwards
+
         FILE *out = awf_create(out_file);
         vector<double> fwflat;
         vector<int> nstates, fwsites;
@@ -181,6 +196,14 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
         awf_write1(out, "fw", AWF_F64, fwflat.size(), &fwflat[0]);
         awf_write1(out, "fw_sites", AWF_I32, fwsites.size(), &fwsites[0]);
         awf_write1(out, "path", AWF_I32, n, &path_alloc[0]);
+        int zero = 0;
+        awf_write1(out, "recomb_pos", AWF_I32, recomb_pos.size(),
+                   recomb_pos.empty() ? &zero : &recomb_pos[0]);
+        awf_write1(out, "recomb_node", AWF_I32, rnode.size(),
+                   rnode.empty() ? &zero : &rnode[0]);
+        awf_write1(out, "recomb_time", AWF_I32, rtime.size(),
+                   rtime.empty() ? &zero : &rtime[0]);
+        awf_write1(out, "next_rand", AWF_I32, 1, &next_rand);
         fclose(out);
     }
 }

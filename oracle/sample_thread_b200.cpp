@@ -12,10 +12,11 @@
 //     resample_arg_thread               sample_thread.cpp:869-875
 // and the C exports arghmm_sample_thread (:1010) and
 // arghmm_sample_arg_thread_internal (:981) with the forward pass and the
-// stochastic traceback replaced by ONE call into libargweaver_b200.so
-// (awb_thread_sample_cond).  Everything after the traceback -- phase sampling,
-// sample_recombinations, add_arg_thread[_path] -- is the reference's own code,
-// called exactly as the reference calls it.  The reference's sample_thread.cpp is
+// stochastic traceback AND the sampling of the recombination points
+// (sample_recombinations, recomb.cpp:151-235) replaced by ONE call into
+// libargweaver_b200.so (awb_thread_sample_recombs).  What follows -- the ARG
+// surgery add_arg_thread[_path] -- is the reference's own code, called exactly
+// as the reference calls it.  The reference's sample_thread.cpp is
 // compiled next to this file with those seven names renamed to ref_* on the
 // compiler command line (no source is modified or copied), so the original
 // bodies stay available as the fallback for model features the device path does
@@ -23,10 +24,14 @@
 //
 // libc rand(): stochastic_traceback consumes one rand() per sampled site, last
 // site first (common.h:272-290).  The adapter draws exactly those values up
-// front, in that order, and ships them; the process's rand() stream is left
-// where the reference would leave it, so sample_recombinations and every later
-// consumer see the same draws and a seeded arg-sample run reproduces the
-// reference's .stats rows.
+// front, in that order, and ships them.  sample_recombinations takes a
+// data-dependent number of further draws: the library snapshots the process's
+// rand() state, runs glibc's generator on the device and advances the process's
+// stream by the number of draws it used (awb_libc_rand_snapshot / _advance).
+// Either way the stream is left where the reference would leave it, so every
+// later consumer sees the same draws and a seeded arg-sample run reproduces the
+// reference's .stats rows.  AWB_ADAPTER_HOST_RECOMBS=1 keeps the reference's own
+// sample_recombinations (the round-1 arrangement).
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -101,8 +106,6 @@ static bool device_covers(const ArgModel *model, const PhaseProbs *phase_pr)
         return false;
     if (model->has_recombmap() && model->recombmap.size() != 1)
         return false;
-    if (model->infsites_penalty != 1.0)
-        return false;
     return true;
 }
 
@@ -170,14 +173,19 @@ struct FlatProblem {
         p.mappings = mappings.data();
         p.blocklens = blocklens.data();
         p.subtree_roots = internal ? roots.data() : NULL;
+        // ArgModel::infsites_penalty (model.h:348); 1.0 = off
+        p.infsites_penalty = model->infsites_penalty;
     }
 };
 
-// forward + traceback on the device.  path_alloc[0..n): state per site.
+// forward + traceback (+ recombination points) on the device.
+// path_alloc[0..n): state per site.  recomb_pos / recombs: filled when given
+// (absolute coordinates, as sample_recombinations returns them).
 static void device_thread(const ArgModel *model, const Sequences *sequences,
                           const LocalTrees *trees, int new_chrom, bool internal,
                           int minage, const double *prior, int last_state,
-                          int *path_alloc)
+                          int *path_alloc, vector<int> *recomb_pos = NULL,
+                          vector<NodePoint> *recombs = NULL)
 {
     const int n = trees->length();
     Timer time;
@@ -188,8 +196,32 @@ static void device_thread(const ArgModel *model, const Sequences *sequences,
     for (int i = 0; i < ndraws; i++)
         draws[i] = rand();
     double logz = 0;
-    if (awb_thread_sample_cond(&fp.p, prior, last_state, draws.data(), RAND_MAX,
-                               path_alloc, &logz)) {
+    int rc;
+    if (recomb_pos && !getenv("AWB_ADAPTER_HOST_RECOMBS")) {
+        vector<int> pos(n > 0 ? n : 1), node(n > 0 ? n : 1), rtime(n > 0 ? n : 1);
+        int nrec = 0, used = 0;
+        rc = awb_thread_sample_recombs(&fp.p, prior, last_state, draws.data(),
+                                       RAND_MAX, NULL, path_alloc, &logz, n,
+                                       &nrec, pos.data(), node.data(),
+                                       rtime.data(), &used);
+        if (!rc) {
+            for (int i = 0; i < nrec; i++) {
+                recomb_pos->push_back(pos[i] + trees->start_coord);
+                recombs->push_back(NodePoint(node[i], rtime[i]));
+            }
+        }
+    } else {
+        rc = awb_thread_sample_cond(&fp.p, prior, last_state, draws.data(),
+                                    RAND_MAX, path_alloc, &logz);
+        if (!rc && recomb_pos) {
+            ArgHmmMatrixIter matrix_iter2(model, NULL, trees, new_chrom);
+            matrix_iter2.set_internal(internal, minage);
+            sample_recombinations(trees, model, &matrix_iter2,
+                                  &path_alloc[-trees->start_coord], *recomb_pos,
+                                  *recombs, internal);
+        }
+    }
+    if (rc) {
         printError("argweaver_b200: %s", awb_last_error());
         abort();                        // the reference's error convention
     }
@@ -211,16 +243,13 @@ void sample_arg_thread(const ArgModel *model, Sequences *sequences,
     int *thread_path = &thread_path_alloc[-trees->start_coord];
 
     ArgHmmMatrixIter matrix_iter(model, sequences, trees, new_chrom);
-    device_thread(model, sequences, trees, new_chrom, false, 0, NULL, -1,
-                  thread_path_alloc);
-
-    // sample recombination points, add thread to ARG: the reference's code
-    Timer time;
-    ArgHmmMatrixIter matrix_iter2(model, NULL, trees, new_chrom);
     vector<int> recomb_pos;
     vector<NodePoint> recombs;
-    sample_recombinations(trees, model, &matrix_iter2,
-                          thread_path, recomb_pos, recombs);
+    device_thread(model, sequences, trees, new_chrom, false, 0, NULL, -1,
+                  thread_path_alloc, &recomb_pos, &recombs);
+
+    // add thread to ARG: the reference's code
+    Timer time;
     add_arg_thread(trees, matrix_iter.states_model,
                    model->ntimes, thread_path, new_chrom,
                    recomb_pos, recombs);
@@ -245,16 +274,12 @@ void sample_arg_thread_internal(
 
     ArgHmmMatrixIter matrix_iter(model, sequences, trees);
     matrix_iter.set_internal(internal, minage);
-    device_thread(model, sequences, trees, -1, internal, minage, NULL, -1,
-                  thread_path_alloc);
-
-    Timer time;
-    ArgHmmMatrixIter matrix_iter2(model, NULL, trees);
-    matrix_iter2.set_internal(internal, minage);
     vector<int> recomb_pos;
     vector<NodePoint> recombs;
-    sample_recombinations(trees, model, &matrix_iter2,
-                          thread_path, recomb_pos, recombs, internal);
+    device_thread(model, sequences, trees, -1, internal, minage, NULL, -1,
+                  thread_path_alloc, &recomb_pos, &recombs);
+
+    Timer time;
     add_arg_thread_path(trees, matrix_iter.states_model,
                         model->ntimes, thread_path,
                         recomb_pos, recombs);
@@ -290,15 +315,12 @@ void cond_sample_arg_thread(const ArgModel *model, const Sequences *sequences,
     const int last = find_vector(states, end_state);
     assert(last != -1);
 
-    device_thread(model, sequences, trees, new_chrom, false, 0, prior.data(),
-                  last, thread_path_alloc);
-    assert(thread_path[trees->start_coord] == j);
-
-    ArgHmmMatrixIter matrix_iter2(model, NULL, trees, new_chrom);
     vector<int> recomb_pos;
     vector<NodePoint> recombs;
-    sample_recombinations(trees, model, &matrix_iter2,
-                          thread_path, recomb_pos, recombs);
+    device_thread(model, sequences, trees, new_chrom, false, 0, prior.data(),
+                  last, thread_path_alloc, &recomb_pos, &recombs);
+    assert(thread_path[trees->start_coord] == j);
+
     add_arg_thread(trees, matrix_iter.states_model,
                    model->ntimes, thread_path, new_chrom,
                    recomb_pos, recombs);
@@ -354,18 +376,14 @@ void cond_sample_arg_thread_internal(
         last = 0;
     }
 
+    vector<int> recomb_pos;
+    vector<NodePoint> recombs;
     device_thread(model, sequences, trees, -1, internal, 0, prior_p, last,
-                  thread_path_alloc);
+                  thread_path_alloc, &recomb_pos, &recombs);
     if (j >= 0)
         assert(thread_path[trees->start_coord] == j);
 
     Timer time;
-    ArgHmmMatrixIter matrix_iter2(model, NULL, trees);
-    matrix_iter2.set_internal(internal);
-    vector<int> recomb_pos;
-    vector<NodePoint> recombs;
-    sample_recombinations(trees, model, &matrix_iter2,
-                          thread_path, recomb_pos, recombs, internal);
     add_arg_thread_path(trees, matrix_iter.states_model,
                         model->ntimes, thread_path,
                         recomb_pos, recombs);

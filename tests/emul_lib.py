@@ -39,7 +39,8 @@ def build():
     so = os.path.join(BUILD, "libhost_emul.so")
     srcs = [os.path.join(HERE, "host_emul.cpp")] + [
         os.path.join(CSRC, f) for f in ("awb_common.cuh", "awb_setup.cuh",
-                                        "awb_emit.cuh", "awb_layout.h")]
+                                        "awb_emit.cuh", "awb_layout.h",
+                                        "awb_recomb.cuh")]
     srcs.append(os.path.join(INC, "argweaver_b200.h"))
     if (not os.path.exists(so) or
             os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs)):
@@ -69,6 +70,9 @@ def lib():
         _lib.emul_lin_unsafe.argtypes = [C.c_void_p]
         _lib.emul_lin_max.restype = C.c_double
         _lib.emul_lin_max.argtypes = [C.c_void_p]
+        _lib.emul_sample_recombs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -100,6 +104,23 @@ class Emul(object):
         rc = lib().emul_get(self.h, name.encode(), out.ctypes.data, nb)
         assert rc == 0
         return out
+
+    def sample_recombs(self, path, rng_state, rand_max=2147483647):
+        """(pos, node, time, draws) of the recombination sampler run on the host
+        over `path` (after setup())."""
+        path = np.ascontiguousarray(path, np.int32)
+        st = np.ascontiguousarray(rng_state, np.int32)
+        cap = len(path)
+        pos = np.empty(cap, np.int32)
+        node = np.empty(cap, np.int32)
+        time = np.empty(cap, np.int32)
+        info = np.zeros(2, np.int32)
+        lib().emul_sample_recombs(self.h, path.ctypes.data, st.ctypes.data,
+                                  int(rand_max), cap, pos.ctypes.data,
+                                  node.ctypes.data, time.ctypes.data,
+                                  info.ctypes.data)
+        n = int(info[0])
+        return pos[:n], node[:n], time[:n], int(info[1])
 
     def lin_unsafe(self):
         return bool(lib().emul_lin_unsafe(self.h))

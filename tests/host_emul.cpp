@@ -19,6 +19,7 @@
 #include "awb_common.cuh"
 #include "awb_emit.cuh"
 #include "awb_layout.h"
+#include "awb_recomb.cuh"
 #include "awb_setup.cuh"
 
 struct Emul {
@@ -201,6 +202,21 @@ double emul_lin_max(void *h)
         if (fabs(lin[i]) > m) m = fabs(lin[i]);
     }
     return m;
+}
+
+// the recombination sampler (awb_recomb.cuh) over a given path, after emul_setup
+int emul_sample_recombs(void *h, const int *path, const int *rng_state, int rand_max,
+                        int cap, int *pos, int *node, int *time, int *info)
+{
+    Emul *e = (Emul *) h;
+    const AwbChain &ch = e->ch;
+    memcpy(ch.path, path, sizeof(int) * ch.nsites);
+    AwbRng rng;
+    for (int i = 0; i < 31; i++) rng.r[i] = rng_state[i];
+    rng.f = rng_state[31];
+    rng.b = rng_state[32];
+    awb_sample_recombs(ch, rng, rand_max, pos, node, time, cap, info, -1);
+    return 0;
 }
 
 void emul_destroy(void *h) { delete (Emul *) h; }

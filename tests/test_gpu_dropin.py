@@ -88,6 +88,29 @@ def test_generated_sites_stats_identical(k, n, iters, tmp_path):
 
 
 @needs_binaries
+def test_infsites_run_stats_identical(tmp_path):
+    """--infsites (ArgModel::infsites_penalty = 1e-100, arg-sample.cpp:1077-1079):
+    the penalised emissions (emit.cpp:457-589, :848-862) run on the device"""
+    extra = ["-c", "10", "-n", "20", "--infsites"]
+    ref, _ = run_sampler(ARG_SAMPLE, SIM1, str(tmp_path / "ref"), extra)
+    dev, r = run_sampler(ARG_SAMPLE_B200, SIM1, str(tmp_path / "dev"), extra,
+                         env={"AWB_ADAPTER_REPORT": "1"})
+    assert_same_stats(ref, dev)
+    assert int(r.stderr.split("reference fallbacks:")[1].split()[0]) == 0
+
+
+@needs_binaries
+def test_host_recombination_sampler_gives_the_same_run(tmp_path):
+    """AWB_ADAPTER_HOST_RECOMBS=1: the reference's own sample_recombinations on
+    the path the device returns -- same .stats as with the device sampler"""
+    extra = ["-c", "10", "-n", "10"]
+    ref, _ = run_sampler(ARG_SAMPLE, SIM1, str(tmp_path / "ref"), extra)
+    dev, _ = run_sampler(ARG_SAMPLE_B200, SIM1, str(tmp_path / "dev"), extra,
+                         env={"AWB_ADAPTER_HOST_RECOMBS": "1"})
+    assert_same_stats(ref, dev)
+
+
+@needs_binaries
 def test_forced_fallback_is_the_reference(tmp_path):
     """AWB_ADAPTER_FORCE_REFERENCE routes every call to the renamed reference
     bodies: the binary is then the reference, bit for bit"""
