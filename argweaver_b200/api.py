@@ -190,7 +190,7 @@ DEBUG_DTYPES = {
     "sw_determprob": np.float64, "sw_recombrow": np.float64,
     "sw_recoalrow": np.float64, "sw_recombsrc": np.int32,
     "sw_recoalsrc": np.int32, "kind": np.uint8, "fw": np.float64,
-    "path": np.int32,
+    "path": np.int32, "fsum": np.float64, "sink": np.float64,
 }
 
 

@@ -407,9 +407,10 @@ extern "C" void awb_batch_destroy(awb_batch *b)
 }
 
 // Shape of the register-resident forward kernel (awb_forward_fast.cuh) for a
-// batch: TMAX (time rows), U (states per compute thread), compute threads NT.
-// U = 1 needs every branch inside one warp (<= 32 states: always so with up to
-// 33 time points); U = 2 / 4 also take branches of 33..64 states.
+// batch: TMAX (time rows), U (consecutive states per compute thread), compute
+// threads NT.  U is chosen so that a window needs at most four compute warps
+// where it can (few warps per window = several windows per SM); a branch of more
+// than 32 states (possible with more than 33 time points) needs U >= 2.
 struct FastShape {
     int tmax, U, NT, threads;
     bool ok;
@@ -420,15 +421,21 @@ static FastShape batch_fast_shape(const awb_batch *b)
     FastShape f;
     const int Tm1 = b->maxT - 1;
     f.tmax = Tm1 <= 20 ? 20 : (Tm1 <= 40 ? 40 : 64);
-    f.U = 1;
-    if (f.tmax > 20 || b->maxcnt > 32 || b->maxNS + AWB_FWD_HELPERS > 1024)
+    if (b->maxNS <= 128 && b->maxcnt <= 32)
+        f.U = 1;
+    else if (b->maxNS <= 256)
         f.U = 2;
-    if (f.U == 2 && (b->maxNS + 63) / 64 * 32 > 512)
+    else
         f.U = 4;
+    if (getenv("AWB_K4_U")) {
+        const int u = atoi(getenv("AWB_K4_U"));
+        if ((u == 1 && b->maxcnt <= 32 && b->maxNS <= 512) || u == 2 || u == 4)
+            f.U = u;
+    }
     f.NT = (b->maxNS + 32 * f.U - 1) / (32 * f.U) * 32;
     f.threads = f.NT + AWB_FWD_HELPERS;
     f.ok = !getenv("AWB_FORCE_GENERIC") && !b->lin_unsafe && b->maxcnt <= 64 &&
-        f.threads <= (f.U == 1 ? 1024 : 608) &&
+        f.threads <= 576 &&
         awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap) <= 200 * 1024;
     return f;
 }
@@ -814,41 +821,63 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
     cudaStream_t st = b->ctx->stream;
     const FastShape f = batch_fast_shape(b);
     const int threads = f.threads;
-    int maxd = 1;
-    while (maxd < b->maxcnt) maxd <<= 1;
     const size_t fsmem = awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap);
     const dim3 grid(b->C, nsub);
+    static bool said = false;
+    const bool verbose = getenv("AWB_VERBOSE") && !said;
+    said = said || verbose;
 #define AWB_LAUNCH_FAST(TM, NL, MT, UU, MB)                                      \
     do {                                                                         \
         if (fsmem > 48 * 1024)                                                   \
             CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT, UU, MB>, \
                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));      \
+        /* several CTAs per SM: the whole shared-memory carve-out */            \
+        CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT, UU, MB>, \
+            cudaFuncAttributePreferredSharedMemoryCarveout,                      \
+            (int) cudaSharedmemCarveoutMaxShared));                              \
+        if (verbose) {                                                           \
+            int nb = 0;                                                          \
+            cudaFuncAttributes fa;                                               \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb,                   \
+                awb_forward_fast_kernel<TM, NL, MT, UU, MB>, threads, fsmem);    \
+            cudaFuncGetAttributes(&fa, awb_forward_fast_kernel<TM, NL, MT, UU, MB>); \
+            fprintf(stderr, "forward kernel <%d,%d,%d,%d,%d>: %d threads, %zu B shared, " \
+                    "%d registers, %zu B local: %d CTAs per SM\n", TM, NL, MT, UU, MB, \
+                    threads, fsmem, fa.numRegs, (size_t) fa.localSizeBytes, nb); \
+        }                                                                        \
         awb_forward_fast_kernel<TM, NL, MT, UU, MB><<<grid, threads, fsmem, st>>>( \
             b->d_chains, seg, pass, b->zcap);                                    \
     } while (0)
-    const bool lev4 = maxd <= 16;
-    const bool two = (long long) b->C * nsub > b->ctx->sm_count && !getenv("AWB_K4_ONE_PER_SM");
-    if (f.tmax == 20 && f.U == 1) {
-        if (threads <= 320) { if (lev4) AWB_LAUNCH_FAST(20, 4, 320, 1, 3); else AWB_LAUNCH_FAST(20, 5, 320, 1, 3); }
-        else if (threads <= 576) {
-            // two CTAs per SM only pay when there are that many (56 registers a
-            // thread instead of 112 cost 14 % on a lone CTA)
-            if (two) { if (lev4) AWB_LAUNCH_FAST(20, 4, 576, 1, 2); else AWB_LAUNCH_FAST(20, 5, 576, 1, 2); }
-            else { if (lev4) AWB_LAUNCH_FAST(20, 4, 576, 1, 1); else AWB_LAUNCH_FAST(20, 5, 576, 1, 1); }
-        }
-        else if (threads <= 768) AWB_LAUNCH_FAST(20, 5, 768, 1, 1);
-        else AWB_LAUNCH_FAST(20, 5, 1024, 1, 1);
-    } else if (f.tmax == 20) {
-        if (f.U == 2) AWB_LAUNCH_FAST(20, 5, 608, 2, 1);
-        else AWB_LAUNCH_FAST(20, 5, 608, 4, 1);
-    } else if (f.tmax == 40) {
-        if (f.U == 2 && threads <= 352) AWB_LAUNCH_FAST(40, 5, 352, 2, 2);
-        else if (f.U == 2) AWB_LAUNCH_FAST(40, 5, 608, 2, 1);
-        else AWB_LAUNCH_FAST(40, 5, 608, 4, 1);
-    } else {
-        if (f.U == 2) AWB_LAUNCH_FAST(64, 5, 608, 2, 1);
-        else AWB_LAUNCH_FAST(64, 5, 608, 4, 1);
-    }
+    // (MAXTHREADS, registers per thread: 7 warps at 72 / 96 registers = 4 / 3
+    // CTAs per SM, 11 warps at 88 = 2)
+    // N1 / N2 / N4: levels of the carry scans for U = 1 / 2 / 4 (a branch of
+    // maxcnt states touches (maxcnt + U - 2) / U + 1 lanes).
+    // Registers per thread: an SM has four register files of 16 K registers and
+    // a CTA's warps are dealt out over them, so n CTAs of w warps need
+    // ceil(n w / 4) warps' worth of registers per file: 6-warp CTAs (4 compute
+    // warps + the scribes) run 3 per SM at 96 registers, 4 at 80.
+    const bool lean = getenv("AWB_K4_LEAN") != NULL;
+#define AWB_LAUNCH_FAST_T(TM, N1, N2, N4)                                        \
+    do {                                                                         \
+        if (threads <= 192) {                                                    \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 192, 1, 80);                   \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 192, 2, 80);              \
+            else if (lean) AWB_LAUNCH_FAST(TM, N4, 192, 4, 80);                  \
+            else AWB_LAUNCH_FAST(TM, N4, 192, 4, 96);                            \
+        } else if (threads <= 320) {                                             \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 320, 1, 96);                   \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 320, 2, 96);              \
+            else AWB_LAUNCH_FAST(TM, N4, 320, 4, 96);                            \
+        } else {                                                                 \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 576, 1, 96);                   \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 576, 2, 96);              \
+            else AWB_LAUNCH_FAST(TM, N4, 576, 4, 96);                            \
+        }                                                                        \
+    } while (0)
+    if (f.tmax == 20) AWB_LAUNCH_FAST_T(20, 5, 4, 3);
+    else if (f.tmax == 40) AWB_LAUNCH_FAST_T(40, 5, 5, 4);
+    else AWB_LAUNCH_FAST_T(64, 5, 5, 4);
+#undef AWB_LAUNCH_FAST_T
 #undef AWB_LAUNCH_FAST
     b->launches++;
     return 0;

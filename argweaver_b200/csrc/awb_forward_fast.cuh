@@ -42,10 +42,13 @@
 //                   TIME-MAJOR order) into the per-time sums F[a] and then,
 //                   one lane per b, into R[b]; a compute thread reads a single
 //                   value.
-//   norm warp       one warp that only waits on barrier 2: column norm, logZ,
-//                   the lagged rescale factor, and the per-time sums of the
-//                   stored column (fsum) for the traceback.  Its division and
-//                   log() are off the critical cycle.
+//                   The second scribe warp (idle while the first forms R when
+//                   there are at most 32 time rows) also keeps the books:
+//                   column norm, logZ, the lagged rescale factor, the per-time
+//                   sums of the stored column (fsum) for the traceback, and
+//                   the L1 prefetches.  A CTA is then 4 + 2 warps for the bench
+//                   shape: 18 warps of three CTAs spread evenly over the four
+//                   register files of an SM (7-warp CTAs do not).
 //
 //   step(site):  STS value (time-major slot)
 //                B1 (compute + F-scribes)
@@ -74,13 +77,14 @@
 
 #define AWB_FWD_RS 4          // rescale period (sites); power of two, >= 4
 #define AWB_FWD_FSCRIBES AWB_NSCRIBE          // F-scribe lanes
-#define AWB_FWD_HELPERS (AWB_NSCRIBE + 32)    // F-scribes + norm warp
+#define AWB_FWD_HELPERS AWB_NSCRIBE           // the two F-scribe warps
 
 // shared memory (doubles): Fs[2][TMAX+2] | Rs[2][TMAX+2] | scaleS[2] | invL[2] |
-// dummy[2] | tmS[TMAX/2][NSCRIBE][2] | colS[2][NS] | zT[zcap]     (NS = state slots)
+// dummy[4] | tmS[TMAX/2][NSCRIBE][2] | colS[2][NS] | cst[2][NS][2] | zT[zcap]
+// (NS = state slots)
 __host__ __device__ inline size_t awb_fwd_fast_smem_bytes(int NS, int TMAX, int zcap)
 {
-    return (2 * (size_t) NS + (size_t) zcap + 4 * (size_t) (TMAX + 2) + 6 +
+    return (6 * (size_t) NS + (size_t) zcap + 4 * (size_t) (TMAX + 2) + 8 +
             (size_t) (TMAX + 1) / 2 * AWB_NSCRIBE * 2) * sizeof(double);
 }
 
@@ -179,6 +183,32 @@ __device__ __forceinline__ double awb_next_in_seg(double v, int clast)
     return r;
 }
 
+// acc += t when bit BIT of `bits` is set: one LOP3 into a predicate and a
+// predicated DADD (a C++ conditional becomes a DADD and two FSEL)
+template <unsigned BIT>
+__device__ __forceinline__ void awb_add_if(double &acc, double t, unsigned bits)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 m;\n\t"
+        "and.b32 m, %2, %3;\n\t"
+        "setp.ne.u32 p, m, 0;\n\t"
+        "@p add.f64 %0, %0, %1;\n\t}"
+        : "+d"(acc) : "d"(t), "r"(bits), "n"(BIT));
+}
+
+// a + b, or 0 when bit BIT of `bits` is set
+template <unsigned BIT>
+__device__ __forceinline__ double awb_sum_unless(double a, double b, unsigned bits)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 m;\n\t"
+        "and.b32 m, %3, %4;\n\t"
+        "setp.ne.u32 p, m, 0;\n\t"
+        "mov.f64 %0, 0d0000000000000000;\n\t"
+        "@!p add.f64 %0, %1, %2;\n\t}"
+        : "=d"(r) : "d"(a), "d"(b), "r"(bits), "n"(BIT));
+    return r;
+}
+
 __device__ __forceinline__ double2 awb_lds2(unsigned addr)
 {
     double2 v;
@@ -197,10 +227,11 @@ __device__ __forceinline__ void awb_bar_sync(int id, int count)
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
-// U: states per compute thread (register sets); MINB: CTAs per SM the register
-// budget is cut for
-template <int TMAX, int NLEV, int MAXTHREADS, int U, int MINB>
-__global__ void __launch_bounds__(MAXTHREADS, MINB)
+// U: consecutive states per compute thread; MAXREG: registers per thread (what
+// lets the wanted number of CTAs share an SM -- __launch_bounds__'s own
+// arithmetic rounds 224 threads up to 256 and leaves registers unused)
+template <int TMAX, int NLEV, int MAXTHREADS, int U, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
 {
     static_assert(TMAX % 4 == 0, "the scribes' R loop takes four rows at a time");
@@ -238,15 +269,19 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     double *RsS = FsS + 2 * (TMAX + 2);        // [2][TMAX+2] R[b] = sum_a tm[a][b] F[a]
     double *scaleS = RsS + 2 * (TMAX + 2);     // [2] rescale factors
     double *invL = scaleS + 2;                 // [2] [0]: 1/norm of the last column
-    double *dummyS = invL + 2;                 // [2] [0]: idle lanes store here; [1] = 1.0
-    double *tmS = dummyS + 2;                  // scribe lane sl keeps column sl of the
+    double *dummyS = invL + 2;                 // [4] [0]: idle lanes store here; [1] = 1.0;
+                                               //   [2] = 0.0
+    double *tmS = dummyS + 4;                  // scribe lane sl keeps column sl of the
                                                //   block's time matrix: [(a/2)][sl][a&1]
     double *colS = tmS + TMS;                  // [2][NS] last column of a block in
                                                //   state order, by block parity
-    double *zT = colS + 2 * NS;                // [zcap] column, time-major rows,
+    double *cstS = colS + 2 * NS;              // [2][NS][2] per-state constants of the
+                                               //   block: (A1, A2) and (A3, inv_emit),
+                                               //   each thread's own entries
+    double *zT = cstS + 4 * NS;                // [zcap] column, time-major rows,
                                                //   zero-padded for the scribes (K1)
 
-    for (int x = tid; x < 2 * NS + zcap + 4 * (TMAX + 2) + 6 + TMS; x += blockDim.x) {
+    for (int x = tid; x < 6 * NS + zcap + 4 * (TMAX + 2) + 8 + TMS; x += blockDim.x) {
         const int y = x - 4 * (TMAX + 2);
         smem_f[x] = ((y >= 0 && y < 4) || y == 5) ? 1.0 : 0.0;   // scaleS, invL, one
     }
@@ -263,120 +298,75 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const unsigned invl_s = (unsigned) __cvta_generic_to_shared(invL);
     const unsigned dummy_s = (unsigned) __cvta_generic_to_shared(dummyS);
     const unsigned tm_s = (unsigned) __cvta_generic_to_shared(tmS);
+    const unsigned cst_s = (unsigned) __cvta_generic_to_shared(cstS);
     constexpr unsigned RSTR = (TMAX + 2) * 8;
 
-    if (tid >= NB1) {
+    if (tid >= NT) {
         // =================================================================
-        // norm warp: waits on barrier 2 only
+        // F-scribes: per-time sums and R between barrier 1 and barrier 2; the
+        // second scribe warp also keeps the books (column norm, logZ, the
+        // lagged rescale factor, fsum for the traceback) while the first one
+        // forms R, and warms the cache in its idle time
         // =================================================================
+        const int sl = tid - NT;                         // scribe lane 0..63
+        const bool bookkeeper = sl >= 32;
+        const double *__restrict__ tmatrixg = chg.tmatrix;
+        const unsigned short *__restrict__ sc_startg = chg.sc_start;
+        const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
+        const unsigned char *__restrict__ sc_rowg = chg.sc_row;
+        const unsigned char *__restrict__ sc_strideg = chg.sc_stride;
+        const unsigned tml_s = tm_s + 16u * (unsigned) sl;      // my column, pair 0
+
+        // ---- bookkeeping state (second warp)
         double lprod = 1.0, lacc = 0.0;
         int nprod = 0;
         double *__restrict__ fsumg = chg.fsum + g.fsoff;
         int bad_site = -1;
-        // This warp has slack, so it also warms the cache for the others: when
-        // a block starts, the per-block tables of the NEXT block (what
-        // load_compute, the switch gather and the scribes read in dependent
-        // chains at the block boundary) are prefetched into L1.
-        int pb = bbeg, pnext = 0;
-        // ... and the emission rows of the variant sites a few sites ahead
-        // (K3 left them in the table; a compute thread reads its entry right
-        // before it needs it).  Cursor (ab, ai) = block / offset of site + LA.
+        // the emission rows of the variant sites a few sites ahead are
+        // prefetched into L1 (K3 left them in the table; a compute thread reads
+        // its entry right before it needs it).  Cursor (ab, ai) = block / offset
+        // of site + LA.
         constexpr int LA = 6;
         const unsigned char *__restrict__ kindn = chg.kind + g.site0;
         const double *fwn = chg.fw - g.fwbias;
         int ab = bbeg, ai = 0, ablen = (ab == bextra) ? 1 : blocklensg[ab];
-        for (int x = 0; x < LA && ab < bend; x++) {
-            if (++ai == ablen) {
-                ab++;
-                ai = 0;
-                ablen = (ab < bend) ? ((ab == bextra) ? 1 : blocklensg[ab]) : 0;
-            }
-        }
         int aS1 = 1;
         long long arow = 0;
-        if (ab < bend) {
-            aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
-            arow = chg.fw_off[ab] + (long long) ai * aS1;
-        }
-        for (int site = 0; site < n; site++) {
-            if (ab < bend) {
-                if (kindn[site + LA] == AWB_SITE_VARIANT)
-                    awb_prefetch_range(fwn + arow, 8ll * aS1, lane);
-                arow += aS1;
+        if (bookkeeper) {
+            for (int x = 0; x < LA && ab < bend; x++) {
                 if (++ai == ablen) {
                     ab++;
                     ai = 0;
-                    if (ab < bend) {
-                        ablen = (ab == bextra) ? 1 : blocklensg[ab];
-                        aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
-                        arow = chg.fw_off[ab];
-                    }
+                    ablen = (ab < bend) ? ((ab == bextra) ? 1 : blocklensg[ab]) : 0;
                 }
             }
-            if (site == pnext) {
-                pnext += (pb == bextra) ? 1 : blocklensg[pb];
-                const int nb = ++pb;
-                if (nb < bend) {
-                    const long long r0n = chg.row_off[nb];
-                    const long long S1n = chg.row_off[nb + 1] - r0n;
-                    const long long tr0n = chg.trow_off[nb];
-                    const long long e0n = chg.ent_off[nb];
-                    const long long nen = chg.ent_off[nb + 1] - e0n;
-                    // (one compact loop over the 16 tables: this code runs once
-                    // per block, cold in the instruction cache, and inlined
-                    // range by range it was several hundred instructions)
-                    const void *pp[16];
-                    long long pl[16];
-                    pp[0] = chg.tmap + tr0n;      pl[0] = 2 * (chg.trow_off[nb + 1] - tr0n);
-                    pp[1] = chg.st_node + r0n;    pl[1] = 2 * S1n;
-                    pp[2] = chg.st_time + r0n;    pl[2] = S1n;
-                    pp[3] = chg.st_age + r0n;     pl[3] = S1n;
-                    pp[4] = chg.iperm + r0n;      pl[4] = 2 * S1n;
-                    pp[5] = chg.inv_emit + r0n;   pl[5] = 8 * S1n;
-                    pp[6] = chg.sw_start + r0n;   pl[6] = 2 * S1n;
-                    pp[7] = chg.sw_cnt + r0n;     pl[7] = 2 * S1n;
-                    pp[8] = chg.sw_src + e0n;     pl[8] = 2 * nen;
-                    pp[9] = chg.sw_prob + e0n;    pl[9] = 8 * nen;
-                    pp[10] = chg.lin + (size_t) nb * 7 * T;              pl[10] = 56ll * T;
-                    pp[11] = chg.tmatrix + (size_t) nb * T * T;          pl[11] = 8ll * T * T;
-                    pp[12] = chg.sc_start + (size_t) nb * AWB_NSCRIBE;   pl[12] = 2 * AWB_NSCRIBE;
-                    pp[13] = chg.sc_cnt + (size_t) nb * AWB_NSCRIBE;     pl[13] = 2 * AWB_NSCRIBE;
-                    pp[14] = chg.sc_row + (size_t) nb * AWB_NSCRIBE;     pl[14] = AWB_NSCRIBE;
-                    pp[15] = chg.sc_stride + (size_t) nb * AWB_NSCRIBE;  pl[15] = AWB_NSCRIBE;
-#pragma unroll 1
-                    for (int r = 0; r < 16; r++)
-                        awb_prefetch_range(pp[r], pl[r], lane);
-                    if (lane == 0) {
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.sc_ch + nb));
-                    }
-                }
+            if (ab < bend) {
+                aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+                arow = chg.fw_off[ab] + (long long) ai * aS1;
             }
-            const unsigned Fa_s = Fs_s + (site & 1) * RSTR + 8u * lane;
-            awb_bar_sync(2, NB2);
+        }
+
+        // norm of column s (lane T-1's "R"), per-time sums, rescale factor, logZ
+        auto keep_books = [&](int s) {
+            const unsigned Fa_s = Fs_s + (s & 1) * RSTR + 8u * lane;
+            const double nrm = awb_lds(Rs_s + (s & 1) * RSTR + 8u * (unsigned) (T - 1));
             // (T - 1 <= 63: at most two rows per lane)
-            const double f0 = (lane < T - 1) ? awb_lds(Fa_s) : 0.0;
-            const double f1 = (lane + 32 < T - 1) ? awb_lds(Fa_s + 256u) : 0.0;
-            double x = f0 + f1;
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1)
-                x += __shfl_xor_sync(0xffffffffu, x, d);
-            const double nrm = x;
             // per-time sums of the column as it is stored (the traceback forms
             // its row totals from these)
             if (lane < T - 1)
-                __stcs(fsumg + (size_t) site * (T - 1) + lane, f0);
+                __stcs(fsumg + (size_t) s * (T - 1) + lane, awb_lds(Fa_s));
             if (lane + 32 < T - 1)
-                __stcs(fsumg + (size_t) site * (T - 1) + lane + 32, f1);
+                __stcs(fsumg + (size_t) s * (T - 1) + lane + 32, awb_lds(Fa_s + 256u));
             if (!(nrm > 0.0) && bad_site < 0)
-                bad_site = site;
-            if ((site & (AWB_FWD_RS - 1)) == 0) {
-                // this factor is applied when column site+3 is formed
+                bad_site = s;
+#ifdef AWB_K4_DEBUG_NRM
+            if (lane == 0 && s < 64) chg.sink[s] = nrm;
+#endif
+            if ((s & (AWB_FWD_RS - 1)) == 0) {
+                // this factor is applied when column s+3 is formed
                 if (lane == 0)
-                    awb_sts(scale_s + 8u * ((site / AWB_FWD_RS) & 1), 1.0 / nrm);
-                if (site + 3 <= n - 1) {
+                    awb_sts(scale_s + 8u * ((s / AWB_FWD_RS) & 1), 1.0 / nrm);
+                if (s + 3 <= n - 1) {
                     lprod *= nrm;
                     if (++nprod == 8) {
                         lacc += log(lprod);
@@ -385,7 +375,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     }
                 }
             }
-            if (site == n - 1 && lane == 0) {
+            if (s == n - 1 && lane == 0) {
                 awb_sts(invl_s, 1.0 / nrm);
                 // (a segment that starts from a stored, normalised column adds
                 // the log-likelihood of its own sites; the recompute pass adds
@@ -402,22 +392,8 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     }
                 }
             }
-        }
-        __syncthreads();                                   // final barrier
-        return;
-    }
+        };
 
-    if (tid >= NT) {
-        // =================================================================
-        // F-scribes: per-time sums between barrier 1 and barrier 2
-        // =================================================================
-        const int sl = tid - NT;                         // scribe lane 0..63
-        const double *__restrict__ tmatrixg = chg.tmatrix;
-        const unsigned short *__restrict__ sc_startg = chg.sc_start;
-        const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
-        const unsigned char *__restrict__ sc_rowg = chg.sc_row;
-        const unsigned char *__restrict__ sc_strideg = chg.sc_stride;
-        const unsigned tml_s = tm_s + 16u * (unsigned) sl;      // my column, pair 0
         int site = 0;
         for (int b = bbeg; b < bend; b++) {
             const int blen = (b == bextra) ? 1 : blocklensg[b];
@@ -433,45 +409,90 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             awb_lane_run(key, lane, seglane, segend);
             const bool sc_last = (lane == segend) && (sc_row != 255);
             const int span = __reduce_max_sync(0xffffffffu, segend - seglane);
-#ifdef AWB_K4_SCRIBE_FMA
-            double um[5];
-#pragma unroll
-            for (int l = 0; l < 5; l++)
-                um[l] = (lane - (1 << l) >= seglane) ? 1.0 : 0.0;
-#endif
             const unsigned z_s = zT_s + 8u * (unsigned) sc_start;
             // the slots of this lane beyond its real ones are padding: zero them
             // for this block (the compute warps only write real slots; the
-            // previous block is past its last barrier 2)
-            for (int q = sc_cnt; q < CH; q++)
-                awb_sts(z_s + zstep * (unsigned) q, 0.0);
+            // previous block is past its last barrier 2).  A lane without a row
+            // owns no slots (its sc_start is 0: zeroing "its" padding would race
+            // with the compute warp that stores slot 0 of the new block).
+            if (sc_row != 255)
+                for (int q = sc_cnt; q < CH; q++)
+                    awb_sts(z_s + zstep * (unsigned) q, 0.0);
             // column `sl` of the block's time-by-time matrix, parked in this
             // lane's own shared-memory slots (nobody else reads them): this
             // lane turns the per-time sums F into R[sl] for the compute warps
-#ifdef AWB_K4_TMREG
-            double tmc[TMAX];
-            {
+            // Lane T-1 holds a column of ones: its "R" is the column norm.
+            if (sl != T - 1 || b == bbeg) {
                 const bool rl = (sl < T - 1) && nstatesg[b] > 0;
-                const double *tmg = tmatrixg + (size_t) b * T * T + (rl ? sl : 0);
-#pragma unroll
-                for (int a = 0; a < TMAX; a++)
-                    tmc[a] = (rl && a < T - 1) ? tmg[a * T] : 0.0;
-            }
-#else
-            {
-                const bool rl = (sl < T - 1) && nstatesg[b] > 0;
+                const double one = (sl == T - 1) ? 1.0 : 0.0;
                 const double *tmg = tmatrixg + (size_t) b * T * T + (rl ? sl : 0);
 #pragma unroll 4
                 for (int a = 0; a < TMAX; a += 2) {
-                    const double t0 = (rl && a < T - 1) ? tmg[a * T] : 0.0;
-                    const double t1 = (rl && a + 1 < T - 1) ? tmg[(a + 1) * T] : 0.0;
+                    const double t0 = (a < T - 1) ? (rl ? tmg[a * T] : one) : 0.0;
+                    const double t1 = (a + 1 < T - 1) ? (rl ? tmg[(a + 1) * T] : one) : 0.0;
                     awb_sts2(tml_s + (unsigned) (a / 2) * (16u * AWB_NSCRIBE), t0, t1);
                 }
             }
-#endif
+            // when a block starts, the per-block tables of the NEXT block (what
+            // load_compute, the switch gather and the scribes read in dependent
+            // chains at the block boundary) are prefetched into L1
+            if (bookkeeper && b + 1 < bend) {
+                const int nb = b + 1;
+                const long long r0n = chg.row_off[nb];
+                const long long S1n = chg.row_off[nb + 1] - r0n;
+                const long long tr0n = chg.trow_off[nb];
+                const long long e0n = chg.ent_off[nb];
+                const long long nen = chg.ent_off[nb + 1] - e0n;
+                // (one compact loop over the 16 tables: this code runs once per
+                // block, cold in the instruction cache, and inlined range by
+                // range it was several hundred instructions)
+                const void *pp[16];
+                long long pl[16];
+                pp[0] = chg.tmap + tr0n;      pl[0] = 2 * (chg.trow_off[nb + 1] - tr0n);
+                pp[1] = chg.st_node + r0n;    pl[1] = 2 * S1n;
+                pp[2] = chg.st_time + r0n;    pl[2] = S1n;
+                pp[3] = chg.st_age + r0n;     pl[3] = S1n;
+                pp[4] = chg.iperm + r0n;      pl[4] = 2 * S1n;
+                pp[5] = chg.inv_emit + r0n;   pl[5] = 8 * S1n;
+                pp[6] = chg.sw_start + r0n;   pl[6] = 2 * S1n;
+                pp[7] = chg.sw_cnt + r0n;     pl[7] = 2 * S1n;
+                pp[8] = chg.sw_src + e0n;     pl[8] = 2 * nen;
+                pp[9] = chg.sw_prob + e0n;    pl[9] = 8 * nen;
+                pp[10] = chg.lin + (size_t) nb * 7 * T;              pl[10] = 56ll * T;
+                pp[11] = chg.tmatrix + (size_t) nb * T * T;          pl[11] = 8ll * T * T;
+                pp[12] = chg.sc_start + (size_t) nb * AWB_NSCRIBE;   pl[12] = 2 * AWB_NSCRIBE;
+                pp[13] = chg.sc_cnt + (size_t) nb * AWB_NSCRIBE;     pl[13] = 2 * AWB_NSCRIBE;
+                pp[14] = chg.sc_row + (size_t) nb * AWB_NSCRIBE;     pl[14] = AWB_NSCRIBE;
+                pp[15] = chg.sc_stride + (size_t) nb * AWB_NSCRIBE;  pl[15] = AWB_NSCRIBE;
+#pragma unroll 1
+                for (int r = 0; r < 16; r++)
+                    awb_prefetch_range(pp[r], pl[r], lane);
+                if (lane == 0) {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.sc_ch + nb));
+                }
+            }
 
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
+                if (bookkeeper && ab < bend) {
+                    // (idle time in front of barrier 1: the compute warps are
+                    // forming the column)
+                    if (kindn[site + LA] == AWB_SITE_VARIANT)
+                        awb_prefetch_range(fwn + arow, 8ll * aS1, lane);
+                    arow += aS1;
+                    if (++ai == ablen) {
+                        ab++;
+                        ai = 0;
+                        if (ab < bend) {
+                            ablen = (ab == bextra) ? 1 : blocklensg[ab];
+                            aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+                            arow = chg.fw_off[ab];
+                        }
+                    }
+                }
                 awb_bar_sync(1, NB1);
                 // each lane sums its CH slots of one (zero-padded) row; the lanes of
                 // a row combine with a segmented scan
@@ -488,34 +509,22 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 double v = v0 + v1;
 #pragma unroll
                 for (int l = 0; l < 5; l++) {
-#ifdef AWB_K4_SCRIBE_FMA
-                    if ((1 << l) <= span) {
-                        const double t = __shfl_up_sync(0xffffffffu, v, 1 << l);
-                        v = fma(t, um[l], v);
-                    }
-#else
                     if ((1 << l) <= span)
                         v = awb_scan_up(v, 1 << l, seglane);
-#endif
                 }
                 if (sc_last)
                     awb_sts(Fp_s + 8u * (unsigned) sc_row, v);
                 awb_bar_sync(3, AWB_FWD_FSCRIBES);
-                if (i + 1 < blen && sl < T - 1) {
+                if ((i + 1 < blen && sl < T - 1) || sl == T - 1) {
                     double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
 #pragma unroll
                     for (int a = 0; a + 3 < TMAX; a += 4) {
                         const double2 f0 = awb_lds2(Fp_s + 8u * a);
                         const double2 f1 = awb_lds2(Fp_s + 8u * a + 16u);
-#ifdef AWB_K4_TMREG
-                        const double2 t0 = make_double2(tmc[a], tmc[a + 1]);
-                        const double2 t1 = make_double2(tmc[a + 2], tmc[a + 3]);
-#else
                         const double2 t0 =
                             awb_lds2(tml_s + (unsigned) (a / 2) * (16u * AWB_NSCRIBE));
                         const double2 t1 =
                             awb_lds2(tml_s + (unsigned) (a / 2 + 1) * (16u * AWB_NSCRIBE));
-#endif
                         ra = fma(t0.x, f0.x, ra);
                         rb = fma(t0.y, f0.y, rb);
                         rc = fma(t1.x, f1.x, rc);
@@ -524,9 +533,15 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     awb_sts(Rs_s + (site & 1) * RSTR + 8u * (unsigned) sl,
                             (ra + rb) + (rc + rd));
                 }
+                // the books of the PREVIOUS site (its norm and per-time sums stay
+                // in their buffers until the site after this one)
+                if (bookkeeper && site > 0)
+                    keep_books(site - 1);
                 awb_bar_sync(2, NB2);
             }
         }
+        if (bookkeeper)
+            keep_books(n - 1);
         __syncthreads();                                   // final barrier
         return;
     }
@@ -543,19 +558,33 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const int warp = tid >> 5;
     double *const sink = chg.sink + tid;
 
-    // ---- my states in the current block (register set u = slot (warp*U+u)*32+lane)
+    // ---- my states in the current block: U consecutive slots of the packed,
+    // node-major order, slot = (warp*32 + lane)*U + u.  A branch's states are
+    // consecutive slots (ascending time), so a lane holds a run of a branch, and
+    // the two exclusive sums along a branch are a scan inside the lane plus a
+    // segmented scan of one value per lane across the warp.
     int jj[U];
     bool active[U], live[U];               // live: active and S > 0
+    unsigned actm = 0;                     // bit u: active[u]
     unsigned zaddr[U], raddr[U];
-    int cfirst[U], clast[U];               // first / last lane of my branch
-    double inv_e[U], Da[U], H[U], A1[U], A2[U], A3[U];
+    double Da[U], H[U];
     double c[U];
+    // the constants only needed after the scans stay in shared memory:
+    // (A1, A2) at cA + 512 u, (A3, inv_emit) at cB + 512 u (16 bytes per lane)
+    unsigned cA = cst_s + 16u * (unsigned) (warp * U * 32 + lane);
+    asm volatile("" : "+r"(cA));           // (keep it: recomputing it costs ten instructions a site)
+    const unsigned cB = cA + 16u * (unsigned) NS;
     double *nxt[U];
     int S = 0, S1 = 1;
     long long r0 = 0;
     unsigned rowstep = 0;                  // bytes between consecutive rows of the block
-    bool wlong = false;                    // this warp holds a branch of > 32 states
-    bool headl[(U + 1) / 2], contl[(U + 1) / 2];
+    // bit u of headm / lastm: slot u is the first / last state of its branch;
+    // prem / postm: the slots in front of my first head / behind my last `last`
+    // (they continue a branch of the lanes below / above)
+    unsigned headm = 0, lastm = 0, prem = 0, postm = 0;
+    // carry scans across the lanes: bit l of upok / dnok = the value 2^l lanes
+    // below / above still belongs to my branch
+    unsigned upok = 0, dnok = 0;
 
     auto load_compute = [&](int bb) {
         S = nstatesg[bb];
@@ -565,57 +594,77 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         const long long tr0 = chg.trow_off[bb];
         const int NSb = (int) (chg.trow_off[bb + 1] - tr0);
         int node[U];
-        wlong = false;
+        actm = 0;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int slot = (warp * U + u) * 32 + lane;
+            const int slot = (warp * 32 + lane) * U + u;
             unsigned short tj = 0xFFFF;
             if (slot < NSb)
                 tj = chg.tmap[tr0 + slot];
             active[u] = (tj != 0xFFFF);
+            if (active[u]) actm |= 1u << u;
             live[u] = active[u] && S > 0;
             jj[u] = active[u] ? (int) tj : 0;
             int atime = 0, cage = 0, tpos = 0;
-            node[u] = -1;
-            inv_e[u] = active[u] ? 1.0 : 0.0;
+            node[u] = -1 - u;
+            double inv_e = active[u] ? 1.0 : 0.0;
+            double A1, A2, A3;
             if (live[u]) {
                 atime = chg.st_time[r0 + jj[u]];
                 cage = chg.st_age[r0 + jj[u]];
                 node[u] = chg.st_node[r0 + jj[u]];
                 tpos = chg.iperm[r0 + jj[u]];
-                inv_e[u] = chg.inv_emit[r0 + jj[u]];
+                inv_e = chg.inv_emit[r0 + jj[u]];
             }
             zaddr[u] = active[u] ? zT_s + 8u * (unsigned) tpos : dummy_s;
             raddr[u] = Rs_s + 8u * (unsigned) atime;
-            const int key = live[u] ? node[u] : (0x10000 + lane);
-            awb_lane_run(key, lane, cfirst[u], clast[u]);
             if (live[u]) {
                 const double *lin = chg.lin + (size_t) bb * 7 * T;
                 const double Bc = cage > 0 ? lin[2 * T + cage - 1] : 0.0;
                 const double a1 = lin[3 * T + atime];
                 Da[u] = lin[0 * T + atime];
                 H[u] = Da[u] * (lin[1 * T + atime] - Bc);
-                A1[u] = a1;
-                A2[u] = fma(Da[u], lin[4 * T + atime] - a1 * Bc, lin[6 * T + atime]);
-                A3[u] = lin[5 * T + atime] - a1 * Bc;
+                A1 = a1;
+                A2 = fma(Da[u], lin[4 * T + atime] - a1 * Bc, lin[6 * T + atime]);
+                A3 = lin[5 * T + atime] - a1 * Bc;
             } else {
                 // idle lane (everything 0), or the size-1 state space (identity)
-                Da[u] = 0.0; H[u] = 0.0; A1[u] = 0.0; A3[u] = 0.0;
-                A2[u] = active[u] ? 1.0 : 0.0;
+                Da[u] = 0.0; H[u] = 0.0; A1 = 0.0; A3 = 0.0;
+                A2 = active[u] ? 1.0 : 0.0;
             }
+            awb_sts2(cA + 512u * u, A1, A2);
+            awb_sts2(cB + 512u * u, A3, inv_e);
         }
-        if (U > 1) {
-            // a branch of 33..64 states fills set u (even) and continues in the
-            // first lanes of set u+1 (K1 packs it that way)
+        // branch structure of my slots (a slot that holds no state is a branch
+        // of its own: node < 0, different for neighbours)
+        const int below = __shfl_up_sync(0xffffffffu, node[U - 1], 1);
+        const int above = __shfl_down_sync(0xffffffffu, node[0], 1);
+        headm = lastm = 0;
 #pragma unroll
-            for (int u = 0; u + 1 < U; u += 2) {
-                const int n31 = __shfl_sync(0xffffffffu, node[u], 31);
-                const int n0 = __shfl_sync(0xffffffffu, node[u + 1], 0);
-                const bool lng = (n31 >= 0) && (n31 == n0);
-                headl[u / 2] = lng && node[u] == n31;
-                contl[u / 2] = lng && node[u + 1] == n31;
-                wlong = wlong || lng;
-            }
+        for (int u = 0; u < U; u++) {
+            const int pn = (u == 0) ? (lane == 0 ? -100 : below) : node[u - 1];
+            const int nn = (u == U - 1) ? (lane == 31 ? -100 : above) : node[u + 1];
+            if (node[u] < 0 || pn != node[u]) headm |= 1u << u;
+            if (node[u] < 0 || nn != node[u]) lastm |= 1u << u;
+        }
+        constexpr unsigned FULL = (1u << U) - 1u;
+        prem = headm ? (((headm & (0u - headm)) - 1u) & FULL) : FULL;
+        postm = lastm ? (~((2u << (31 - __clz(lastm))) - 1u) & FULL) : FULL;
+        const unsigned hb = __ballot_sync(0xffffffffu, headm != 0);
+        const unsigned lb = __ballot_sync(0xffffffffu, lastm != 0);
+        const unsigned hbelow = hb & ((1u << lane) - 1u);
+        const unsigned labove = (lane == 31) ? 0u : (lb & (0xffffffffu << (lane + 1)));
+        // my first branch starts in lane L0 (its last head), my last one ends in
+        // lane L1 (its first `last`).  The carries are scans of one value per
+        // lane, shifted by one lane: the value of lane x sits in lane x + 1 (up)
+        // or x - 1 (down), so the valid range is [L0 + 1, me] / [me, L1 - 1]
+        const int L0 = hbelow ? (31 - __clz(hbelow)) : 0;
+        const int L1 = labove ? (__ffs(labove) - 1) : 31;
+        upok = dnok = 0;
+#pragma unroll
+        for (int l = 0; l < NLEV; l++) {
+            if (lane - (1 << l) >= L0 + 1) upok |= 1u << l;
+            if (lane + (1 << l) <= L1 - 1) dnok |= 1u << l;
         }
     };
 
@@ -663,83 +712,109 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         for (int u = 0; u < U; u++)
             awb_sts(zaddr[u], c[u]);
         awb_bar_sync(1, NB1);
+        // (nothing below may move in front of the barrier the scribes wait at --
+        // ptxas would hoist the register-only scans: they hang on a value, 0.0,
+        // loaded behind it)
+        const double zero = awb_lds(dummy_s + 16u);
 
-        // branch scans in registers while the F-scribes sum the rows.
-        // Exclusive sums PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a: the
-        // neighbour's term first, then an inclusive scan of those (an inclusive
-        // scan minus the own term cancels: h grows like exp(cumulative
-        // coalescent rate), so y0 can exceed the sum below it by many orders)
-        double W[U];
+        // branch sums in registers while the F-scribes sum the rows.
+        // Exclusive sums PY = sum_{a<b} x_a (h[a] - Bc), Q = sum_{a>b} x_a along
+        // the branch (exclusive by construction: an inclusive scan minus the own
+        // term cancels -- h grows like exp(cumulative coalescent rate), so a
+        // term can exceed the sum below it by many orders): first inside the
+        // lane, then one carry per lane and direction across the warp.
         double py[U], q[U], x0[U], y0[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            x0[u] = Da[u] * c[u];
-            y0[u] = H[u] * c[u];
-#ifdef AWB_K4_INCL
-            py[u] = y0[u];
-            q[u] = x0[u];
-#else
-            py[u] = awb_prev_in_seg(y0[u], cfirst[u]);
-            q[u] = awb_next_in_seg(x0[u], clast[u]);
-#endif
+            x0[u] = fma(Da[u], c[u], zero);
+            y0[u] = fma(H[u], c[u], zero);
         }
-#pragma unroll
-        for (int l = 0; l < NLEV; l++) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                py[u] = awb_scan_up(py[u], 1 << l, cfirst[u]);
-                q[u] = awb_scan_down(q[u], 1 << l, clast[u]);
+        py[0] = 0.0;
+        q[U - 1] = 0.0;
+        if constexpr (U == 2) {
+            py[1] = awb_sum_unless<2u>(py[0], y0[0], headm);
+            q[0] = awb_sum_unless<1u>(q[1], x0[1], lastm);
+        }
+        if constexpr (U == 4) {
+            py[1] = awb_sum_unless<2u>(py[0], y0[0], headm);
+            py[2] = awb_sum_unless<4u>(py[1], y0[1], headm);
+            py[3] = awb_sum_unless<8u>(py[2], y0[2], headm);
+            q[2] = awb_sum_unless<4u>(q[3], x0[3], lastm);
+            q[1] = awb_sum_unless<2u>(q[2], x0[2], lastm);
+            q[0] = awb_sum_unless<1u>(q[1], x0[1], lastm);
+        }
+        // vU: what my last branch has so far (for the lanes above), vD: what my
+        // first branch has from here up (for the lanes below); shifted by one
+        // lane (the end lanes receive their own value and never use it)
+        double vU = __shfl_up_sync(0xffffffffu, py[U - 1] + y0[U - 1], 1);
+        double vD = __shfl_down_sync(0xffffffffu, q[0] + x0[0], 1);
+        {
+            double t;
+#define AWB_CARRY_LEVEL(LV)                                                   \
+            if (NLEV > LV) {                                                  \
+                t = __shfl_up_sync(0xffffffffu, vU, 1 << LV);                 \
+                awb_add_if<(1u << LV)>(vU, t, upok);                          \
+                t = __shfl_down_sync(0xffffffffu, vD, 1 << LV);               \
+                awb_add_if<(1u << LV)>(vD, t, dnok);                          \
             }
+            AWB_CARRY_LEVEL(0)
+            AWB_CARRY_LEVEL(1)
+            AWB_CARRY_LEVEL(2)
+            AWB_CARRY_LEVEL(3)
+            AWB_CARRY_LEVEL(4)
+#undef AWB_CARRY_LEVEL
         }
-        if (U > 1 && wlong) {
-            // carries of a branch that runs from set u into set u+1
-#pragma unroll
-            for (int u = 0; u + 1 < U; u += 2) {
-                const double up = __shfl_sync(0xffffffffu, py[u] + y0[u], 31);
-                const double dn = __shfl_sync(0xffffffffu, q[u + 1] + x0[u + 1], 0);
-                if (contl[u / 2]) py[u + 1] += up;
-                if (headl[u / 2]) q[u] += dn;
-            }
+        awb_add_if<1u>(py[0], vU, prem);
+        awb_add_if<(1u << (U - 1))>(q[U - 1], vD, postm);
+        if constexpr (U == 2) {
+            awb_add_if<2u>(py[1], vU, prem);
+            awb_add_if<1u>(q[0], vD, postm);
         }
-#ifdef AWB_K4_INCL
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            py[u] -= y0[u];
-            q[u] -= x0[u];
+        if constexpr (U == 4) {
+            awb_add_if<2u>(py[1], vU, prem);
+            awb_add_if<4u>(py[2], vU, prem);
+            awb_add_if<8u>(py[3], vU, prem);
+            awb_add_if<4u>(q[2], vD, postm);
+            awb_add_if<2u>(q[1], vD, postm);
+            awb_add_if<1u>(q[0], vD, postm);
         }
-#endif
         const unsigned kd = kind_next;
         kind_next = *kp++;
-        double e[U];
+        // the lagged rescale factor every fourth site ((site & 3) == 2), the
+        // constant 1.0 otherwise: branch-free.  (The factor was published after
+        // barrier 2 of an earlier site: it can be read in front of this one.)
+        const bool resc = rcnt == 0;
+        const double sc = awb_lds(resc ? scale_s + sofs : dummy_s + 8u);
+        double W[U], e[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            W[u] = fma(A1[u], py[u], fma(c[u], A2[u], A3[u] * q[u]));
-            e[u] = inv_e[u];
+            const double2 a12 = awb_lds2(cA + 512u * u);
+            const double2 a3e = awb_lds2(cB + 512u * u);
+            W[u] = fma(a12.x, py[u], fma(c[u], a12.y, a3e.x * q[u]));
+            e[u] = a3e.y;
         }
         if (kd != AWB_SITE_INVARIANT) {             // uniform, ~3 % of the sites
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (kd == AWB_SITE_VARIANT)
-                    e[u] = live[u] ? *nxt[u] : inv_e[u];
+                    e[u] = live[u] ? *nxt[u] : e[u];
                 else
                     e[u] = active[u] ? 1.0 : 0.0;
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            e[u] *= sc;
         awb_bar_sync(2, NB2);
 
-        // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes.
-        // The lagged rescale factor every fourth site ((site & 3) == 2), the
-        // constant 1.0 otherwise: branch-free (a branch around a volatile load
-        // costs a branch resolution per warp and site)
-        const bool resc = rcnt == 0;
-        const double sc = awb_lds(resc ? scale_s + sofs : dummy_s + 8u);
+        // R[atime] = sum_a tm[a][atime] * F[a], formed by the F-scribes
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const double cn = (awb_lds(raddr[u] + rofs) + W[u]) * (e[u] * sc);
-            __stcs(nxt[u], cn);                 // streaming: L1 is for the block tables
+            const double cn = (awb_lds(raddr[u] + rofs) + W[u]) * e[u];
+            if (actm & (1u << u))
+                __stcs(nxt[u], cn);             // streaming: L1 is for the block tables
             c[u] = cn;
-            if (active[u])
-                nxt[u] = (double *) ((char *) nxt[u] + rowstep);
+            nxt[u] = (double *) ((char *) nxt[u] + rowstep);
         }
         sofs ^= resc ? 8u : 0u;
         rcnt = (rcnt + 1) & (AWB_FWD_RS - 1);
@@ -798,7 +873,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     double *w0 = rowb + jj[u];
                     double e = 1.0;
                     if (S > 0) {
-                        e = inv_e[u];
+                        e = awb_lds2(cB + 512u * u).y;
                         if (kd == AWB_SITE_VARIANT)
                             e = *w0;
                         else if (kd == AWB_SITE_MASKED)

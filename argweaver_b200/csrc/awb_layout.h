@@ -920,6 +920,7 @@ inline bool awb_layout_find(const AwbLayout &L, const char *name, size_t &off,
         { "fw", L.o_fw, (size_t) L.fw_off[L.B] * 8, false },
         { "path", L.o_path, (size_t) L.n * 4, false },
         { "fsum", L.o_fsum, (size_t) L.n * (T > 1 ? T - 1 : 1) * 8, false },
+        { "sink", L.o_sink, 1024 * 8, false },
         { "ent_off", L.o_ent_off, (B + 1) * 8, false },
         { "band_off", L.o_band_off, (B + 1) * 8, false },
     };
