@@ -413,10 +413,14 @@ extern "C" void awb_batch_destroy(awb_batch *b)
 // than 32 states (possible with more than 33 time points) needs U >= 2.
 struct FastShape {
     int tmax, U, NT, threads;
+    int bookw;          // 1: a warp of its own keeps the books (one window per SM)
     bool ok;
 };
 
-static FastShape batch_fast_shape(const awb_batch *b)
+// dense: more CTAs than SMs in the launch -- few warps per window, several
+// windows per SM; else: one window per SM, many warps per window (the per-site
+// chain is shorter with one state per thread)
+static FastShape batch_fast_shape(const awb_batch *b, bool dense = true)
 {
     FastShape f;
     const int Tm1 = b->maxT - 1;
@@ -427,15 +431,22 @@ static FastShape batch_fast_shape(const awb_batch *b)
         f.U = 2;
     else
         f.U = 4;
+    if (!dense) {
+        if (b->maxNS <= 512 && b->maxcnt <= 32)
+            f.U = 1;
+        else if (b->maxNS <= 1024)
+            f.U = 2;
+    }
     if (getenv("AWB_K4_U")) {
         const int u = atoi(getenv("AWB_K4_U"));
         if ((u == 1 && b->maxcnt <= 32 && b->maxNS <= 512) || u == 2 || u == 4)
             f.U = u;
     }
     f.NT = (b->maxNS + 32 * f.U - 1) / (32 * f.U) * 32;
-    f.threads = f.NT + AWB_FWD_HELPERS;
+    f.bookw = (dense || getenv("AWB_K4_NOBOOKW")) ? 0 : 1;
+    f.threads = f.NT + AWB_FWD_HELPERS + 32 * f.bookw;
     f.ok = !getenv("AWB_FORCE_GENERIC") && !b->lin_unsafe && b->maxcnt <= 64 &&
-        f.threads <= 576 &&
+        f.threads <= 608 &&
         awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap) <= 200 * 1024;
     return f;
 }
@@ -819,10 +830,24 @@ static int launch_emit(awb_batch *b, int seg, int pass)
 static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
 {
     cudaStream_t st = b->ctx->stream;
-    const FastShape f = batch_fast_shape(b);
+    const bool dense = (long long) b->C * nsub > b->ctx->sm_count;
+    FastShape f = batch_fast_shape(b, dense);
+    if (!f.ok)
+        f = batch_fast_shape(b);
     const int threads = f.threads;
     const size_t fsmem = awb_fwd_fast_smem_bytes(f.NT * f.U, f.tmax, b->zcap);
     const dim3 grid(b->C, nsub);
+    // CTAs per SM the register files allow (four files of 16 K registers, a
+    // CTA's warps dealt out over them)
+    int want = 1;
+    if (dense) {
+        const int regs = (threads <= 192 && f.U <= 2 || getenv("AWB_K4_LEAN")) ? 80 : 96;
+        for (want = 4; want > 1; want--)
+            if ((want * (threads / 32) + 3) / 4 * 32 * regs <= 16384)
+                break;
+    }
+    int carve = (int) (((fsmem + 1024) * want * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
     static bool said = false;
     const bool verbose = getenv("AWB_VERBOSE") && !said;
     said = said || verbose;
@@ -831,10 +856,10 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
         if (fsmem > 48 * 1024)                                                   \
             CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT, UU, MB>, \
                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));      \
-        /* several CTAs per SM: the whole shared-memory carve-out */            \
+        /* shared memory for the CTAs that are to share an SM, the rest of the  \
+           256 KB stays L1 (the kernel lives on its L1 prefetches) */            \
         CUDA_OK(cudaFuncSetAttribute(awb_forward_fast_kernel<TM, NL, MT, UU, MB>, \
-            cudaFuncAttributePreferredSharedMemoryCarveout,                      \
-            (int) cudaSharedmemCarveoutMaxShared));                              \
+            cudaFuncAttributePreferredSharedMemoryCarveout, carve));             \
         if (verbose) {                                                           \
             int nb = 0;                                                          \
             cudaFuncAttributes fa;                                               \
@@ -842,8 +867,8 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
                 awb_forward_fast_kernel<TM, NL, MT, UU, MB>, threads, fsmem);    \
             cudaFuncGetAttributes(&fa, awb_forward_fast_kernel<TM, NL, MT, UU, MB>); \
             fprintf(stderr, "forward kernel <%d,%d,%d,%d,%d>: %d threads, %zu B shared, " \
-                    "%d registers, %zu B local: %d CTAs per SM\n", TM, NL, MT, UU, MB, \
-                    threads, fsmem, fa.numRegs, (size_t) fa.localSizeBytes, nb); \
+                    "%d registers, %zu B local, carve-out %d %%: %d CTAs per SM\n", TM, NL, MT, UU, MB, \
+                    threads, fsmem, fa.numRegs, (size_t) fa.localSizeBytes, carve, nb); \
         }                                                                        \
         awb_forward_fast_kernel<TM, NL, MT, UU, MB><<<grid, threads, fsmem, st>>>( \
             b->d_chains, seg, pass, b->zcap);                                    \
@@ -859,19 +884,19 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
     const bool lean = getenv("AWB_K4_LEAN") != NULL;
 #define AWB_LAUNCH_FAST_T(TM, N1, N2, N4)                                        \
     do {                                                                         \
-        if (threads <= 192) {                                                    \
-            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 192, 1, 80);                   \
-            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 192, 2, 80);              \
-            else if (lean) AWB_LAUNCH_FAST(TM, N4, 192, 4, 80);                  \
-            else AWB_LAUNCH_FAST(TM, N4, 192, 4, 96);                            \
-        } else if (threads <= 320) {                                             \
-            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 320, 1, 96);                   \
-            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 320, 2, 96);              \
-            else AWB_LAUNCH_FAST(TM, N4, 320, 4, 96);                            \
+        if (f.bookw) {                                                           \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 1, 1, 96);                     \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 1, 2, 96);                \
+            else AWB_LAUNCH_FAST(TM, N4, 1, 4, 96);                              \
+        } else if (threads <= 192) {                                             \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 0, 1, 80);                     \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 0, 2, 80);                \
+            else if (lean) AWB_LAUNCH_FAST(TM, N4, 0, 4, 80);                    \
+            else AWB_LAUNCH_FAST(TM, N4, 0, 4, 96);                              \
         } else {                                                                 \
-            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 576, 1, 96);                   \
-            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 576, 2, 96);              \
-            else AWB_LAUNCH_FAST(TM, N4, 576, 4, 96);                            \
+            if (f.U == 1) AWB_LAUNCH_FAST(TM, N1, 0, 1, 96);                     \
+            else if (f.U == 2) AWB_LAUNCH_FAST(TM, N2, 0, 2, 96);                \
+            else AWB_LAUNCH_FAST(TM, N4, 0, 4, 96);                              \
         }                                                                        \
     } while (0)
     if (f.tmax == 20) AWB_LAUNCH_FAST_T(20, 5, 4, 3);

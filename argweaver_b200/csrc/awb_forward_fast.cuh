@@ -230,7 +230,9 @@ __device__ __forceinline__ void awb_bar_sync(int id, int count)
 // U: consecutive states per compute thread; MAXREG: registers per thread (what
 // lets the wanted number of CTAs share an SM -- __launch_bounds__'s own
 // arithmetic rounds 224 threads up to 256 and leaves registers unused)
-template <int TMAX, int NLEV, int MAXTHREADS, int U, int MAXREG>
+// BOOKW: 1 = a warp of its own keeps the books (one window per SM: the shortest
+// per-site chain), 0 = the second scribe warp does (6-warp CTAs, several per SM)
+template <int TMAX, int NLEV, int BOOKW, int U, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
 awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
 {
@@ -242,10 +244,10 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     seg -= (int) blockIdx.y;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int NT = blockDim.x - AWB_FWD_HELPERS;     // compute threads
+    const int NT = blockDim.x - AWB_FWD_HELPERS - 32 * BOOKW;     // compute threads
     const int NS = NT * U;                           // state slots
     const int NB1 = NT + AWB_FWD_FSCRIBES;           // barrier 1 participants
-    const int NB2 = NT + AWB_FWD_HELPERS;            // barrier 2 participants
+    const int NB2 = blockDim.x;                      // barrier 2 participants
     const int T = chg.model.ntimes;
     // the blocks / sites of this launch (checkpointed table: one segment)
     const AwbSeg g = awb_seg(chg, seg);
@@ -301,6 +303,167 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     const unsigned cst_s = (unsigned) __cvta_generic_to_shared(cstS);
     constexpr unsigned RSTR = (TMAX + 2) * 8;
 
+    // ---- who keeps the books: a warp of its own, or the second scribe warp
+    const bool bookkeeper = BOOKW ? (tid >= NB1) : (tid >= NT + 32);
+    // ---- bookkeeping state (second warp)
+    double lprod = 1.0, lacc = 0.0;
+    int nprod = 0;
+    double *__restrict__ fsumg = chg.fsum + g.fsoff;
+    int bad_site = -1;
+    // the emission rows of the variant sites a few sites ahead are
+    // prefetched into L1 (K3 left them in the table; a compute thread reads
+    // its entry right before it needs it).  Cursor (ab, ai) = block / offset
+    // of site + LA.
+    constexpr int LA = 6;
+    const unsigned char *__restrict__ kindn = chg.kind + g.site0;
+    const double *fwn = chg.fw - g.fwbias;
+    int ab = bbeg, ai = 0, ablen = (ab == bextra) ? 1 : blocklensg[ab];
+    int aS1 = 1;
+    long long arow = 0;
+    unsigned kahead = bookkeeper ? kindn[LA] : 0;
+    if (bookkeeper) {
+        for (int x = 0; x < LA && ab < bend; x++) {
+            if (++ai == ablen) {
+                ab++;
+                ai = 0;
+                ablen = (ab < bend) ? ((ab == bextra) ? 1 : blocklensg[ab]) : 0;
+            }
+        }
+        if (ab < bend) {
+            aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+            arow = chg.fw_off[ab] + (long long) ai * aS1;
+        }
+    }
+
+    // norm of column s (lane T-1's "R"), per-time sums, rescale factor, logZ
+    auto keep_books = [&](int s) {
+        const unsigned Fa_s = Fs_s + (s & 1) * RSTR + 8u * lane;
+        const double nrm = awb_lds(Rs_s + (s & 1) * RSTR + 8u * (unsigned) (T - 1));
+        // (T - 1 <= 63: at most two rows per lane)
+        // per-time sums of the column as it is stored (the traceback forms
+        // its row totals from these)
+        if (lane < T - 1)
+            __stcs(fsumg + (size_t) s * (T - 1) + lane, awb_lds(Fa_s));
+        if (lane + 32 < T - 1)
+            __stcs(fsumg + (size_t) s * (T - 1) + lane + 32, awb_lds(Fa_s + 256u));
+        if (!(nrm > 0.0) && bad_site < 0)
+            bad_site = s;
+#ifdef AWB_K4_DEBUG_NRM
+        if (lane == 0 && s < 64) chg.sink[s] = nrm;
+#endif
+        if ((s & (AWB_FWD_RS - 1)) == 0) {
+            // this factor is applied when column s+3 is formed
+            if (lane == 0)
+                awb_sts(scale_s + 8u * ((s / AWB_FWD_RS) & 1), 1.0 / nrm);
+            if (s + 3 <= n - 1) {
+                lprod *= nrm;
+                if (++nprod == 8) {
+                    lacc += log(lprod);
+                    lprod = 1.0;
+                    nprod = 0;
+                }
+            }
+        }
+        if (s == n - 1 && lane == 0) {
+            awb_sts(invl_s, 1.0 / nrm);
+            // (a segment that starts from a stored, normalised column adds
+            // the log-likelihood of its own sites; the recompute pass adds
+            // nothing)
+            const double lz = log(nrm) + log(lprod) + lacc;
+            if (pass == 0) {
+                if (seg <= 0 || !chg.ckpt) {
+                    chg.logz[0] = lz;
+                    chg.status[0] = bad_site < 0 ? -1 : g.site0 + bad_site;
+                } else {
+                    chg.logz[0] += lz;
+                    if (bad_site >= 0 && chg.status[0] < 0)
+                        chg.status[0] = g.site0 + bad_site;
+                }
+            }
+        }
+    };
+
+
+    auto prefetch_next_block = [&](int b) {
+        if (b + 1 < bend) {
+        const int nb = b + 1;
+        const long long r0n = chg.row_off[nb];
+        const long long S1n = chg.row_off[nb + 1] - r0n;
+        const long long tr0n = chg.trow_off[nb];
+        const long long e0n = chg.ent_off[nb];
+        const long long nen = chg.ent_off[nb + 1] - e0n;
+        // (one compact loop over the 16 tables: this code runs once per
+        // block, cold in the instruction cache, and inlined range by
+        // range it was several hundred instructions)
+        const void *pp[16];
+        long long pl[16];
+        pp[0] = chg.tmap + tr0n;      pl[0] = 2 * (chg.trow_off[nb + 1] - tr0n);
+        pp[1] = chg.st_node + r0n;    pl[1] = 2 * S1n;
+        pp[2] = chg.st_time + r0n;    pl[2] = S1n;
+        pp[3] = chg.st_age + r0n;     pl[3] = S1n;
+        pp[4] = chg.iperm + r0n;      pl[4] = 2 * S1n;
+        pp[5] = chg.inv_emit + r0n;   pl[5] = 8 * S1n;
+        pp[6] = chg.sw_start + r0n;   pl[6] = 2 * S1n;
+        pp[7] = chg.sw_cnt + r0n;     pl[7] = 2 * S1n;
+        pp[8] = chg.sw_src + e0n;     pl[8] = 2 * nen;
+        pp[9] = chg.sw_prob + e0n;    pl[9] = 8 * nen;
+        pp[10] = chg.lin + (size_t) nb * 7 * T;              pl[10] = 56ll * T;
+        pp[11] = chg.tmatrix + (size_t) nb * T * T;          pl[11] = 8ll * T * T;
+        pp[12] = chg.sc_start + (size_t) nb * AWB_NSCRIBE;   pl[12] = 2 * AWB_NSCRIBE;
+        pp[13] = chg.sc_cnt + (size_t) nb * AWB_NSCRIBE;     pl[13] = 2 * AWB_NSCRIBE;
+        pp[14] = chg.sc_row + (size_t) nb * AWB_NSCRIBE;     pl[14] = AWB_NSCRIBE;
+        pp[15] = chg.sc_stride + (size_t) nb * AWB_NSCRIBE;  pl[15] = AWB_NSCRIBE;
+#pragma unroll 1
+        for (int r = 0; r < 16; r++)
+            awb_prefetch_range(pp[r], pl[r], lane);
+        if (lane == 0) {
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.sc_ch + nb));
+        }
+    }
+    };
+
+    // emission rows LA sites ahead (the kind byte was loaded one site ago:
+    // nothing here waits for global memory)
+    auto look_ahead = [&](int site) {
+        const unsigned kcur = kahead;
+        kahead = kindn[site + 1 + LA];
+        if (ab < bend) {
+            if (kcur == AWB_SITE_VARIANT)
+                awb_prefetch_range(fwn + arow, 8ll * aS1, lane);
+            arow += aS1;
+            if (++ai == ablen) {
+                ab++;
+                ai = 0;
+                if (ab < bend) {
+                    ablen = (ab == bextra) ? 1 : blocklensg[ab];
+                    aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
+                    arow = chg.fw_off[ab];
+                }
+            }
+        }
+    };
+
+    if (BOOKW && tid >= NB1) {
+        // =================================================================
+        // bookkeeping warp: waits on barrier 2 only
+        // =================================================================
+        int site = 0;
+        for (int b = bbeg; b < bend; b++) {
+            const int blen = (b == bextra) ? 1 : blocklensg[b];
+            prefetch_next_block(b);
+            for (int i = 0; i < blen; i++, site++) {
+                look_ahead(site);
+                awb_bar_sync(2, NB2);
+                keep_books(site);
+            }
+        }
+        __syncthreads();                                   // final barrier
+        return;
+    }
+
     if (tid >= NT) {
         // =================================================================
         // F-scribes: per-time sums and R between barrier 1 and barrier 2; the
@@ -309,90 +472,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         // forms R, and warms the cache in its idle time
         // =================================================================
         const int sl = tid - NT;                         // scribe lane 0..63
-        const bool bookkeeper = sl >= 32;
         const double *__restrict__ tmatrixg = chg.tmatrix;
         const unsigned short *__restrict__ sc_startg = chg.sc_start;
         const unsigned short *__restrict__ sc_cntg = chg.sc_cnt;
         const unsigned char *__restrict__ sc_rowg = chg.sc_row;
         const unsigned char *__restrict__ sc_strideg = chg.sc_stride;
         const unsigned tml_s = tm_s + 16u * (unsigned) sl;      // my column, pair 0
-
-        // ---- bookkeeping state (second warp)
-        double lprod = 1.0, lacc = 0.0;
-        int nprod = 0;
-        double *__restrict__ fsumg = chg.fsum + g.fsoff;
-        int bad_site = -1;
-        // the emission rows of the variant sites a few sites ahead are
-        // prefetched into L1 (K3 left them in the table; a compute thread reads
-        // its entry right before it needs it).  Cursor (ab, ai) = block / offset
-        // of site + LA.
-        constexpr int LA = 6;
-        const unsigned char *__restrict__ kindn = chg.kind + g.site0;
-        const double *fwn = chg.fw - g.fwbias;
-        int ab = bbeg, ai = 0, ablen = (ab == bextra) ? 1 : blocklensg[ab];
-        int aS1 = 1;
-        long long arow = 0;
-        if (bookkeeper) {
-            for (int x = 0; x < LA && ab < bend; x++) {
-                if (++ai == ablen) {
-                    ab++;
-                    ai = 0;
-                    ablen = (ab < bend) ? ((ab == bextra) ? 1 : blocklensg[ab]) : 0;
-                }
-            }
-            if (ab < bend) {
-                aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
-                arow = chg.fw_off[ab] + (long long) ai * aS1;
-            }
-        }
-
-        // norm of column s (lane T-1's "R"), per-time sums, rescale factor, logZ
-        auto keep_books = [&](int s) {
-            const unsigned Fa_s = Fs_s + (s & 1) * RSTR + 8u * lane;
-            const double nrm = awb_lds(Rs_s + (s & 1) * RSTR + 8u * (unsigned) (T - 1));
-            // (T - 1 <= 63: at most two rows per lane)
-            // per-time sums of the column as it is stored (the traceback forms
-            // its row totals from these)
-            if (lane < T - 1)
-                __stcs(fsumg + (size_t) s * (T - 1) + lane, awb_lds(Fa_s));
-            if (lane + 32 < T - 1)
-                __stcs(fsumg + (size_t) s * (T - 1) + lane + 32, awb_lds(Fa_s + 256u));
-            if (!(nrm > 0.0) && bad_site < 0)
-                bad_site = s;
-#ifdef AWB_K4_DEBUG_NRM
-            if (lane == 0 && s < 64) chg.sink[s] = nrm;
-#endif
-            if ((s & (AWB_FWD_RS - 1)) == 0) {
-                // this factor is applied when column s+3 is formed
-                if (lane == 0)
-                    awb_sts(scale_s + 8u * ((s / AWB_FWD_RS) & 1), 1.0 / nrm);
-                if (s + 3 <= n - 1) {
-                    lprod *= nrm;
-                    if (++nprod == 8) {
-                        lacc += log(lprod);
-                        lprod = 1.0;
-                        nprod = 0;
-                    }
-                }
-            }
-            if (s == n - 1 && lane == 0) {
-                awb_sts(invl_s, 1.0 / nrm);
-                // (a segment that starts from a stored, normalised column adds
-                // the log-likelihood of its own sites; the recompute pass adds
-                // nothing)
-                const double lz = log(nrm) + log(lprod) + lacc;
-                if (pass == 0) {
-                    if (seg <= 0 || !chg.ckpt) {
-                        chg.logz[0] = lz;
-                        chg.status[0] = bad_site < 0 ? -1 : g.site0 + bad_site;
-                    } else {
-                        chg.logz[0] += lz;
-                        if (bad_site >= 0 && chg.status[0] < 0)
-                            chg.status[0] = g.site0 + bad_site;
-                    }
-                }
-            }
-        };
 
         int site = 0;
         for (int b = bbeg; b < bend; b++) {
@@ -433,66 +518,11 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     awb_sts2(tml_s + (unsigned) (a / 2) * (16u * AWB_NSCRIBE), t0, t1);
                 }
             }
-            // when a block starts, the per-block tables of the NEXT block (what
-            // load_compute, the switch gather and the scribes read in dependent
-            // chains at the block boundary) are prefetched into L1
-            if (bookkeeper && b + 1 < bend) {
-                const int nb = b + 1;
-                const long long r0n = chg.row_off[nb];
-                const long long S1n = chg.row_off[nb + 1] - r0n;
-                const long long tr0n = chg.trow_off[nb];
-                const long long e0n = chg.ent_off[nb];
-                const long long nen = chg.ent_off[nb + 1] - e0n;
-                // (one compact loop over the 16 tables: this code runs once per
-                // block, cold in the instruction cache, and inlined range by
-                // range it was several hundred instructions)
-                const void *pp[16];
-                long long pl[16];
-                pp[0] = chg.tmap + tr0n;      pl[0] = 2 * (chg.trow_off[nb + 1] - tr0n);
-                pp[1] = chg.st_node + r0n;    pl[1] = 2 * S1n;
-                pp[2] = chg.st_time + r0n;    pl[2] = S1n;
-                pp[3] = chg.st_age + r0n;     pl[3] = S1n;
-                pp[4] = chg.iperm + r0n;      pl[4] = 2 * S1n;
-                pp[5] = chg.inv_emit + r0n;   pl[5] = 8 * S1n;
-                pp[6] = chg.sw_start + r0n;   pl[6] = 2 * S1n;
-                pp[7] = chg.sw_cnt + r0n;     pl[7] = 2 * S1n;
-                pp[8] = chg.sw_src + e0n;     pl[8] = 2 * nen;
-                pp[9] = chg.sw_prob + e0n;    pl[9] = 8 * nen;
-                pp[10] = chg.lin + (size_t) nb * 7 * T;              pl[10] = 56ll * T;
-                pp[11] = chg.tmatrix + (size_t) nb * T * T;          pl[11] = 8ll * T * T;
-                pp[12] = chg.sc_start + (size_t) nb * AWB_NSCRIBE;   pl[12] = 2 * AWB_NSCRIBE;
-                pp[13] = chg.sc_cnt + (size_t) nb * AWB_NSCRIBE;     pl[13] = 2 * AWB_NSCRIBE;
-                pp[14] = chg.sc_row + (size_t) nb * AWB_NSCRIBE;     pl[14] = AWB_NSCRIBE;
-                pp[15] = chg.sc_stride + (size_t) nb * AWB_NSCRIBE;  pl[15] = AWB_NSCRIBE;
-#pragma unroll 1
-                for (int r = 0; r < 16; r++)
-                    awb_prefetch_range(pp[r], pl[r], lane);
-                if (lane == 0) {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(nstatesg + nb));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(blocklensg + nb));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.fw_off + nb));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(chg.sc_ch + nb));
-                }
-            }
+            if (bookkeeper)
+                prefetch_next_block(b);
 
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
-                if (bookkeeper && ab < bend) {
-                    // (idle time in front of barrier 1: the compute warps are
-                    // forming the column)
-                    if (kindn[site + LA] == AWB_SITE_VARIANT)
-                        awb_prefetch_range(fwn + arow, 8ll * aS1, lane);
-                    arow += aS1;
-                    if (++ai == ablen) {
-                        ab++;
-                        ai = 0;
-                        if (ab < bend) {
-                            ablen = (ab == bextra) ? 1 : blocklensg[ab];
-                            aS1 = nstatesg[ab] > 0 ? nstatesg[ab] : 1;
-                            arow = chg.fw_off[ab];
-                        }
-                    }
-                }
                 awb_bar_sync(1, NB1);
                 // each lane sums its CH slots of one (zero-padded) row; the lanes of
                 // a row combine with a segmented scan
@@ -535,8 +565,11 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 }
                 // the books of the PREVIOUS site (its norm and per-time sums stay
                 // in their buffers until the site after this one)
-                if (bookkeeper && site > 0)
-                    keep_books(site - 1);
+                if (bookkeeper) {
+                    if (site > 0)
+                        keep_books(site - 1);
+                    look_ahead(site);
+                }
                 awb_bar_sync(2, NB2);
             }
         }
@@ -569,6 +602,8 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
     unsigned zaddr[U], raddr[U];
     double Da[U], H[U];
     double c[U];
+    constexpr bool CREG = (U <= 2);        // few states per thread: all constants in registers
+    double A1r[CREG ? U : 1], A2r[CREG ? U : 1], A3r[CREG ? U : 1], ier[CREG ? U : 1];
     // the constants only needed after the scans stay in shared memory:
     // (A1, A2) at cA + 512 u, (A3, inv_emit) at cB + 512 u (16 bytes per lane)
     unsigned cA = cst_s + 16u * (unsigned) (warp * U * 32 + lane);
@@ -632,8 +667,12 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                 Da[u] = 0.0; H[u] = 0.0; A1 = 0.0; A3 = 0.0;
                 A2 = active[u] ? 1.0 : 0.0;
             }
-            awb_sts2(cA + 512u * u, A1, A2);
-            awb_sts2(cB + 512u * u, A3, inv_e);
+            if constexpr (CREG) {
+                A1r[u] = A1; A2r[u] = A2; A3r[u] = A3; ier[u] = inv_e;
+            } else {
+                awb_sts2(cA + 512u * u, A1, A2);
+                awb_sts2(cB + 512u * u, A3, inv_e);
+            }
         }
         // branch structure of my slots (a slot that holds no state is a branch
         // of its own: node < 0, different for neighbours)
@@ -788,10 +827,15 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
         double W[U], e[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const double2 a12 = awb_lds2(cA + 512u * u);
-            const double2 a3e = awb_lds2(cB + 512u * u);
-            W[u] = fma(a12.x, py[u], fma(c[u], a12.y, a3e.x * q[u]));
-            e[u] = a3e.y;
+            if constexpr (CREG) {
+                W[u] = fma(A1r[u], py[u], fma(c[u], A2r[u], A3r[u] * q[u]));
+                e[u] = ier[u];
+            } else {
+                const double2 a12 = awb_lds2(cA + 512u * u);
+                const double2 a3e = awb_lds2(cB + 512u * u);
+                W[u] = fma(a12.x, py[u], fma(c[u], a12.y, a3e.x * q[u]));
+                e[u] = a3e.y;
+            }
         }
         if (kd != AWB_SITE_INVARIANT) {             // uniform, ~3 % of the sites
 #pragma unroll
@@ -873,7 +917,10 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     double *w0 = rowb + jj[u];
                     double e = 1.0;
                     if (S > 0) {
-                        e = awb_lds2(cB + 512u * u).y;
+                        if constexpr (CREG)
+                            e = ier[u];
+                        else
+                            e = awb_lds2(cB + 512u * u).y;
                         if (kd == AWB_SITE_VARIANT)
                             e = *w0;
                         else if (kd == AWB_SITE_MASKED)
