@@ -265,6 +265,7 @@ struct awb_batch {
     size_t windows_bytes;        // arena bytes of the windows (before the chain records)
     bool with_band;              // the generic kernel's tables are part of the arena
     int nslots;                  // checkpointed table: segment tables per window
+    int nsub;                    //   ... and segments the second pass rebuilds at once
     bool bound;                  // batch_bind has run
     char *arena;
     size_t arena_bytes;
@@ -499,8 +500,10 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         std::vector<std::string> errs(nproblems);
         std::vector<char> ok(nproblems, 0);
         const int keep = (flags & AWB_KEEP_DEBUG) ? 1 : 0;
-        // checkpointed table: segments of at most 2^24 doubles (128 MiB) per problem
-        long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 24) : 0;
+        // checkpointed table: segments of at most 2^23 doubles (64 MiB) per problem
+        // (small enough for half a dozen tables per window next to the per-block
+        // tables, so that the second pass can rebuild three segments at once)
+        long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 23) : 0;
         if (seg_cap && getenv("AWB_SEG_DOUBLES"))
             seg_cap = atoll(getenv("AWB_SEG_DOUBLES"));
         unsigned hw = std::thread::hardware_concurrency();
@@ -562,6 +565,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
     b->windows_bytes = 0;
     b->nslots = 1;
+    b->nsub = 1;
     b->bound = false;
     if (getenv("AWB_VERBOSE"))
         fprintf(stderr, "awb_batch_create: layout %.1f ms\n",
@@ -619,6 +623,8 @@ static int batch_bind(awb_batch *b)
         }
         b->windows_bytes = total;
         b->nslots = nslots;
+        b->nsub = nslots >= 7 ? 4 : (nslots >= 5 ? 3 : (nslots >= 3 ? 2 : 1));
+        if (getenv("AWB_NO_PAIRS")) b->nsub = 1;
         // chain records and the error word live at the tail of the arena
         chains_off = total;
         total += awb_align(sizeof(AwbChain) * nproblems);
@@ -1107,15 +1113,19 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         // same forward pass: the rebuilt segments have taken turns in table 0,
         // which is also the first resident one, so every table is rebuilt)
         const int pass = b->tables_stale ? 2 : 1;
-        // With three or more tables per window two consecutive segments are
-        // rebuilt side by side (independent chains: each starts from its own
-        // stored column), which puts two CTAs on every SM; the traceback then
-        // walks through them in order.  Never across the boundary of the
-        // resident segments of the longest window, whose tables are still in use.
-        const bool pairs = b->nslots >= 3 && !getenv("AWB_NO_PAIRS");
+        // With three or more tables per window consecutive segments are rebuilt
+        // side by side (independent chains: each starts from its own stored
+        // column), which puts several CTAs on every SM; the traceback then walks
+        // through them in order.  Never across the boundary of the resident
+        // segments of the longest window, whose tables are still in use.
+        const int G = b->nsub;
         for (int s = b->maxseg - 1; s >= 0;) {
             const bool res_s = s >= b->maxseg - b->nslots;
-            const int nsub = (pairs && !res_s && s >= 1) ? 2 : 1;
+            int nsub = 1;
+            if (!res_s && G > 1) {
+                // groups are aligned on multiples of G (tables go by s mod G)
+                nsub = s % G + 1;
+            }
             for (int y = 0; y < nsub; y++)
                 if (launch_emit(b, s - y, pass))
                     return 1;

@@ -634,7 +634,7 @@ def bench_b200(a, rank, world, local_rank):
                 "table_gb_per_gpu": fw_bytes / 1e9,
                 "parallelism": "windows sharded across GPUs, one CTA per window",
                 "forward_kernel": fast_path,
-                "table": ("checkpointed: %d segments of <= 128 MiB per window, "
+                "table": ("checkpointed: %d segments of <= 64 MiB per window, "
                           "%d segment tables kept per window (all the device "
                           "memory allows); the traceback rebuilds the other "
                           "%d segments (forward recursion runs %.2f times per "

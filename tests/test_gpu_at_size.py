@@ -2,7 +2,7 @@
 unmodified arghmm_forward_alg + stochastic_traceback, sample_thread.cpp:394-460,
 522-569) on the BASELINE shapes: forward rows within 1e-9 relative, sampled
 paths identical for the same libc rand() draws, for the whole-table mode and
-for the checkpointed table with its default 128 MiB segments -- the path the
+for the checkpointed table with its default 64 MiB segments -- the path the
 benchmark runs.  logZ (which the reference does not compute) is checked against
 the pinned C oracle."""
 

@@ -309,7 +309,7 @@ def test_checkpointed_batch_with_given_prior_and_last_state(libc_rand, monkeypat
 @pytest.mark.parametrize("resident", ["1", "3"])
 def test_checkpointed_equals_whole_table_at_size(resident, libc_rand, monkeypatch):
     """BASELINE config 3 shape (k=50, T=20), 3e5 sites, leaf and subtree
-    threading: the checkpointed table (several 128 MiB segments, 1 or 3 of them
+    threading: the checkpointed table (several 64 MiB segments, 1 or 3 of them
     resident) gives the same paths and logZ as the whole table."""
     monkeypatch.setenv("AWB_RESIDENT_SEGS", resident)
     n = 300000
