@@ -96,6 +96,10 @@ def lib():
         L.awb_sites_mapping.argtypes = [C.c_void_p]
         L.awb_sites_compress.argtypes = [C.c_void_p, C.c_int]
         L.awb_sites_to_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.awb_batch_kernel_times.argtypes = [C.c_void_p, C.c_int]
+        L.awb_batch_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p,
+                                                 C.POINTER(C.c_double),
+                                                 C.POINTER(C.c_int)]
         L.awb_libc_rand_snapshot.argtypes = [C.c_void_p]
         L.awb_libc_rand_advance.argtypes = [C.c_longlong]
         L.awb_libc_rand_advance.restype = None
@@ -340,6 +344,27 @@ class Batch(object):
         _check(lib().awb_batch_timings(self.h, C.byref(a), C.byref(b),
                                        C.byref(c)))
         return dict(setup_ms=a.value, forward_ms=b.value, traceback_ms=c.value)
+
+    KERNEL_CLASSES = ("kind", "block_setup", "tmatrix", "switch_setup", "emit",
+                      "forward", "traceback", "recomb")
+
+    def kernel_times(self, enable=True):
+        """Start (and reset) per-kernel device timing (CUDA events around every
+        launch on the batch's stream)."""
+        _check(lib().awb_batch_kernel_times(self.h, 1 if enable else 0))
+        return self
+
+    def get_kernel_times(self):
+        """dict kernel class -> ms since kernel_times(), plus 'forward_bytes'
+        (algorithmic bytes of the forward launches) and 'forward_launches'."""
+        ms = np.zeros(len(self.KERNEL_CLASSES), np.float32)
+        fb, fl = C.c_double(), C.c_int()
+        _check(lib().awb_batch_get_kernel_times(self.h, ms.ctypes.data,
+                                                C.byref(fb), C.byref(fl)))
+        out = {k: float(v) for k, v in zip(self.KERNEL_CLASSES, ms)}
+        out["forward_bytes"] = fb.value
+        out["forward_launches"] = fl.value
+        return out
 
     # ---- results
     def path(self, i=0, out=None):

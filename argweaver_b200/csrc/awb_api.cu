@@ -66,6 +66,24 @@ extern "C" int awb_device_count(void)
     return n;
 }
 
+// Host threads for the layout / staging work of one batch: the machine's cores
+// shared out over the ranks of this node (torchrun's LOCAL_WORLD_SIZE: eight
+// ranks that each spawn a thread per core oversubscribe the host eightfold);
+// AWB_HOST_THREADS overrides.
+static int host_threads(int nwork)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = hw ? (int) hw : 1;
+    const char *lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 1)
+        n = (n + atoi(lws) - 1) / atoi(lws);
+    const char *env = getenv("AWB_HOST_THREADS");
+    if (env && atoi(env) > 0)
+        n = atoi(env);
+    if (n > nwork) n = nwork;
+    return n < 1 ? 1 : n;
+}
+
 // ---------------------------------------------------------------- kernels
 
 __global__ void awb_kind_kernel(const AwbChain *chains)
@@ -293,6 +311,42 @@ struct awb_batch {
     int *d_rec_info, *d_rng;
     std::vector<long long> rec_off;
     bool recombs_done;
+    // per-kernel device times (awb_batch_kernel_times): event pairs around the
+    // launches of each kernel class, summed when they are read
+    bool ktimes;
+    std::vector<cudaEvent_t> kev;      // start, stop, start, stop, ...
+    std::vector<int> kclass;
+    size_t kev_used;
+    double k4_bytes;                   // algorithmic bytes of the forward launches
+    int k4_launches;
+};
+
+enum { AWB_K_KIND = 0, AWB_K_BLOCK, AWB_K_TMATRIX, AWB_K_SWITCH, AWB_K_EMIT,
+       AWB_K_FORWARD, AWB_K_TRACEBACK, AWB_K_RECOMB, AWB_K_NCLASS };
+
+// brackets one launch (or a run of launches of one class) with events
+struct KTimer {
+    awb_batch *b;
+    bool on;
+    KTimer(awb_batch *b_, int cls) : b(b_), on(b_->ktimes) {
+        if (!on) return;
+        if (b->kev_used + 2 > b->kev.size()) {
+            cudaEvent_t e0, e1;
+            if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+                on = false;
+                return;
+            }
+            b->kev.push_back(e0);
+            b->kev.push_back(e1);
+        }
+        b->kclass.push_back(cls);
+        cudaEventRecord(b->kev[b->kev_used], b->ctx->stream);
+    }
+    ~KTimer() {
+        if (!on) return;
+        cudaEventRecord(b->kev[b->kev_used + 1], b->ctx->stream);
+        b->kev_used += 2;
+    }
 };
 
 extern "C" int awb_ctx_create(int device, awb_ctx **out)
@@ -400,6 +454,8 @@ extern "C" void awb_batch_destroy(awb_batch *b)
         else
             cudaFree(b->arena);
     }
+    for (size_t i = 0; i < b->kev.size(); i++)
+        cudaEventDestroy(b->kev[i]);
     if (b->d_rec) cudaFree(b->d_rec);
     if (b->d_rec_off) cudaFree(b->d_rec_off);
     if (b->d_rec_info) cudaFree(b->d_rec_info);
@@ -493,6 +549,10 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->d_rec_off = NULL;
     b->d_rec_info = b->d_rng = NULL;
     b->recombs_done = false;
+    b->ktimes = false;
+    b->kev_used = 0;
+    b->k4_bytes = 0;
+    b->k4_launches = 0;
 
     const auto t_create0 = std::chrono::steady_clock::now();
     // host layout of every problem (integer work), one host thread per problem
@@ -506,8 +566,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
         long long seg_cap = (flags & AWB_CHECKPOINT) ? (1ll << 23) : 0;
         if (seg_cap && getenv("AWB_SEG_DOUBLES"))
             seg_cap = atoll(getenv("AWB_SEG_DOUBLES"));
-        unsigned hw = std::thread::hardware_concurrency();
-        const int nthreads = (int) std::min<unsigned>(hw ? hw : 1, (unsigned) nproblems);
+        const int nthreads = host_threads(nproblems);
         auto work = [&](int t) {
             for (int c = t; c < nproblems; c += nthreads)
                 ok[c] = awb_layout_build(problems[c], keep, b->L[c], errs[c],
@@ -690,8 +749,7 @@ static int batch_bind(awb_batch *b)
                 cudaGetLastError();     // no staging: the copies work without it
         }
         if (ctx->stage) {
-            unsigned hw = std::thread::hardware_concurrency();
-            const int nthreads = (int) std::min<unsigned>(hw ? hw : 1, (unsigned) nproblems);
+            const int nthreads = host_threads(nproblems);
             auto work = [&](int t) {
                 for (int c = t; c < nproblems; c += nthreads) {
                     char *dst = ctx->stage + soff[c];
@@ -825,6 +883,7 @@ static int launch_emit(awb_batch *b, int seg, int pass)
     if (b->ckpt && gx * b->C > cap)
         gx = (cap + b->C - 1) / b->C;
     dim3 grid(gx, b->C);
+    KTimer kt(b, AWB_K_EMIT);
     awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
         b->d_chains, scratch, seg, pass);
     b->launches++;
@@ -905,6 +964,32 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
             else AWB_LAUNCH_FAST(TM, N4, 0, 4, 96);                              \
         }                                                                        \
     } while (0)
+    if (b->ktimes) {
+        // algorithmic bytes of this launch: 8 B per site*state of the segments
+        // it computes
+        for (int c = 0; c < b->C; c++) {
+            const AwbLayout &L = b->L[c];
+            for (int y = 0; y < nsub; y++) {
+                const int sg = seg - y;
+                long long d0, d1;
+                if (!b->ckpt) {
+                    if (y > 0) continue;
+                    d0 = 0;
+                    d1 = L.fw_off[L.B];
+                } else {
+                    if (sg < 0 || sg >= L.nseg) continue;
+                    const int R = b->nslots < L.nseg ? b->nslots : L.nseg;
+                    if (pass == 1 && sg >= L.nseg - R) continue;     // still resident
+                    const int b0 = L.seg_start[sg], b1 = L.seg_start[sg + 1];
+                    d0 = L.fw_off[b0];
+                    d1 = L.fw_off[b1] + (b1 < L.B ? (L.nstates[b1] > 0 ? L.nstates[b1] : 1) : 0);
+                }
+                b->k4_bytes += 8.0 * (double) (d1 - d0);
+            }
+        }
+        b->k4_launches++;
+    }
+    KTimer kt(b, AWB_K_FORWARD);
     if (f.tmax == 20) AWB_LAUNCH_FAST_T(20, 5, 4, 3);
     else if (f.tmax == 40) AWB_LAUNCH_FAST_T(40, 5, 5, 4);
     else AWB_LAUNCH_FAST_T(64, 5, 5, 4);
@@ -928,6 +1013,7 @@ static int launch_traceback(awb_batch *b, int rand_max, int seg)
         awb_traceback_kernel<NV, SPW, VPT><<<b->C, AWB_TB_THREADS, smem, st>>>( \
             b->d_chains, rand_max, maxS1, b->maxT, maxent, seg, \
             b->lin_unsafe ? 1 : 0); } while (0)
+    KTimer kt(b, AWB_K_TRACEBACK);
     if (maxS1 <= 128) AWB_LAUNCH_TB(4, 2, 1);
     else if (maxS1 <= 256) AWB_LAUNCH_TB(8, 2, 1);
     else if (maxS1 <= 512) AWB_LAUNCH_TB(16, 2, 1);
@@ -960,12 +1046,17 @@ extern "C" int awb_batch_setup(awb_batch *b)
         const int Cg = g1 - g0;
         {
             dim3 grid((b->maxB + 63) / 64, Cg);
-            awb_block_setup_kernel<<<grid, 64, 0, st>>>(chains, b->d_err);
+            {
+                KTimer kt(b, AWB_K_BLOCK);
+                awb_block_setup_kernel<<<grid, 64, 0, st>>>(chains, b->d_err);
+            }
             dim3 grid2(b->maxB, Cg);
+            KTimer kt(b, AWB_K_TMATRIX);
             awb_tmatrix_kernel<<<grid2, 128, 0, st>>>(chains);
         }
         if (b->maxB > 1) {
             dim3 grid((b->maxB - 1 + wpc - 1) / wpc, Cg);
+            KTimer kt(b, AWB_K_SWITCH);
             awb_switch_setup_kernel<<<grid, 32 * wpc, (size_t) wpc * sw_scratch, st>>>(
                 chains, b->d_err, sw_scratch);
         }
@@ -975,6 +1066,7 @@ extern "C" int awb_batch_setup(awb_batch *b)
         CUDA_OK(cudaStreamWaitEvent(st, b->ctx->seq_ev, 0));
         dim3 grid((b->maxn + 255) / 256, b->C);
         if (grid.x > 4096) grid.x = 4096;
+        KTimer kt(b, AWB_K_KIND);
         awb_kind_kernel<<<grid, 256, 0, st>>>(b->d_chains);
         if (b->any_packed) {
             dim3 grid2((b->maxnvar + 255) / 256, b->C);
@@ -1192,6 +1284,36 @@ extern "C" int awb_batch_timings(awb_batch *b, float *setup_ms, float *forward_m
     return 0;
 }
 
+extern "C" int awb_batch_kernel_times(awb_batch *b, int enable)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    b->ktimes = enable != 0;
+    b->kev_used = 0;
+    b->kclass.clear();
+    b->k4_bytes = 0;
+    b->k4_launches = 0;
+    return 0;
+}
+
+extern "C" int awb_batch_get_kernel_times(awb_batch *b, float *ms, double *forward_bytes,
+                                          int *forward_launches)
+{
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    for (int k = 0; k < AWB_K_NCLASS; k++)
+        ms[k] = 0;
+    for (size_t i = 0; i < b->kclass.size(); i++) {
+        float v = 0;
+        if (cudaEventElapsedTime(&v, b->kev[2 * i], b->kev[2 * i + 1]) == cudaSuccess)
+            ms[b->kclass[i]] += v;
+    }
+    cudaGetLastError();
+    if (forward_bytes) *forward_bytes = b->k4_bytes;
+    if (forward_launches) *forward_launches = b->k4_launches;
+    return 0;
+}
+
 extern "C" double awb_batch_states_sites(const awb_batch *b, int i)
 {
     return b->L[i].states_sites;
@@ -1392,8 +1514,11 @@ extern "C" int awb_batch_sample_recombs(awb_batch *b, const int *rng_states,
     }
     CUDA_OK(cudaMemcpyAsync(b->d_rng, rng_states, sizeof(int) * AWB_RNG_WORDS * b->C,
                             cudaMemcpyHostToDevice, st));
-    awb_recomb_kernel<<<b->C, 32, 0, st>>>(b->d_chains, b->d_rng, rand_max, b->d_rec,
-                                           b->d_rec_off, b->d_rec_info);
+    {
+        KTimer kt(b, AWB_K_RECOMB);
+        awb_recomb_kernel<<<b->C, 32, 0, st>>>(b->d_chains, b->d_rng, rand_max, b->d_rec,
+                                               b->d_rec_off, b->d_rec_info);
+    }
     CUDA_OK(cudaGetLastError());
     // (rng_states and rec_off may be pageable: the copies above must not outlive them)
     CUDA_OK(cudaStreamSynchronize(st));

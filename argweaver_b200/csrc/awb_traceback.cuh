@@ -30,7 +30,8 @@
 // that chain: the per-block tables (transition vectors, the time-by-time
 // matrix, per-state node/time/age, the switch CSR of the block and the last
 // forward row of the block before it) are copied into shared memory with
-// cp.async ONE BLOCK AHEAD, double buffered; the block scalars are fetched two
+// cp.async.bulk (one instruction per table, completion counted in bytes by an
+// mbarrier) ONE BLOCK AHEAD, double buffered; the block scalars are fetched two
 // blocks ahead; the forward rows of the next block's first wave are prefetched
 // into L2; and a warp issues all loads of its rows before it consumes any.
 #ifndef AWB_TRACEBACK_CUH
@@ -97,20 +98,23 @@ struct AwbTbBuf {
 
 __host__ __device__ inline AwbTbBuf awb_tb_buf_layout(int maxS1, int maxT, int maxent)
 {
+    // every array starts on a 16-byte boundary and keeps the source's offset
+    // within a 16-byte line (the bulk copies move whole aligned lines): slack
+    // for that offset and for the rounded-up tail
     AwbTbBuf L;
     unsigned o = 0;
-    L.tv = o;   o += (unsigned) (AWB_TM_NVEC * maxT) * 8u;
-    L.tm = o;   o += (unsigned) (maxT * maxT) * 8u;
-    L.last = o; o += (unsigned) maxS1 * 8u;
-    L.ep = o;   o += (unsigned) (maxent + 1) * 8u;
-    // 16-/8-bit arrays keep the source's offset within a 4-byte word (cp.async
-    // moves aligned words), hence the slack
-    L.es = o;   o += (((unsigned) maxent * 2u + 8u) + 7u) & ~7u;
-    L.sws = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
-    L.swc = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
-    L.stn = o;  o += (((unsigned) maxS1 * 2u + 8u) + 7u) & ~7u;
-    L.stt = o;  o += (((unsigned) maxS1 + 8u) + 7u) & ~7u;
-    L.sta = o;  o += (((unsigned) maxS1 + 8u) + 7u) & ~7u;
+#define AWB_TB_SLOT(name, bytes) do { L.name = o; o += (((unsigned) (bytes)) + 32u + 15u) & ~15u; } while (0)
+    AWB_TB_SLOT(tv, (AWB_TM_NVEC * maxT) * 8);
+    AWB_TB_SLOT(tm, (maxT * maxT) * 8);
+    AWB_TB_SLOT(last, maxS1 * 8);
+    AWB_TB_SLOT(ep, (maxent + 1) * 8);
+    AWB_TB_SLOT(es, maxent * 2);
+    AWB_TB_SLOT(sws, maxS1 * 2);
+    AWB_TB_SLOT(swc, maxS1 * 2);
+    AWB_TB_SLOT(stn, maxS1 * 2);
+    AWB_TB_SLOT(stt, maxS1);
+    AWB_TB_SLOT(sta, maxS1);
+#undef AWB_TB_SLOT
     L.bytes = (o + 15u) & ~15u;
     return L;
 }
@@ -127,35 +131,52 @@ __host__ __device__ inline size_t awb_tb_smem_bytes(int maxS1, int maxT, int max
     return n + 16;
 }
 
-__device__ __forceinline__ void awb_cp_async4(unsigned dst, const void *src)
+// ---- bulk asynchronous copies (cp.async.bulk, the non-tensor form of TMA) with
+// an mbarrier that counts the bytes: one thread issues one instruction per
+// table instead of 512 threads issuing 4- and 8-byte cp.async each.
+__device__ __forceinline__ void awb_mbar_init(unsigned bar, unsigned count)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src)
-                 : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void awb_cp_async8(unsigned dst, const void *src)
+__device__ __forceinline__ void awb_mbar_expect_tx(unsigned bar, unsigned bytes)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src)
-                 : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(bar), "r"(bytes) : "memory");
 }
 
-// copy n doubles (8-byte aligned source)
-__device__ inline void awb_tb_copy8(unsigned dst, const double *src, int n)
+__device__ __forceinline__ void awb_mbar_wait(unsigned bar, unsigned parity)
 {
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        awb_cp_async8(dst + 8u * (unsigned) i, src + i);
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "AWB_MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra AWB_MBAR_DONE;\n\t"
+                 "bra AWB_MBAR_WAIT;\n\t"
+                 "AWB_MBAR_DONE:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
 }
 
-// copy nbytes from an arbitrarily aligned source as aligned 4-byte words;
-// element 0 lands at dst + (src & 3).  Returns that skew.
-__device__ inline unsigned awb_tb_copy_bytes(unsigned dst, const void *src, int nbytes)
+__device__ __forceinline__ void awb_bulk_g2s(unsigned dst, const void *src, unsigned bytes,
+                                             unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// One table: the aligned 16-byte lines that hold [src, src + nbytes).  Element 0
+// lands at dst + (src & 15); returns that skew.  issue: this thread sends it.
+__device__ __forceinline__ unsigned awb_tb_bulk(unsigned dst, const void *src, int nbytes,
+                                                unsigned bar, bool issue, unsigned &total)
 {
     const unsigned long long a = (unsigned long long) src;
-    const unsigned skew = (unsigned) (a & 3ull);
-    const char *base = (const char *) (a - skew);
-    const int nw = (int) ((skew + (unsigned) nbytes + 3u) >> 2);
-    for (int i = threadIdx.x; i < nw; i += blockDim.x)
-        awb_cp_async4(dst + 4u * (unsigned) i, base + 4 * i);
+    const unsigned skew = (unsigned) (a & 15ull);
+    if (nbytes > 0) {
+        const unsigned n = (skew + (unsigned) nbytes + 15u) & ~15u;
+        if (issue)
+            awb_bulk_g2s(dst, (const void *) (a - skew), n, bar);
+        total += n;
+    }
     return skew;
 }
 
@@ -271,33 +292,66 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     unsigned short *swJ = (unsigned short *) (swA + (maxent + 1));
     const unsigned smem_s = (unsigned) __cvta_generic_to_shared(tb_smem);
 
-    // skews of the 16-/8-bit arrays of each buffer (source alignment)
+    // offset of element 0 of every array of each buffer within its 16-byte line
+    // (source alignment)
     unsigned sk_es[2], sk_sws[2], sk_swc[2], sk_stn[2], sk_stt[2], sk_sta[2];
+    unsigned sk_tv[2], sk_tm[2], sk_last[2], sk_ep[2];
+    // one mbarrier per buffer: thread 0 announces the bytes of a block's tables
+    // and sends the copies, everybody waits on the phase
+    __shared__ __align__(8) unsigned long long tb_mbar[2];
+    const unsigned mbar_s = (unsigned) __cvta_generic_to_shared(tb_mbar);
+    unsigned phase[2] = { 0u, 0u };
+    if (tid == 0) {
+        awb_mbar_init(mbar_s, 1);
+        awb_mbar_init(mbar_s + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    // issue the asynchronous copy of block bb's tables into buffer q
+    // issue the asynchronous copy of block bb's tables into buffer q (two
+    // rounds: the byte count goes to the barrier before the first copy starts)
     auto preload = [&](const AwbTbBlk &m, int bb, int q) {
         const unsigned base = smem_s + (unsigned) q * BL.bytes;
+        const unsigned bar = mbar_s + 8u * (unsigned) q;
         sk_es[q] = sk_sws[q] = sk_swc[q] = sk_stn[q] = sk_stt[q] = sk_sta[q] = 0;
-        if (bb < bmin)
-            return;
-        if (m.S > 0) {
-            if (closed_form)
-                awb_tb_copy8(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
-                             AWB_TM_NVEC * T);
-            else
-                awb_tb_copy8(base + BL.tv, ling + (size_t) bb * 7 * T, 7 * T);
-            awb_tb_copy8(base + BL.tm, tmatrixg + (size_t) bb * T * T, T * T);
-            sk_stn[q] = awb_tb_copy_bytes(base + BL.stn, st_nodeg + m.r0, 2 * m.S);
-            sk_stt[q] = awb_tb_copy_bytes(base + BL.stt, st_timeg + m.r0, m.S);
-            sk_sta[q] = awb_tb_copy_bytes(base + BL.sta, st_ageg + m.r0, m.S);
+        sk_tv[q] = sk_tm[q] = sk_last[q] = sk_ep[q] = 0;
+#pragma unroll 1
+        for (int round = 0; round < 2; round++) {
+            const bool issue = (round == 1) && tid == 0;
+            unsigned total = 0;
+            if (bb >= bmin && m.S > 0) {
+                if (closed_form)
+                    sk_tv[q] = awb_tb_bulk(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
+                                           8 * AWB_TM_NVEC * T, bar, issue, total);
+                else
+                    sk_tv[q] = awb_tb_bulk(base + BL.tv, ling + (size_t) bb * 7 * T,
+                                           8 * 7 * T, bar, issue, total);
+                sk_tm[q] = awb_tb_bulk(base + BL.tm, tmatrixg + (size_t) bb * T * T,
+                                       8 * T * T, bar, issue, total);
+                sk_stn[q] = awb_tb_bulk(base + BL.stn, st_nodeg + m.r0, 2 * m.S, bar, issue, total);
+                sk_stt[q] = awb_tb_bulk(base + BL.stt, st_timeg + m.r0, m.S, bar, issue, total);
+                sk_sta[q] = awb_tb_bulk(base + BL.sta, st_ageg + m.r0, m.S, bar, issue, total);
+            }
+            if (bb > bmin) {
+                sk_last[q] = awb_tb_bulk(base + BL.last, fwg + m.fwoff - m.n1(), 8 * m.n1(),
+                                         bar, issue, total);
+                sk_ep[q] = awb_tb_bulk(base + BL.ep, sw_probg + m.entoff, 8 * m.nent(),
+                                       bar, issue, total);
+                sk_es[q] = awb_tb_bulk(base + BL.es, sw_srcg + m.entoff, 2 * m.nent(),
+                                       bar, issue, total);
+                sk_sws[q] = awb_tb_bulk(base + BL.sws, sw_startg + m.r0, 2 * m.S1(),
+                                        bar, issue, total);
+                sk_swc[q] = awb_tb_bulk(base + BL.swc, sw_cntg + m.r0, 2 * m.S1(),
+                                        bar, issue, total);
+            }
+            if (round == 0 && tid == 0)
+                awb_mbar_expect_tx(bar, total);
         }
-        if (bb > bmin) {
-            awb_tb_copy8(base + BL.last, fwg + m.fwoff - m.n1(), m.n1());
-            awb_tb_copy8(base + BL.ep, sw_probg + m.entoff, m.nent());
-            sk_es[q] = awb_tb_copy_bytes(base + BL.es, sw_srcg + m.entoff, 2 * m.nent());
-            sk_sws[q] = awb_tb_copy_bytes(base + BL.sws, sw_startg + m.r0, 2 * m.S1());
-            sk_swc[q] = awb_tb_copy_bytes(base + BL.swc, sw_cntg + m.r0, 2 * m.S1());
-        }
+    };
+    // wait until buffer q's tables have landed
+    auto landed = [&](int q) {
+        awb_mbar_wait(mbar_s + 8u * (unsigned) q, phase[q]);
+        phase[q] ^= 1u;
     };
     // forward rows of the first wave of block m into L2
     auto prefetch_rows = [&](const AwbTbBlk &m) {
@@ -324,7 +378,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         sm.failmask[2] = 0;
     }
     preload(mC, btop, btop & 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- last column (sample_thread.cpp:534-539)
     {
@@ -346,7 +399,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         if (tid == 0 && !g.extra)
             pathg[n - 1] = k;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    landed(btop & 1);
     __syncthreads();
 
     int par = 0;
@@ -354,7 +407,6 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         const int q = b & 1;
         // ---- one block ahead: tables of block b-1; two ahead: scalars of b-2
         preload(mN, b - 1, q ^ 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
         const AwbTbBlk mNN = awb_tb_blk(P, b - 2, bmin, bextra);
         if (b > bmin)
             prefetch_rows(mN);
@@ -364,8 +416,8 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         // draw of the switch step, fetched now so that it is there when needed
         const int r_sw = (b > bmin) ? randg[roff - (pos - 1)] : 0;
         const unsigned char *bp = bufp[q];
-        const double *linS = (const double *) (bp + BL.tv);   // lin[7][T] (K1)
-        const double *tmS = (const double *) (bp + BL.tm);
+        const double *linS = (const double *) (bp + BL.tv + sk_tv[q]);   // lin[7][T] (K1)
+        const double *tmS = (const double *) (bp + BL.tm + sk_tm[q]);
         const short *stN = (const short *) (bp + BL.stn + sk_stn[q]);
         const signed char *stT = (const signed char *) (bp + BL.stt + sk_stt[q]);
         const signed char *stA = (const signed char *) (bp + BL.sta + sk_sta[q]);
@@ -559,14 +611,14 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         if (b > bmin) {
             if (tid == 0) {
                 const int n1 = mC.n1();
-                const double *col1 = (const double *) (bp + BL.last);
+                const double *col1 = (const double *) (bp + BL.last + sk_last[q]);
                 const unsigned short *sws = (const unsigned short *) (bp + BL.sws + sk_sws[q]);
                 const unsigned short *swc = (const unsigned short *) (bp + BL.swc + sk_swc[q]);
                 const int st = sws[k];
                 const int cn = swc[k];
                 const unsigned short *es =
                     (const unsigned short *) (bp + BL.es + sk_es[q]) + st;
-                const double *ep = (const double *) (bp + BL.ep) + st;
+                const double *ep = (const double *) (bp + BL.ep + sk_ep[q]) + st;
                 // entries sorted by source index = the order sample() walks A[]
                 for (int x = 0; x < cn; x++) {
                     const unsigned short jj = es[x];
@@ -603,7 +655,7 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         }
 
         // ---- the tables of block b-1 have landed; everyone is done with buffer q
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        landed(q ^ 1);
         __syncthreads();
         mC = mN;
         mN = mNN;

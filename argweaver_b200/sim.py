@@ -148,6 +148,23 @@ def simulate_problem(k, nsites, ntimes=20, maxtime=200e3, popsize=1e4,
     return d
 
 
+def pack_problem(d):
+    """The same problem with its alignment given as variant columns only
+    (awb_problem.var_pos / var_cols, the form a .sites file holds): every column
+    in which the sequences differ, or which is masked ('N').  The other columns
+    read 'A' in every row, as make_sequences_from_sites fills them
+    (sequences.cpp:323-352); under Jukes-Cantor an invariant column has the same
+    likelihood whatever its base."""
+    seqs = np.asarray(d["seqs"])
+    var = np.nonzero((seqs != seqs[0]).any(axis=0) | (seqs[0] == ord("N")))[0]
+    q = {k: v for k, v in d.items() if k != "seqs"}
+    q["var_pos"] = var.astype(np.int32)
+    q["var_cols"] = np.ascontiguousarray(seqs[:, var].T)
+    q["nseqs"] = np.int32(seqs.shape[0])
+    q["seqlen"] = np.int32(seqs.shape[1])
+    return q
+
+
 def write_sites(filename, seqs, compress=10, chrom="chr", names=None):
     """Write the variant columns of `seqs` as a reference .sites file
     (sequences.cpp:136-158): compressed site i sits at bp i*compress+1."""

@@ -59,17 +59,19 @@ UNIT = "sites*states/s"
 REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
 
 # BASELINE.json configs[i-1].  `windows`: independent windows per GPU (0: one per
-# SM with the checkpointed table); `total_windows`: fixed number shared out over
+# SM with the checkpointed table; 592 = four per SM for the small shapes, whose
+# forward kernel is a 6-warp CTA; 48 = what fits for config 4's 2.8 GB of
+# per-block tables per window); `total_windows`: fixed number shared out over
 # the ranks (strong scaling).
 CONFIGS = {
-    1: dict(k=8, sites=10000, ntimes=20, windows=148, checkpoint=0,
+    1: dict(k=8, sites=10000, ntimes=20, windows=592, checkpoint=0,
             name="config1: arg-sim -k 8 -L 100000 -N 10000 -r 1.6e-8 -m 1.8e-8, "
                  "--ntimes 20 --maxtime 200e3 -c 10 (README quick start)"),
-    2: dict(k=20, sites=100000, ntimes=20, windows=148, checkpoint=0,
+    2: dict(k=20, sites=100000, ntimes=20, windows=592, checkpoint=0,
             name="config2: k=20, L=1 Mb, ntimes=20, c=10: full-thread resampling"),
     3: dict(k=50, sites=1000000, ntimes=20, windows=148, checkpoint=1,
             name="config3: arg-sim k=50, L=10 Mb, ntimes=20, maxtime=200e3, c=10"),
-    4: dict(k=100, sites=1000000, ntimes=40, windows=12, checkpoint=0,
+    4: dict(k=100, sites=1000000, ntimes=40, windows=48, checkpoint=1,
             name="config4: k=100, L=10 Mb, ntimes=40, c=10: large state space"),
     5: dict(k=50, sites=1000000, ntimes=20, total_windows=8, checkpoint=0,
             name="config5: arg-sample-genome, k=50, 8 independent 10 Mb windows "
@@ -96,6 +98,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-seqs", action="store_true",
+                    help="upload dense character rows instead of the variant "
+                         "columns only (the .sites form)")
     ap.add_argument("--mcmc-iters", type=int, default=-1,
                     help="iterations of the arg-sample pair (metric ii); default: "
                          "100 for config 1, 3 for config 2, none otherwise; 0: skip")
@@ -469,7 +474,13 @@ def bench_b200(a, rank, world, local_rank):
         # the simulator's SPRs keep node indices stable, i.e. the default node
         # mapping (identity except the broken node): not passed, made on device
         d.pop("mappings", None)
-        for key in ("seqs", "ptrees", "ages", "sprs", "blocklens"):
+        if not a.dense_seqs:
+            # the alignment as its variant columns (what a .sites file holds)
+            d = sim.pack_problem(d)
+        for key in ("seqs", "var_pos", "var_cols", "ptrees", "ages", "sprs",
+                    "blocklens"):
+            if key not in d:
+                continue
             d[key], t = pinned_like(np.ascontiguousarray(d[key]))
             keep.append(t)
         r = np.random.RandomState(seed).randint(0, 2**31 - 1, a.sites)
@@ -515,7 +526,9 @@ def bench_b200(a, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    ktimes = None
     if W > 0:
+        batch.kernel_times(True)   # CUDA events around every launch, on its stream
         ctx.record(0)
         for _ in range(a.steps):
             step()
@@ -528,6 +541,7 @@ def bench_b200(a, rank, world, local_rank):
     clocks = sampler.stop()
     if W > 0:
         ms_local = ctx.elapsed_ms(0, 1) / a.steps
+        ktimes = batch.get_kernel_times()
         launches = (batch.kernel_launches() - launches0) // max(a.steps, 1)
         if a.steps > 8:
             stage = batch.timings()
@@ -588,6 +602,10 @@ def bench_b200(a, rank, world, local_rank):
     ss = shard.all_sum(ss_local, d_)
     fwd_ms = shard.all_max(stage["forward_ms"], d_)
     fw_bytes_all = shard.all_sum(fw_bytes, d_)
+    # the forward kernel's own launches (both passes of a checkpointed table):
+    # slowest rank's kernel time, bytes summed over the ranks
+    k4_ms = shard.all_max(ktimes["forward"] / a.steps if ktimes else 0.0, d_)
+    k4_bytes_all = shard.all_sum(ktimes["forward_bytes"] / a.steps if ktimes else 0.0, d_)
     e2e_ms = shard.all_max(e2e_ms_local, d_) if e2e_ms_local is not None else None
     h2d_all = shard.all_sum(float(h2d), d_)
     d2h_all = shard.all_sum(float(d2h), d_)
@@ -603,8 +621,10 @@ def bench_b200(a, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else \
             "fallback 6650 GB/s (B200_PROFILING.md)"
-        # per GPU: the slowest rank's forward stage over its share of the bytes
-        achieved = (fw_bytes_all / world) / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+        # per GPU: the forward kernel's launches of one step (timed with CUDA
+        # events around each launch on its stream) over the bytes they computed
+        achieved = (k4_bytes_all / world) / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+        k4_n = ktimes["forward_launches"] // max(a.steps, 1) if ktimes else 0
         # DRAM traffic of the same kernel: NOT measured in this run -- taken
         # from the committed ncu capture of the same configuration, if any
         traffic, traffic_src = None, None
@@ -664,11 +684,17 @@ def bench_b200(a, rank, world, local_rank):
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": fw_bytes,
-                "note": "8 B per site*state (FP64 forward-table store) over the "
-                        "forward stage of the step (per-segment emission + forward "
-                        "kernels); with the checkpointed table the traceback stage "
-                        "runs the same kernels once more"},
+                "launches_per_step": k4_n,
+                "kernel_ms_per_step": k4_ms,
+                "algorithmic_bytes_per_step": k4_bytes_all / world,
+                "algorithmic_bytes_per_launch": (k4_bytes_all / world / k4_n) if k4_n else None,
+                "note": "8 B per site*state (FP64 forward-table store) that the "
+                        "forward kernel's launches of one step computed (first pass "
+                        "and, with the checkpointed table, the segments the second "
+                        "pass rebuilds), over the summed duration of those "
+                        "launches, CUDA events around each launch"},
+            "kernel_ms": None if not ktimes else {
+                k2: ktimes[k2] / a.steps for k2 in api.Batch.KERNEL_CLASSES},
             "logz_mean": float(np.mean(logz_all)),
         }
         if world == 1 and not a.no_cpu_baseline:

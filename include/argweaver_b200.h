@@ -195,6 +195,18 @@ int awb_thread_sample_cond(const awb_problem *p, const double *prior,
 int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
                       double *logz);
 
+/* Device time per kernel class, measured with CUDA events around every launch on
+ * the batch's stream (bench.py's roofline figure).  awb_batch_kernel_times(b, 1)
+ * starts (and resets) the collection; awb_batch_get_kernel_times sums what has
+ * been launched since: ms[AWB_KERNEL_CLASSES] in the order kind, block setup,
+ * time matrices, switch setup, emission, forward, traceback, recombination;
+ * forward_bytes = algorithmic bytes of the forward launches (8 B per site*state
+ * they computed). */
+#define AWB_KERNEL_CLASSES 8
+int awb_batch_kernel_times(awb_batch *b, int enable);
+int awb_batch_get_kernel_times(awb_batch *b, float *ms, double *forward_bytes,
+                               int *forward_launches);
+
 /* Recombination points of the sampled thread, the step right after the
  * traceback (sample_recombinations, recomb.cpp:151-235, with
  * recomb_prob_unnormalized :14-117 and get_possible_recomb :122-141), on the
