@@ -96,6 +96,8 @@ def lib():
         L.awb_sites_mapping.argtypes = [C.c_void_p]
         L.awb_sites_compress.argtypes = [C.c_void_p, C.c_int]
         L.awb_sites_to_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.awb_batch_phase_probs.argtypes = [C.c_void_p]
+        L.awb_batch_get_phase_probs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.awb_batch_kernel_times.argtypes = [C.c_void_p, C.c_int]
         L.awb_batch_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p,
                                                  C.POINTER(C.c_double),
@@ -278,6 +280,18 @@ class Batch(object):
             ls = self._ls.ctypes.data
         _check(lib().awb_batch_traceback(self.h, ra, int(rand_max), ls))
         return self
+
+    def phase_probs(self):
+        """Unphased data: evaluate P(phasing as given | sampled state) at the
+        heterozygous sites (after traceback)."""
+        _check(lib().awb_batch_phase_probs(self.h))
+        return self
+
+    def get_phase_probs(self, i=0):
+        """[nsites] doubles, -1 where the unphased individual is not heterozygous."""
+        out = np.empty(self.nsites(i), np.float64)
+        _check(lib().awb_batch_get_phase_probs(self.h, i, out.ctypes.data))
+        return out
 
     def sample_recombs(self, rng_states, rand_max=RAND_MAX):
         """Recombination points of the sampled paths (sample_recombinations,

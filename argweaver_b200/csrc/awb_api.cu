@@ -228,6 +228,75 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     }
 }
 
+// Unphased data, after the traceback: one warp per site range, like the emission
+// kernel; for every heterozygous variant site the two phasings are evaluated at
+// the sampled state alone.  out[site] = e1 / (e1 + e2), -1 elsewhere.
+__global__ void awb_phase_kernel(const AwbChain *chains, int scratch_bytes, double *out,
+                                 const long long *out_off)
+{
+    extern __shared__ unsigned char emit_smem[];
+    const AwbChain &ch = chains[blockIdx.y];
+    const int wpc = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int V = ch.nnodes;
+    unsigned char *scratch = emit_smem + (size_t) warp * scratch_bytes;
+    int *sparent = (int *) (scratch + ((awb_emit_scratch_bytes(V) + 15) & ~(size_t) 15));
+    int *sage = sparent + V;
+    short *sc0 = (short *) (sage + V);
+    short *sc1 = sc0 + V;
+    short *sorder = sc1 + V;
+    short *slstart = sorder + V;        // [V + 2]
+    int staged = -1;
+    double *o = out + out_off[blockIdx.y];
+    const int first = 0, last = ch.nsites;
+    const int nw = gridDim.x * wpc;
+    const int per = (((last - first) + nw - 1) / nw + 31) & ~31;
+    const int w0 = first + (blockIdx.x * wpc + warp) * per;
+    const int w1 = w0 + per < last ? w0 + per : last;
+    int b = -1;
+    for (int base = w0; base < w1; base += 32) {
+      const int mine = base + lane;
+      if (mine < w1)
+          o[mine] = -1.0;
+      unsigned vm = __ballot_sync(0xffffffffu, mine < w1 &&
+                                  ch.kind[mine] == AWB_SITE_VARIANT);
+      while (vm) {
+        const int i = base + __ffs(vm) - 1;
+        vm &= vm - 1;
+        if (!awb_site_het(ch, i))
+            continue;
+        if (b < 0)
+            b = awb_find_block(ch, i);
+        else
+            while (ch.block_start[b + 1] <= i)
+                b++;
+        if (ch.nstates[b] == 0)
+            continue;
+        if (b != staged) {
+            const size_t ob = (size_t) b * V;
+            __syncwarp();
+            for (int x = lane; x < V; x += 32) {
+                sparent[x] = ch.ptrees[ob + x];
+                sage[x] = ch.ages[ob + x];
+                sc0[x] = ch.child0[ob + x];
+                sc1[x] = ch.child1[ob + x];
+                sorder[x] = ch.order[ob + x];
+            }
+            for (int x = lane; x < V + 2; x += 32)
+                slstart[x] = ch.lstart[(size_t) b * (V + 2) + x];
+            staged = b;
+            __syncwarp();
+        }
+        const double pr = awb_phase_prob(ch, i, b, ch.path[i], lane, 32, scratch, sparent,
+                                         sage, sc0, sc1, sorder, slstart);
+        __syncwarp();
+        if (lane == 0)
+            o[i] = pr;
+      }
+    }
+}
+
 // one warp per window (awb_recomb.cuh)
 __global__ void awb_recomb_kernel(const AwbChain *chains, const int *rng_states,
                                   int rand_max, int *out, const long long *out_off,
@@ -309,6 +378,9 @@ struct awb_batch {
     int *d_rec;
     long long *d_rec_off;
     int *d_rec_info, *d_rng;
+    double *d_phase;             // awb_batch_phase_probs: [sum of nsites]
+    long long *d_phase_off;
+    std::vector<long long> phase_off;
     std::vector<long long> rec_off;
     bool recombs_done;
     // per-kernel device times (awb_batch_kernel_times): event pairs around the
@@ -460,6 +532,8 @@ extern "C" void awb_batch_destroy(awb_batch *b)
     if (b->d_rec_off) cudaFree(b->d_rec_off);
     if (b->d_rec_info) cudaFree(b->d_rec_info);
     if (b->d_rng) cudaFree(b->d_rng);
+    if (b->d_phase) cudaFree(b->d_phase);
+    if (b->d_phase_off) cudaFree(b->d_phase_off);
     delete b;
 }
 
@@ -549,6 +623,8 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->d_rec_off = NULL;
     b->d_rec_info = b->d_rng = NULL;
     b->recombs_done = false;
+    b->d_phase = NULL;
+    b->d_phase_off = NULL;
     b->ktimes = false;
     b->kev_used = 0;
     b->k4_bytes = 0;
@@ -1439,6 +1515,55 @@ extern "C" int64_t awb_batch_debug_bytes(awb_batch *b, int i, const char *name)
     if (!awb_layout_find(b->L[i], name, off, bytes))
         return -1;
     return (int64_t) bytes;
+}
+
+// ---------------------------------------------------------------- phase probabilities
+
+extern "C" int awb_batch_phase_probs(awb_batch *b)
+{
+    if (!b->forward_done || !b->rand_in_use)
+        return fail("awb_batch_phase_probs: the traceback has not run");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (!b->d_phase) {
+        b->phase_off.assign(b->C + 1, 0);
+        for (int c = 0; c < b->C; c++)
+            b->phase_off[c + 1] = b->phase_off[c] + b->L[c].n;
+        CUDA_OK(cudaMalloc((void **) &b->d_phase, sizeof(double) * (size_t) b->phase_off[b->C]));
+        CUDA_OK(cudaMalloc((void **) &b->d_phase_off, sizeof(long long) * (b->C + 1)));
+        CUDA_OK(cudaMemcpyAsync(b->d_phase_off, b->phase_off.data(),
+                                sizeof(long long) * (b->C + 1), cudaMemcpyHostToDevice, st));
+    }
+    const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
+                               (((size_t) b->maxV * 16 + 4 + 15) & ~(size_t) 15));
+    int wpc = 8;
+    while (wpc > 1 && (size_t) wpc * scratch > 160 * 1024)
+        wpc >>= 1;
+    if ((size_t) wpc * scratch > 200 * 1024)
+        return fail("tree too large for the emission kernel's shared memory");
+    int gx = (b->maxn + 32 * wpc - 1) / (32 * wpc);
+    const int cap = b->ctx->sm_count * 16;
+    if (gx * b->C > cap) gx = (cap + b->C - 1) / b->C;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, b->C);
+    CUDA_OK(cudaFuncSetAttribute(awb_phase_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    awb_phase_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
+        b->d_chains, scratch, b->d_phase, b->d_phase_off);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    b->launches++;
+    return 0;
+}
+
+extern "C" int awb_batch_get_phase_probs(awb_batch *b, int i, double *p)
+{
+    if (!b->d_phase) return fail("awb_batch_get_phase_probs: nothing computed");
+    CUDA_OK(cudaSetDevice(b->ctx->device));
+    CUDA_OK(cudaMemcpyAsync(p, b->d_phase + b->phase_off[i], sizeof(double) * b->L[i].n,
+                            cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
 }
 
 // ---------------------------------------------------------------- recombination points

@@ -69,6 +69,7 @@ struct AwbChain {
     // [seg_start[s], seg_start[s+1]) plus the first row of the next block);
     // ckptcol[s] is the stored first column of segment s (s >= 1)
     int ckpt, nseg;
+    int phase_row1, phase_row2;   // unphased individual: its two rows (leaf order; -1: off)
     int nsub;                 // segments rebuilt side by side by the second pass (1..4)
     int nslots;               // segment tables in fw / fsum (the last nslots segments
                               //   of the forward pass stay resident for the traceback)

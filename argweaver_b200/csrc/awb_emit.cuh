@@ -1,5 +1,6 @@
-// awb_emit.cuh -- emissions of the threading HMM (reference emit.cpp:650-845,
-// phased, no infinite-sites penalty).
+// awb_emit.cuh -- emissions of the threading HMM (reference emit.cpp:650-869),
+// with the infinite-sites penalty (:457-589, :848-862) and the integration
+// over the two phasings of one individual (:705-742, :834-842).
 //
 // Invariant sites (~97 % of compressed sites) share one per-state constant per
 // block (inv_emit, computed by awb_block_setup); masked sites emit 1.  Only
@@ -99,19 +100,25 @@ AWB_HD inline int awb_lanes_or(int x)
 // tree arrays of block b: parent/age (int), child0/child1/order (short).  The
 // CUDA kernel stages them in shared memory (the pruning loops walk them with
 // dependent accesses); the host emulation passes the global arrays.
-AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
-                                 int nlanes, unsigned char *scratch,
-                                 const int *parent, const int *age,
-                                 const short *c0, const short *c1,
-                                 const short *order, const short *lstart,
-                                 long long fwbias = 0)
+// swap: the rows of the two haplotypes of the unphased individual change
+// places (the other phasing of a heterozygous site).  only_state >= 0: evaluate
+// that state alone and return its emission (all lanes); nothing is stored.
+AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int lane,
+                                         int nlanes, unsigned char *scratch,
+                                         const int *parent, const int *age,
+                                         const short *c0, const short *c1,
+                                         const short *order, const short *lstart,
+                                         long long fwbias, int swap, int only_state)
 {
     const AwbModel &m = ch.model;
     const int V = ch.nnodes;
     const int T = m.ntimes;
     const int S = ch.nstates[b];
     if (S == 0)
-        return;                         // emit.cpp:665-669
+        return 1.0;                     // emit.cpp:665-669
+    // row of the alignment that leaf j (or the new leaf, j = nrows - 1) reads
+    const int pr1 = swap ? ch.phase_row1 : -1, pr2 = swap ? ch.phase_row2 : -1;
+#define AWB_ROW_OF(j) ch.rowidx[(j) == pr1 ? pr2 : ((j) == pr2 ? pr1 : (j))]
     const bool internal = ch.internal != 0;
     const int root = ch.root[b];
     const int maintree_root = internal ? c1[root] : root;
@@ -141,7 +148,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         nomut[j] = nomu_j;
         inmain[j] = 0;
         if (c0[j] == -1)
-            awb_leaf_row(awb_seq_at(ch, ch.rowidx[j], col, vc), inner + 4 * j);
+            awb_leaf_row(awb_seq_at(ch, AWB_ROW_OF(j), col, vc), inner + 4 * j);
     }
     AWB_LANESYNC();
 
@@ -226,7 +233,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                 const int j = order[q0 + idx];
                 if (c0[j] == -1) {
                     sets[j] = (unsigned char)
-                        awb_base_bit(awb_seq_at(ch, ch.rowidx[j], col, vc));
+                        awb_base_bit(awb_seq_at(ch, AWB_ROW_OF(j), col, vc));
                 } else {
                     const int l = sets[c0[j]], r = sets[c1[j]];
                     sets[j] = (unsigned char) ((l & r) ? (l & r) : (l | r));
@@ -246,7 +253,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         if (internal) {
             cset = sets[subtree_root];
         } else {
-            cset = awb_base_bit(awb_seq_at(ch, ch.rowidx[ch.nrows - 1], col, vc));
+            cset = awb_base_bit(awb_seq_at(ch, AWB_ROW_OF(ch.nrows - 1), col, vc));
             subset = cset;
         }
         // distinct bases on the two sides: the lineage can go anywhere
@@ -276,7 +283,7 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
         for (int x = 0; x < 4; x++)
             in2[x] = inner[4 * subtree_root + x];
     } else {
-        awb_leaf_row(awb_seq_at(ch, ch.rowidx[ch.nrows - 1], col, vc), in2);
+        awb_leaf_row(awb_seq_at(ch, AWB_ROW_OF(ch.nrows - 1), col, vc), in2);
     }
     // branch of the threaded lineage below the coalescence point: from the
     // subtree root's time (internal) or from time 0.0 (external) up to the
@@ -288,7 +295,10 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
     const long long row0 = ch.row_off[b];
     double *out = ch.fw + (ch.fw_off[b] - fwbias) +
         (long long) (i - ch.block_start[b]) * S;
-    for (int k = lane; k < S; k += nlanes) {
+    double ret = 0.0;
+    const int kbeg = only_state >= 0 ? only_state : lane;
+    const int kend = only_state >= 0 ? only_state + 1 : S;
+    for (int k = kbeg; k < kend; k += nlanes) {
         const int node2 = ch.st_node[row0 + k];
         const int p = parent[node2];
         const int bt = ch.st_time[row0 + k];
@@ -328,8 +338,59 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
             if (!valid)
                 emit *= ch.infsites_penalty;
         }
-        out[k] = emit;
+        if (only_state >= 0)
+            ret = emit;
+        else if (swap)
+            out[k] = (out[k] + emit) * 0.5;     // emit.cpp:840-841
+        else
+            out[k] = emit;
     }
+#undef AWB_ROW_OF
+    return ret;
+}
+
+// is site i heterozygous in the unphased individual (emit.cpp:716-717)?
+AWB_HD inline bool awb_site_het(const AwbChain &ch, int i)
+{
+    if (ch.phase_row1 < 0 || ch.phase_row2 < 0)
+        return false;
+    const size_t col = (size_t) ch.start_coord + i;
+    const int vc = ch.seqs ? -1 : awb_var_find(ch, (long long) col);
+    return awb_seq_at(ch, ch.rowidx[ch.phase_row1], col, vc) !=
+        awb_seq_at(ch, ch.rowidx[ch.phase_row2], col, vc);
+}
+
+AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
+                                 int nlanes, unsigned char *scratch,
+                                 const int *parent, const int *age,
+                                 const short *c0, const short *c1,
+                                 const short *order, const short *lstart,
+                                 long long fwbias = 0)
+{
+    awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age, c0, c1, order,
+                        lstart, fwbias, 0, -1);
+    if (awb_site_het(ch, i)) {
+        // the other phasing; the row becomes the mean of the two
+        AWB_LANESYNC();
+        awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age, c0, c1, order,
+                            lstart, fwbias, 1, -1);
+    }
+}
+
+// P(the data's phasing | state) at a heterozygous site: e1 / (e1 + e2), what
+// calc_emissions hands to PhaseProbs::add (emit.cpp:838-839)
+AWB_HD inline double awb_phase_prob(const AwbChain &ch, int i, int b, int state, int lane,
+                                    int nlanes, unsigned char *scratch,
+                                    const int *parent, const int *age,
+                                    const short *c0, const short *c1,
+                                    const short *order, const short *lstart)
+{
+    const double e1 = awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age,
+                                          c0, c1, order, lstart, 0, 0, state);
+    AWB_LANESYNC();
+    const double e2 = awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age,
+                                          c0, c1, order, lstart, 0, 1, state);
+    return e1 / (e1 + e2);
 }
 
 #endif // AWB_EMIT_CUH

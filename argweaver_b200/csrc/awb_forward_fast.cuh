@@ -456,6 +456,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             prefetch_next_block(b);
             for (int i = 0; i < blen; i++, site++) {
                 look_ahead(site);
+                __syncwarp();
                 awb_bar_sync(2, NB2);
                 keep_books(site);
             }
@@ -520,6 +521,9 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
             }
             if (bookkeeper)
                 prefetch_next_block(b);
+            // (the per-block code above diverges, and bar.sync is an aligned
+            // barrier: every lane of the warp has to arrive together)
+            __syncwarp();
 
             for (int i = 0; i < blen; i++, site++) {
                 const unsigned Fp_s = Fs_s + (site & 1) * RSTR;
@@ -934,6 +938,7 @@ awb_forward_fast_kernel(const AwbChain *chains, int seg, int pass, int zcap)
                     nxt[u] = sink;
                 }
             }
+            __syncwarp();       // (the gather above diverges)
         }
     }
 

@@ -409,6 +409,18 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             }
     }
     if (p.nleaves != (V + 1) / 2) { err = "nleaves != (nnodes+1)/2"; return false; }
+    if (p.unphased) {
+        const int nr = p.nleaves + (p.internal ? 0 : 1);
+        if (p.phase_row1 < 0 || p.phase_row1 >= nr || p.phase_row2 < 0 ||
+            p.phase_row2 >= nr || p.phase_row1 == p.phase_row2) {
+            err = "phase_row1 / phase_row2 must be two different rows of the leaf order";
+            return false;
+        }
+        if (p.infsites_penalty > 0.0 && p.infsites_penalty < 1.0) {
+            err = "unphased emissions are not combined with the infinite-sites penalty";
+            return false;
+        }
+    }
     for (int i = 0; i + 1 < T; i++)
         if (!(p.times[i + 1] > p.times[i])) { err = "times must increase"; return false; }
     L.B = B; L.V = V; L.T = T;
@@ -801,6 +813,11 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
         AWB_P(const int *, var_pos, o_varpos);
     } else {
         AWB_P(const unsigned char *, seqs, o_seqs);
+    }
+    ch.phase_row1 = ch.phase_row2 = -1;
+    if (p.unphased) {
+        ch.phase_row1 = p.phase_row1;
+        ch.phase_row2 = p.phase_row2;
     }
     ch.default_char = p.default_char ? p.default_char : 'A';
     ch.infsites_penalty = (p.infsites_penalty > 0.0 && p.infsites_penalty < 1.0) ?

@@ -23,6 +23,7 @@ class AwbProblem(C.Structure):
         ("subtree_roots", _c_int_p),
         ("nvar", C.c_int), ("var_pos", _c_int_p), ("var_cols", _c_u8_p),
         ("default_char", C.c_ubyte), ("infsites_penalty", C.c_double),
+        ("unphased", C.c_int), ("phase_row1", C.c_int), ("phase_row2", C.c_int),
     ]
 
 
@@ -56,6 +57,11 @@ def normalize(d):
     else:
         q["seqs"] = np.ascontiguousarray(d["seqs"], np.uint8)
     q["infsites_penalty"] = float(_scalar(d, "infsites_penalty", 0.0))
+    # unphased individual: its two rows in the leaf order, or None
+    q["phase_rows"] = None
+    if d.get("phase_rows") is not None:
+        pr = np.asarray(d["phase_rows"]).reshape(-1)
+        q["phase_rows"] = (int(pr[0]), int(pr[1]))
     q["seqids"] = np.ascontiguousarray(d["seqids"], np.int32)
     q["new_chrom"] = int(_scalar(d, "new_chrom"))
     q["internal"] = int(_scalar(d, "internal"))
@@ -115,6 +121,9 @@ def make_problem(d):
         p.var_pos = q["var_pos"].ctypes.data_as(_c_int_p)
         p.var_cols = q["var_cols"].ctypes.data_as(_c_u8_p)
     p.infsites_penalty = q["infsites_penalty"]
+    if q["phase_rows"] is not None:
+        p.unphased = 1
+        p.phase_row1, p.phase_row2 = q["phase_rows"]
     p.nleaves = len(q["seqids"])
     p.seqids = q["seqids"].ctypes.data_as(_c_int_p)
     p.new_chrom = q["new_chrom"]

@@ -86,6 +86,18 @@ typedef struct awb_problem {
      * that would need a second mutation at a site have their emission multiplied
      * by this penalty (emit.cpp:457-589, :848-862).  0 or >= 1: off. */
     double infsites_penalty;
+
+    /* Optional emission mode: unphased data (ArgModel::unphased, emit.cpp:705-742,
+     * :834-842).  phase_row1 / phase_row2 are the two haplotypes of one
+     * individual as positions in the leaf order (PhaseProbs::treemap1/2,
+     * sequences.h:174-206: 0..nleaves-1, or nleaves for the new chromosome in
+     * external mode); at the sites where they differ the emission is the mean
+     * over the two phasings.  awb_batch_phase_probs gives, after the traceback,
+     * the probability of the data's phasing at the sampled state of each such
+     * site -- what PhaseProbs::sample_phase draws against.  Not combined with
+     * infsites_penalty. */
+    int unphased;               /* 0: off */
+    int phase_row1, phase_row2;
 } awb_problem;
 
 typedef struct awb_ctx awb_ctx;       /* one CUDA device + stream             */
@@ -194,6 +206,12 @@ int awb_thread_sample_cond(const awb_problem *p, const double *prior,
                            int *path, double *logz);
 int awb_forward_table(const awb_problem *p, const double *prior, double *fw,
                       double *logz);
+
+/* Unphased data: P(phasing as given | sampled state) for the heterozygous sites of
+ * problem i's unphased individual, after awb_batch_traceback.  p[nsites]: -1 at
+ * the other sites. */
+int awb_batch_phase_probs(awb_batch *b);
+int awb_batch_get_phase_probs(awb_batch *b, int i, double *p);
 
 /* Device time per kernel class, measured with CUDA events around every launch on
  * the batch's stream (bench.py's roofline figure).  awb_batch_kernel_times(b, 1)

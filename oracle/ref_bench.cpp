@@ -23,6 +23,7 @@
 #include <sys/time.h>
 #include <sys/wait.h>
 #include <unistd.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,7 @@ static double now_s()
 }
 
 struct Loaded {
+    int phase_row1, phase_row2;     // unphased individual (leaf order), or -1
     awf_file *af;
     ArgModel *model;
     Sequences *sequences;
@@ -78,6 +80,12 @@ static void load(const char *fn, Loaded &L)
     L.sequences = new Sequences(&L.rows[0], nseqs, seqlen);
     L.internal = awf_int(af, "internal") != 0;
     L.new_chrom = awf_int(af, "new_chrom");
+    // optional emission mode: unphased data (emit.cpp:705-742, :834-842)
+    L.phase_row1 = L.phase_row2 = -1;
+    if (awf_find(af, "phase_rows")) {
+        L.phase_row1 = ((int *) awf_need(af, "phase_rows")->data)[0];
+        L.phase_row2 = ((int *) awf_need(af, "phase_rows")->data)[1];
+    }
 
     awf_array *pt = awf_need(af, "ptrees");
     const int B = pt->dims[0], V = pt->dims[1];
@@ -137,11 +145,28 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
     const ArgModel *model = L.model;
     const int n = trees->length();
 
+    // unphased: a PhaseProbs with the two rows set by hand (its constructor
+    // wants name pairs; it returns at once for a phased model)
+    PhaseProbs phase_pr(0, 0, L.sequences, trees, model);
+    PhaseProbs *pp = NULL;
+    if (L.phase_row1 >= 0) {
+        const int nl = trees->get_num_leaves();
+        phase_pr.treemap1 = L.phase_row1;
+        phase_pr.treemap2 = L.phase_row2;
+        phase_pr.hap1 = L.phase_row1 < nl ? trees->seqids[L.phase_row1] : L.new_chrom;
+        phase_pr.hap2 = L.phase_row2 < nl ? trees->seqids[L.phase_row2] : L.new_chrom;
+        phase_pr.seqs = L.sequences;
+        phase_pr.offset = 0;
+        phase_pr.probs.clear();
+        L.model->unphased = true;
+        pp = &phase_pr;
+    }
+
     double t0 = now_s();
     ArgHmmForwardTable forward(trees->start_coord, n);
     ArgHmmMatrixIter matrix_iter(model, L.sequences, trees, L.new_chrom);
     matrix_iter.set_internal(L.internal, 0);
-    arghmm_forward_alg(trees, model, L.sequences, &matrix_iter, &forward, NULL,
+    arghmm_forward_alg(trees, model, L.sequences, &matrix_iter, &forward, pp,
                        false, L.internal);
     double t1 = now_s();
 
@@ -156,6 +181,22 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
     double t2 = now_s();
     *tf = t1 - t0;
     *tt = t2 - t1;
+
+    // P(phasing as given | sampled state) at the heterozygous sites, then the
+    // phase draw (sample_thread.cpp:614-616: one frand() per such site, before
+    // the recombination points)
+    vector<int> phase_pos;
+    vector<double> phase_p;
+    if (pp) {
+        for (map<int, vector<double> >::iterator it = phase_pr.probs.begin();
+             it != phase_pr.probs.end(); ++it) {
+            phase_pos.push_back(it->first - trees->start_coord);
+            phase_p.push_back(it->second[thread_path[it->first]]);
+        }
+        if (out_file)
+            phase_pr.sample_phase(thread_path);
+        L.model->unphased = false;
+    }
 
     if (out_file) {
         // the step after the traceback (sample_thread.cpp:617-622): the libc
@@ -204,6 +245,11 @@ static void run_once(Loaded &L, unsigned rand_seed, double *tf, double *tt,
         awf_write1(out, "recomb_time", AWF_I32, rtime.size(),
                    rtime.empty() ? &zero : &rtime[0]);
         awf_write1(out, "next_rand", AWF_I32, 1, &next_rand);
+        double dzero = 0;
+        awf_write1(out, "phase_pos", AWF_I32, phase_pos.size(),
+                   phase_pos.empty() ? &zero : &phase_pos[0]);
+        awf_write1(out, "phase_p", AWF_F64, phase_p.size(),
+                   phase_p.empty() ? &dzero : &phase_p[0]);
         fclose(out);
     }
 }

@@ -20,7 +20,8 @@
 // compiled next to this file with those seven names renamed to ref_* on the
 // compiler command line (no source is modified or copied), so the original
 // bodies stay available as the fallback for model features the device path does
-// not cover (--unphased, real --mutmap/--recombmap files with several regions).
+// not cover (--unphased together with --infsites, real --mutmap/--recombmap
+// files with several regions).
 //
 // libc rand(): stochastic_traceback consumes one rand() per sampled site, last
 // site first (common.h:272-290).  The adapter draws exactly those values up
@@ -100,8 +101,8 @@ static bool device_covers(const ArgModel *model, const PhaseProbs *phase_pr)
 {
     if (getenv("AWB_ADAPTER_FORCE_REFERENCE"))
         return false;
-    if (model->unphased || phase_pr)
-        return false;
+    if ((model->unphased || phase_pr) && model->infsites_penalty < 1.0)
+        return false;               // (this combination stays on the reference path)
     if (model->has_mutmap() && model->mutmap.size() != 1)
         return false;
     if (model->has_recombmap() && model->recombmap.size() != 1)
@@ -178,53 +179,120 @@ struct FlatProblem {
     }
 };
 
-// forward + traceback (+ recombination points) on the device.
+// one context (device + stream) for the life of the process
+static awb_ctx *adapter_ctx()
+{
+    static awb_ctx *ctx = NULL;
+    if (!ctx) {
+        const char *env = getenv("AWB_DEVICE");
+        if (awb_ctx_create(env ? atoi(env) : 0, &ctx)) {
+            printError("argweaver_b200: %s", awb_last_error());
+            abort();
+        }
+    }
+    return ctx;
+}
+
+static void device_fail()
+{
+    printError("argweaver_b200: %s", awb_last_error());
+    abort();                            // the reference's error convention
+}
+
+// forward + traceback (+ phase draw, + recombination points) on the device.
 // path_alloc[0..n): state per site.  recomb_pos / recombs: filled when given
-// (absolute coordinates, as sample_recombinations returns them).
+// (absolute coordinates, as sample_recombinations returns them).  phase_pr:
+// unphased data -- its probabilities are filled at the sampled states and
+// sample_phase is called where the reference calls it (after the traceback,
+// before the recombination points).
 static void device_thread(const ArgModel *model, const Sequences *sequences,
                           const LocalTrees *trees, int new_chrom, bool internal,
                           int minage, const double *prior, int last_state,
                           int *path_alloc, vector<int> *recomb_pos = NULL,
-                          vector<NodePoint> *recombs = NULL)
+                          vector<NodePoint> *recombs = NULL,
+                          PhaseProbs *phase_pr = NULL)
 {
     const int n = trees->length();
     Timer time;
     FlatProblem fp(model, sequences, trees, new_chrom, internal, minage);
+    // unphased: only when both haplotypes are rows of this call (emit.cpp:711-714)
+    const int nrows = trees->get_num_leaves() + (internal ? 0 : 1);
+    const bool phase = model->unphased && phase_pr &&
+        phase_pr->treemap1 >= 0 && phase_pr->treemap1 < nrows &&
+        phase_pr->treemap2 >= 0 && phase_pr->treemap2 < nrows;
+    if (phase) {
+        fp.p.unphased = 1;
+        fp.p.phase_row1 = phase_pr->treemap1;
+        fp.p.phase_row2 = phase_pr->treemap2;
+    }
     // the draws stochastic_traceback would take, in its order
     const int ndraws = last_state >= 0 ? n - 1 : n;
     vector<int> draws(n > 0 ? n : 1);
     for (int i = 0; i < ndraws; i++)
         draws[i] = rand();
-    double logz = 0;
-    int rc;
-    if (recomb_pos && !getenv("AWB_ADAPTER_HOST_RECOMBS")) {
-        vector<int> pos(n > 0 ? n : 1), node(n > 0 ? n : 1), rtime(n > 0 ? n : 1);
-        int nrec = 0, used = 0;
-        rc = awb_thread_sample_recombs(&fp.p, prior, last_state, draws.data(),
-                                       RAND_MAX, NULL, path_alloc, &logz, n,
-                                       &nrec, pos.data(), node.data(),
-                                       rtime.data(), &used);
-        if (!rc) {
-            for (int i = 0; i < nrec; i++) {
-                recomb_pos->push_back(pos[i] + trees->start_coord);
-                recombs->push_back(NodePoint(node[i], rtime[i]));
+
+    awb_batch *b = NULL;
+    if (awb_batch_create(adapter_ctx(), 1, &fp.p, 0, &b))
+        device_fail();
+    const double *priors[1] = { prior };
+    const int *rands[1] = { draws.data() };
+    if (awb_batch_upload(b) || awb_batch_setup(b) ||
+        awb_batch_forward(b, prior ? priors : NULL) ||
+        awb_batch_traceback(b, rands, RAND_MAX, last_state >= 0 ? &last_state : NULL) ||
+        awb_batch_sync(b))
+        device_fail();
+    int bad = -1;
+    if (awb_batch_get_status(b, 0, &bad))
+        device_fail();
+    if (bad >= 0) {
+        printError("argweaver_b200: forward column %d has no positive entry", bad);
+        abort();                        // sample_thread.cpp:443-444
+    }
+    if (awb_batch_get_path(b, 0, path_alloc))
+        device_fail();
+
+    if (model->unphased && phase_pr) {
+        if (phase) {
+            vector<double> pp(n > 0 ? n : 1);
+            if (awb_batch_phase_probs(b) || awb_batch_get_phase_probs(b, 0, pp.data()))
+                device_fail();
+            phase_pr->probs.clear();
+            for (int i = 0; i < n; i++) {
+                if (pp[i] < 0)
+                    continue;
+                vector<double> v(path_alloc[i] + 1, 0.0);
+                v[path_alloc[i]] = pp[i];
+                phase_pr->probs[i + trees->start_coord] = v;
             }
         }
-    } else {
-        rc = awb_thread_sample_cond(&fp.p, prior, last_state, draws.data(),
-                                    RAND_MAX, path_alloc, &logz);
-        if (!rc && recomb_pos) {
-            ArgHmmMatrixIter matrix_iter2(model, NULL, trees, new_chrom);
-            matrix_iter2.set_internal(internal, minage);
-            sample_recombinations(trees, model, &matrix_iter2,
-                                  &path_alloc[-trees->start_coord], *recomb_pos,
-                                  *recombs, internal);
+        // sample_thread.cpp:614-616 / :675-676
+        phase_pr->sample_phase(&path_alloc[-trees->start_coord]);
+    }
+
+    if (recomb_pos && !getenv("AWB_ADAPTER_HOST_RECOMBS")) {
+        // the process's rand() stream as it stands now; the device runs glibc's
+        // generator from there and says how many draws it took
+        int state[AWB_RNG_WORDS];
+        vector<int> pos(n > 0 ? n : 1), node(n > 0 ? n : 1), rtime(n > 0 ? n : 1);
+        int nrec = 0, used = 0;
+        if (awb_libc_rand_snapshot(state) ||
+            awb_batch_sample_recombs(b, state, RAND_MAX) ||
+            awb_batch_get_recomb_count(b, 0, &nrec, &used) ||
+            awb_batch_get_recombs(b, 0, nrec, pos.data(), node.data(), rtime.data()))
+            device_fail();
+        awb_libc_rand_advance(used);
+        for (int i = 0; i < nrec; i++) {
+            recomb_pos->push_back(pos[i] + trees->start_coord);
+            recombs->push_back(NodePoint(node[i], rtime[i]));
         }
+    } else if (recomb_pos) {
+        ArgHmmMatrixIter matrix_iter2(model, NULL, trees, new_chrom);
+        matrix_iter2.set_internal(internal, minage);
+        sample_recombinations(trees, model, &matrix_iter2,
+                              &path_alloc[-trees->start_coord], *recomb_pos,
+                              *recombs, internal);
     }
-    if (rc) {
-        printError("argweaver_b200: %s", awb_last_error());
-        abort();                        // the reference's error convention
-    }
+    awb_batch_destroy(b);
     awb_adapter_device_calls++;
     awb_adapter_device_seconds += time.time();
     printTimerLog(time, LOG_LOW, "forward+trace on the device (%6d blocks):",
@@ -243,10 +311,17 @@ void sample_arg_thread(const ArgModel *model, Sequences *sequences,
     int *thread_path = &thread_path_alloc[-trees->start_coord];
 
     ArgHmmMatrixIter matrix_iter(model, sequences, trees, new_chrom);
+    // (sample_thread.cpp:586-591)
+    PhaseProbs phase_pr(new_chrom, trees->get_num_leaves(),
+                        sequences, trees, model);
+    if (model->unphased)
+        printf("treemap = %i %i\n", phase_pr.treemap1, phase_pr.treemap2);
+
     vector<int> recomb_pos;
     vector<NodePoint> recombs;
     device_thread(model, sequences, trees, new_chrom, false, 0, NULL, -1,
-                  thread_path_alloc, &recomb_pos, &recombs);
+                  thread_path_alloc, &recomb_pos, &recombs,
+                  model->unphased ? &phase_pr : NULL);
 
     // add thread to ARG: the reference's code
     Timer time;
@@ -274,10 +349,12 @@ void sample_arg_thread_internal(
 
     ArgHmmMatrixIter matrix_iter(model, sequences, trees);
     matrix_iter.set_internal(internal, minage);
+    if (phase_pr != NULL)               // (sample_thread.cpp:652-653)
+        printf("treemap = %i %i\n", phase_pr->treemap1, phase_pr->treemap2);
     vector<int> recomb_pos;
     vector<NodePoint> recombs;
     device_thread(model, sequences, trees, -1, internal, minage, NULL, -1,
-                  thread_path_alloc, &recomb_pos, &recombs);
+                  thread_path_alloc, &recomb_pos, &recombs, phase_pr);
 
     Timer time;
     add_arg_thread_path(trees, matrix_iter.states_model,

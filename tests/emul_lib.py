@@ -70,6 +70,7 @@ def lib():
         _lib.emul_lin_unsafe.argtypes = [C.c_void_p]
         _lib.emul_lin_max.restype = C.c_double
         _lib.emul_lin_max.argtypes = [C.c_void_p]
+        _lib.emul_phase_probs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.emul_sample_recombs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
@@ -121,6 +122,12 @@ class Emul(object):
                                   info.ctypes.data)
         n = int(info[0])
         return pos[:n], node[:n], time[:n], int(info[1])
+
+    def phase_probs(self, path):
+        path = np.ascontiguousarray(path, np.int32)
+        out = np.empty(len(path), np.float64)
+        lib().emul_phase_probs(self.h, path.ctypes.data, out.ctypes.data)
+        return out
 
     def lin_unsafe(self):
         return bool(lib().emul_lin_unsafe(self.h))

@@ -219,6 +219,27 @@ int emul_sample_recombs(void *h, const int *path, const int *rng_state, int rand
     return 0;
 }
 
+// unphased data: P(phasing as given | path state) at the heterozygous variant
+// sites (awb_emit.cuh awb_phase_prob), -1 elsewhere; after emul_setup
+int emul_phase_probs(void *h, const int *path, double *out)
+{
+    Emul *e = (Emul *) h;
+    const AwbChain &ch = e->ch;
+    for (int i = 0; i < ch.nsites; i++) {
+        out[i] = -1.0;
+        if (ch.kind[i] != AWB_SITE_VARIANT || !awb_site_het(ch, i))
+            continue;
+        const int b = awb_find_block(ch, i);
+        if (ch.nstates[b] == 0)
+            continue;
+        const size_t o = (size_t) b * ch.nnodes;
+        out[i] = awb_phase_prob(ch, i, b, path[i], 0, 1, e->scratch.data(), ch.ptrees + o,
+                                ch.ages + o, ch.child0 + o, ch.child1 + o, ch.order + o,
+                                ch.lstart + (size_t) b * (ch.nnodes + 2));
+    }
+    return 0;
+}
+
 void emul_destroy(void *h) { delete (Emul *) h; }
 
 } // extern "C"

@@ -36,6 +36,8 @@ def problem_for_file(d):
             q[k] = np.asarray(q[k], np.int32).reshape(-1)[:1]
     for k in ("rho", "mu"):
         q[k] = np.asarray(q[k], np.float64).reshape(-1)[:1]
+    if d.get("phase_rows") is not None:
+        q["phase_rows"] = np.asarray(d["phase_rows"], np.int32).reshape(-1)[:2]
     if "infsites_penalty" in d:
         q["infsites_penalty"] = np.asarray(d["infsites_penalty"],
                                            np.float64).reshape(-1)[:1]

@@ -100,6 +100,22 @@ def test_infsites_run_stats_identical(tmp_path):
 
 
 @needs_binaries
+def test_unphased_run_stats_identical(tmp_path):
+    """--unphased (ArgModel::unphased): emissions averaged over the two phasings
+    of the individual being threaded, PhaseProbs filled from the device, the
+    reference's own sample_phase flipping alleles where it calls it -- the data
+    itself changes from iteration to iteration, so the .stats rows only agree
+    if every phase probability and every draw does"""
+    extra = ["-c", "10", "-n", "20", "--unphased"]
+    ref, _ = run_sampler(ARG_SAMPLE, SIM1, str(tmp_path / "ref"), extra)
+    dev, r = run_sampler(ARG_SAMPLE_B200, SIM1, str(tmp_path / "dev"), extra,
+                         env={"AWB_ADAPTER_REPORT": "1"})
+    assert_same_stats(ref, dev)
+    assert int(r.stderr.split("reference fallbacks:")[1].split()[0]) == 0
+    assert int(r.stderr.split("device thread samples:")[1].split()[0]) >= 20
+
+
+@needs_binaries
 def test_host_recombination_sampler_gives_the_same_run(tmp_path):
     """AWB_ADAPTER_HOST_RECOMBS=1: the reference's own sample_recombinations on
     the path the device returns -- same .stats as with the device sampler"""
