@@ -116,6 +116,9 @@ __global__ void awb_kind_packed_kernel(const AwbChain *chains)
     }
 }
 
+// (tried: __launch_bounds__(64, 16) -- 64 registers instead of 86, 16 instead of
+// 10 CTAs per SM -- made it 58 % slower: the spilled arrays cost more than the
+// extra warps hide)
 __global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
 {
     const AwbChain &ch = chains[blockIdx.y];
@@ -191,6 +194,64 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
     // through those
     const int first = g.site0 + 1, last = g.site0 + g.nsites;
     const int nw = gridDim.x * wpc;
+    auto stage = [&](int b) {
+        const size_t o = (size_t) b * V;
+        __syncwarp();
+        for (int x = lane; x < V; x += 32) {
+            sparent[x] = ch.ptrees[o + x];
+            sage[x] = ch.ages[o + x];
+            sc0[x] = ch.child0[o + x];
+            sc1[x] = ch.child1[o + x];
+            sorder[x] = ch.order[o + x];
+        }
+        for (int x = lane; x < V + 2; x += 32)
+            slstart[x] = ch.lstart[(size_t) b * (V + 2) + x];
+        staged = b;
+        __syncwarp();
+    };
+    if (!ch.seqs) {
+        // the alignment as variant columns: the sites with work are listed
+        // (var_pos, ascending).  The warps take the columns of the segment in
+        // turn (every column costs about the same: an even share without any
+        // scanning), and the column index spares the per-site search.
+        int v0, v1;
+        {
+            const long long c0s = (long long) ch.start_coord + first;
+            const long long c1s = (long long) ch.start_coord + last;
+            int lo = 0, hi = ch.nvar;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch.var_pos[mid] < c0s) lo = mid + 1; else hi = mid; }
+            v0 = lo;
+            hi = ch.nvar;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch.var_pos[mid] < c1s) lo = mid + 1; else hi = mid; }
+            v1 = lo;
+        }
+        int b = g.b0;
+        for (int v = v0 + blockIdx.x * wpc + warp; v < v1; v += nw) {
+            const int i = (int) ((long long) ch.var_pos[v] - ch.start_coord);
+            if (ch.kind[i] != AWB_SITE_VARIANT)
+                continue;
+            // the block of site i, from the block of the previous column on
+            if (ch.block_start[b + 1] <= i) {
+                int lo = b + 1, hi = ch.ntrees - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (ch.block_start[mid] <= i) lo = mid; else hi = mid - 1;
+                }
+                b = lo;
+            }
+            if (b != staged)
+                stage(b);
+            awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder,
+                          slstart, g.fwbias, v);
+            __syncwarp();
+        }
+        return;
+    }
+    // dense rows: every warp takes a contiguous range of sites (consecutive
+    // variant sites mostly share their block: the tree stays staged, and the
+    // block index only moves forward), scans it 32 sites at a time for variant
+    // ones (one coalesced load and a ballot; ~97 % of the sites are skipped) and
+    // works through those
     const int per = (((last - first) + nw - 1) / nw + 31) & ~31;
     const int w0 = first + (blockIdx.x * wpc + warp) * per;
     const int w1 = w0 + per < last ? w0 + per : last;
@@ -207,20 +268,8 @@ __global__ void awb_emit_kernel(const AwbChain *chains, int scratch_bytes, int s
         else
             while (ch.block_start[b + 1] <= i)
                 b++;
-        if (b != staged) {
-            const size_t o = (size_t) b * V;
-            for (int x = lane; x < V; x += 32) {
-                sparent[x] = ch.ptrees[o + x];
-                sage[x] = ch.ages[o + x];
-                sc0[x] = ch.child0[o + x];
-                sc1[x] = ch.child1[o + x];
-                sorder[x] = ch.order[o + x];
-            }
-            for (int x = lane; x < V + 2; x += 32)
-                slstart[x] = ch.lstart[(size_t) b * (V + 2) + x];
-            staged = b;
-            __syncwarp();
-        }
+        if (b != staged)
+            stage(b);
         awb_emit_site(ch, i, b, lane, 32, scratch, sparent, sage, sc0, sc1, sorder,
                       slstart, g.fwbias);
         __syncwarp();
@@ -352,7 +401,7 @@ struct awb_batch {
     size_t windows_bytes;        // arena bytes of the windows (before the chain records)
     bool with_band;              // the generic kernel's tables are part of the arena
     int nslots;                  // checkpointed table: segment tables per window
-    int nsub;                    //   ... and segments the second pass rebuilds at once
+    int nrot;                    //   ... and segments the second pass rebuilds at once
     bool bound;                  // batch_bind has run
     char *arena;
     size_t arena_bytes;
@@ -400,7 +449,10 @@ enum { AWB_K_KIND = 0, AWB_K_BLOCK, AWB_K_TMATRIX, AWB_K_SWITCH, AWB_K_EMIT,
 struct KTimer {
     awb_batch *b;
     bool on;
-    KTimer(awb_batch *b_, int cls) : b(b_), on(b_->ktimes) {
+    cudaStream_t st;
+    size_t at;
+    KTimer(awb_batch *b_, int cls, cudaStream_t st_ = 0) : b(b_), on(b_->ktimes) {
+        st = st_ ? st_ : b->ctx->stream;
         if (!on) return;
         if (b->kev_used + 2 > b->kev.size()) {
             cudaEvent_t e0, e1;
@@ -412,12 +464,13 @@ struct KTimer {
             b->kev.push_back(e1);
         }
         b->kclass.push_back(cls);
-        cudaEventRecord(b->kev[b->kev_used], b->ctx->stream);
+        at = b->kev_used;
+        b->kev_used += 2;
+        cudaEventRecord(b->kev[at], st);
     }
     ~KTimer() {
         if (!on) return;
-        cudaEventRecord(b->kev[b->kev_used + 1], b->ctx->stream);
-        b->kev_used += 2;
+        cudaEventRecord(b->kev[at + 1], st);
     }
 };
 
@@ -434,6 +487,7 @@ extern "C" int awb_ctx_create(int device, awb_ctx **out)
     ctx->device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+
     for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
         CUDA_OK(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming));
@@ -477,6 +531,7 @@ extern "C" void awb_ctx_destroy(awb_ctx *ctx)
         cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+
     for (int i = 0; i < AWB_UPLOAD_GROUPS; i++)
         cudaEventDestroy(ctx->up_ev[i]);
     cudaEventDestroy(ctx->order_ev);
@@ -700,7 +755,7 @@ extern "C" int awb_batch_create(awb_ctx *ctx, int nproblems,
     b->with_band = !batch_fast_path(b) || (flags & AWB_KEEP_DEBUG);
     b->windows_bytes = 0;
     b->nslots = 1;
-    b->nsub = 1;
+    b->nrot = 1;
     b->bound = false;
     if (getenv("AWB_VERBOSE"))
         fprintf(stderr, "awb_batch_create: layout %.1f ms\n",
@@ -758,8 +813,19 @@ static int batch_bind(awb_batch *b)
         }
         b->windows_bytes = total;
         b->nslots = nslots;
-        b->nsub = nslots >= 7 ? 4 : (nslots >= 5 ? 3 : (nslots >= 3 ? 2 : 1));
-        if (getenv("AWB_NO_PAIRS")) b->nsub = 1;
+        // as many segments side by side as the dense forward kernel puts CTAs on
+        // an SM (and as there are tables); fewer than three tables: one
+        b->nrot = 1;
+        if (nslots >= 3) {
+            const FastShape f = batch_fast_shape(b, true);
+            const int regs = (f.threads <= 192 && f.U <= 2) ? 80 : 96;
+            int want = 4;
+            for (; want > 1; want--)
+                if ((want * (f.threads / 32) + 3) / 4 * 32 * regs <= 16384)
+                    break;
+            if (want < 2) want = 2;
+            b->nrot = want < nslots ? want : nslots;
+        }
         // chain records and the error word live at the tail of the arena
         chains_off = total;
         total += awb_align(sizeof(AwbChain) * nproblems);
@@ -800,6 +866,7 @@ static int batch_bind(awb_batch *b)
     for (int c = 0; c < nproblems; c++) {
         awb_layout_bind(b->L[c], b->P[c], b->arena + b->arena_off[c],
                         b->h_chains[c]);
+        b->h_chains[c].nrot = b->nrot;
         b->h_chains[c].need_band = batch_fast_path(b) ? 0 : 1;
     }
     b->stage_chains = NULL;
@@ -943,9 +1010,9 @@ extern "C" int awb_batch_upload(awb_batch *b)
 
 // ---- kernel launchers (seg: segment of a checkpointed table, else 0)
 
-static int launch_emit(awb_batch *b, int seg, int pass)
+static int launch_emit(awb_batch *b, int seg, int pass, cudaStream_t st = 0)
 {
-    cudaStream_t st = b->ctx->stream;
+    if (!st) st = b->ctx->stream;
     const int scratch = (int) (((awb_emit_scratch_bytes(b->maxV) + 15) & ~(size_t) 15) +
                                (((size_t) b->maxV * 16 + 4 + 15) & ~(size_t) 15));
     int wpc = 8;
@@ -959,7 +1026,7 @@ static int launch_emit(awb_batch *b, int seg, int pass)
     if (b->ckpt && gx * b->C > cap)
         gx = (cap + b->C - 1) / b->C;
     dim3 grid(gx, b->C);
-    KTimer kt(b, AWB_K_EMIT);
+    KTimer kt(b, AWB_K_EMIT, st);
     awb_emit_kernel<<<grid, 32 * wpc, (size_t) wpc * scratch, st>>>(
         b->d_chains, scratch, seg, pass);
     b->launches++;
@@ -968,9 +1035,10 @@ static int launch_emit(awb_batch *b, int seg, int pass)
 
 // nsub: segments per chain worked on at once (seg, seg-1, ...): only the second
 // pass of a checkpointed table has independent segments
-static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
+static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1,
+                               cudaStream_t st = 0)
 {
-    cudaStream_t st = b->ctx->stream;
+    if (!st) st = b->ctx->stream;
     const bool dense = (long long) b->C * nsub > b->ctx->sm_count;
     FastShape f = batch_fast_shape(b, dense);
     if (!f.ok)
@@ -1065,7 +1133,7 @@ static int launch_forward_fast(awb_batch *b, int seg, int pass, int nsub = 1)
         }
         b->k4_launches++;
     }
-    KTimer kt(b, AWB_K_FORWARD);
+    KTimer kt(b, AWB_K_FORWARD, st);
     if (f.tmax == 20) AWB_LAUNCH_FAST_T(20, 5, 4, 3);
     else if (f.tmax == 40) AWB_LAUNCH_FAST_T(40, 5, 5, 4);
     else AWB_LAUNCH_FAST_T(64, 5, 5, 4);
@@ -1283,16 +1351,29 @@ extern "C" int awb_batch_traceback(awb_batch *b, const int *const *rand_ints,
         const int pass = b->tables_stale ? 2 : 1;
         // With three or more tables per window consecutive segments are rebuilt
         // side by side (independent chains: each starts from its own stored
-        // column), which puts several CTAs on every SM; the traceback then walks
-        // through them in order.  Never across the boundary of the resident
-        // segments of the longest window, whose tables are still in use.
-        const int G = b->nsub;
+        // column), which puts several CTAs on every SM -- as many as the dense
+        // forward kernel fits there; the traceback then walks through them in
+        // order.  A group never straddles the resident boundary of any window
+        // (above it that window's tables are still in use; below it all of them
+        // are free); segment s lives in table R-1 - s mod nrot (AwbSeg).
+        // (Tried: the next group rebuilt on a second stream while the traceback
+        // walks the current one, tables rotating with twice the period: 1 % --
+        // the traceback's CTAs fill the SMs' shared memory, the rebuild waits.)
+        const int G = b->nrot;
+        std::vector<char> boundary(b->maxseg + 1, 0);
+        for (int c = 0; c < b->C; c++) {
+            const int ns = b->L[c].nseg;
+            const int R = b->nslots < ns ? b->nslots : ns;
+            boundary[ns - R] = 1;          // segments >= ns - R are resident
+        }
         for (int s = b->maxseg - 1; s >= 0;) {
             const bool res_s = s >= b->maxseg - b->nslots;
             int nsub = 1;
-            if (!res_s && G > 1) {
-                // groups are aligned on multiples of G (tables go by s mod G)
-                nsub = s % G + 1;
+            if (!res_s && G > 1 && !getenv("AWB_NO_PAIRS")) {
+                // down to the next multiple of G, or to a window's boundary
+                while (nsub < G && (s - nsub + 1) % G != 0 && s - nsub >= 0 &&
+                       !boundary[s - nsub + 1])
+                    nsub++;
             }
             for (int y = 0; y < nsub; y++)
                 if (launch_emit(b, s - y, pass))

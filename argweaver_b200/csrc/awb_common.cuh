@@ -70,7 +70,7 @@ struct AwbChain {
     // ckptcol[s] is the stored first column of segment s (s >= 1)
     int ckpt, nseg;
     int phase_row1, phase_row2;   // unphased individual: its two rows (leaf order; -1: off)
-    int nsub;                 // segments rebuilt side by side by the second pass (1..4)
+    int nrot;                 // the second pass rebuilds this many segments side by side
     int nslots;               // segment tables in fw / fsum (the last nslots segments
                               //   of the forward pass stay resident for the traceback)
     int seg_sites;            // sites per segment table (fsum stride between tables)
@@ -238,17 +238,17 @@ AWB_HD inline AwbSeg awb_seg(const AwbChain &ch, int s)
     g.site0 = ch.block_start[g.b0];
     g.nsites = ch.block_start[g.b1] - g.site0 + g.extra;
     // the last nslots segments have a table of their own (and stay resident
-    // after the forward pass); all earlier ones take turns in the top nsub tables
-    // (segment s in table R-1 - s mod nsub; table 0 when there are fewer than
+    // after the forward pass); all earlier ones take turns in the top nrot tables
+    // (segment s in table R-1 - s mod nrot; table 0 when there are fewer than
     // three): those are the tables of the last segments, which the traceback has
-    // left behind by the time it rebuilds an earlier segment -- so nsub
-    // consecutive segments can be rebuilt side by side (awb_api.cu keeps
-    // 2 nsub <= R + 1, so that a group that straddles a window's resident
-    // boundary never lands on a table still in use)
+    // left behind by the time it rebuilds an earlier segment -- so nrot
+    // consecutive segments can be rebuilt side by side (awb_api.cu never lets
+    // such a group straddle a window's resident boundary, above which its tables
+    // are still in use)
     const int R = ch.nslots < ch.nseg ? ch.nslots : ch.nseg;
     g.resident = s >= ch.nseg - R;
-    const int G = ch.nsub > 1 ? ch.nsub : 1;
-    const int slot = g.resident ? s - (ch.nseg - R) : (R >= 3 ? R - 1 - (s % G) : 0);
+    const int M = ch.nrot > 1 ? ch.nrot : 1;
+    const int slot = g.resident ? s - (ch.nseg - R) : (R >= M ? R - 1 - (s % M) : 0);
     g.fwbias = ch.fw_off[g.b0] - (long long) slot * ch.seg_doubles;
     g.fsoff = (long long) slot * ch.seg_sites * (ch.model.ntimes - 1);
     return g;

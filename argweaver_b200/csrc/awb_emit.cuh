@@ -108,7 +108,8 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
                                          const int *parent, const int *age,
                                          const short *c0, const short *c1,
                                          const short *order, const short *lstart,
-                                         long long fwbias, int swap, int only_state)
+                                         long long fwbias, int swap, int only_state,
+                                         int vc_hint = -1)
 {
     const AwbModel &m = ch.model;
     const int V = ch.nnodes;
@@ -124,7 +125,8 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
     const int maintree_root = internal ? c1[root] : root;
     const int subtree_root = internal ? c0[root] : root;
     const size_t col = (size_t) ch.start_coord + i;
-    const int vc = ch.seqs ? -1 : awb_var_find(ch, (long long) col);
+    // (vc_hint: the caller already knows the site's variant column)
+    const int vc = ch.seqs ? -1 : (vc_hint >= 0 ? vc_hint : awb_var_find(ch, (long long) col));
 
     double *inner = (double *) scratch;
     double *outer = inner + 4 * (size_t) V;
@@ -365,15 +367,15 @@ AWB_HD inline void awb_emit_site(const AwbChain &ch, int i, int b, int lane,
                                  const int *parent, const int *age,
                                  const short *c0, const short *c1,
                                  const short *order, const short *lstart,
-                                 long long fwbias = 0)
+                                 long long fwbias = 0, int vc_hint = -1)
 {
     awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age, c0, c1, order,
-                        lstart, fwbias, 0, -1);
+                        lstart, fwbias, 0, -1, vc_hint);
     if (awb_site_het(ch, i)) {
         // the other phasing; the row becomes the mean of the two
         AWB_LANESYNC();
         awb_emit_site_phase(ch, i, b, lane, nlanes, scratch, parent, age, c0, c1, order,
-                            lstart, fwbias, 1, -1);
+                            lstart, fwbias, 1, -1, vc_hint);
     }
 }
 

@@ -224,7 +224,11 @@ __device__ __forceinline__ void awb_sts2(unsigned addr, double x, double y)
 
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
 {
+#ifdef AWB_BAR_UNALIGNED
+    asm volatile("barrier.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+#else
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+#endif
 }
 
 // U: consecutive states per compute thread; MAXREG: registers per thread (what

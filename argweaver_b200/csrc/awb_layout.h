@@ -791,7 +791,7 @@ inline void awb_layout_bind(const AwbLayout &L, const awb_problem &p, char *base
     ch.ckpt = L.ckpt;
     ch.nseg = L.nseg;
     ch.nslots = L.nslots;
-    ch.nsub = L.nslots >= 7 ? 4 : (L.nslots >= 5 ? 3 : (L.nslots >= 3 ? 2 : 1));
+    ch.nrot = 1;                        // (the batch sets it: awb_api.cu)
     ch.seg_doubles = L.seg_doubles;
     ch.seg_sites = L.seg_sites;
     ch.seg_start = L.ckpt ? (const int *) (base + L.o_seg_start) : 0;

@@ -20,18 +20,18 @@ def main(path, src_path):
     def find(marker):
         return next(i for i, l in src.items() if marker in l)
 
-    norm0 = find("norm warp: waits on barrier 2 only")
-    scr0 = find("F-scribes: per-time sums between barrier 1")
+    book0 = find("who keeps the books")
+    scr0 = find("F-scribes: per-time sums and R between barrier 1")
     comp0 = find("// compute warps")
     reg = collections.OrderedDict((k, collections.Counter())
-                                  for k in ("norm warp", "scribe warps", "compute warps",
+                                  for k in ("bookkeeping (lambdas + its own warp)", "scribe warps", "compute warps",
                                             "inlined (shuffles, asm)"))
     smp = collections.Counter()
     for r in data:
         ln = int(r[0])
         infile = ln in src and src[ln].strip()[:20] == r[1].strip()[:20]
-        key = ("inlined (shuffles, asm)" if not infile or ln < norm0 else
-               "norm warp" if ln < scr0 else "scribe warps" if ln < comp0 else
+        key = ("inlined (shuffles, asm)" if not infile or ln < book0 else
+               "bookkeeping (lambdas + its own warp)" if ln < scr0 else "scribe warps" if ln < comp0 else
                "compute warps")
         smp[key] += num(r[6])
         for i, h in stall:
