@@ -222,13 +222,12 @@ __device__ __forceinline__ void awb_sts2(unsigned addr, double x, double y)
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(x), "d"(y) : "memory");
 }
 
+// (compute-sanitizer's synccheck reports these barriers: it flags a named barrier
+// that warps of one CTA enter from different places in the code -- what the warp
+// roles below do by design; scripts/sync_probe.cu isolates it)
 __device__ __forceinline__ void awb_bar_sync(int id, int count)
 {
-#ifdef AWB_BAR_UNALIGNED
-    asm volatile("barrier.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
-#else
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
-#endif
 }
 
 // U: consecutive states per compute thread; MAXREG: registers per thread (what
