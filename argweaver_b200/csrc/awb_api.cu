@@ -1654,8 +1654,8 @@ extern "C" int awb_batch_get_phase_probs(awb_batch *b, int i, double *p)
 // of it (glibc stdlib/random_r.c: __initstate_r / __setstate_r).
 extern "C" int awb_libc_rand_snapshot(int *state)
 {
-    static char tmp[128];
-    char *old = initstate(1u, tmp, sizeof(tmp));
+    static int tmp[32];                 // (a state array has to be word aligned)
+    char *old = initstate(1u, (char *) tmp, sizeof(tmp));
     if (!old)
         return fail("initstate failed");
     const int *w = (const int *) old;

@@ -167,16 +167,12 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
             const int j = order[q0 + (idx >> 2)];
             const int a = idx & 3;
             const int k1 = c0[j], k2 = c1[j];
-            double p1 = 0.0, p2 = 0.0;
-            for (int x = 0; x < 4; x++) {
-                if (a == x) {
-                    p1 += inner[4 * k1 + x] * nomut[k1];
-                    p2 += inner[4 * k2 + x] * nomut[k2];
-                } else {
-                    p1 += inner[4 * k1 + x] * mut[k1];
-                    p2 += inner[4 * k2 + x] * mut[k2];
-                }
-            }
+            // Jukes-Cantor: sum_x v[x] P(a,x) = mut * sum_x v[x] + (nomut - mut) * v[a]
+            const double *v1 = inner + 4 * k1, *v2 = inner + 4 * k2;
+            const double p1 = fma(nomut[k1] - mut[k1], v1[a],
+                                  mut[k1] * ((v1[0] + v1[1]) + (v1[2] + v1[3])));
+            const double p2 = fma(nomut[k2] - mut[k2], v2[a],
+                                  mut[k2] * ((v2[0] + v2[1]) + (v2[2] + v2[3])));
             inner[4 * j + a] = p1 * p2;
         }
         AWB_LANESYNC();
@@ -198,16 +194,11 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
                 in = (p != -1) && inmain[p];
                 if (in) {
                     const int sib = (c0[p] == j) ? c1[p] : c0[p];
-                    double p1 = 0.0, p2 = 0.0;
-                    for (int x = 0; x < 4; x++) {
-                        if (a == x) {
-                            p1 += inner[4 * sib + x] * nomut[sib];
-                            p2 += outer[4 * p + x] * nomut[p];
-                        } else {
-                            p1 += inner[4 * sib + x] * mut[sib];
-                            p2 += outer[4 * p + x] * mut[p];
-                        }
-                    }
+                    const double *v1 = inner + 4 * sib, *v2 = outer + 4 * p;
+                    const double p1 = fma(nomut[sib] - mut[sib], v1[a],
+                                          mut[sib] * ((v1[0] + v1[1]) + (v1[2] + v1[3])));
+                    const double p2 = fma(nomut[p] - mut[p], v2[a],
+                                          mut[p] * ((v2[0] + v2[1]) + (v2[2] + v2[3])));
                     outer[4 * j + a] = (p != maintree_root) ? p1 * p2 : p1;
                 }
             }
@@ -293,6 +284,8 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
     const double *tab0 = internal ?
         ch.ptab + (size_t) age[subtree_root] * T * 2 : ch.ptab + (size_t) T * T * 2;
 
+    const double in2sum = (in2[0] + in2[1]) + (in2[2] + in2[3]);
+
     // per-state emission (emit.cpp:778-805, calc_emit :620-645)
     const long long row0 = ch.row_off[b];
     double *out = ch.fw + (ch.fw_off[b] - fwbias) +
@@ -315,24 +308,19 @@ AWB_HD inline double awb_emit_site_phase(const AwbChain &ch, int i, int b, int l
         const double mu2 = t2[0], no2 = t2[1];
         const double *in_n = inner + 4 * node2;
         const double *out_n = outer + 4 * node2;
+        // (Jukes-Cantor as above: one sum per vector, one FMA per base)
+        const double s1 = mu0 * in2sum;
+        const double s2 = mu1 * ((in_n[0] + in_n[1]) + (in_n[2] + in_n[3]));
+        const double s3 = mu2 * ((out_n[0] + out_n[1]) + (out_n[2] + out_n[3]));
+        const double d0 = no0 - mu0, d1 = no1 - mu1, d2 = no2 - mu2;
+        const bool rootbr = node2 == maintree_root;
         double emit = 0.0;
+#pragma unroll
         for (int a = 0; a < 4; a++) {
-            double p1 = 0.0, p2 = 0.0, p3 = 0.0;
-            for (int x = 0; x < 4; x++) {
-                if (a == x) {
-                    p1 += in2[x] * no0;
-                    p2 += in_n[x] * no1;
-                    p3 += out_n[x] * no2;
-                } else {
-                    p1 += in2[x] * mu0;
-                    p2 += in_n[x] * mu1;
-                    p3 += out_n[x] * mu2;
-                }
-            }
-            if (node2 != maintree_root)
-                emit += p1 * p2 * p3 * .25;
-            else
-                emit += p1 * p2 * .25;
+            const double p1 = fma(d0, in2[a], s1);
+            const double p2 = fma(d1, in_n[a], s2);
+            const double p3 = rootbr ? 1.0 : fma(d2, out_n[a], s3);
+            emit += p1 * p2 * p3 * .25;
         }
         if (infsites && !allvalid) {
             const bool valid = (cset & anc[node2]) ||

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--internal", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--checkpoint", type=int, default=0)
+    ap.add_argument("--packed", type=int, default=0,
+                    help="alignment as variant columns (the .sites form)")
     ap.add_argument("--rho", type=float, default=1.6e-8,
                     help="recombination rate of the simulation (lower: longer blocks)")
     a = ap.parse_args()
@@ -25,6 +27,8 @@ def main():
         t0 = time.time()
         ds = [sim.simulate_problem(a.k, a.sites, ntimes=a.ntimes, seed=100 + c,
                                    internal=bool(a.internal), rho=a.rho) for c in range(C)]
+        if a.packed:
+            ds = [sim.pack_problem(d) for d in ds]
         print("blocks per window: %d (%.1f sites per block)"
               % (len(ds[0]["blocklens"]), a.sites / float(len(ds[0]["blocklens"]))))
         rs = [np.random.RandomState(c).randint(0, 2**31 - 1, a.sites).astype(np.int32)
