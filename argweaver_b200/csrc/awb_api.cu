@@ -1468,6 +1468,11 @@ extern "C" int awb_batch_get_kernel_times(awb_batch *b, float *ms, double *forwa
     cudaGetLastError();
     if (forward_bytes) *forward_bytes = b->k4_bytes;
     if (forward_launches) *forward_launches = b->k4_launches;
+    // (the events are reused: the next read covers what is launched from here on)
+    b->kev_used = 0;
+    b->kclass.clear();
+    b->k4_bytes = 0;
+    b->k4_launches = 0;
     return 0;
 }
 

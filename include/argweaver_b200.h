@@ -216,7 +216,7 @@ int awb_batch_get_phase_probs(awb_batch *b, int i, double *p);
 /* Device time per kernel class, measured with CUDA events around every launch on
  * the batch's stream (bench.py's roofline figure).  awb_batch_kernel_times(b, 1)
  * starts (and resets) the collection; awb_batch_get_kernel_times sums what has
- * been launched since: ms[AWB_KERNEL_CLASSES] in the order kind, block setup,
+ * been launched since the start or the previous read: ms[AWB_KERNEL_CLASSES] in the order kind, block setup,
  * time matrices, switch setup, emission, forward, traceback, recombination;
  * forward_bytes = algorithmic bytes of the forward launches (8 B per site*state
  * they computed). */
