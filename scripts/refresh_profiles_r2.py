@@ -91,20 +91,8 @@ print("forward DRAM traffic: read %.1f GB, write %.1f GB, algorithmic %.1f GB (x
          (traffic["dram_bytes_read"] + traffic["dram_bytes_write"]) /
          max(traffic["algorithmic_bytes"], 1)))
 
-# sanitizer summaries
-with open(P + "r2_compute_sanitizer.txt", "w") as f:
-    for tool in ("memcheck", "racecheck", "synccheck"):
-        fn = G + "sanitizer_%s.log" % tool
-        if not os.path.exists(fn):
-            continue
-        txt = open(fn).read()
-        f.write("== compute-sanitizer --tool %s (scripts/gpu_sanitize.sh)\n" % tool)
-        for l in txt.splitlines():
-            if re.search(r"SUMMARY|passed|failed", l):
-                f.write(l + "\n")
-        locs = collections.Counter(re.findall(r"Device Frame: (.*)", txt))
-        for k, v in locs.most_common(5):
-            f.write("   %4d x %s\n" % (v, k[:160]))
+# (profiles/r2_compute_sanitizer.txt is written by hand from the logs of
+# scripts/gpu_sanitize.sh and scripts/sync_probe.cu: it carries the probe's outcomes)
 
 # SASS of the shipped kernels: the mnemonics that matter (bulk copies, mbarrier)
 sass = subprocess.run(["cuobjdump", "-sass", "argweaver_b200/csrc/libargweaver_b200.so"],
