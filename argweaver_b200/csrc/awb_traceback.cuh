@@ -159,25 +159,11 @@ __device__ __forceinline__ void awb_mbar_wait(unsigned bar, unsigned parity)
 __device__ __forceinline__ void awb_bulk_g2s(unsigned dst, const void *src, unsigned bytes,
                                              unsigned bar)
 {
+    // (whole aligned 16-byte lines: the caller passes the line that holds the
+    // first byte and a size rounded up; element 0 lands at dst + (src & 15))
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
                  "[%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// One table: the aligned 16-byte lines that hold [src, src + nbytes).  Element 0
-// lands at dst + (src & 15); returns that skew.  issue: this thread sends it.
-__device__ __forceinline__ unsigned awb_tb_bulk(unsigned dst, const void *src, int nbytes,
-                                                unsigned bar, bool issue, unsigned &total)
-{
-    const unsigned long long a = (unsigned long long) src;
-    const unsigned skew = (unsigned) (a & 15ull);
-    if (nbytes > 0) {
-        const unsigned n = (skew + (unsigned) nbytes + 15u) & ~15u;
-        if (issue)
-            awb_bulk_g2s(dst, (const void *) (a - skew), n, bar);
-        total += n;
-    }
-    return skew;
 }
 
 // Block-wide sample() over the S1 weights held VPT per thread (thread t holds
@@ -308,44 +294,68 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
     }
     __syncthreads();
 
-    // issue the asynchronous copy of block bb's tables into buffer q (two
-    // rounds: the byte count goes to the barrier before the first copy starts)
+    // issue the asynchronous copy of block bb's tables into buffer q.  Every
+    // thread needs the skews; thread 0 alone adds up the bytes, announces them to
+    // the barrier and sends the copies (its plan is kept in registers meanwhile).
     auto preload = [&](const AwbTbBlk &m, int bb, int q) {
         const unsigned base = smem_s + (unsigned) q * BL.bytes;
         const unsigned bar = mbar_s + 8u * (unsigned) q;
         sk_es[q] = sk_sws[q] = sk_swc[q] = sk_stn[q] = sk_stt[q] = sk_sta[q] = 0;
         sk_tv[q] = sk_tm[q] = sk_last[q] = sk_ep[q] = 0;
-#pragma unroll 1
-        for (int round = 0; round < 2; round++) {
-            const bool issue = (round == 1) && tid == 0;
+        const bool have = bb >= bmin && m.S > 0, sw = bb > bmin;
+        // table x of the block: source, bytes, destination (nothing kept in
+        // registers between the uses: thread 0 evaluates it again)
+        auto table = [&](int x, const void *&src, int &nby, unsigned &dst) {
+            src = 0; nby = 0; dst = base;
+            switch (x) {
+            case 0:
+                src = closed_form ? (const void *) (tmvecg + (size_t) bb * AWB_TM_NVEC * T)
+                                  : (const void *) (ling + (size_t) bb * 7 * T);
+                nby = have ? (closed_form ? 8 * AWB_TM_NVEC * T : 8 * 7 * T) : 0;
+                dst = base + BL.tv; break;
+            case 1: src = tmatrixg + (size_t) bb * T * T; nby = have ? 8 * T * T : 0;
+                dst = base + BL.tm; break;
+            case 2: src = st_nodeg + m.r0; nby = have ? 2 * m.S : 0; dst = base + BL.stn; break;
+            case 3: src = st_timeg + m.r0; nby = have ? m.S : 0; dst = base + BL.stt; break;
+            case 4: src = st_ageg + m.r0; nby = have ? m.S : 0; dst = base + BL.sta; break;
+            case 5: src = fwg + m.fwoff - m.n1(); nby = sw ? 8 * m.n1() : 0;
+                dst = base + BL.last; break;
+            case 6: src = sw_probg + m.entoff; nby = sw ? 8 * m.nent() : 0;
+                dst = base + BL.ep; break;
+            case 7: src = sw_srcg + m.entoff; nby = sw ? 2 * m.nent() : 0;
+                dst = base + BL.es; break;
+            case 8: src = sw_startg + m.r0; nby = sw ? 2 * m.S1() : 0; dst = base + BL.sws; break;
+            default: src = sw_cntg + m.r0; nby = sw ? 2 * m.S1() : 0; dst = base + BL.swc; break;
+            }
+        };
+        unsigned sk[10];
+#pragma unroll
+        for (int x = 0; x < 10; x++) {
+            const void *src; int nby; unsigned dst;
+            table(x, src, nby, dst);
+            sk[x] = nby > 0 ? (unsigned) ((unsigned long long) src & 15ull) : 0u;
+        }
+        sk_tv[q] = sk[0]; sk_tm[q] = sk[1]; sk_stn[q] = sk[2]; sk_stt[q] = sk[3];
+        sk_sta[q] = sk[4]; sk_last[q] = sk[5]; sk_ep[q] = sk[6]; sk_es[q] = sk[7];
+        sk_sws[q] = sk[8]; sk_swc[q] = sk[9];
+        if (tid == 0) {
             unsigned total = 0;
-            if (bb >= bmin && m.S > 0) {
-                if (closed_form)
-                    sk_tv[q] = awb_tb_bulk(base + BL.tv, tmvecg + (size_t) bb * AWB_TM_NVEC * T,
-                                           8 * AWB_TM_NVEC * T, bar, issue, total);
-                else
-                    sk_tv[q] = awb_tb_bulk(base + BL.tv, ling + (size_t) bb * 7 * T,
-                                           8 * 7 * T, bar, issue, total);
-                sk_tm[q] = awb_tb_bulk(base + BL.tm, tmatrixg + (size_t) bb * T * T,
-                                       8 * T * T, bar, issue, total);
-                sk_stn[q] = awb_tb_bulk(base + BL.stn, st_nodeg + m.r0, 2 * m.S, bar, issue, total);
-                sk_stt[q] = awb_tb_bulk(base + BL.stt, st_timeg + m.r0, m.S, bar, issue, total);
-                sk_sta[q] = awb_tb_bulk(base + BL.sta, st_ageg + m.r0, m.S, bar, issue, total);
+#pragma unroll
+            for (int x = 0; x < 10; x++) {
+                const void *src; int nby; unsigned dst;
+                table(x, src, nby, dst);
+                if (nby > 0)
+                    total += (sk[x] + (unsigned) nby + 15u) & ~15u;
             }
-            if (bb > bmin) {
-                sk_last[q] = awb_tb_bulk(base + BL.last, fwg + m.fwoff - m.n1(), 8 * m.n1(),
-                                         bar, issue, total);
-                sk_ep[q] = awb_tb_bulk(base + BL.ep, sw_probg + m.entoff, 8 * m.nent(),
-                                       bar, issue, total);
-                sk_es[q] = awb_tb_bulk(base + BL.es, sw_srcg + m.entoff, 2 * m.nent(),
-                                       bar, issue, total);
-                sk_sws[q] = awb_tb_bulk(base + BL.sws, sw_startg + m.r0, 2 * m.S1(),
-                                        bar, issue, total);
-                sk_swc[q] = awb_tb_bulk(base + BL.swc, sw_cntg + m.r0, 2 * m.S1(),
-                                        bar, issue, total);
+            awb_mbar_expect_tx(bar, total);
+#pragma unroll
+            for (int x = 0; x < 10; x++) {
+                const void *src; int nby; unsigned dst;
+                table(x, src, nby, dst);
+                if (nby > 0)
+                    awb_bulk_g2s(dst, (const char *) src - sk[x],
+                                 (sk[x] + (unsigned) nby + 15u) & ~15u, bar);
             }
-            if (round == 0 && tid == 0)
-                awb_mbar_expect_tx(bar, total);
         }
     };
     // wait until buffer q's tables have landed
@@ -363,6 +373,11 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
         const long long nbytes = (long long) nrows * m.S1() * 8;
         for (long long o = (long long) tid * 128; o < nbytes; o += 128ll * AWB_TB_THREADS)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
+        // ... and their per-time sums (the wave's row totals come from them)
+        const char *f0 = (const char *) (fsumg + (size_t) (m.pos + m.blen - 1 - nrows) * (T - 1));
+        const long long fbytes = (long long) nrows * (T - 1) * 8;
+        for (long long o = (long long) tid * 128; o < fbytes + 128; o += 128ll * AWB_TB_THREADS)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(f0 + o));
     };
 
     // draw used for site s: the reference consumes one rand() per sampled site,
