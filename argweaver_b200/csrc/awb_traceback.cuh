@@ -665,13 +665,14 @@ awb_traceback_kernel(const AwbChain *chains, int rand_max, int maxS1, int maxT,
                 sm.kcur = kk;
                 pathg[pos - 1] = kk;
             }
-            __syncthreads();
-            k = sm.kcur;
         }
 
         // ---- the tables of block b-1 have landed; everyone is done with buffer q
+        // (one barrier for both: it also publishes the state thread 0 sampled)
         landed(q ^ 1);
         __syncthreads();
+        if (b > bmin)
+            k = sm.kcur;
         mC = mN;
         mN = mNN;
     }
