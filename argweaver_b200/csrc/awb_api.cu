@@ -116,10 +116,18 @@ __global__ void awb_kind_packed_kernel(const AwbChain *chains)
     }
 }
 
+// K1: a thread per block.  Thread-per-block work is bound by the number of
+// memory instructions -- every access of a warp goes to 32 different lines, ~32
+// cycles of the L1 pipe each -- which is why the worker packs its state tables
+// into 8-byte stores and keeps counters in difference arrays (awb_setup.cuh).
 // (tried: __launch_bounds__(64, 16) -- 64 registers instead of 86, 16 instead of
-// 10 CTAs per SM -- made it 58 % slower: the spilled arrays cost more than the
-// extra warps hide)
-__global__ void awb_block_setup_kernel(const AwbChain *chains, int *err)
+// 10 CTAs per SM -- 58 % slower: the spilled arrays cost more than the extra
+// warps hide.  Tried: the node arrays of a warp's 32 blocks staged in shared
+// memory as [node][lane], copied in and out coalesced -- 47 KB a warp at 99
+// nodes leaves 4 warps per SM, and the latency of one warp per scheduler costs
+// more (11.5 ms) than the bank-conflict-free accesses save (10.8 ms in place).)
+__global__ void __launch_bounds__(32)
+awb_block_setup_kernel(const AwbChain *chains, int *err)
 {
     const AwbChain &ch = chains[blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,10 +1197,10 @@ extern "C" int awb_batch_setup(awb_batch *b)
         const AwbChain *chains = b->d_chains + g0;
         const int Cg = g1 - g0;
         {
-            dim3 grid((b->maxB + 63) / 64, Cg);
+            dim3 grid((b->maxB + 31) / 32, Cg);
             {
                 KTimer kt(b, AWB_K_BLOCK);
-                awb_block_setup_kernel<<<grid, 64, 0, st>>>(chains, b->d_err);
+                awb_block_setup_kernel<<<grid, 32, 0, st>>>(chains, b->d_err);
             }
             dim3 grid2(b->maxB, Cg);
             KTimer kt(b, AWB_K_TMATRIX);

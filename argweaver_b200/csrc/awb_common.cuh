@@ -337,6 +337,9 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
         }
     }
     for (int len = 63; len >= 0; len--) {
+        // first fit: a warp that had no room for a branch of this length has
+        // none for the next one of the same length either
+        int w = 0;
         for (int i = head[len]; i != 0xFFFF; i = nxt[i]) {
             const int c = len == 63 ? cnt[i] : len + 1;
             int slot;
@@ -348,7 +351,6 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
                 fill[nw++] = 32;
                 fill[nw++] = 32;
             } else {
-                int w = 0;
                 while (w < nw && fill[w] + c > 32)
                     w++;
                 if (w == nw)

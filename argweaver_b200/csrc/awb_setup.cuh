@@ -21,6 +21,8 @@
 #ifndef AWB_SETUP_CUH
 #define AWB_SETUP_CUH
 
+#include <string.h>
+
 #include "awb_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -67,6 +69,85 @@ AWB_HD inline void awb_tmatrix_fill(const AwbChain &ch, int b, int first, int st
     }
 }
 
+AWB_HD inline void awb_store2(double *p, double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
+// Consecutive 2-byte / 1-byte / 8-byte values of a global array, stored 8 (16)
+// bytes at a time: a thread per block writes its state tables element by
+// element, every store of a warp touches 32 different sectors, and the number
+// of stores is what K1's time is made of.  The first and last group of a block
+// are written element-wise (they share their 8 bytes with the neighbour blocks).
+template <class E>
+struct AwbPacker {
+    static const int N = 8 / (int) sizeof(E);     // elements per 8-byte store
+    static const int BITS = 8 * (int) sizeof(E);
+    E *base;
+    long long pos;
+    unsigned long long acc;
+    int lo;             // first slot of the current group that is this block's
+    AWB_HD void init(E *arr, long long start)
+    {
+        base = arr;
+        pos = start;
+        acc = 0;
+        lo = (int) (start & (N - 1));
+    }
+    // (not through a cast pointer: the arrays are read back as E right away)
+    AWB_HD void store8(E *at)
+    {
+#ifdef __CUDA_ARCH__
+        asm volatile("st.u64 [%0], %1;" :: "l"(at), "l"(acc) : "memory");
+#else
+        memcpy(at, &acc, 8);
+#endif
+    }
+    AWB_HD void part(long long g0, int from, int to)
+    {
+        for (int q = from; q < to; q++)
+            base[g0 + q] = (E) (acc >> (BITS * q));
+    }
+    AWB_HD void put(unsigned v)
+    {
+        const int sl = (int) (pos & (N - 1));
+        const unsigned long long mask = (1ull << BITS) - 1ull;
+        acc |= ((unsigned long long) v & mask) << (BITS * sl);
+        pos++;
+        if (sl == N - 1) {
+            if (lo)
+                part(pos - N, lo, N);
+            else
+                store8(base + pos - N);
+            acc = 0;
+            lo = 0;
+        }
+    }
+    // the unfinished last group
+    AWB_HD void flush()
+    {
+        const int end = (int) (pos & (N - 1));
+        if (end)
+            part(pos - end, lo, end);
+        acc = 0;
+        lo = end;
+    }
+};
+
+AWB_HD inline void awb_zero_shorts(short *arr, long long start, int n)
+{
+    AwbPacker<short> pk;
+    pk.init(arr, start);
+    for (int i = 0; i < n; i++)
+        pk.put(0u);
+    pk.flush();
+}
+
 AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 {
     const AwbModel &m = ch.model;
@@ -79,6 +160,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     short *c1 = ch.child1 + (size_t) b * V;
     short *nfirst = ch.node_first + (size_t) b * V;
     short *ncnt = ch.node_cnt + (size_t) b * V;
+    short *order = ch.order + (size_t) b * V;
     const long long row0 = ch.row_off[b];
     if (ch.gen_mappings) {
         // make_node_mapping (local_tree.h:767-776): identity, except that the
@@ -93,9 +175,16 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 
     // ---- children in node-index order (local_tree.h:188-229)
     int root = -1;
-    for (int i = 0; i < V; i++) {
-        c0[i] = -1;
-        c1[i] = -1;
+    {
+        AwbPacker<short> p0, p1;
+        p0.init(ch.child0, (long long) b * V);
+        p1.init(ch.child1, (long long) b * V);
+        for (int i = 0; i < V; i++) {
+            p0.put(0xFFFFu);
+            p1.put(0xFFFFu);
+        }
+        p0.flush();
+        p1.flush();
     }
     for (int i = 0; i < V; i++) {
         const int p = parent[i];
@@ -122,11 +211,9 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     //      the emission kernel work through a level in parallel (nfirst holds
     //      the heights here; it is filled with its real content further down).
     {
-        short *order = ch.order + (size_t) b * V;
         short *lstart = ch.lstart + (size_t) b * (V + 2);
         int i;
-        for (i = 0; i < V; i++)
-            ncnt[i] = 0;
+        awb_zero_shorts(ch.node_cnt, (long long) b * V, V);
         for (i = 0; i < V; i++) {
             if (c0[i] != -1)
                 break;
@@ -205,8 +292,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     }
 
     // ---- which nodes carry states (states.cpp:124-143): ncnt = -1 marks ignored
-    for (int i = 0; i < V; i++)
-        ncnt[i] = 0;
+    awb_zero_shorts(ch.node_cnt, (long long) b * V, V);
     if (internal) {
         ncnt[root] = -1;
         int top = 0;
@@ -238,37 +324,56 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 
     // ---- states, node-major (states.cpp:53-74 / :146-165)
     int ns = 0;
-    for (int i = 0; i < V; i++) {
-        if (full_tree || ncnt[i] < 0) {
-            nfirst[i] = -1;
-            ncnt[i] = 0;
-            continue;
-        }
-        const int p = parent[i];
-        const int lo = awb_imax(age[i], minage);
-        const int hi = (p == -1 || (internal && p == root)) ? T - 2 : age[p];
-        const int cnt = hi - lo + 1;
-        if (cnt <= 0) {
-            nfirst[i] = -1;
-            ncnt[i] = 0;
-            continue;
-        }
-        nfirst[i] = (short) ns;
-        ncnt[i] = (short) cnt;
-        if (ns + cnt <= S) {
-            // (values in registers: the arrays may alias as far as the compiler
-            // knows, and every store would make it read age[i] etc. again)
-            const double *iev = ie[i == maintree_root ? 1 : 0];
-            const signed char ag = (signed char) age[i];
-            const long long k0 = row0 + ns - lo;
-            for (int t = lo; t <= hi; t++) {
-                ch.st_node[k0 + t] = (short) i;
-                ch.st_time[k0 + t] = (signed char) t;
-                ch.st_age[k0 + t] = ag;
-                ch.inv_emit[k0 + t] = iev[t];
+    {
+        // (the state tables are written through packers: 8 bytes a store)
+        AwbPacker<short> pk_node;
+        AwbPacker<signed char> pk_time, pk_age;
+        pk_node.init(ch.st_node, row0);
+        pk_time.init(ch.st_time, row0);
+        pk_age.init(ch.st_age, row0);
+        double ie_held = 0.0;       // inv_emit of an even row waiting for its neighbour
+        for (int i = 0; i < V; i++) {
+            if (full_tree || ncnt[i] < 0) {
+                nfirst[i] = -1;
+                ncnt[i] = 0;
+                continue;
             }
+            const int p = parent[i];
+            const int ai = age[i];
+            const int lo = awb_imax(ai, minage);
+            const int hi = (p == -1 || (internal && p == root)) ? T - 2 : age[p];
+            const int cnt = hi - lo + 1;
+            if (cnt <= 0) {
+                nfirst[i] = -1;
+                ncnt[i] = 0;
+                continue;
+            }
+            nfirst[i] = (short) ns;
+            ncnt[i] = (short) cnt;
+            if (ns + cnt <= S) {
+                const double *iev = ie[i == maintree_root ? 1 : 0];
+                long long k = row0 + ns;
+                for (int t = lo; t <= hi; t++, k++) {
+                    pk_node.put((unsigned) i);
+                    pk_time.put((unsigned) t);
+                    pk_age.put((unsigned) ai);
+                    if (k & 1) {
+                        if (k > row0)
+                            awb_store2(ch.inv_emit + k - 1, ie_held, iev[t]);
+                        else
+                            ch.inv_emit[k] = iev[t];
+                    } else {
+                        ie_held = iev[t];
+                    }
+                }
+            }
+            ns += cnt;
         }
-        ns += cnt;
+        pk_node.flush();
+        pk_time.flush();
+        pk_age.flush();
+        if (ns <= S && ns > 0 && ((row0 + ns) & 1))
+            ch.inv_emit[row0 + ns - 1] = ie_held;      // an even last row
     }
     if (ns != S)
         return 1;   // host layout and device enumeration disagree
@@ -280,24 +385,33 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     // ---- lineage counts (local_tree.cpp:34-69 / :82-131)
     //      counted in thread-local arrays (one thread per block on the GPU: the
     //      increments would be scattered read-modify-writes in global memory)
-    int nbranches[AWB_MAXT], nrecombs[AWB_MAXT], ncoals[AWB_MAXT];
-    for (int i = 0; i < T; i++)
-        nbranches[i] = nrecombs[i] = ncoals[i] = 0;
+    //      A branch from age a to its parent's age pa adds one to nbranches on
+    //      [a, pa) -- [a, pa] for the top branch -- and one to nrecombs and
+    //      ncoals on [a, pa]: difference arrays, then prefix sums.
+    int nbranches[AWB_MAXT + 1], nrecombs[AWB_MAXT + 1], ncoals[AWB_MAXT + 1];
+    for (int i = 0; i <= T; i++)
+        nbranches[i] = nrecombs[i] = 0;
     for (int i = 0; i < V; i++) {
         if (internal && (i == subtree_root || i == root))
             continue;
         const int p = parent[i];
         const bool top = internal ? (p == root) : (p == -1);
         const int pa = top ? T - 2 : age[p];
-        for (int j = age[i]; j < pa; j++) {
-            nbranches[j]++;
-            nrecombs[j]++;
-            ncoals[j]++;
+        const int a = awb_imin(age[i], pa);
+        nbranches[a]++;
+        nbranches[top ? pa + 1 : pa]--;
+        nrecombs[a]++;
+        nrecombs[pa + 1]--;
+    }
+    {
+        int rb = 0, rr = 0;
+        for (int i = 0; i < T; i++) {
+            rb += nbranches[i];
+            rr += nrecombs[i];
+            nbranches[i] = rb;
+            nrecombs[i] = rr;
+            ncoals[i] = rr;
         }
-        nrecombs[pa]++;
-        ncoals[pa]++;
-        if (top)
-            nbranches[pa]++;
     }
     if (internal) {
         const int sa = age[subtree_root];
@@ -344,6 +458,8 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         // running cumulative coalescent rates C[2b-2], C[2b-1] (trans.cpp:44-54)
         double Cm2 = 0.0, Cm1 = 0.0;       // C[2b-2], C[2b-1] for b = 0
         double cr_m1 = 0.0;                // coal_rates[2b-1]
+        double lnb_prev = 0.0;             // tv[LNB][bb - 1]
+        double *lin = ch.lin + (size_t) b * 7 * T;
         for (int bb = 0; bb < T - 1; bb++) {
             const double cr0 = m.coal_time_steps[2 * bb] * nbranches[bb] /
                 (2.0 * m.popsizes[bb]);                       // coal_rates[2b]
@@ -359,23 +475,42 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             }
             const double nb = nbranches[bb], nr = nrecombs[bb];
             const double term = Cm1 + log(m.time_steps[bb] * (nb + 1.0) / (nr + 1.0));
-            tv[AWB_TM_LNB * T + bb] = (bb == 0) ? term :
-                awb_logadd(tv[AWB_TM_LNB * T + bb - 1], term);
+            const double lnb = (bb == 0) ? term : awb_logadd(lnb_prev, term);
+            tv[AWB_TM_LNB * T + bb] = lnb;
             const double le2 = -Cm2 +
                 (bb < T - 2 ? log(1 - exp(-cr0 - cr_m1)) : 0.0);
             tv[AWB_TM_LNE2 * T + bb] = le2;
             const int below = (bb < root_age_index) ? 1 : 0;
-            tv[AWB_TM_LNNEGG1 * T + bb] = Cm1 + log(-m.time_steps[bb] * (
+            const double lnnegg1 = Cm1 + log(-m.time_steps[bb] * (
                 (nb / (nr + 1.0 + below)) - (nb + 1.0) / (nr + 1.0)));
+            tv[AWB_TM_LNNEGG1 * T + bb] = lnnegg1;
             const double g = (bb < T - 2 ? 1.0 - exp(-cr0) : 1.0);
-            tv[AWB_TM_G2 * T + bb] = g * m.time_steps[bb] * (nb + 1.0) / (nr + 1.0);
-            tv[AWB_TM_G3 * T + bb] = g * m.time_steps[bb] *
-                (nb / (nr + 1.0 + below));
+            const double g2 = g * m.time_steps[bb] * (nb + 1.0) / (nr + 1.0);
+            const double g3 = g * m.time_steps[bb] * (nb / (nr + 1.0 + below));
+            tv[AWB_TM_G2 * T + bb] = g2;
+            tv[AWB_TM_G3 * T + bb] = g3;
             tv[AWB_TM_LNG4 * T + bb] = -Cm2 +
                 (bb < T - 2 ? log(1.0 - exp(-cr0 - cr_m1)) : 0.0);
-            tv[AWB_TM_D * T + bb] = (1.0 - exp(-m.rho * treelen2)) / treelen2_b;
-            tv[AWB_TM_E * T + bb] = 1.0 / ncoals[bb];
-            tv[AWB_TM_NORECOMBS * T + bb] = exp(-fmax(m.rho * treelen2, m.rho));
+            const double Dv = (1.0 - exp(-m.rho * treelen2)) / treelen2_b;
+            const double Ev = 1.0 / ncoals[bb];
+            const double nrc = exp(-fmax(m.rho * treelen2, m.rho));
+            tv[AWB_TM_D * T + bb] = Dv;
+            tv[AWB_TM_E * T + bb] = Ev;
+            tv[AWB_TM_NORECOMBS * T + bb] = nrc;
+            // the linear-domain vectors of the fast forward kernel, from the
+            // values at hand (the stored ones need not be read back)
+            {
+                const double Bx = exp(lnb);
+                const double pre = (bb > 0) ? exp(le2 + lnb_prev) : 0.0;
+                lin[0 * T + bb] = Dv;
+                lin[1 * T + bb] = Bx - exp(lnnegg1);
+                lin[2 * T + bb] = Bx;
+                lin[3 * T + bb] = Ev * exp(le2);
+                lin[4 * T + bb] = Ev * (pre + g3);
+                lin[5 * T + bb] = Ev * (pre + g2);
+                lin[6 * T + bb] = nrc;
+            }
+            lnb_prev = lnb;
             // advance: C[2b] = C[2b-1] + cr0 ; C[2b+1] = C[2b] + cr1
             const double C2b = Cm1 + cr0;
             Cm2 = C2b;
@@ -384,6 +519,8 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         }
         for (int k = 0; k < AWB_TM_NVEC; k++)
             tv[k * T + T - 1] = 0.0;
+        for (int k = 0; k < 7; k++)
+            lin[k * T + T - 1] = 0.0;
     }
 
     // ---- time-major permutation, row starts, partial slots
@@ -430,12 +567,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         unsigned char *sct = ch.sc_stride + (size_t) b * AWB_NSCRIBE;
         int zbase[AWB_MAXT];
         {
-            for (int l = 0; l < AWB_NSCRIBE; l++) {
-                scs[l] = 0;
-                scc[l] = 0;
-                scr[l] = 255;
-                sct[l] = 1;
-            }
             int wrow[AWB_MAXT];
             for (int t = 0; t < T - 1; t++)
                 wrow[t] = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
@@ -443,38 +574,72 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             if (awb_scribe_plan(wrow, T - 1, CH) > ch.zcap)
                 return 7;       // the host layout sized the buffer with the same code
             ch.sc_ch[b] = (unsigned short) CH;
+            // (the four tables are written once, lane by lane, through packers;
+            // a lane without a row: start 0, count 0, row 255, stride 1)
+            AwbPacker<unsigned short> pks, pkc;
+            AwbPacker<unsigned char> pkr, pkt;
+            pks.init(ch.sc_start, (long long) b * AWB_NSCRIBE);
+            pkc.init(ch.sc_cnt, (long long) b * AWB_NSCRIBE);
+            pkr.init(ch.sc_row, (long long) b * AWB_NSCRIBE);
+            pkt.init(ch.sc_stride, (long long) b * AWB_NSCRIBE);
             int l = 0, zb = 0;
             for (int t = 0; t < T - 1; t++) {
                 // every row gets at least one lane: an empty row sums zeros
-                const int w = (S == 0) ? (t == 0 ? 1 : 0) : rowstart[t + 1] - rowstart[t];
+                const int w = wrow[t];
                 const int nl = w == 0 ? 1 : (w + CH - 1) / CH;
-                if ((l & 31) + nl > 32) l = (l + 31) & ~31;
+                if ((l & 31) + nl > 32) {
+                    for (; l & 31; l++) {
+                        pks.put(0u); pkc.put(0u); pkr.put(255u); pkt.put(1u);
+                    }
+                }
                 zbase[t] = zb - (S == 0 ? 0 : rowstart[t]);   // padded slot = zbase + time-major position
                 for (int i = 0; i < nl; i++) {
-                    scs[l] = (unsigned short) (zb + i);
-                    scc[l] = (unsigned short) (w > i ? (w - i + nl - 1) / nl : 0);   // real slots
-                    scr[l] = (unsigned char) t;
-                    sct[l] = (unsigned char) nl;
+                    pks.put((unsigned) (zb + i));
+                    pkc.put((unsigned) (w > i ? (w - i + nl - 1) / nl : 0));   // real slots
+                    pkr.put((unsigned) t);
+                    pkt.put((unsigned) nl);
                     l++;
                 }
                 zb += nl * CH;
             }
+            for (; l < AWB_NSCRIBE; l++) {
+                pks.put(0u); pkc.put(0u); pkr.put(255u); pkt.put(1u);
+            }
+            pks.flush(); pkc.flush(); pkr.flush(); pkt.flush();
         }
 
         if (S > 0) {
-            for (int i = 0; i < V; i++) {
-                const int cnt = ncnt[i];
-                if (cnt <= 0) continue;
-                const int lo = awb_imax(age[i], minage);
-                const int nf = nfirst[i];
-                for (int x = 0; x < cnt; x++) {
-                    const int tt = lo + x;
-                    const int pos = rowpos[tt]++;
-                    const int st = nf + x;
-                    ch.perm[row0 + pos] = (unsigned short) st;
-                    ch.iperm[row0 + st] = (unsigned short) (zbase[tt] + pos);
+            // (the states come in order, st = 0, 1, ..: iperm goes through a
+            // packer; perm is the generic forward kernel's)
+            AwbPacker<unsigned short> pk_iperm;
+            pk_iperm.init(ch.iperm, row0);
+            const bool want_perm = ch.need_band != 0;
+            if (!want_perm) {
+                // one running counter per row: the next padded slot
+                for (int t = 0; t < T - 1; t++)
+                    zbase[t] += rowpos[t];
+                for (int i = 0; i < V; i++) {
+                    const int cnt = ncnt[i];
+                    if (cnt <= 0) continue;
+                    const int lo = awb_imax(age[i], minage);
+                    for (int x = 0; x < cnt; x++)
+                        pk_iperm.put((unsigned) zbase[lo + x]++);
+                }
+            } else {
+                for (int i = 0; i < V; i++) {
+                    const int cnt = ncnt[i];
+                    if (cnt <= 0) continue;
+                    const int lo = awb_imax(age[i], minage);
+                    const int nf = nfirst[i];
+                    for (int x = 0; x < cnt; x++) {
+                        const int tt = lo + x;
+                        const int pos = rowpos[tt]++;
+                        ch.perm[row0 + pos] = (unsigned short) (nf + x);
+                        pk_iperm.put((unsigned) (zbase[tt] + pos));
+                    }
                 }
             }
+            pk_iperm.flush();
         }
         if (S == 0)
             ch.perm[row0] = 0;
@@ -545,25 +710,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                 if (tpos > NSb)
                     return 6;
             }
-        }
-
-        // linear-domain transition vectors
-        double *lin = ch.lin + (size_t) b * 7 * T;
-        for (int t = 0; t < T; t++) {
-            const bool ok = t < T - 1;
-            const double Bx = ok ? exp(tv[AWB_TM_LNB * T + t]) : 0.0;
-            const double NG1 = ok ? exp(tv[AWB_TM_LNNEGG1 * T + t]) : 0.0;
-            const double e2 = ok ? exp(tv[AWB_TM_LNE2 * T + t]) : 0.0;
-            const double E = ok ? tv[AWB_TM_E * T + t] : 0.0;
-            const double pre = (ok && t > 0) ?
-                exp(tv[AWB_TM_LNE2 * T + t] + tv[AWB_TM_LNB * T + t - 1]) : 0.0;
-            lin[0 * T + t] = ok ? tv[AWB_TM_D * T + t] : 0.0;
-            lin[1 * T + t] = Bx - NG1;
-            lin[2 * T + t] = Bx;
-            lin[3 * T + t] = E * e2;
-            lin[4 * T + t] = ok ? E * (pre + tv[AWB_TM_G3 * T + t]) : 0.0;
-            lin[5 * T + t] = ok ? E * (pre + tv[AWB_TM_G2 * T + t]) : 0.0;
-            lin[6 * T + t] = ok ? tv[AWB_TM_NORECOMBS * T + t] : 0.0;
         }
     }
 

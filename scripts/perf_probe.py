@@ -22,6 +22,8 @@ def main():
                     help="alignment as variant columns (the .sites form)")
     ap.add_argument("--rho", type=float, default=1.6e-8,
                     help="recombination rate of the simulation (lower: longer blocks)")
+    ap.add_argument("--ktimes", type=int, default=0,
+                    help="also print the per-kernel times (CUDA events around each launch)")
     a = ap.parse_args()
     for C in [int(x) for x in a.chains.split(",")]:
         t0 = time.time()
@@ -42,7 +44,13 @@ def main():
             b.upload()
             b.sync()
             tu = time.time() - t0
+            if a.ktimes:
+                b.kernel_times(True)
             b.setup().forward().traceback(rs).sync()
+            if a.ktimes:
+                kt = b.get_kernel_times()
+                print("kernel ms: " + " ".join("%s %.2f" % (k, v) for k, v in kt.items()
+                                                if k != "forward_bytes"), flush=True)
             tm = b.timings()
             ss = b.total_states_sites()
             print("k=%d n=%d T=%d C=%d int=%d | gen %.1fs create %.3fs upload %.3fs | "

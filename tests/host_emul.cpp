@@ -46,6 +46,10 @@ void *emul_create(const awb_problem *p)
         memcpy(&e->arena[e->L.copies[i].dst_off], e->L.copies[i].src,
                e->L.copies[i].bytes);
     awb_layout_bind(e->L, *p, e->arena.data(), e->ch);
+    // (the fast forward kernel's batches run K1 without the generic kernel's
+    // tables: AWB_EMUL_NO_BAND=1 takes that branch; emul_forward needs them)
+    if (getenv("AWB_EMUL_NO_BAND") && atoi(getenv("AWB_EMUL_NO_BAND")))
+        e->ch.need_band = 0;
     e->scratch.assign(awb_emit_scratch_bytes(p->nnodes) + 64, 0);
     return e;
 }

@@ -93,6 +93,33 @@ def test_setup_workers_generated(k, n, T, internal, seed):
                                        internal=internal))
 
 
+def _raw(e, name):
+    nb = el.lib().emul_array_bytes(e.h, name.encode())
+    out = np.empty(nb, np.uint8)
+    assert el.lib().emul_get(e.h, name.encode(), out.ctypes.data, nb) == 0
+    return out
+
+
+@pytest.mark.parametrize("k,n,T,internal,seed",
+                         [(6, 700, 20, 0, 1), (9, 900, 20, 1, 2), (33, 6000, 20, 0, 3),
+                          (20, 6000, 40, 1, 4), (12, 4000, 64, 0, 5)])
+def test_block_setup_without_generic_tables(k, n, T, internal, seed, monkeypatch):
+    # batches on the fast forward kernel run K1 with need_band = 0 (no perm, no
+    # band, one running slot counter per time row): every table the fast path
+    # reads is byte-identical to the full run's
+    d = sim.simulate_problem(k, n, ntimes=T, seed=seed, internal=internal)
+    monkeypatch.delenv("AWB_EMUL_NO_BAND", raising=False)
+    a = el.Emul(d).setup()
+    monkeypatch.setenv("AWB_EMUL_NO_BAND", "1")
+    b = el.Emul(d).setup()
+    for name in ["st_node", "st_time", "inv_emit", "tmvec", "rowstart", "tmap", "iperm",
+                 "lin", "node_first", "node_cnt", "child0", "child1", "order", "root",
+                 "lineages", "treelen", "tm_minage", "tmatrix", "sw_start", "sw_cnt",
+                 "sw_src", "sw_prob"]:
+        assert np.array_equal(_raw(a, name), _raw(b, name)), name
+    assert not np.array_equal(_raw(a, "perm"), _raw(b, "perm")) or k <= 6
+
+
 @pytest.mark.parametrize("k,T,popsize", [(30, 64, 200.), (24, 64, 100.)])
 def test_setup_workers_skewed_time_rows(k, T, popsize):
     # all lineages coalesce in the first few of 63 time rows: one wide row and
