@@ -126,6 +126,7 @@ __global__ void awb_kind_packed_kernel(const AwbChain *chains)
 // memory as [node][lane], copied in and out coalesced -- 47 KB a warp at 99
 // nodes leaves 4 warps per SM, and the latency of one warp per scheduler costs
 // more (11.5 ms) than the bank-conflict-free accesses save (10.8 ms in place).)
+template <int VCAP>
 __global__ void __launch_bounds__(32)
 awb_block_setup_kernel(const AwbChain *chains, int *err)
 {
@@ -133,7 +134,7 @@ awb_block_setup_kernel(const AwbChain *chains, int *err)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= ch.ntrees)
         return;
-    const int rc = awb_block_setup(ch, b);
+    const int rc = awb_block_setup_t<VCAP>(ch, b);
     if (rc)
         atomicMax(err, 100 + rc);
 }
@@ -1200,7 +1201,12 @@ extern "C" int awb_batch_setup(awb_batch *b)
             dim3 grid((b->maxB + 31) / 32, Cg);
             {
                 KTimer kt(b, AWB_K_BLOCK);
-                awb_block_setup_kernel<<<grid, 32, 0, st>>>(chains, b->d_err);
+                if (b->maxV <= AWB_K1_VCAP_SMALL)
+                    awb_block_setup_kernel<AWB_K1_VCAP_SMALL><<<grid, 32, 0, st>>>(chains, b->d_err);
+                else if (b->maxV <= AWB_K1_VCAP_MID)
+                    awb_block_setup_kernel<AWB_K1_VCAP_MID><<<grid, 32, 0, st>>>(chains, b->d_err);
+                else
+                    awb_block_setup_kernel<AWB_MAXV><<<grid, 32, 0, st>>>(chains, b->d_err);
             }
             dim3 grid2(b->maxB, Cg);
             KTimer kt(b, AWB_K_TMATRIX);

@@ -317,15 +317,16 @@ AWB_HD inline int awb_imin(int a, int b) { return a < b ? a : b; }
 // of thread slots (a multiple of 32).  A branch of 33..64 states takes the slots
 // of two whole warps, starting at an even one: the forward kernel then keeps
 // it in two register sets of one warp (awb_forward_fast.cuh).
-AWB_HD inline int awb_pack_branches(const short *cnt, int V,
-                                    unsigned short *tmap, const short *nfirst,
-                                    int cap)
+template <int VCAP>
+AWB_HD inline int awb_pack_branches_t(const short *cnt, int V,
+                                      unsigned short *tmap, const short *nfirst,
+                                      int cap)
 {
     unsigned char fill[AWB_MAXS / 32 + 2];
     int nw = 0;
     // the branches of each length, in node order: one pass over cnt (K1 reads
     // it from global memory), linked through nxt
-    unsigned short head[64], nxt[AWB_MAXV];
+    unsigned short head[64], nxt[VCAP];
     for (int l = 0; l < 64; l++)
         head[l] = 0xFFFF;
     for (int i = V - 1; i >= 0; i--) {
@@ -366,6 +367,13 @@ AWB_HD inline int awb_pack_branches(const short *cnt, int V,
         }
     }
     return 32 * (nw > 0 ? nw : 1);
+}
+
+AWB_HD inline int awb_pack_branches(const short *cnt, int V,
+                                    unsigned short *tmap, const short *nfirst,
+                                    int cap)
+{
+    return awb_pack_branches_t<AWB_MAXV>(cnt, V, tmap, nfirst, cap);
 }
 
 // The F-scribes' plan of one block (awb_setup.cuh K1 fills it in,

@@ -139,28 +139,30 @@ struct AwbPacker {
     }
 };
 
-AWB_HD inline void awb_zero_shorts(short *arr, long long start, int n)
-{
-    AwbPacker<short> pk;
-    pk.init(arr, start);
-    for (int i = 0; i < n; i++)
-        pk.put(0u);
-    pk.flush();
-}
-
-AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
+// VCAP: capacity of the per-node working arrays (>= nnodes).  They are the
+// thread's own (local memory on the GPU): the worker walks parent / age /
+// children many times, and where the global arrays cost a warp 32 cache lines
+// an access (32 blocks, 32 rows), element i of 32 threads' local arrays is ONE
+// line -- consecutive blocks are nearly the same tree, so the lanes of a warp
+// ask for the same i nearly all the time.  The results (children, state ranges,
+// post-order) are copied out once, packed.
+template <int VCAP>
+AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
 {
     const AwbModel &m = ch.model;
     const int T = m.ntimes;
     const int V = ch.nnodes;
     const bool internal = ch.internal != 0;
-    const int *parent = ch.ptrees + (size_t) b * V;
-    const int *age = ch.ages + (size_t) b * V;
-    short *c0 = ch.child0 + (size_t) b * V;
-    short *c1 = ch.child1 + (size_t) b * V;
-    short *nfirst = ch.node_first + (size_t) b * V;
-    short *ncnt = ch.node_cnt + (size_t) b * V;
-    short *order = ch.order + (size_t) b * V;
+    short parent[VCAP], c0[VCAP], c1[VCAP], nfirst[VCAP], ncnt[VCAP], order[VCAP];
+    signed char age[VCAP];
+    {
+        const int *gp = ch.ptrees + (size_t) b * V;
+        const int *ga = ch.ages + (size_t) b * V;
+        for (int i = 0; i < V; i++) {
+            parent[i] = (short) gp[i];
+            age[i] = (signed char) ga[i];
+        }
+    }
     const long long row0 = ch.row_off[b];
     if (ch.gen_mappings) {
         // make_node_mapping (local_tree.h:767-776): identity, except that the
@@ -175,16 +177,9 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
 
     // ---- children in node-index order (local_tree.h:188-229)
     int root = -1;
-    {
-        AwbPacker<short> p0, p1;
-        p0.init(ch.child0, (long long) b * V);
-        p1.init(ch.child1, (long long) b * V);
-        for (int i = 0; i < V; i++) {
-            p0.put(0xFFFFu);
-            p1.put(0xFFFFu);
-        }
-        p0.flush();
-        p1.flush();
+    for (int i = 0; i < V; i++) {
+        c0[i] = -1;
+        c1[i] = -1;
     }
     for (int i = 0; i < V; i++) {
         const int p = parent[i];
@@ -213,7 +208,8 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     {
         short *lstart = ch.lstart + (size_t) b * (V + 2);
         int i;
-        awb_zero_shorts(ch.node_cnt, (long long) b * V, V);
+        for (i = 0; i < V; i++)
+            ncnt[i] = 0;
         for (i = 0; i < V; i++) {
             if (c0[i] != -1)
                 break;
@@ -292,7 +288,8 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     }
 
     // ---- which nodes carry states (states.cpp:124-143): ncnt = -1 marks ignored
-    awb_zero_shorts(ch.node_cnt, (long long) b * V, V);
+    for (int i = 0; i < V; i++)
+        ncnt[i] = 0;
     if (internal) {
         ncnt[root] = -1;
         int top = 0;
@@ -377,6 +374,28 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
     }
     if (ns != S)
         return 1;   // host layout and device enumeration disagree
+    {
+        // the node tables the later kernels read
+        AwbPacker<short> p0, p1, pf, pc, po;
+        const long long o = (long long) b * V;
+        p0.init(ch.child0, o);
+        p1.init(ch.child1, o);
+        pf.init(ch.node_first, o);
+        pc.init(ch.node_cnt, o);
+        po.init(ch.order, o);
+        for (int i = 0; i < V; i++) {
+            p0.put((unsigned) c0[i]);
+            p1.put((unsigned) c1[i]);
+            pf.put((unsigned) nfirst[i]);
+            pc.put((unsigned) ncnt[i]);
+            po.put((unsigned) order[i]);
+        }
+        p0.flush();
+        p1.flush();
+        pf.flush();
+        pc.flush();
+        po.flush();
+    }
     if (S == 0) {
         ch.st_node[row0] = -1;
         ch.st_time[row0] = -1;
@@ -561,10 +580,6 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
         // words, no bank conflicts), and EVERY lane reads exactly CH slots -- the
         // padding holds zeros -- so the summation loop has no clamps or masks.
         // iperm[state] is the state's padded slot.
-        unsigned short *scs = ch.sc_start + (size_t) b * AWB_NSCRIBE;
-        unsigned short *scc = ch.sc_cnt + (size_t) b * AWB_NSCRIBE;
-        unsigned char *scr = ch.sc_row + (size_t) b * AWB_NSCRIBE;
-        unsigned char *sct = ch.sc_stride + (size_t) b * AWB_NSCRIBE;
         int zbase[AWB_MAXT];
         {
             int wrow[AWB_MAXT];
@@ -689,7 +704,7 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
             // first-fit-decreasing packing when it fits the reserved slots (it
             // nearly always does, and is tighter); else node order, which is
             // what the host reserved (awb_count_states)
-            if (awb_pack_branches(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb) {
+            if (awb_pack_branches_t<VCAP>(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb) {
                 for (int t = 0; t < NSb; t++)
                     ch.tmap[tr0 + t] = 0xFFFF;
                 int tpos = 0;
@@ -762,6 +777,21 @@ AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
                                      ch.minage, m);
     }
     return 0;
+}
+
+// working-array capacities the kernels are built for (the stack of a thread is
+// sized by the largest array, and the driver reserves it for every thread that
+// can be resident)
+#define AWB_K1_VCAP_SMALL 128
+#define AWB_K1_VCAP_MID 256
+
+AWB_HD inline int awb_block_setup(const AwbChain &ch, int b)
+{
+    if (ch.nnodes <= AWB_K1_VCAP_SMALL)
+        return awb_block_setup_t<AWB_K1_VCAP_SMALL>(ch, b);
+    if (ch.nnodes <= AWB_K1_VCAP_MID)
+        return awb_block_setup_t<AWB_K1_VCAP_MID>(ch, b);
+    return awb_block_setup_t<AWB_MAXV>(ch, b);
 }
 
 // ---------------------------------------------------------------------------
