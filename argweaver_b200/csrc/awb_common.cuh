@@ -20,6 +20,8 @@
 #ifndef AWB_COMMON_CUH
 #define AWB_COMMON_CUH
 
+#include <string.h>
+
 #include <math.h>
 #include <stdint.h>
 
@@ -309,23 +311,146 @@ AWB_HD inline double awb_prob_branch(double t, double mu, bool mut)
 AWB_HD inline int awb_imax(int a, int b) { return a > b ? a : b; }
 AWB_HD inline int awb_imin(int a, int b) { return a < b ? a : b; }
 
+AWB_HD inline void awb_store2(double *p, double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
+// two doubles with one 16-byte store where the address allows it
+AWB_HD inline void awb_store_pair(double *p, double a, double b)
+{
+    if ((((size_t) p) & 15) == 0) {
+        awb_store2(p, a, b);
+    } else {
+        p[0] = a;
+        p[1] = b;
+    }
+}
+
+// two ints from an 8-byte aligned address
+AWB_HD inline void awb_load2i(const int *p, int &a, int &b)
+{
+#ifdef __CUDA_ARCH__
+    const int2 v = *reinterpret_cast<const int2 *>(p);
+    a = v.x;
+    b = v.y;
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
+
+// Consecutive 1-, 2- or 4-byte values of a global array, stored 8 bytes at a
+// time: a thread per block writes its state tables element by
+// element, every store of a warp touches 32 different sectors, and the number
+// of stores is what K1's time is made of.  The first and last group of a block
+// are written element-wise (they share their 8 bytes with the neighbour blocks).
+template <class E>
+struct AwbPacker {
+    static const int N = 8 / (int) sizeof(E);     // elements per 8-byte store
+    static const int BITS = 8 * (int) sizeof(E);
+    E *base;
+    long long pos;
+    unsigned long long acc;
+    int lo;             // first slot of the current group that is this block's
+    AWB_HD void init(E *arr, long long start)
+    {
+        base = arr;
+        pos = start;
+        acc = 0;
+        lo = (int) (start & (N - 1));
+    }
+    // (not through a cast pointer: the arrays are read back as E right away)
+    AWB_HD void store8(E *at)
+    {
+#ifdef __CUDA_ARCH__
+        asm volatile("st.u64 [%0], %1;" :: "l"(at), "l"(acc) : "memory");
+#else
+        memcpy(at, &acc, 8);
+#endif
+    }
+    AWB_HD void part(long long g0, int from, int to)
+    {
+        for (int q = from; q < to; q++)
+            base[g0 + q] = (E) (acc >> (BITS * q));
+    }
+    AWB_HD void put(unsigned v)
+    {
+        const int sl = (int) (pos & (N - 1));
+        const unsigned long long mask = (1ull << BITS) - 1ull;
+        acc |= ((unsigned long long) v & mask) << (BITS * sl);
+        pos++;
+        if (sl == N - 1) {
+            if (lo)
+                part(pos - N, lo, N);
+            else
+                store8(base + pos - N);
+            acc = 0;
+            lo = 0;
+        }
+    }
+    // the unfinished last group
+    AWB_HD void flush()
+    {
+        const int end = (int) (pos & (N - 1));
+        if (end)
+            part(pos - end, lo, end);
+        acc = 0;
+        lo = end;
+    }
+};
+
 // Thread packing of the fast forward kernel: every branch (cnt[i] consecutive
 // states of node i) gets consecutive lanes of ONE warp.  First-fit in
 // decreasing branch length, so the number of warps is close to S/32.  Used by
 // the host layout (to size the thread map) and by K1 (to fill it): both must
-// run the same code.  tmap/nfirst may be NULL (count only).  Returns the number
-// of thread slots (a multiple of 32).  A branch of 33..64 states takes the slots
-// of two whole warps, starting at an even one: the forward kernel then keeps
-// it in two register sets of one warp (awb_forward_fast.cuh).
+// run the same code.  A branch of 33..64 states takes the slots of two whole
+// warps, starting at an even one: the forward kernel then keeps it in two
+// register sets of one warp (awb_forward_fast.cuh).
+//
+// The placement only builds, per warp of slots ("row"), the list of its
+// branches in slot order; awb_pack_emit then writes the whole map front to
+// back through a packer (8 bytes a store; K1 is a thread per block and the
+// number of its stores is its time).
+#define AWB_PACK_ROWS (AWB_MAXS / 16 + 2)     // > 2048/17 one-per-row branches, > 2*2048/33 long ones
+
 template <int VCAP>
-AWB_HD inline int awb_pack_branches_t(const short *cnt, int V,
-                                      unsigned short *tmap, const short *nfirst,
-                                      int cap)
+struct AwbRowLists {
+    unsigned short rhead[AWB_PACK_ROWS], rtail[AWB_PACK_ROWS], rnext[VCAP];
+    int nw;                                   // rows in use
+    AWB_HD void open_row()
+    {
+        rhead[nw] = 0xFFFF;
+        rtail[nw] = 0xFFFF;
+        nw++;
+    }
+    AWB_HD void append(int w, int i)
+    {
+        rnext[i] = 0xFFFF;
+        if (rhead[w] == 0xFFFF)
+            rhead[w] = (unsigned short) i;
+        else
+            rnext[rtail[w]] = (unsigned short) i;
+        rtail[w] = (unsigned short) i;
+    }
+};
+
+// First-fit decreasing.  Returns the number of thread slots (a multiple of 32;
+// more than any map can hold when the rows run out).  rl may be NULL (count
+// only).
+template <int VCAP>
+AWB_HD inline int awb_pack_place(const short *cnt, int V, AwbRowLists<VCAP> *rl)
 {
-    unsigned char fill[AWB_MAXS / 32 + 2];
+    unsigned char fill[AWB_PACK_ROWS];
     int nw = 0;
-    // the branches of each length, in node order: one pass over cnt (K1 reads
-    // it from global memory), linked through nxt
+    if (rl)
+        rl->nw = 0;
+    // the branches of each length, in node order, linked through nxt
     unsigned short head[64], nxt[VCAP];
     for (int l = 0; l < 64; l++)
         head[l] = 0xFFFF;
@@ -343,37 +468,98 @@ AWB_HD inline int awb_pack_branches_t(const short *cnt, int V,
         int w = 0;
         for (int i = head[len]; i != 0xFFFF; i = nxt[i]) {
             const int c = len == 63 ? cnt[i] : len + 1;
-            int slot;
+            if (nw + 3 > AWB_PACK_ROWS)
+                return 32 * 4 * AWB_PACK_ROWS;
             if (c > 32) {
                 // 33..64 states: two whole warps' worth of slots starting at an
                 // even one (the long branches come first, two each)
-                nw = (nw + 1) & ~1;
-                slot = 32 * nw;
+                if (nw & 1) {
+                    fill[nw++] = 32;
+                    if (rl) rl->open_row();
+                }
                 fill[nw++] = 32;
                 fill[nw++] = 32;
+                if (rl) {
+                    rl->open_row();
+                    rl->open_row();
+                    rl->append(nw - 2, i);
+                }
             } else {
                 while (w < nw && fill[w] + c > 32)
                     w++;
-                if (w == nw)
+                if (w == nw) {
                     fill[nw++] = 0;
-                slot = 32 * w + fill[w];
+                    if (rl) rl->open_row();
+                }
                 fill[w] = (unsigned char) (fill[w] + c);
-            }
-            if (tmap && slot + c <= cap) {
-                const int nf = nfirst[i];
-                for (int t = 0; t < c; t++)
-                    tmap[slot + t] = (unsigned short) (nf + t);
+                if (rl) rl->append(w, i);
             }
         }
     }
     return 32 * (nw > 0 ? nw : 1);
 }
 
-AWB_HD inline int awb_pack_branches(const short *cnt, int V,
-                                    unsigned short *tmap, const short *nfirst,
-                                    int cap)
+// Node order (what the host reserves when it does not run the packing): a
+// branch that would straddle a warp starts the next one, a long branch takes
+// two whole warps from an even one.
+template <int VCAP>
+AWB_HD inline int awb_pack_place_in_order(const short *cnt, int V, AwbRowLists<VCAP> *rl)
 {
-    return awb_pack_branches_t<AWB_MAXV>(cnt, V, tmap, nfirst, cap);
+    int tpos = 0;
+    rl->nw = 0;
+    for (int i = 0; i < V; i++) {
+        const int c = cnt[i];
+        if (c <= 0) continue;
+        if (c > 32)
+            tpos = (tpos + 63) & ~63;
+        else if ((tpos & 31) + c > 32)
+            tpos = (tpos + 31) & ~31;
+        const int w = tpos >> 5;
+        if (w + 3 > AWB_PACK_ROWS)
+            return 32 * 4 * AWB_PACK_ROWS;
+        while (rl->nw <= w + (c > 32 ? 1 : 0))
+            rl->open_row();
+        rl->append(w, i);
+        tpos += c;
+        if (c > 32)
+            tpos = (tpos + 63) & ~63;
+    }
+    return tpos;
+}
+
+// the map of `cap` slots from the row lists: tmap[start + slot] = state, 0xFFFF
+// for a slot without one
+template <int VCAP>
+AWB_HD inline void awb_pack_emit(const AwbRowLists<VCAP> &rl, const short *cnt,
+                                 const short *nfirst, unsigned short *tmap, long long start,
+                                 int cap)
+{
+    AwbPacker<unsigned short> pk;
+    pk.init(tmap, start);
+    int done = 0;
+    for (int w = 0; w < rl.nw && done < cap; w++) {
+        int end = 32 * (w + 1);
+        for (int i = rl.rhead[w]; i != 0xFFFF; i = rl.rnext[i]) {
+            const int c = cnt[i], nf = nfirst[i];
+            if (c > 32)
+                end += 32;                      // this row and the next
+            for (int t = 0; t < c && done < cap; t++, done++)
+                pk.put((unsigned) (nf + t));
+        }
+        if (end > 32 * (w + 1))
+            w++;
+        for (; done < end && done < cap; done++)
+            pk.put(0xFFFFu);
+    }
+    for (; done < cap; done++)
+        pk.put(0xFFFFu);
+    pk.flush();
+}
+
+// count only (host layout)
+AWB_HD inline int awb_pack_branches(const short *cnt, int V)
+{
+    return awb_pack_place<AWB_MAXV>(cnt, V, (AwbRowLists<AWB_MAXV> *) 0);
 }
 
 // The F-scribes' plan of one block (awb_setup.cuh K1 fills it in,

@@ -519,7 +519,7 @@ inline bool awb_layout_build(const awb_problem &p, int keep_debug, AwbLayout &L,
             // K1 packs first-fit-decreasing when that is tighter; the exact
             // count only matters for a block that could raise the maximum
             const int ffd = S > 0 ?
-                awb_pack_branches(awb_pack_scratch().data(), V, 0, 0, 0) : 32;
+                awb_pack_branches(awb_pack_scratch().data(), V) : 32;
             const int used = ffd < NSb ? ffd : NSb;
             if (used > L.maxNS) L.maxNS = used;
         }

@@ -21,8 +21,6 @@
 #ifndef AWB_SETUP_CUH
 #define AWB_SETUP_CUH
 
-#include <string.h>
-
 #include "awb_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -69,76 +67,6 @@ AWB_HD inline void awb_tmatrix_fill(const AwbChain &ch, int b, int first, int st
     }
 }
 
-AWB_HD inline void awb_store2(double *p, double a, double b)
-{
-#ifdef __CUDA_ARCH__
-    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
-#else
-    p[0] = a;
-    p[1] = b;
-#endif
-}
-
-// Consecutive 2-byte / 1-byte / 8-byte values of a global array, stored 8 (16)
-// bytes at a time: a thread per block writes its state tables element by
-// element, every store of a warp touches 32 different sectors, and the number
-// of stores is what K1's time is made of.  The first and last group of a block
-// are written element-wise (they share their 8 bytes with the neighbour blocks).
-template <class E>
-struct AwbPacker {
-    static const int N = 8 / (int) sizeof(E);     // elements per 8-byte store
-    static const int BITS = 8 * (int) sizeof(E);
-    E *base;
-    long long pos;
-    unsigned long long acc;
-    int lo;             // first slot of the current group that is this block's
-    AWB_HD void init(E *arr, long long start)
-    {
-        base = arr;
-        pos = start;
-        acc = 0;
-        lo = (int) (start & (N - 1));
-    }
-    // (not through a cast pointer: the arrays are read back as E right away)
-    AWB_HD void store8(E *at)
-    {
-#ifdef __CUDA_ARCH__
-        asm volatile("st.u64 [%0], %1;" :: "l"(at), "l"(acc) : "memory");
-#else
-        memcpy(at, &acc, 8);
-#endif
-    }
-    AWB_HD void part(long long g0, int from, int to)
-    {
-        for (int q = from; q < to; q++)
-            base[g0 + q] = (E) (acc >> (BITS * q));
-    }
-    AWB_HD void put(unsigned v)
-    {
-        const int sl = (int) (pos & (N - 1));
-        const unsigned long long mask = (1ull << BITS) - 1ull;
-        acc |= ((unsigned long long) v & mask) << (BITS * sl);
-        pos++;
-        if (sl == N - 1) {
-            if (lo)
-                part(pos - N, lo, N);
-            else
-                store8(base + pos - N);
-            acc = 0;
-            lo = 0;
-        }
-    }
-    // the unfinished last group
-    AWB_HD void flush()
-    {
-        const int end = (int) (pos & (N - 1));
-        if (end)
-            part(pos - end, lo, end);
-        acc = 0;
-        lo = end;
-    }
-};
-
 // VCAP: capacity of the per-node working arrays (>= nnodes).  They are the
 // thread's own (local memory on the GPU): the worker walks parent / age /
 // children many times, and where the global arrays cost a warp 32 cache lines
@@ -158,7 +86,24 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
     {
         const int *gp = ch.ptrees + (size_t) b * V;
         const int *ga = ch.ages + (size_t) b * V;
-        for (int i = 0; i < V; i++) {
+        // (two nodes a load; ptrees and ages sit at the same offset of arrays
+        // aligned alike)
+        int i = 0;
+        if ((((size_t) gp) & 7) && V > 0) {
+            parent[0] = (short) gp[0];
+            age[0] = (signed char) ga[0];
+            i = 1;
+        }
+        for (; i + 1 < V; i += 2) {
+            int p0, p1, a0, a1;
+            awb_load2i(gp + i, p0, p1);
+            awb_load2i(ga + i, a0, a1);
+            parent[i] = (short) p0;
+            parent[i + 1] = (short) p1;
+            age[i] = (signed char) a0;
+            age[i + 1] = (signed char) a1;
+        }
+        if (i < V) {
             parent[i] = (short) gp[i];
             age[i] = (signed char) ga[i];
         }
@@ -442,12 +387,19 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
     }
     nbranches[T - 1] = 1;
     {
-        int *lg = ch.lineages + (size_t) b * 3 * T;
+        AwbPacker<int> pb, pr, pc;
+        const long long lg = (long long) b * 3 * T;
+        pb.init(ch.lineages, lg);
+        pr.init(ch.lineages, lg + T);
+        pc.init(ch.lineages, lg + 2 * T);
         for (int i = 0; i < T; i++) {
-            lg[i] = nbranches[i];
-            lg[T + i] = nrecombs[i];
-            lg[2 * T + i] = ncoals[i];
+            pb.put((unsigned) nbranches[i]);
+            pr.put((unsigned) nrecombs[i]);
+            pc.put((unsigned) ncoals[i]);
         }
+        pb.flush();
+        pr.flush();
+        pc.flush();
     }
 
     // ---- tree length (local_tree.cpp:136-176), summed in node order
@@ -479,6 +431,8 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
         double cr_m1 = 0.0;                // coal_rates[2b-1]
         double lnb_prev = 0.0;             // tv[LNB][bb - 1]
         double *lin = ch.lin + (size_t) b * 7 * T;
+        const int NROW = AWB_TM_NVEC + 7;  // rows of tv, then of lin
+        double cur[AWB_TM_NVEC + 7], prv[AWB_TM_NVEC + 7];
         for (int bb = 0; bb < T - 1; bb++) {
             const double cr0 = m.coal_time_steps[2 * bb] * nbranches[bb] /
                 (2.0 * m.popsizes[bb]);                       // coal_rates[2b]
@@ -495,39 +449,49 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
             const double nb = nbranches[bb], nr = nrecombs[bb];
             const double term = Cm1 + log(m.time_steps[bb] * (nb + 1.0) / (nr + 1.0));
             const double lnb = (bb == 0) ? term : awb_logadd(lnb_prev, term);
-            tv[AWB_TM_LNB * T + bb] = lnb;
             const double le2 = -Cm2 +
                 (bb < T - 2 ? log(1 - exp(-cr0 - cr_m1)) : 0.0);
-            tv[AWB_TM_LNE2 * T + bb] = le2;
             const int below = (bb < root_age_index) ? 1 : 0;
             const double lnnegg1 = Cm1 + log(-m.time_steps[bb] * (
                 (nb / (nr + 1.0 + below)) - (nb + 1.0) / (nr + 1.0)));
-            tv[AWB_TM_LNNEGG1 * T + bb] = lnnegg1;
             const double g = (bb < T - 2 ? 1.0 - exp(-cr0) : 1.0);
             const double g2 = g * m.time_steps[bb] * (nb + 1.0) / (nr + 1.0);
             const double g3 = g * m.time_steps[bb] * (nb / (nr + 1.0 + below));
-            tv[AWB_TM_G2 * T + bb] = g2;
-            tv[AWB_TM_G3 * T + bb] = g3;
-            tv[AWB_TM_LNG4 * T + bb] = -Cm2 +
-                (bb < T - 2 ? log(1.0 - exp(-cr0 - cr_m1)) : 0.0);
             const double Dv = (1.0 - exp(-m.rho * treelen2)) / treelen2_b;
             const double Ev = 1.0 / ncoals[bb];
             const double nrc = exp(-fmax(m.rho * treelen2, m.rho));
-            tv[AWB_TM_D * T + bb] = Dv;
-            tv[AWB_TM_E * T + bb] = Ev;
-            tv[AWB_TM_NORECOMBS * T + bb] = nrc;
+            cur[AWB_TM_LNB] = lnb;
+            cur[AWB_TM_LNE2] = le2;
+            cur[AWB_TM_LNNEGG1] = lnnegg1;
+            cur[AWB_TM_G2] = g2;
+            cur[AWB_TM_G3] = g3;
+            cur[AWB_TM_LNG4] = le2;             // (trans.cpp:93: the same expression)
+            cur[AWB_TM_D] = Dv;
+            cur[AWB_TM_E] = Ev;
+            cur[AWB_TM_NORECOMBS] = nrc;
             // the linear-domain vectors of the fast forward kernel, from the
             // values at hand (the stored ones need not be read back)
             {
                 const double Bx = exp(lnb);
                 const double pre = (bb > 0) ? exp(le2 + lnb_prev) : 0.0;
-                lin[0 * T + bb] = Dv;
-                lin[1 * T + bb] = Bx - exp(lnnegg1);
-                lin[2 * T + bb] = Bx;
-                lin[3 * T + bb] = Ev * exp(le2);
-                lin[4 * T + bb] = Ev * (pre + g3);
-                lin[5 * T + bb] = Ev * (pre + g2);
-                lin[6 * T + bb] = nrc;
+                cur[AWB_TM_NVEC + 0] = Dv;
+                cur[AWB_TM_NVEC + 1] = Bx - exp(lnnegg1);
+                cur[AWB_TM_NVEC + 2] = Bx;
+                cur[AWB_TM_NVEC + 3] = Ev * exp(le2);
+                cur[AWB_TM_NVEC + 4] = Ev * (pre + g3);
+                cur[AWB_TM_NVEC + 5] = Ev * (pre + g2);
+                cur[AWB_TM_NVEC + 6] = nrc;
+            }
+            // two time points a store
+            if (bb & 1) {
+#pragma unroll
+                for (int k = 0; k < NROW; k++)
+                    awb_store_pair((k < AWB_TM_NVEC ? tv + k * T : lin + (k - AWB_TM_NVEC) * T) +
+                                   bb - 1, prv[k], cur[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NROW; k++)
+                    prv[k] = cur[k];
             }
             lnb_prev = lnb;
             // advance: C[2b] = C[2b-1] + cr0 ; C[2b+1] = C[2b] + cr1
@@ -536,14 +500,19 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
             Cm1 = C2b + cr1;
             cr_m1 = cr1;
         }
-        for (int k = 0; k < AWB_TM_NVEC; k++)
-            tv[k * T + T - 1] = 0.0;
-        for (int k = 0; k < 7; k++)
-            lin[k * T + T - 1] = 0.0;
+        // the last time point holds zeros; with it, the row of an even T - 2
+#pragma unroll
+        for (int k = 0; k < NROW; k++) {
+            double *dst = (k < AWB_TM_NVEC ? tv + k * T : lin + (k - AWB_TM_NVEC) * T);
+            if ((T - 1) & 1)
+                awb_store_pair(dst + T - 2, prv[k], 0.0);
+            else
+                dst[T - 1] = 0.0;
+        }
     }
 
     // ---- time-major permutation, row starts, partial slots
-    unsigned short *rowstart = ch.rowstart + (size_t) b * (T + 1);
+    unsigned short rowstart[AWB_MAXT + 1];      // (kept here too: read below)
     unsigned short *pstart = ch.pstart + (size_t) b * (T + 1);
     {
         // states per time row (difference array over the branches), row starts,
@@ -570,6 +539,13 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
                 q += run;
         }
         rowstart[T] = (unsigned short) q;
+        {
+            AwbPacker<unsigned short> pk;
+            pk.init(ch.rowstart, (long long) b * (T + 1));
+            for (int t = 0; t <= T; t++)
+                pk.put(rowstart[t]);
+            pk.flush();
+        }
 
         // ---- the F-scribes' view of the column (awb_forward_fast.cuh).  The 64
         // scribe lanes are shared out over the T-1 time rows, nl lanes for a row
@@ -693,38 +669,25 @@ AWB_HD inline int awb_block_setup_t(const AwbChain &ch, int b)
         // node-major thread map; a branch never straddles a warp
         const long long tr0 = ch.trow_off[b];
         const int NSb = (int) (ch.trow_off[b + 1] - tr0);
-        // (trow_off and NSb are multiples of 32 slots: 8-byte stores)
-        for (int t = 0; t < NSb / 4; t++)
-            ((unsigned long long *) (ch.tmap + tr0))[t] = 0xFFFFFFFFFFFFFFFFull;
         if (S == 0) {
-            ch.tmap[tr0] = 0;
+            AwbPacker<unsigned short> pk;
+            pk.init(ch.tmap, tr0);
+            pk.put(0u);
+            for (int t = 1; t < NSb; t++)
+                pk.put(0xFFFFu);
+            pk.flush();
             ch.iperm[row0] = 0;
             ch.st_age[row0] = 0;
         } else {
             // first-fit-decreasing packing when it fits the reserved slots (it
             // nearly always does, and is tighter); else node order, which is
             // what the host reserved (awb_count_states)
-            if (awb_pack_branches_t<VCAP>(ncnt, V, ch.tmap + tr0, nfirst, NSb) > NSb) {
-                for (int t = 0; t < NSb; t++)
-                    ch.tmap[tr0 + t] = 0xFFFF;
-                int tpos = 0;
-                for (int i = 0; i < V; i++) {
-                    const int cnt = ncnt[i];
-                    if (cnt <= 0) continue;
-                    if (cnt > 32)
-                        tpos = (tpos + 63) & ~63;
-                    else if ((tpos & 31) + cnt > 32)
-                        tpos = (tpos + 31) & ~31;
-                    for (int t = 0; t < cnt; t++)
-                        if (tpos + t < NSb)
-                            ch.tmap[tr0 + tpos + t] = (unsigned short) (nfirst[i] + t);
-                    tpos += cnt;
-                    if (cnt > 32)
-                        tpos = (tpos + 63) & ~63;
-                }
-                if (tpos > NSb)
+            AwbRowLists<VCAP> rl;
+            if (awb_pack_place<VCAP>(ncnt, V, &rl) > NSb) {
+                if (awb_pack_place_in_order<VCAP>(ncnt, V, &rl) > NSb)
                     return 6;
             }
+            awb_pack_emit<VCAP>(rl, ncnt, nfirst, ch.tmap, tr0, NSb);
         }
     }
 
