@@ -54,6 +54,21 @@ void *emul_create(const awb_problem *p)
     return e;
 }
 
+// the forward kernel's thread map of one block (first-fit decreasing, or node
+// order): returns the slots used, fills tmap[0..cap) when given
+int emul_pack_branches(const short *cnt, const short *nfirst, int V, int in_order,
+                       unsigned short *tmap, int cap)
+{
+    static AwbRowLists<AWB_MAXV> rl;
+    const int n = in_order ? awb_pack_place_in_order<AWB_MAXV>(cnt, V, &rl)
+                           : awb_pack_place<AWB_MAXV>(cnt, V, &rl);
+    if (!in_order && n != awb_pack_branches(cnt, V))
+        return -1;                      // count-only mode disagrees
+    if (tmap && n <= cap)
+        awb_pack_emit<AWB_MAXV>(rl, cnt, nfirst, tmap, 0, cap);
+    return n;
+}
+
 const char *emul_error(void *h) { return ((Emul *) h)->err.c_str(); }
 int emul_code(void *h) { return ((Emul *) h)->code; }
 

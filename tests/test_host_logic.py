@@ -120,6 +120,48 @@ def test_block_setup_without_generic_tables(k, n, T, internal, seed, monkeypatch
     assert not np.array_equal(_raw(a, "perm"), _raw(b, "perm")) or k <= 6
 
 
+@pytest.mark.parametrize("maxlen,in_order", [(19, 0), (39, 0), (64, 0), (19, 1), (64, 1)])
+def test_thread_map_packing(maxlen, in_order):
+    # the forward kernel's thread map: every state exactly once, a branch in
+    # consecutive slots of one warp (33..64 states: two whole warps from an even
+    # one), everything else empty, nothing written past the map
+    import ctypes as C
+    L = el.lib()
+    L.emul_pack_branches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int]
+    rs = np.random.RandomState(maxlen + in_order)
+    for rep in range(300):
+        V = int(rs.randint(1, 400))
+        cnt = np.where(rs.rand(V) < 0.25, 0, rs.randint(1, maxlen + 1, V)).astype(np.int16)
+        over = np.cumsum(cnt) > 2048                      # at most 2048 states
+        cnt[over] = 0
+        S = int(cnt.sum())
+        if S == 0:
+            continue
+        nfirst = np.where(cnt > 0, np.cumsum(cnt) - cnt, -1).astype(np.int16)
+        n = L.emul_pack_branches(cnt.ctypes.data, nfirst.ctypes.data, V, in_order, None, 0)
+        assert n >= S and n > 0 and (in_order or n % 32 == 0)
+        cap = (n + 31) // 32 * 32 + 32 * int(rs.randint(0, 3))
+        tmap = np.full(cap + 8, 0x1234, np.uint16)
+        assert L.emul_pack_branches(cnt.ctypes.data, nfirst.ctypes.data, V, in_order,
+                                    tmap.ctypes.data, cap) == n
+        assert np.all(tmap[cap:] == 0x1234)
+        m = tmap[:cap]
+        used = m[m != 0xFFFF]
+        assert sorted(used.tolist()) == list(range(S))
+        slot_of = np.full(S, -1)
+        slot_of[m[m != 0xFFFF]] = np.nonzero(m != 0xFFFF)[0]
+        for i in np.nonzero(cnt > 0)[0]:
+            sl = slot_of[nfirst[i]:nfirst[i] + cnt[i]]
+            assert np.all(np.diff(sl) == 1)
+            if cnt[i] > 32:
+                assert sl[0] % 64 == 0
+                lo = sl[0]
+                assert np.all(m[lo + cnt[i]:lo + 64] == 0xFFFF)
+            else:
+                assert sl[0] // 32 == sl[-1] // 32
+
+
 @pytest.mark.parametrize("k,T,popsize", [(30, 64, 200.), (24, 64, 100.)])
 def test_setup_workers_skewed_time_rows(k, T, popsize):
     # all lineages coalesce in the first few of 63 time rows: one wide row and
